@@ -1,0 +1,102 @@
+/* libtqb200 — C ABI of the B200-native statevector engine that drops in behind TorchQuantum's
+ * gate-application hot path.  Plain pointers and sizes only; every pointer is DEVICE memory
+ * unless its name ends in _host; `stream` is a cudaStream_t passed as void*.  All functions
+ * return 0 on success, -1 on failure (message via tqb_last_error()).  Nothing here falls back
+ * to the CPU.
+ *
+ * State layout: complex64 interleaved (re, im) float pairs, [bsz][2^n], wire w of the reference
+ * (torchquantum/device/devices.py:57-71: dim 1+w of the [bsz,2,...,2] tensor) is index bit
+ * n-1-w.  `prog_dev` is a gate program in the wire format of torchquantum_b200/csrc/tqb_program.h
+ * produced by the host planner (torchquantum_b200/plan.py).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo's torchquantum/):
+ *   tqb_build_mats        <- the 26 `*_matrix(params)` builders + constant tables
+ *                            (functional/rx.py:19-115, ry.py:19-104, rz.py:19-171, u3.py:19-112,
+ *                            rot.py:19-89, u1.py, u2.py, r.py, phase_shift.py, single_excitation.py,
+ *                            xx_min_yy.py, xx_plus_yy.py, global_phase.py; mat_dict
+ *                            functional/__init__.py:97-123) incl. `inverse` (gate_wrapper.py:427-432)
+ *   tqb_pass_forward      <- apply_unitary_bmm / apply_unitary_einsum, one call per gate
+ *                            (functional/gate_wrapper.py:96-140, :18-93), here many gates per pass
+ *   tqb_pass_backward +   <- torch autograd through every bmm/permute/cos/sin node of the above
+ *   tqb_build_mats_bwd       (exercised by examples/mnist/mnist.py:143-146); here an adjoint sweep
+ *   tqb_apply_dense       <- the same bmm for arbitrary 2^k x 2^k matrices (qft, qubitunitary*)
+ *   tqb_expval_pauli      <- expval_joint_analytical (measurement/measurements.py:232-279)
+ *   tqb_expval_z          <- the marginal/eigenvalue part of expval / MeasureAll (:297-312)
+ *   tqb_probs, tqb_sample_counts <- measure (:37-74): |psi|^2 on the host + random.choices
+ */
+#ifndef TQB200_H
+#define TQB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQB_ABI_VERSION 1
+
+int tqb_abi_version(void);
+const char* tqb_last_error(void);
+
+/* Fill the per-sample gate-matrix rows mats[bsz][mat_stride] from parameters.
+ * table_dev: n_records x 8 int32 (kind, flags, param offset, matrix offset, const offset, n floats,
+ * n params, 0).  params_sh: [P_sh] shared parameters; params_ps: [bsz][ps_stride] per-sample. */
+int tqb_build_mats(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
+                   const float* params_ps, int ps_stride, const float* consts, float* mats,
+                   long long mat_stride, void* stream);
+
+/* dL/dtheta from dL/dU rows (gmats): per-sample parameters -> gparams_ps[bsz][ps_stride];
+ * shared parameters -> per-sample partials gparams_sh_partial[bsz][sh_stride] (caller sums over bsz). */
+int tqb_build_mats_bwd(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
+                       const float* params_ps, int ps_stride, const float* gmats, long long mat_stride,
+                       float* gparams_sh_partial, int sh_stride, float* gparams_ps, void* stream);
+
+/* One fused pass over the state: every tile of 2^T amplitudes is read from `src`, staged on chip,
+ * the whole gate list of the pass applied to it, and written to `dst` (dst may equal src).
+ * ext_hi: bits OR-ed above the tile index when gates are controlled by / diagonal in qubits that
+ * live on other ranks (sharded statevector). */
+int tqb_pass_forward(const float* src, float* dst, int n_qubits, long long bsz, const int32_t* prog_dev, int T, int R,
+                     int L, const float* mats, long long mat_stride, unsigned ext_hi, void* stream);
+
+/* Adjoint sweep of the same pass: reads the pass OUTPUT psi and dL/dpsi_out, writes the pass INPUT
+ * psi and dL/dpsi_in (dst may alias src); writes (single tile per sample) or atomically
+ * accumulates (several tiles: pre-zero) the dL/dU rows. */
+int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi_dst, float* lam_dst, int n_qubits,
+                      long long bsz, const int32_t* prog_dev, int T, int R, int L, const float* mats,
+                      float* gmats, long long mat_stride, unsigned ext_hi, void* stream);
+
+/* out = U_wires in (out of place); mats: complex64 [2^k][2^k] per sample with stride
+ * mat_stride_complex (0 = shared); bitpos_dev: k bit positions, matrix MSB first;
+ * conj_transpose != 0 applies U^H. */
+int tqb_apply_dense(const float* in, float* out, int n_qubits, long long bsz, const float* mats,
+                    long long mat_stride_complex, int k, const int* bitpos_dev, int conj_transpose,
+                    void* stream);
+/* G[b][r][c] = sum_rest lam_out[b][r,rest] conj(psi_in[b][c,rest]) (complex64 [bsz][2^k][2^k]) */
+int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long long bsz, int k,
+                   const int* bitpos_dev, float* G, void* stream);
+
+/* out[bsz][n_terms] = <psi|P_t|psi>, P_t given by x/z bit masks and the number of Y factors.
+ * Pre-zero `out` when n_qubits > 12 (several blocks per sample accumulate atomically). */
+int tqb_expval_pauli(const float* state, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
+                     const unsigned long long* zmask_dev, const int* ny_dev, int n_terms, float* out,
+                     void* stream);
+int tqb_expval_pauli_bwd(const float* state, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
+                         const unsigned long long* zmask_dev, const int* ny_dev, int n_terms,
+                         const float* grad_out, float* grad_state, void* stream);
+
+/* out[bsz][n+1]: column j < n is <Z> of index bit j, column n is the squared norm.
+ * Pre-zero `out` when n_qubits > 12. */
+int tqb_expval_z(const float* state, int n_qubits, long long bsz, float* out, void* stream);
+int tqb_expval_z_bwd(const float* state, int n_qubits, long long bsz, const float* grad_out, float* grad_state,
+                     void* stream);
+
+/* probs[bsz][2^n] float32 with the reference's host rounding (float32 hypot, then squared). */
+int tqb_probs(const float* state, int n_qubits, long long bsz, float* probs, void* stream);
+/* counts[bsz][2^n] (pre-zeroed int32) += histogram of n_shots inverse-CDF draws per sample from
+ * uniforms[bsz][n_shots] (float32 of Python's random.random()), CDF = sequential float32 sums. */
+int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const float* uniforms, int n_shots,
+                      float* cdf_scratch, int* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

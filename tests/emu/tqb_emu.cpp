@@ -1,0 +1,248 @@
+// TEST INFRASTRUCTURE ONLY — host build of the gate-pass kernel body (csrc/tqb_core.cuh) behind
+// the same C ABI as libtqb200.so, operating on HOST memory with the CUDA block/thread structure
+// emulated sequentially.  It lets the CPU test-suite (-m "not gpu") drive the host planner, the
+// autograd wiring and the program wire format end to end without a GPU.  The product package
+// never loads this library (torchquantum_b200/_native.py only loads the CUDA build and raises if
+// it is missing); tests inject it explicitly.
+//
+// Build: g++ -std=c++17 -O2 -shared -fPIC -o tests/emu/libtqb200_emu.so tests/emu/tqb_emu.cpp
+#include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "../../torchquantum_b200/csrc/tqb_core.cuh"
+#include "../../include/tqb200.h"
+
+using namespace tqb;
+
+static char g_err[256] = "";
+static int fail_msg(const char* m) { snprintf(g_err, sizeof(g_err), "%s", m); return -1; }
+
+struct EmuExec {
+  int nthreads;
+  template <class F> void par(F f) { for (int t = 0; t < nthreads; ++t) f(t); }
+  template <int N> void reduce_add(float* dst, float* v, int) { for (int i = 0; i < N; ++i) dst[i] += v[i]; }
+  void global_add(float* p, float v) { *p += v; }
+};
+
+template <int R, bool BWD>
+static void emu_blocks(BlockCtx c, unsigned ntiles, long long grid, unsigned ext_hi) {
+  const SmemLayout l = smem_layout(c.T, c.L, c.S, BWD);
+  std::vector<unsigned char> smem(l.total + 16);
+  unsigned char* base = smem.data();
+  base += (16 - ((uintptr_t)base & 15)) & 15;
+  c.s_psi = reinterpret_cast<float2*>(base + l.psi);
+  c.s_lam = reinterpret_cast<float2*>(base + l.lam);
+  c.s_mat = reinterpret_cast<float*>(base + l.mat);
+  c.s_grad = reinterpret_cast<float*>(base + l.grad);
+  c.s_prog = reinterpret_cast<int32_t*>(base + l.prog);
+  c.s_scat = reinterpret_cast<u64*>(base + l.scat);
+  for (long long blk = 0; blk < grid; ++blk) {
+    unsigned tile_id = 0;
+    if (ntiles > 1) { tile_id = (unsigned)(blk % ntiles); c.sample0 = (int)(blk / ntiles); }
+    else c.sample0 = (int)(blk * c.S);
+    c.tile_ext = tile_id | ext_hi;
+    c.outer_off = ntiles > 1 ? outer_offset(c.prog, c.n, tile_id) : 0ull;
+    EmuExec ex{c.nthreads};
+    run_block<R, BWD>(ex, c);
+  }
+}
+
+static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz, const int32_t* prog, int T, int R,
+                    int L, const float* mats, float* gmats, long long mat_stride, unsigned ext_hi) {
+  if (T < 1 || T > TQB_MAX_T || T > n || R < 1 || R > TQB_MAX_R || R > T || L < 1 || L > T)
+    return fail_msg("tqb pass: bad tile geometry");
+  if (prog[TQB_H_MAGIC] != TQB_MAGIC || prog[TQB_H_T] != T || prog[TQB_H_R] != R || prog[TQB_H_L] != L)
+    return fail_msg("tqb pass: program header mismatch");
+  if (bsz <= 0) return 0;
+  BlockCtx c;
+  c.T = T; c.R = R; c.L = L; c.n = n; c.bsz = (int)bsz;
+  const int items = 1 << (T - R);
+  c.tps = items < 256 ? items : 256;
+  unsigned ntiles;
+  long long grid;
+  if (n == T) {
+    ntiles = 1;
+    int S = c.tps >= 128 ? 1 : 128 / c.tps;
+    const size_t budget = 160 * 1024;
+    while (S > 1 && smem_layout(T, L, S, bwd).total > budget) S >>= 1;
+    if (S * c.tps < 32) S = 32 / c.tps;
+    c.S = S;
+    grid = (bsz + S - 1) / S;
+  } else {
+    c.S = 1;
+    ntiles = 1u << (n - T);
+    grid = bsz * (long long)ntiles;
+  }
+  c.nthreads = c.S * c.tps;
+  c.multi_tile = ntiles > 1;
+  c.sample_stride = 1ull << n;
+  c.prog = prog; c.psi = reinterpret_cast<float2*>(psi); c.lam = reinterpret_cast<float2*>(lam);
+  c.psi_src = reinterpret_cast<const float2*>(psi_src); c.lam_src = reinterpret_cast<const float2*>(lam_src);
+  c.mats = mats; c.gmats = gmats; c.mat_stride = mat_stride;
+#define TQB_DISPATCH(RR) \
+  case RR: if (bwd) emu_blocks<RR, true>(c, ntiles, grid, ext_hi); else emu_blocks<RR, false>(c, ntiles, grid, ext_hi); return 0;
+  switch (R) { TQB_DISPATCH(1) TQB_DISPATCH(2) TQB_DISPATCH(3) TQB_DISPATCH(4) }
+#undef TQB_DISPATCH
+  return fail_msg("bad R");
+}
+
+typedef std::complex<float> cf;
+typedef std::complex<double> cd;
+
+extern "C" {
+
+int tqb_abi_version(void) { return TQB_ABI_VERSION; }
+const char* tqb_last_error(void) { return g_err; }
+
+int tqb_pass_forward(const float* src, float* dst, int n, long long bsz, const int32_t* prog, int T, int R, int L,
+                     const float* mats, long long mat_stride, unsigned ext_hi, void*) {
+  return run_pass(false, src, nullptr, dst, nullptr, n, bsz, prog, T, R, L, mats, nullptr, mat_stride, ext_hi);
+}
+int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz,
+                      const int32_t* prog, int T, int R, int L, const float* mats, float* gmats, long long mat_stride,
+                      unsigned ext_hi, void*) {
+  return run_pass(true, psi_src, lam_src, psi, lam, n, bsz, prog, T, R, L, mats, gmats, mat_stride, ext_hi);
+}
+
+int tqb_build_mats(const int32_t* table, int nrec, long long bsz, const float* psh, const float* pps, int ps_stride,
+                   const float* consts, float* mats, long long mat_stride, void*) {
+  for (long long b = 0; b < bsz; ++b)
+    for (int r = 0; r < nrec; ++r)
+      build_one(table + r * TQB_B_WORDS, (int)b, psh, pps, ps_stride, consts, mats + b * mat_stride);
+  return 0;
+}
+int tqb_build_mats_bwd(const int32_t* table, int nrec, long long bsz, const float* psh, const float* pps,
+                       int ps_stride, const float* gmats, long long mat_stride, float* gsh, int sh_stride, float* gps,
+                       void*) {
+  for (long long b = 0; b < bsz; ++b)
+    for (int r = 0; r < nrec; ++r)
+      build_one_bwd(table + r * TQB_B_WORDS, (int)b, psh, pps, ps_stride, gmats + b * mat_stride,
+                    gsh + b * sh_stride, gps + b * ps_stride);
+  return 0;
+}
+
+int tqb_apply_dense(const float* in_, float* out_, int n, long long bsz, const float* mats_, long long mstride, int k,
+                    const int* bitpos, int conj_t, void*) {
+  const cf* in = reinterpret_cast<const cf*>(in_);
+  cf* out = reinterpret_cast<cf*>(out_);
+  const cf* mats = reinterpret_cast<const cf*>(mats_);
+  const int d = 1 << k;
+  for (long long b = 0; b < bsz; ++b)
+    for (u64 amp = 0; amp < (1ull << n); ++amp) {
+      u64 mask = 0; int row = 0;
+      for (int q = 0; q < k; ++q) { mask |= 1ull << bitpos[q]; row = (row << 1) | (int)((amp >> bitpos[q]) & 1); }
+      cf acc = 0;
+      for (int col = 0; col < d; ++col) {
+        u64 j = amp & ~mask;
+        for (int q = 0; q < k; ++q) if ((col >> (k - 1 - q)) & 1) j |= 1ull << bitpos[q];
+        cf m = conj_t ? std::conj(mats[b * mstride + (long long)col * d + row]) : mats[b * mstride + (long long)row * d + col];
+        acc += m * in[(b << n) + j];
+      }
+      out[(b << n) + amp] = acc;
+    }
+  return 0;
+}
+
+int tqb_dense_grad(const float* psi_, const float* lam_, int n, long long bsz, int k, const int* bitpos, float* G_, void*) {
+  const cf* psi = reinterpret_cast<const cf*>(psi_);
+  const cf* lam = reinterpret_cast<const cf*>(lam_);
+  cf* G = reinterpret_cast<cf*>(G_);
+  const int d = 1 << k;
+  for (long long i = 0; i < bsz * d * d; ++i) G[i] = 0;
+  for (long long b = 0; b < bsz; ++b)
+    for (u64 amp = 0; amp < (1ull << n); ++amp) {
+      u64 mask = 0; int row = 0;
+      for (int q = 0; q < k; ++q) { mask |= 1ull << bitpos[q]; row = (row << 1) | (int)((amp >> bitpos[q]) & 1); }
+      for (int col = 0; col < d; ++col) {
+        u64 j = amp & ~mask;
+        for (int q = 0; q < k; ++q) if ((col >> (k - 1 - q)) & 1) j |= 1ull << bitpos[q];
+        G[(b * d + row) * d + col] += lam[(b << n) + amp] * std::conj(psi[(b << n) + j]);
+      }
+    }
+  return 0;
+}
+
+static cf pauli_apply(const cf* psi, u64 k, u64 x, u64 z, int ny) {  // (P psi)[k]
+  const u64 j = k ^ x;
+  cf v = psi[j];
+  static const cf iph[4] = {cf(1, 0), cf(0, 1), cf(-1, 0), cf(0, -1)};
+  v *= iph[ny & 3];
+  if (__builtin_popcountll(j & z) & 1) v = -v;
+  return v;
+}
+
+int tqb_expval_pauli(const float* state, int n, long long bsz, const unsigned long long* xm, const unsigned long long* zm,
+                     const int* ny, int nt, float* out, void*) {
+  const cf* s = reinterpret_cast<const cf*>(state);
+  for (long long b = 0; b < bsz; ++b)
+    for (int t = 0; t < nt; ++t) {
+      double acc = 0;
+      for (u64 k = 0; k < (1ull << n); ++k) acc += (std::conj(s[(b << n) + k]) * pauli_apply(s + (b << n), k, xm[t], zm[t], ny[t])).real();
+      out[b * nt + t] += (float)acc;
+    }
+  return 0;
+}
+int tqb_expval_pauli_bwd(const float* state, int n, long long bsz, const unsigned long long* xm,
+                         const unsigned long long* zm, const int* ny, int nt, const float* gout, float* grad, void*) {
+  const cf* s = reinterpret_cast<const cf*>(state);
+  cf* g = reinterpret_cast<cf*>(grad);
+  for (long long b = 0; b < bsz; ++b)
+    for (u64 k = 0; k < (1ull << n); ++k) {
+      cf acc = 0;
+      for (int t = 0; t < nt; ++t) acc += 2.f * gout[b * nt + t] * pauli_apply(s + (b << n), k, xm[t], zm[t], ny[t]);
+      g[(b << n) + k] = acc;
+    }
+  return 0;
+}
+int tqb_expval_z(const float* state, int n, long long bsz, float* out, void*) {
+  const cf* s = reinterpret_cast<const cf*>(state);
+  for (long long b = 0; b < bsz; ++b) {
+    std::vector<double> acc(n + 1, 0.0);
+    for (u64 k = 0; k < (1ull << n); ++k) {
+      const double p = std::norm(cd(s[(b << n) + k]));
+      acc[n] += p;
+      for (int j = 0; j < n; ++j) acc[j] += ((k >> j) & 1) ? -p : p;
+    }
+    for (int j = 0; j <= n; ++j) out[b * (n + 1) + j] += (float)acc[j];
+  }
+  return 0;
+}
+int tqb_expval_z_bwd(const float* state, int n, long long bsz, const float* gout, float* grad, void*) {
+  const cf* s = reinterpret_cast<const cf*>(state);
+  cf* g = reinterpret_cast<cf*>(grad);
+  for (long long b = 0; b < bsz; ++b)
+    for (u64 k = 0; k < (1ull << n); ++k) {
+      float w = gout[b * (n + 1) + n];
+      for (int j = 0; j < n; ++j) w += ((k >> j) & 1) ? -gout[b * (n + 1) + j] : gout[b * (n + 1) + j];
+      g[(b << n) + k] = 2.f * w * s[(b << n) + k];
+    }
+  return 0;
+}
+int tqb_probs(const float* state, int n, long long bsz, float* probs, void*) {
+  for (long long i = 0; i < (bsz << n); ++i) {
+    const double re = state[2 * i], im = state[2 * i + 1];
+    const float m = (float)std::sqrt(re * re + im * im);
+    probs[i] = m * m;
+  }
+  return 0;
+}
+int tqb_sample_counts(const float* probs, int n, long long bsz, const float* u, int shots, float* cdf, int* counts, void*) {
+  const long long N = 1ll << n;
+  for (long long b = 0; b < bsz; ++b) {
+    float run = 0.f;
+    for (long long k = 0; k < N; ++k) { run = k == 0 ? probs[b * N] : run + probs[b * N + k]; cdf[b * N + k] = run; }
+    for (int s = 0; s < shots; ++s) {
+      const float r = u[b * shots + s] * cdf[b * N + N - 1];
+      long long lo = 0, hi = N - 1;
+      while (lo < hi) { const long long mid = (lo + hi) >> 1; if (r < cdf[b * N + mid]) hi = mid; else lo = mid + 1; }
+      counts[b * N + lo] += 1;
+    }
+  }
+  return 0;
+}
+}  // extern "C"

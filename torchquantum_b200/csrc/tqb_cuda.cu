@@ -1,0 +1,553 @@
+// sm_100a kernels + the C ABI of libtqb200.so (declared in include/tqb200.h).
+// Build: nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "tqb_core.cuh"
+#include "../../include/tqb200.h"
+
+using namespace tqb;
+
+static thread_local char g_err[256] = "";
+static int fail(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+static int fail_msg(const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return -1;
+}
+#define TQB_CHECK_LAUNCH(name)                    \
+  do {                                            \
+    cudaError_t e_ = cudaGetLastError();          \
+    if (e_ != cudaSuccess) return fail(name, e_); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// fused gate pass (forward / adjoint backward)
+// ---------------------------------------------------------------------------------------
+struct CudaExec {
+  template <class F>
+  __device__ __forceinline__ void par(F f) {
+    f((int)threadIdx.x);
+    __syncthreads();
+  }
+  // sum v[0..N) over the `width` consecutive lanes that share a sample, add into shared dst
+  template <int N>
+  __device__ __forceinline__ void reduce_add(float* dst, float* v, int width) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = v[i];
+      for (int o = width >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      v[i] = s;
+    }
+    if (((threadIdx.x & 31) & (width - 1)) == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) atomicAdd(dst + i, v[i]);
+    }
+  }
+  __device__ __forceinline__ void global_add(float* p, float v) { atomicAdd(p, v); }
+};
+
+struct PassArgs {
+  int T, R, L, n, S, tps, bsz;
+  unsigned ntiles, ext_hi;
+  const int32_t* prog;
+  const float2* psi_src;
+  const float2* lam_src;
+  float2* psi;
+  float2* lam;
+  const float* mats;
+  float* gmats;
+  long long mat_stride;
+};
+
+template <int R, bool BWD>
+__global__ void __launch_bounds__(256) tqb_pass_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockCtx c;
+  c.T = a.T; c.R = R; c.L = a.L; c.n = a.n; c.S = a.S; c.tps = a.tps; c.nthreads = a.S * a.tps;
+  c.bsz = a.bsz;
+  c.multi_tile = a.ntiles > 1;
+  unsigned tile_id = 0;
+  if (a.ntiles > 1) { tile_id = blockIdx.x % a.ntiles; c.sample0 = blockIdx.x / a.ntiles; }
+  else c.sample0 = blockIdx.x * a.S;
+  c.tile_ext = tile_id | a.ext_hi;
+  c.outer_off = a.ntiles > 1 ? outer_offset(a.prog, a.n, tile_id) : 0ull;
+  c.sample_stride = 1ull << a.n;
+  c.prog = a.prog; c.psi_src = a.psi_src; c.lam_src = a.lam_src; c.psi = a.psi; c.lam = a.lam; c.mats = a.mats; c.gmats = a.gmats;
+  c.mat_stride = a.mat_stride;
+  const SmemLayout l = smem_layout(a.T, a.L, a.S, BWD);
+  c.s_psi = reinterpret_cast<float2*>(smem + l.psi);
+  c.s_lam = reinterpret_cast<float2*>(smem + l.lam);
+  c.s_mat = reinterpret_cast<float*>(smem + l.mat);
+  c.s_grad = reinterpret_cast<float*>(smem + l.grad);
+  c.s_prog = reinterpret_cast<int32_t*>(smem + l.prog);
+  c.s_scat = reinterpret_cast<u64*>(smem + l.scat);
+  CudaExec ex;
+  run_block<R, BWD>(ex, c);
+}
+
+template <int R, bool BWD>
+static int launch_pass(const PassArgs& a, size_t smem, long long grid, cudaStream_t st) {
+  static int configured_smem = 0;  // per instantiation
+  if ((int)smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(tqb_pass_kernel<R, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(pass)", e);
+    configured_smem = (int)smem;
+  }
+  tqb_pass_kernel<R, BWD><<<(unsigned)grid, a.S * a.tps, smem, st>>>(a);
+  TQB_CHECK_LAUNCH("tqb_pass_kernel");
+  return 0;
+}
+
+static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz, const int32_t* prog, int T, int R,
+                    int L, const float* mats, float* gmats, long long mat_stride, unsigned ext_hi, void* stream) {
+  if (T < 1 || T > TQB_MAX_T || T > n || R < 1 || R > TQB_MAX_R || R > T || L < 1 || L > T)
+    return fail_msg("tqb pass: bad tile geometry");
+  if (bsz <= 0) return 0;
+  PassArgs a;
+  a.T = T; a.R = R; a.L = L; a.n = n; a.bsz = (int)bsz;
+  const int items = 1 << (T - R);
+  a.tps = items < 256 ? items : 256;
+  long long grid;
+  if (n == T) {
+    a.ntiles = 1;
+    // samples per CTA: fill 128 threads, bounded by what the staged segment matrices cost
+    int S = a.tps >= 128 ? 1 : 128 / a.tps;
+    const size_t budget = 160 * 1024;
+    while (S > 1 && smem_layout(T, L, S, bwd).total > budget) S >>= 1;
+    if (S * a.tps < 32) S = 32 / a.tps;  // whole warps for the shuffle reductions
+    a.S = S;
+    grid = (bsz + S - 1) / S;
+  } else {
+    a.S = 1;
+    a.ntiles = 1u << (n - T);
+    grid = bsz * (long long)a.ntiles;
+  }
+  if (grid > 0x7fffffffLL) return fail_msg("tqb pass: grid too large");
+  a.ext_hi = ext_hi;
+  a.prog = prog; a.psi = reinterpret_cast<float2*>(psi); a.lam = reinterpret_cast<float2*>(lam);
+  a.psi_src = reinterpret_cast<const float2*>(psi_src); a.lam_src = reinterpret_cast<const float2*>(lam_src);
+  a.mats = mats; a.gmats = gmats; a.mat_stride = mat_stride;
+  const size_t smem = smem_layout(T, L, a.S, bwd).total;
+  if (smem > 227 * 1024) return fail_msg("tqb pass: tile does not fit shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+#define TQB_DISPATCH(RR)                                             \
+  case RR:                                                           \
+    return bwd ? launch_pass<RR, true>(a, smem, grid, st) : launch_pass<RR, false>(a, smem, grid, st);
+  switch (R) {
+    TQB_DISPATCH(1)
+    TQB_DISPATCH(2)
+    TQB_DISPATCH(3)
+    TQB_DISPATCH(4)
+  }
+#undef TQB_DISPATCH
+  return fail_msg("tqb pass: bad R");
+}
+
+// ---------------------------------------------------------------------------------------
+// parameter -> matrix builder and its backward
+// ---------------------------------------------------------------------------------------
+__global__ void tqb_build_kernel(const int32_t* table, int nrec, long long bsz, const float* params_sh,
+                                 const float* params_ps, int ps_stride, const float* consts, float* mats,
+                                 long long mat_stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bsz * nrec) return;
+  const int r = (int)(i % nrec);
+  const long long b = i / nrec;
+  build_one(table + r * TQB_B_WORDS, (int)b, params_sh, params_ps, ps_stride, consts, mats + b * mat_stride);
+}
+
+__global__ void tqb_build_bwd_kernel(const int32_t* table, int nrec, long long bsz, const float* params_sh,
+                                     const float* params_ps, int ps_stride, const float* gmats, long long mat_stride,
+                                     float* gsh, int sh_stride, float* gps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bsz * nrec) return;
+  const int r = (int)(i % nrec);
+  const long long b = i / nrec;
+  build_one_bwd(table + r * TQB_B_WORDS, (int)b, params_sh, params_ps, ps_stride, gmats + b * mat_stride,
+                gsh + b * sh_stride, gps + b * ps_stride);
+}
+
+// ---------------------------------------------------------------------------------------
+// generic dense k-qubit gate, out of place (rare: qft / qubitunitary on >= 3 wires)
+// ---------------------------------------------------------------------------------------
+__global__ void tqb_dense_kernel(const float2* in, float2* out, int n, long long total, const float2* mats,
+                                 long long mat_stride, int k, const int* bitpos /* msb first */, int conj_t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const u64 amp = (u64)i & ((1ull << n) - 1ull);
+  const long long b = i >> n;
+  u64 mask = 0;
+  int row = 0;
+  for (int q = 0; q < k; ++q) {
+    const int p = bitpos[q];
+    mask |= 1ull << p;
+    row = (row << 1) | (int)((amp >> p) & 1ull);
+  }
+  const u64 base = amp & ~mask;
+  const int d = 1 << k;
+  const float2* m = mats + b * mat_stride;
+  const float2* src = in + (b << n);
+  float2 acc = make_float2(0.f, 0.f);
+  for (int col = 0; col < d; ++col) {
+    u64 j = base;
+    for (int q = 0; q < k; ++q)
+      if ((col >> (k - 1 - q)) & 1) j |= 1ull << bitpos[q];
+    const float2 v = src[j];
+    float2 mv = conj_t ? m[(long long)col * d + row] : m[(long long)row * d + col];
+    if (conj_t) mv.y = -mv.y;
+    acc = cadd(acc, cmul(mv, v));
+  }
+  out[i] = acc;
+}
+
+// G[b][r][c] = sum_rest lam[b][r,rest] conj(psi[b][c,rest])  (one block per (b, r, c))
+__global__ void tqb_dense_grad_kernel(const float2* psi, const float2* lam, int n, int k, const int* bitpos,
+                                      float2* G) {
+  const int d = 1 << k;
+  const int c = blockIdx.x % d, r = (blockIdx.x / d) % d;
+  const long long b = blockIdx.x / (d * d);
+  u64 rbits = 0, cbits = 0;
+  u32 sp[32];
+  for (int q = 0; q < k; ++q) {
+    if ((r >> (k - 1 - q)) & 1) rbits |= 1ull << bitpos[q];
+    if ((c >> (k - 1 - q)) & 1) cbits |= 1ull << bitpos[q];
+    sp[q] = bitpos[q];
+  }
+  for (int a2 = 0; a2 < k; ++a2)
+    for (int b2 = 0; b2 + 1 < k - a2; ++b2)
+      if (sp[b2] > sp[b2 + 1]) { u32 t = sp[b2]; sp[b2] = sp[b2 + 1]; sp[b2 + 1] = t; }
+  const u64 nrest = 1ull << (n - k);
+  float2 acc = make_float2(0.f, 0.f);
+  for (u64 w = threadIdx.x; w < nrest; w += blockDim.x) {
+    u64 base = w;
+    for (int q = 0; q < k; ++q) base = ((base >> sp[q]) << (sp[q] + 1)) | (base & ((1ull << sp[q]) - 1ull));
+    const float2 l = lam[(b << n) + (base | rbits)], p = psi[(b << n) + (base | cbits)];
+    acc = cadd(acc, cmulc(p, l));
+  }
+  __shared__ float2 red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] = cadd(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) G[blockIdx.x] = red[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+#define TQB_TERM_BATCH 8
+// out[b][t] (+)= <psi_b| P_t |psi_b>,  P|k> = i^ny (-1)^popc(k&z) |k^x>
+__global__ void __launch_bounds__(256) tqb_expval_pauli_kernel(const float2* state, int n, const u64* xm,
+                                                                const u64* zm, const int* ny, int nterms,
+                                                                float* out, int chunk_log2, int use_atomic) {
+  const long long b = blockIdx.y;
+  const float2* psi = state + (b << n);
+  const u64 k0 = (u64)blockIdx.x << chunk_log2;
+  const u64 k1 = k0 + (1ull << chunk_log2);
+  __shared__ float red[8][TQB_TERM_BATCH];
+  for (int t0 = 0; t0 < nterms; t0 += TQB_TERM_BATCH) {
+    float acc[TQB_TERM_BATCH];
+    u64 x[TQB_TERM_BATCH], z[TQB_TERM_BATCH];
+    int ph[TQB_TERM_BATCH];
+#pragma unroll
+    for (int t = 0; t < TQB_TERM_BATCH; ++t) {
+      acc[t] = 0.f;
+      const int tt = t0 + t < nterms ? t0 + t : nterms - 1;
+      x[t] = xm[tt]; z[t] = zm[tt]; ph[t] = ny[tt] & 3;
+    }
+    for (u64 k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      const float2 a = psi[k];
+#pragma unroll
+      for (int t = 0; t < TQB_TERM_BATCH; ++t) {
+        const float2 c = x[t] ? psi[k ^ x[t]] : a;
+        float2 w = cmulc(c, a);  // conj(psi[k^x]) psi[k]
+        float v = (ph[t] == 0) ? w.x : (ph[t] == 1) ? -w.y : (ph[t] == 2) ? -w.x : w.y;
+        if (__popcll(k & z[t]) & 1) v = -v;
+        acc[t] += v;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TQB_TERM_BATCH; ++t) {
+      const float s = warp_sum(acc[t]);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < TQB_TERM_BATCH && t0 + (int)threadIdx.x < nterms) {
+      float s = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+      float* dst = out + b * nterms + t0 + threadIdx.x;
+      if (use_atomic) atomicAdd(dst, s); else *dst = s;
+    }
+    __syncthreads();
+  }
+}
+
+// grad[b][k] = sum_t 2 g[b][t] (P_t psi)[k],  (P psi)[k] = i^ny (-1)^popc((k^x)&z) psi[k^x]
+__global__ void tqb_expval_pauli_bwd_kernel(const float2* state, int n, long long total, const u64* xm,
+                                            const u64* zm, const int* ny, int nterms, const float* gout,
+                                            float2* grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const u64 k = (u64)i & ((1ull << n) - 1ull);
+  const long long b = i >> n;
+  const float2* psi = state + (b << n);
+  float2 acc = make_float2(0.f, 0.f);
+  for (int t = 0; t < nterms; ++t) {
+    const u64 j = k ^ xm[t];
+    float2 v = psi[j];
+    const int ph = ny[t] & 3;
+    if (ph == 1) v = make_float2(-v.y, v.x);
+    else if (ph == 2) v = make_float2(-v.x, -v.y);
+    else if (ph == 3) v = make_float2(v.y, -v.x);
+    float g = 2.f * gout[b * nterms + t];
+    if (__popcll(j & zm[t]) & 1) g = -g;
+    acc.x += g * v.x; acc.y += g * v.y;
+  }
+  grad[i] = acc;
+}
+
+// out[b][j] (+)= sum_k |psi_k|^2 (1 - 2 bit_j(k)) for j < n ; out[b][n] (+)= sum_k |psi_k|^2
+__global__ void __launch_bounds__(256) tqb_expval_z_kernel(const float2* state, int n, float* out, int chunk_log2,
+                                                            int use_atomic) {
+  const long long b = blockIdx.y;
+  const float2* psi = state + (b << n);
+  const u64 k0 = (u64)blockIdx.x << chunk_log2;
+  const int nloc = chunk_log2;  // bits that vary inside this block's chunk
+  float tot = 0.f;
+  float s1[TQB_MAX_T + 2];      // sum over amplitudes with local bit j set (chunk_log2 <= 14)
+#pragma unroll
+  for (int j = 0; j < TQB_MAX_T + 2; ++j) s1[j] = 0.f;
+  for (u32 k = threadIdx.x; k < (1u << nloc); k += blockDim.x) {
+    const float2 a = psi[k0 + k];
+    const float p = a.x * a.x + a.y * a.y;
+    tot += p;
+#pragma unroll
+    for (int j = 0; j < TQB_MAX_T + 2; ++j) if (j < nloc && ((k >> j) & 1u)) s1[j] += p;
+  }
+  __shared__ float red[TQB_MAX_T + 3];
+  if (threadIdx.x < TQB_MAX_T + 3) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&red[TQB_MAX_T + 2], tot);
+#pragma unroll
+  for (int j = 0; j < TQB_MAX_T + 2; ++j) {
+    if (j < nloc) {
+      const float s = warp_sum(s1[j]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&red[j], s);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x <= n) {
+    const int j = threadIdx.x;
+    const float total = red[TQB_MAX_T + 2];
+    float v;
+    if (j == n) v = total;
+    else if (j < nloc) v = total - 2.f * red[j];
+    else v = ((k0 >> j) & 1ull) ? -total : total;
+    float* dst = out + b * (n + 1) + j;
+    if (use_atomic) atomicAdd(dst, v); else *dst = v;
+  }
+}
+
+// grad[b][k] = 2 psi[k] (g[b][n] + sum_j g[b][j] (1 - 2 bit_j(k)))
+__global__ void tqb_expval_z_bwd_kernel(const float2* state, int n, long long total, const float* gout, float2* grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const u64 k = (u64)i & ((1ull << n) - 1ull);
+  const long long b = i >> n;
+  const float* g = gout + b * (n + 1);
+  float w = g[n];
+  for (int j = 0; j < n; ++j) w += ((k >> j) & 1ull) ? -g[j] : g[j];
+  const float2 a = state[i];
+  grad[i] = make_float2(2.f * w * a.x, 2.f * w * a.y);
+}
+
+// probabilities exactly as numpy does on the host: m = float32(|psi|) (correctly rounded hypot),
+// p = float32(m*m)   (measurement/measurements.py:47-55)
+__global__ void tqb_probs_kernel(const float2* state, long long total, float* probs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float2 a = state[i];
+  const float m = (float)sqrt((double)a.x * (double)a.x + (double)a.y * (double)a.y);
+  probs[i] = __fmul_rn(m, m);
+}
+
+// sequential float32 running sum per sample (same rounding order as itertools.accumulate)
+__global__ void tqb_cdf_kernel(const float* probs, long long bsz, long long N, float* cdf) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bsz) return;
+  const float* p = probs + b * N;
+  float* c = cdf + b * N;
+  float run = 0.f;
+  for (long long k = 0; k < N; ++k) {
+    run = k == 0 ? p[0] : __fadd_rn(run, p[k]);
+    c[k] = run;
+  }
+}
+
+// counts[b][bisect_right(cdf_b, float32(u)*total, 0, N-1)] += 1   (CPython random.choices)
+__global__ void tqb_sample_kernel(const float* cdf, const float* u, long long bsz, long long N, int shots,
+                                  int* counts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bsz * shots) return;
+  const long long b = i / shots;
+  const float* c = cdf + b * N;
+  const float r = __fmul_rn(u[i], c[N - 1]);
+  long long lo = 0, hi = N - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (r < c[mid]) hi = mid; else lo = mid + 1;
+  }
+  atomicAdd(counts + b * N + lo, 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int tqb_abi_version(void) { return TQB_ABI_VERSION; }
+const char* tqb_last_error(void) { return g_err; }
+
+int tqb_pass_forward(const float* src, float* dst, int n_qubits, long long bsz, const int32_t* prog_dev, int T, int R,
+                     int L, const float* mats, long long mat_stride, unsigned ext_hi, void* stream) {
+  return run_pass(false, src, nullptr, dst, nullptr, n_qubits, bsz, prog_dev, T, R, L, mats, nullptr, mat_stride, ext_hi, stream);
+}
+
+int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi_dst, float* lam_dst, int n_qubits,
+                      long long bsz, const int32_t* prog_dev, int T, int R, int L, const float* mats, float* gmats,
+                      long long mat_stride, unsigned ext_hi, void* stream) {
+  return run_pass(true, psi_src, lam_src, psi_dst, lam_dst, n_qubits, bsz, prog_dev, T, R, L, mats, gmats, mat_stride, ext_hi, stream);
+}
+
+int tqb_build_mats(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
+                   const float* params_ps, int ps_stride, const float* consts, float* mats, long long mat_stride,
+                   void* stream) {
+  if (n_records <= 0 || bsz <= 0) return 0;
+  const long long total = bsz * n_records;
+  tqb_build_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      table_dev, n_records, bsz, params_sh, params_ps, ps_stride, consts, mats, mat_stride);
+  TQB_CHECK_LAUNCH("tqb_build_kernel");
+  return 0;
+}
+
+int tqb_build_mats_bwd(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
+                       const float* params_ps, int ps_stride, const float* gmats, long long mat_stride,
+                       float* gparams_sh_partial, int sh_stride, float* gparams_ps, void* stream) {
+  if (n_records <= 0 || bsz <= 0) return 0;
+  const long long total = bsz * n_records;
+  tqb_build_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      table_dev, n_records, bsz, params_sh, params_ps, ps_stride, gmats, mat_stride, gparams_sh_partial, sh_stride,
+      gparams_ps);
+  TQB_CHECK_LAUNCH("tqb_build_bwd_kernel");
+  return 0;
+}
+
+int tqb_apply_dense(const float* in, float* out, int n_qubits, long long bsz, const float* mats,
+                    long long mat_stride_complex, int k, const int* bitpos_dev, int conj_transpose, void* stream) {
+  const long long total = bsz << n_qubits;
+  if (total <= 0) return 0;
+  tqb_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n_qubits, total,
+      reinterpret_cast<const float2*>(mats), mat_stride_complex, k, bitpos_dev, conj_transpose);
+  TQB_CHECK_LAUNCH("tqb_dense_kernel");
+  return 0;
+}
+
+int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long long bsz, int k,
+                   const int* bitpos_dev, float* G, void* stream) {
+  if (bsz <= 0) return 0;
+  if (k > 10) return fail_msg("tqb_dense_grad: k too large");
+  const long long blocks = bsz << (2 * k);
+  tqb_dense_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(psi_in), reinterpret_cast<const float2*>(lam_out), n_qubits, k, bitpos_dev,
+      reinterpret_cast<float2*>(G));
+  TQB_CHECK_LAUNCH("tqb_dense_grad_kernel");
+  return 0;
+}
+
+static int expval_chunk_log2(int n) { return n < 12 ? n : 12; }
+
+int tqb_expval_pauli(const float* state, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
+                     const unsigned long long* zmask_dev, const int* ny_dev, int n_terms, float* out, void* stream) {
+  if (bsz <= 0 || n_terms <= 0) return 0;
+  const int cl = expval_chunk_log2(n_qubits);
+  dim3 grid(1u << (n_qubits - cl), (unsigned)bsz);
+  if (bsz > 65535) return fail_msg("tqb_expval_pauli: bsz > 65535");
+  tqb_expval_pauli_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(state), n_qubits,
+                                                                 xmask_dev, zmask_dev, ny_dev, n_terms, out, cl,
+                                                                 grid.x > 1);
+  TQB_CHECK_LAUNCH("tqb_expval_pauli_kernel");
+  return 0;
+}
+
+int tqb_expval_pauli_bwd(const float* state, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
+                         const unsigned long long* zmask_dev, const int* ny_dev, int n_terms, const float* grad_out,
+                         float* grad_state, void* stream) {
+  const long long total = bsz << n_qubits;
+  if (total <= 0) return 0;
+  tqb_expval_pauli_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(state), n_qubits, total, xmask_dev, zmask_dev, ny_dev, n_terms, grad_out,
+      reinterpret_cast<float2*>(grad_state));
+  TQB_CHECK_LAUNCH("tqb_expval_pauli_bwd_kernel");
+  return 0;
+}
+
+int tqb_expval_z(const float* state, int n_qubits, long long bsz, float* out, void* stream) {
+  if (bsz <= 0) return 0;
+  if (bsz > 65535) return fail_msg("tqb_expval_z: bsz > 65535");
+  const int cl = expval_chunk_log2(n_qubits);
+  dim3 grid(1u << (n_qubits - cl), (unsigned)bsz);
+  tqb_expval_z_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(state), n_qubits, out,
+                                                             cl, grid.x > 1);
+  TQB_CHECK_LAUNCH("tqb_expval_z_kernel");
+  return 0;
+}
+
+int tqb_expval_z_bwd(const float* state, int n_qubits, long long bsz, const float* grad_out, float* grad_state,
+                     void* stream) {
+  const long long total = bsz << n_qubits;
+  if (total <= 0) return 0;
+  tqb_expval_z_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(state), n_qubits, total, grad_out, reinterpret_cast<float2*>(grad_state));
+  TQB_CHECK_LAUNCH("tqb_expval_z_bwd_kernel");
+  return 0;
+}
+
+int tqb_probs(const float* state, int n_qubits, long long bsz, float* probs, void* stream) {
+  const long long total = bsz << n_qubits;
+  if (total <= 0) return 0;
+  tqb_probs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(state), total, probs);
+  TQB_CHECK_LAUNCH("tqb_probs_kernel");
+  return 0;
+}
+
+int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const float* uniforms, int n_shots,
+                      float* cdf_scratch, int* counts, void* stream) {
+  if (bsz <= 0) return 0;
+  const long long N = 1ll << n_qubits;
+  cudaStream_t st = (cudaStream_t)stream;
+  tqb_cdf_kernel<<<(unsigned)((bsz + 31) / 32), 32, 0, st>>>(probs, bsz, N, cdf_scratch);
+  TQB_CHECK_LAUNCH("tqb_cdf_kernel");
+  const long long total = bsz * n_shots;
+  if (total > 0) {
+    tqb_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cdf_scratch, uniforms, bsz, N, n_shots, counts);
+    TQB_CHECK_LAUNCH("tqb_sample_kernel");
+  }
+  return 0;
+}
+
+}  // extern "C"

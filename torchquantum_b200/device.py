@@ -1,0 +1,153 @@
+"""QuantumDevice — drop-in for torchquantum/device/devices.py:36-136.
+
+Same constructor, buffers (`state`, `states`), reset/clone/set helpers and gate methods, but gates
+are *queued* and run as fused passes when the state is read (`.states`, `get_states_1d()`,
+measurement): the lazy queue is what lets many gates share one trip through HBM.
+The exposed `states` tensor is always contiguous `[bsz] + [2] * n_wires` complex64.
+"""
+from typing import Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine
+from .macro import C_DTYPE
+
+__all__ = ["QuantumDevice"]
+
+
+class QuantumDevice(nn.Module):
+    def __init__(self, n_wires: int, device_name: str = "default", bsz: int = 1,
+                 device: Union[torch.device, str] = "cpu", record_op: bool = False):
+        super().__init__()
+        self.n_wires = n_wires
+        self.device_name = device_name
+        self.bsz = bsz
+        self.device = device
+        _state = torch.zeros(2 ** n_wires, dtype=C_DTYPE)
+        _state[0] = 1 + 0j
+        _state = torch.reshape(_state, [2] * n_wires).to(device)
+        self.register_buffer("state", _state)
+        self._queue = []
+        self._flat = None
+        self._buffers["states"] = None
+        self.reset_states(bsz)
+        self.record_op = record_op
+        self._op_history = []
+        self._history_pending = []
+
+    # --- state container --------------------------------------------------------------
+    def _set_flat(self, flat):
+        self._queue = []
+        self._flat = flat
+        self._buffers["states"] = None  # materialised lazily as a view
+
+    @property
+    def states(self):
+        self.flush()
+        v = self._flat.reshape([self._flat.shape[0]] + [2] * self.n_wires)
+        self._buffers["states"] = v
+        return v
+
+    @states.setter
+    def states(self, value):
+        bsz = value.shape[0]
+        self._set_flat(value.reshape(bsz, 2 ** self.n_wires))
+
+    def __setattr__(self, name, value):
+        # `states` is a registered buffer name (checkpoint compatibility), so nn.Module would
+        # store the tensor itself; route it through the property instead
+        if name == "states":
+            type(self).states.fset(self, value)
+        else:
+            super().__setattr__(name, value)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.flush()
+        self._buffers["states"] = None
+        super()._apply(fn, *args, **kwargs)
+        self._flat = fn(self._flat)
+        self.device = self.state.device
+        return self
+
+    def flush(self):
+        """Run every queued gate (fused) and materialise the state."""
+        if self._queue:
+            q, self._queue = self._queue, []
+            self._flat = engine.run_circuit(self._flat, self.n_wires, q)
+
+    def enqueue(self, name, wires, params, inverse):
+        self._queue.append((name, wires, params, inverse))
+
+    def reset_op_history(self):
+        self._op_history = []
+        self._history_pending = []
+
+    @property
+    def op_history(self):
+        # the reference converts params to python lists per gate (a D2H sync each,
+        # functional/gate_wrapper.py:380-391); here the conversion is deferred to the first read
+        for entry in self._history_pending:
+            p = entry["params"]
+            if p is not None:
+                entry["params"] = p.squeeze().detach().cpu().numpy().tolist()
+        self._history_pending = []
+        return self._op_history
+
+    @op_history.setter
+    def op_history(self, value):
+        self._op_history = value
+        self._history_pending = []
+
+    def _record(self, entry):
+        self._op_history.append(entry)
+        self._history_pending.append(entry)
+
+    def clone_states(self, existing_states: torch.Tensor):
+        self.states = existing_states.clone()
+
+    def set_states(self, states: torch.Tensor):
+        self.states = states
+
+    def reset_states(self, bsz: int):
+        flat = torch.zeros(bsz, 2 ** self.n_wires, dtype=C_DTYPE, device=self.state.device)
+        flat[:, 0] = 1
+        self._set_flat(flat)
+
+    def reset_identity_states(self):
+        self._set_flat(torch.eye(2 ** self.n_wires, device=self.state.device, dtype=C_DTYPE))
+
+    def reset_all_eq_states(self, bsz: int):
+        energy = np.sqrt(1 / (2 ** self.n_wires) / 2)
+        flat = torch.ones(bsz, 2 ** self.n_wires, dtype=C_DTYPE, device=self.state.device) * (energy + energy * 1j)
+        self._set_flat(flat)
+
+    def get_states_1d(self):
+        self.flush()
+        return self._flat
+
+    def get_state_1d(self):
+        return torch.reshape(self.state, [2 ** self.n_wires])
+
+    @property
+    def name(self):
+        return self.__class__.__name__
+
+    def __repr__(self):
+        return (f" class: {self.name} \n device name: {self.device_name} \n number of qubits: {self.n_wires} \n"
+                f" batch size: {self.bsz} \n current computing device: {self.state.device} \n"
+                f" recording op history: {self.record_op} \n"
+                f" current states: {repr(self.get_states_1d().cpu().detach().numpy())}")
+
+
+def _bind_functionals():
+    from .functional import func_name_dict, func_name_dict_collect
+
+    for name, func in func_name_dict.items():
+        setattr(QuantumDevice, name, func)
+    for name, func in func_name_dict_collect.items():
+        setattr(QuantumDevice, name, func)
+
+
+_bind_functionals()

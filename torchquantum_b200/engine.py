@@ -1,0 +1,251 @@
+"""Execution engine: runs a planned circuit through the C ABI (libtqb200.so) and wires the
+adjoint backward into torch autograd.
+
+Forward of a fused stage:  parameters --tqb_build_mats--> per-sample matrix rows;
+state --tqb_pass_forward (one launch per pass)--> new state.  Only the *output* state is kept for
+the backward, which un-applies the gates in reverse (tqb_pass_backward) while accumulating
+dL/dU, then maps dL/dU to dL/dtheta (tqb_build_mats_bwd): training memory is O(2^n) per sample
+instead of the reference's O(depth * 2^n) autograd tape.
+"""
+import numpy as np
+import torch
+
+from . import _codes as C
+from . import _native
+from . import gates as G
+from . import plan as P
+
+_PLAN_CACHE = {}
+_DEV_CACHE = {}
+STATS = {"launches": 0, "plans_built": 0}
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def get_plan(n, key, grad_mode, n_total=None):
+    k = (n, n_total, grad_mode, key)
+    plan = _PLAN_CACHE.get(k)
+    if plan is None:
+        plan = P.build_plan(n, key, grad_mode, n_total)
+        _PLAN_CACHE[k] = plan
+        STATS["plans_built"] += 1
+        if len(_PLAN_CACHE) > 512:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    return plan
+
+
+def _dev(obj, attr, device):
+    """numpy array attribute of a plan object -> cached device tensor."""
+    k = (id(obj), attr, str(device))
+    t = _DEV_CACHE.get(k)
+    if t is None:
+        t = torch.from_numpy(np.ascontiguousarray(getattr(obj, attr))).to(device)
+        _DEV_CACHE[k] = (t, obj)  # keep obj alive so id() stays unique
+        if len(_DEV_CACHE) > 8192:
+            _DEV_CACHE.pop(next(iter(_DEV_CACHE)))
+        return t
+    return t[0]
+
+
+def _build_mats(stage, bsz, psh, pps, externs, device):
+    mats = torch.empty(bsz, stage.M, dtype=torch.float32, device=device)
+    table = _dev(stage, "table", device)
+    consts = _dev(stage, "consts", device)
+    _native.call("tqb_build_mats", _ptr(table), table.shape[0], bsz, _ptr(psh), _ptr(pps),
+                 pps.shape[1] if pps is not None else 0, _ptr(consts), _ptr(mats), stage.M,
+                 _native.stream_ptr(mats))
+    STATS["launches"] += 1
+    for (rec, moff, dim, inverse), u in zip(stage.externs, externs):
+        m = u.detach().to(torch.complex64)
+        if inverse:
+            m = m.conj().transpose(-1, -2)
+        m = torch.view_as_real(m.contiguous()).reshape(-1, 2 * dim * dim)
+        mats[:, moff:moff + 2 * dim * dim] = m  # broadcasts a shared matrix over the batch
+    return mats
+
+
+class FusedFn(torch.autograd.Function):
+    """state [bsz, 2^n] complex64 -> state, through all passes of one fused stage."""
+
+    @staticmethod
+    def forward(ctx, state, psh, pps, stage, n, ext_hi, *externs):
+        _native.check_device(state)
+        state = state.contiguous()
+        bsz = state.shape[0]
+        dev = state.device
+        mats = _build_mats(stage, bsz, psh, pps, externs, dev)
+        out = torch.empty_like(state)
+        src = state
+        stream = _native.stream_ptr(state)
+        for pp in stage.passes:
+            prog = _dev(pp, "prog", dev)
+            _native.call("tqb_pass_forward", _ptr(src), _ptr(out), n, bsz, _ptr(prog), pp.T, pp.R, pp.L,
+                         _ptr(mats), stage.M, ext_hi, stream)
+            STATS["launches"] += 1
+            src = out
+        if not stage.passes:
+            out.copy_(state)
+        ctx.stage, ctx.n, ctx.ext_hi = stage, n, ext_hi
+        ctx.n_ext = len(externs)
+        ctx.save_for_backward(state if stage.save_input else out, psh, pps, mats, *externs)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        stage, n, ext_hi = ctx.stage, ctx.n, ctx.ext_hi
+        saved = ctx.saved_tensors
+        psi0, psh, pps, mats = saved[:4]
+        externs = saved[4:]
+        bsz = psi0.shape[0]
+        dev = psi0.device
+        grad_out = grad_out.contiguous()
+        multi = any(pp.T < n for pp in stage.passes)
+        gmats = (torch.zeros if multi else torch.empty)(bsz, stage.M, dtype=torch.float32, device=dev)
+        psi = torch.empty_like(psi0)
+        lam = torch.empty_like(psi0)
+        psrc, lsrc = psi0, grad_out
+        stream = _native.stream_ptr(psi0)
+        for pp in reversed(stage.passes):
+            prog = _dev(pp, "prog", dev)
+            _native.call("tqb_pass_backward", _ptr(psrc), _ptr(lsrc), _ptr(psi), _ptr(lam), n, bsz, _ptr(prog),
+                         pp.T, pp.R, pp.L, _ptr(mats), _ptr(gmats), stage.M, ext_hi, stream)
+            STATS["launches"] += 1
+            psrc, lsrc = psi, lam
+        if not stage.passes:
+            lam.copy_(grad_out)
+        gsh = gps = None
+        if stage.any_grad and (stage.P_sh or stage.P_ps):
+            table = _dev(stage, "table", dev)
+            gsh_part = torch.zeros(bsz, max(stage.P_sh, 1), dtype=torch.float32, device=dev)
+            gps_full = torch.zeros(bsz, max(stage.P_ps, 1), dtype=torch.float32, device=dev)
+            _native.call("tqb_build_mats_bwd", _ptr(table), table.shape[0], bsz, _ptr(psh), _ptr(pps),
+                         pps.shape[1], _ptr(gmats), stage.M, _ptr(gsh_part), gsh_part.shape[1],
+                         _ptr(gps_full), stream)
+            STATS["launches"] += 1
+            if stage.P_sh and ctx.needs_input_grad[1]:
+                gsh = gsh_part.sum(0)
+            if stage.P_ps and ctx.needs_input_grad[2]:
+                gps = gps_full
+        gext = []
+        for i, ((rec, moff, dim, inverse), u) in enumerate(zip(stage.externs, externs)):
+            if not ctx.needs_input_grad[6 + i]:
+                gext.append(None)
+                continue
+            g = torch.view_as_complex(gmats[:, moff:moff + 2 * dim * dim].reshape(bsz, dim, dim, 2).contiguous())
+            if inverse:  # applied A = U^H  =>  dL/dU = (dL/dA)^H
+                g = g.conj().transpose(-1, -2)
+            gext.append(g.sum(0) if u.dim() == 2 else g)
+        gstate = lam if ctx.needs_input_grad[0] else None
+        return (gstate, gsh, gps, None, None, None, *gext)
+
+
+class DenseFn(torch.autograd.Function):
+    """Generic k-qubit dense gate (qft, qubitunitary on >= 3 wires), out of place."""
+
+    @staticmethod
+    def forward(ctx, state, mat, bitpos, n, inverse):
+        _native.check_device(state)
+        state = state.contiguous()
+        bsz = state.shape[0]
+        m = mat.to(torch.complex64).contiguous()
+        k = len(bitpos)
+        out = torch.empty_like(state)
+        bp = torch.tensor(bitpos, dtype=torch.int32, device=state.device)
+        _native.call("tqb_apply_dense", _ptr(state), _ptr(out), n, bsz, _ptr(m), (4 ** k) if m.dim() == 3 else 0,
+                     k, _ptr(bp), 1 if inverse else 0, _native.stream_ptr(state))
+        STATS["launches"] += 1
+        ctx.save_for_backward(state, m, bp)
+        ctx.n, ctx.inverse, ctx.k = n, inverse, k
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        state, m, bp = ctx.saved_tensors
+        n, inverse, k = ctx.n, ctx.inverse, ctx.k
+        bsz = state.shape[0]
+        grad_out = grad_out.contiguous()
+        stream = _native.stream_ptr(state)
+        gstate = gmat = None
+        if ctx.needs_input_grad[0]:
+            gstate = torch.empty_like(state)
+            _native.call("tqb_apply_dense", _ptr(grad_out), _ptr(gstate), n, bsz, _ptr(m),
+                         (4 ** k) if m.dim() == 3 else 0, k, _ptr(bp), 0 if inverse else 1, stream)
+            STATS["launches"] += 1
+        if ctx.needs_input_grad[1]:
+            g = torch.empty(bsz, 2 ** k, 2 ** k, dtype=torch.complex64, device=state.device)
+            _native.call("tqb_dense_grad", _ptr(state), _ptr(grad_out), n, bsz, k, _ptr(bp), _ptr(g), stream)
+            STATS["launches"] += 1
+            if inverse:
+                g = g.conj().transpose(-1, -2)
+            gmat = g.sum(0) if m.dim() == 2 else g
+        return gstate, gmat, None, None, None
+
+
+def _reset(state, n, wires):
+    """functional/reset.py:19-42 — zero the |1> slice of each wire, renormalise
+    (util/utils.py:789-814).  Non-unitary and rare: plain torch ops on the device tensor."""
+    s = state.reshape([state.shape[0]] + [2] * n).clone()
+    for w in wires:
+        idx = [slice(None)] * s.dim()
+        idx[w + 1] = 1
+        s[tuple(idx)] = 0
+    flat = s.reshape(state.shape[0], -1)
+    energy = (flat.abs() ** 2).sum(-1)
+    fix = torch.zeros_like(flat)
+    fix[:, 0] = (energy == 0).to(flat.dtype)
+    flat = flat + fix
+    return flat * torch.sqrt(1 / (flat.abs() ** 2).sum(-1)).unsqueeze(-1)
+
+
+def run_circuit(state, n, records, n_total=None, ext_hi=0):
+    """state: [bsz, 2^n] complex64; records: list of (name, wires, params, inverse) with canonical
+    names and normalised params (2-D float tensors, or complex matrices for unitary-like gates)."""
+    bsz = state.shape[0]
+    grad_mode = torch.is_grad_enabled() and (
+        state.requires_grad or any(r[2] is not None and r[2].requires_grad for r in records))
+    key = []
+    for name, wires, params, inverse in records:
+        pmode, grad, ext_dim = None, False, 0
+        if params is not None:
+            grad = grad_mode and params.requires_grad
+            if name in G.UNITARY_LIKE:
+                pmode, ext_dim = "ext", params.shape[-1]
+            else:
+                if params.shape[0] == 1:
+                    pmode = "sh"
+                elif params.shape[0] == bsz:
+                    pmode = "ps"
+                else:
+                    raise RuntimeError(
+                        f"{name}: parameter batch {params.shape[0]} does not match state batch {bsz}")
+                if G.SPECS[name].n_params != params.shape[1]:
+                    raise RuntimeError(f"{name}: expected {G.SPECS[name].n_params} parameters, got {params.shape[1]}")
+        key.append((name, wires, inverse, pmode, grad, ext_dim))
+    plan = get_plan(n, tuple(key), grad_mode, n_total)
+    for stage in plan.stages:
+        if stage.kind == "fused":
+            dev = state.device
+            if stage.sh_recs:
+                psh = torch.cat([records[r][2].reshape(1, -1) for r in stage.sh_recs], dim=1).reshape(-1)
+                psh = psh.to(device=dev, dtype=torch.float32)
+            else:
+                psh = torch.zeros(1, dtype=torch.float32, device=dev)
+            if stage.ps_recs:
+                pps = torch.cat([records[r][2] for r in stage.ps_recs], dim=1).to(device=dev, dtype=torch.float32)
+                pps = pps.contiguous()
+            else:
+                pps = torch.zeros(bsz, 1, dtype=torch.float32, device=dev)
+            externs = [records[e[0]][2].to(dev) for e in stage.externs]
+            state = FusedFn.apply(state, psh, pps, stage, n, ext_hi, *externs)
+        elif stage.kind == "dense":
+            name, wires, params, inverse = records[stage.rec]
+            if stage.const is not None:
+                mat = torch.from_numpy(stage.const).to(state.device)
+            else:
+                mat = params.to(state.device)
+            state = DenseFn.apply(state, mat, tuple(stage.bitpos), n, inverse)
+        else:
+            state = _reset(state, n, stage.wires)
+    return state
