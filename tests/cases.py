@@ -1,0 +1,189 @@
+"""Parity cases shared by the CPU suite (kernel source compiled for the host, tests/emu) and the
+GPU suite (libtqb200.so on the B200): each function drives the public API of torchquantum_b200 on
+`device` and compares with golden vectors of the real reference or with the CPU oracle."""
+import random
+
+import numpy as np
+import torch
+
+import torchquantum_b200 as tq
+import torchquantum_b200.functional as tqf
+from oracle import tq_oracle as O
+from torchquantum_b200.measurement import (expval, expval_joint_analytical, expval_joint_analytical_multi,
+                                           measure)
+from tests.helpers import assert_close, load, op_params
+
+
+def apply_ops(qdev, ops, device, requires_grad=False):
+    leaves = []
+    for op in ops:
+        kw = {}
+        if op.get("params") is not None:
+            p = op["params"]
+            if not isinstance(p, torch.Tensor):
+                p = op_params(op).to(device)
+                if requires_grad:
+                    p.requires_grad_(True)
+                leaves.append(p)
+            kw["params"] = p
+        if op.get("n_wires") is not None:
+            kw["n_wires"] = op["n_wires"]
+        getattr(tqf, op["name"])(qdev, wires=op["wires"], inverse=op.get("inverse", False), **kw)
+    return leaves
+
+
+def check_all_gates(device):
+    z, man = load("gates.npz")
+    n, init = man["n"], torch.tensor(z["init"]).to(device)
+    for case in man["cases"]:
+        q = tq.QuantumDevice(n_wires=n, bsz=init.shape[0], device=device)
+        q.set_states(init.clone())
+        if case["name"] == "qubitunitaryfast":
+            tqf.qubitunitaryfast(q, wires=case["wires"], params=torch.tensor(z[case["mat"]]).to(device))
+        elif case["name"] == "reset":
+            tqf.reset(q, wires=case["wires"])
+        else:
+            apply_ops(q, [case], device)
+        assert_close(q.get_states_1d(), z[case["out"]], what=f"{case['name']} {case['wires']}")
+
+
+def check_random_circuits(device, min_n=0):
+    z, man = load("circuits.npz")
+    for c in man:
+        if c["n"] < min_n:
+            continue
+        pre = c["prefix"]
+        init = torch.tensor(z[pre + "init"]).to(device).requires_grad_(True)
+        q = tq.QuantumDevice(n_wires=c["n"], bsz=c["bsz"], device=device)
+        q.set_states(init)
+        leaves = apply_ops(q, c["ops"], device, requires_grad=True)
+        states = q.get_states_1d()
+        assert_close(states, z[pre + "states"], what=pre + "states")
+        ev = expval_joint_analytical_multi(q, c["obs"])
+        assert_close(ev, z[pre + "ev"], what=pre + "ev")
+        assert_close(expval_joint_analytical(q, c["obs"][0]), z[pre + "ev"][:, 0], what=pre + "ev0")
+        w, proj = torch.tensor(z[pre + "w"]).to(device), torch.tensor(z[pre + "proj"]).to(device)
+        loss = (ev * w).sum() + (states * proj.conj()).real.sum()
+        assert_close(loss, z[pre + "loss"], what=pre + "loss")
+        grads = torch.autograd.grad(loss, leaves + [init])
+        for gi, g in enumerate(grads[:-1]):
+            assert_close(g, z[pre + f"g{gi}"], rtol=1e-4, what=pre + f"grad{gi}")  # reference tests: grads 1e-4
+        assert_close(grads[-1], z[pre + "ginit"], rtol=1e-4, what=pre + "grad_init")
+
+
+class _Obs:
+    """Minimal observable (eigvals + diagonalizing gates) for expval() before operators exist."""
+
+    def __init__(self, letter):
+        self.letter = letter
+        self.eigvals = torch.tensor([1, -1], dtype=torch.complex64)
+
+    def diagonalizing_gates(self):
+        seq = {"X": ["hadamard"], "Y": ["pauliz", "s", "hadamard"], "Z": []}[self.letter]
+        return [lambda qdev, wires, _n=name: getattr(tqf, _n)(qdev, wires=wires) for name in seq]
+
+
+def check_expval_per_wire(device):
+    z, man = load("circuits.npz")
+    for c in man:
+        pre = c["prefix"]
+        q = tq.QuantumDevice(n_wires=c["n"], bsz=c["bsz"], device=device)
+        q.set_states(torch.tensor(z[pre + "init"]).to(device))
+        apply_ops(q, c["ops"], device)
+        ev = expval(q, list(range(c["n"])), [_Obs(l) for l in c["obs_wires"]])
+        assert_close(ev, z[pre + "ev_wires"], what=pre + "ev_wires")
+        assert_close(q.get_states_1d(), z[pre + "states_after_expval"], what=pre + "mutated state")
+
+
+def check_measure_bit_exact(device):
+    z, man = load("measure.npz")
+    for ci, c in enumerate(man):
+        q = tq.QuantumDevice(n_wires=c["n"], bsz=c["bsz"], device=device)
+        q.set_states(torch.tensor(z[f"m{ci}_states"]).to(device))
+        random.seed(c["seed"])
+        res = measure(q, n_shots=c["shots"])
+        counts = np.array([list(d.values()) for d in res])
+        assert np.array_equal(counts, z[f"m{ci}_counts"]), f"histogram {ci} differs"
+        assert list(res[0].keys()) == ["{:0{}b}".format(k, c["n"]) for k in range(2 ** c["n"])]
+        assert random.random() == c["next_random"]
+
+
+def check_mnist_cfg1(device):
+    import torch.nn.functional as F
+
+    z, man = load("mnist_cfg1.npz")
+    n, bsz = man["n"], man["bsz"]
+    x = torch.tensor(z["x"]).to(device).requires_grad_(True)
+    q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+    leaves = []
+    for op in man["ops"]:
+        kw = {}
+        if "input_idx" in op:
+            kw["params"] = x[:, op["input_idx"]]
+        elif op["params"] is not None:
+            t = torch.tensor(op["params"], dtype=torch.float32, device=device).reshape(1, -1)
+            if op["trainable"]:
+                t.requires_grad_(True)
+                leaves.append(t)
+            kw["params"] = t
+        getattr(tqf, op["name"])(q, wires=op["wires"], inverse=op["inverse"], **kw)
+    assert_close(q.get_states_1d(), z["states"], what="cfg1 states")
+    out = expval(q, list(range(n)), [_Obs("Z")] * n)
+    assert_close(out, z["out"], what="cfg1 MeasureAll")
+    loss = F.nll_loss(F.log_softmax(out.reshape(bsz, 2, 2).sum(-1), dim=1), torch.tensor(z["target"]).to(device))
+    assert_close(loss, z["loss"], what="cfg1 loss")
+    grads = torch.autograd.grad(loss, [x] + leaves)
+    assert_close(grads[0], z["grad_x"], rtol=1e-4, what="cfg1 grad_x")
+    for g, w in zip(grads[1:], man["param_grads"]):
+        assert_close(g.reshape(-1), torch.tensor(w["grad"]), rtol=1e-4, what="cfg1 param grad")
+
+
+def brickwork_ops(n, depth, seed, per_sample_bsz=None):
+    """BASELINE config-4 family: per layer one of rx/ry/rz with theta~U(-pi,pi)
+    on every wire, then a brickwork of CNOTs."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for layer in range(depth):
+        for w in range(n):
+            name = ["rx", "ry", "rz"][rng.integers(3)]
+            shape = (per_sample_bsz if per_sample_bsz else 1, 1)
+            ops.append({"name": name, "wires": [w],
+                        "params": torch.tensor(rng.uniform(-np.pi, np.pi, size=shape), dtype=torch.float32)})
+        for w in range(layer % 2, n - 1, 2):
+            ops.append({"name": "cnot", "wires": [w, w + 1]})
+    return ops
+
+
+def check_against_oracle(device, n, bsz, ops, grad=False, rtol=1e-5):
+    """Engine vs CPU oracle on the same op list."""
+    ops_dev = []
+    for op in ops:
+        o = dict(op)
+        if o.get("params") is not None:
+            o["params"] = o["params"].to(device)
+            if grad:
+                o["params"] = o["params"].clone().requires_grad_(True)
+        ops_dev.append(o)
+    q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+    apply_ops(q, ops_dev, device)
+    states = q.get_states_1d()
+    ops_cpu = []
+    for op in ops:
+        o = dict(op)
+        if grad and o.get("params") is not None:
+            o["params"] = o["params"].clone().requires_grad_(True)
+        ops_cpu.append(o)
+    want = O.run_ops(n, bsz, ops_cpu)
+    assert_close(states, want, rtol=rtol, what=f"states n={n}")
+    if grad:
+        obs = "".join("ZXYI"[i % 4] for i in range(n))
+        ev = expval_joint_analytical(q, obs).sum()
+        ev_cpu = O.expval_joint_rotated(want, obs).sum()
+        assert_close(ev, ev_cpu, rtol=1e-4, what="expval")
+        leaves = [o["params"] for o in ops_dev if o.get("params") is not None]
+        leaves_cpu = [o["params"] for o in ops_cpu if o.get("params") is not None]
+        g = torch.autograd.grad(ev, leaves)
+        g_cpu = torch.autograd.grad(ev_cpu, leaves_cpu)
+        assert_close(torch.cat([a.reshape(-1) for a in g]), torch.cat([a.reshape(-1) for a in g_cpu]), rtol=1e-4,
+                     what=f"grads n={n}")
+    return states

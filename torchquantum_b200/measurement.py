@@ -1,0 +1,260 @@
+"""Measurement — drop-in for torchquantum/measurement/measurements.py.
+
+* `expval_joint_analytical` (:232-279): the reference builds the dense 2^n x 2^n Kronecker product
+  of the Pauli string and does a matmul (O(4^n) memory, infeasible beyond n ~ 14); here a fused
+  kernel evaluates <psi|P|psi> from the x/z bit masks of the string in one pass (O(2^n)).
+* `expval` / `MeasureAll` (:282-343): diagonalising gates are queued on the device (the reference
+  also mutates the device state), then ONE kernel pass yields <Z> of every wire.
+* `measure` (:37-74): probabilities, the sequential float32 CDF and the inverse-CDF draws run on
+  the device; uniforms come from Python's global `random` stream, so histograms are bit-exact
+  with the reference's `random.choices` and the shared stream advances identically.
+"""
+import random
+from collections import OrderedDict
+from typing import List, Union
+
+import numpy as np
+import torch
+
+from . import _native
+from .engine import STATS, _ptr
+
+__all__ = ["expval_joint_analytical", "expval_joint_analytical_multi", "expval", "measure", "gen_bitstrings",
+           "expval_joint_sampling", "expval_joint_sampling_grouping", "find_observable_groups"]
+
+
+def gen_bitstrings(n_wires):
+    return ["{:0{}b}".format(k, n_wires) for k in range(2 ** n_wires)]
+
+
+def pauli_masks(observable: str):
+    """x mask, z mask, number of Y factors; char j is wire j = index bit n-1-j."""
+    observable = observable.upper()
+    n = len(observable)
+    x = z = ny = 0
+    for w, ch in enumerate(observable):
+        bit = 1 << (n - 1 - w)
+        if ch == "X":
+            x |= bit
+        elif ch == "Y":
+            x |= bit
+            z |= bit
+            ny += 1
+        elif ch == "Z":
+            z |= bit
+        elif ch != "I":
+            raise KeyError(ch)
+    return x, z, ny
+
+
+_MASK_CACHE = {}
+
+
+def _mask_tensors(observables, device):
+    key = (tuple(observables), str(device))
+    t = _MASK_CACHE.get(key)
+    if t is None:
+        ms = [pauli_masks(o) for o in observables]
+        xm = torch.tensor([m[0] for m in ms], dtype=torch.int64, device=device)
+        zm = torch.tensor([m[1] for m in ms], dtype=torch.int64, device=device)
+        ny = torch.tensor([m[2] for m in ms], dtype=torch.int32, device=device)
+        t = (xm, zm, ny)
+        if len(_MASK_CACHE) > 1024:
+            _MASK_CACHE.clear()
+        _MASK_CACHE[key] = t
+    return t
+
+
+class _ExpvalPauliFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, n, xm, zm, ny):
+        _native.check_device(state)
+        state = state.contiguous()
+        bsz, nt = state.shape[0], xm.shape[0]
+        out = torch.zeros(bsz, nt, dtype=torch.float32, device=state.device)
+        _native.call("tqb_expval_pauli", _ptr(state), n, bsz, _ptr(xm), _ptr(zm), _ptr(ny), nt, _ptr(out),
+                     _native.stream_ptr(state))
+        STATS["launches"] += 1
+        ctx.save_for_backward(state, xm, zm, ny)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        state, xm, zm, ny = ctx.saved_tensors
+        gout = gout.contiguous()
+        grad = torch.empty_like(state)
+        _native.call("tqb_expval_pauli_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(xm), _ptr(zm), _ptr(ny),
+                     xm.shape[0], _ptr(gout), _ptr(grad), _native.stream_ptr(state))
+        STATS["launches"] += 1
+        return grad, None, None, None, None
+
+
+class _ExpvalZFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, n):
+        _native.check_device(state)
+        state = state.contiguous()
+        bsz = state.shape[0]
+        out = torch.zeros(bsz, n + 1, dtype=torch.float32, device=state.device)
+        _native.call("tqb_expval_z", _ptr(state), n, bsz, _ptr(out), _native.stream_ptr(state))
+        STATS["launches"] += 1
+        ctx.save_for_backward(state)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (state,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        grad = torch.empty_like(state)
+        _native.call("tqb_expval_z_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(gout), _ptr(grad),
+                     _native.stream_ptr(state))
+        STATS["launches"] += 1
+        return grad, None
+
+
+def expval_joint_analytical_multi(qdev, observables: List[str]):
+    """All Pauli strings in one kernel launch -> [bsz, len(observables)] float32."""
+    for o in observables:
+        assert len(o) == qdev.n_wires
+    states = qdev.get_states_1d()
+    xm, zm, ny = _mask_tensors(observables, states.device)
+    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny)
+
+
+def expval_joint_analytical(qdev, observable: str):
+    """<psi_b| P |psi_b> for the Pauli string `observable` (char j acts on wire j) -> [bsz] float32."""
+    return expval_joint_analytical_multi(qdev, [observable])[:, 0]
+
+
+def expval(qdev, wires: Union[int, List[int]], observables):
+    """Per-wire expectation values (measurements.py:282-312): rotates each wire into its
+    observable's eigenbasis IN PLACE on the device, then reads the marginals."""
+    if isinstance(wires, (int, np.integer)):
+        wires, observables = [wires], [observables]
+    for wire, observable in zip(wires, observables):
+        for rotation in observable.diagonalizing_gates():
+            rotation(qdev, wires=wire)
+    n = qdev.n_wires
+    z = _ExpvalZFn.apply(qdev.get_states_1d(), n)
+    norm = z[:, n]
+    cols = []
+    for wire, observable in zip(wires, observables):
+        ev = observable.eigvals.real.to(device=z.device, dtype=torch.float32)
+        zw = z[:, n - 1 - int(wire)]
+        cols.append(ev[0] * (norm + zw) * 0.5 + ev[1] * (norm - zw) * 0.5)
+    return torch.stack(cols, dim=-1)
+
+
+def measure(qdev, n_shots=1024, draw_id=None):
+    """Sample bitstrings (measurements.py:37-74) -> list[OrderedDict[bitstring -> count]] with all
+    2^n keys.  Bit-exact with the reference under the shared global `random` stream."""
+    n = qdev.n_wires
+    states = qdev.get_states_1d().detach().contiguous()
+    _native.check_device(states)
+    bsz, N = states.shape
+    dev = states.device
+    stream = _native.stream_ptr(states)
+    probs = torch.empty(bsz, N, dtype=torch.float32, device=dev)
+    _native.call("tqb_probs", _ptr(states), n, bsz, _ptr(probs), stream)
+    # one random.random() per (sample, shot), in the reference's order; float32(u) is what NumPy 2
+    # promotes to when multiplying by the float32 total
+    u = np.array([random.random() for _ in range(bsz * n_shots)], dtype=np.float64).astype(np.float32)
+    u_dev = torch.from_numpy(u).to(dev)
+    cdf = torch.empty(bsz, N, dtype=torch.float32, device=dev)
+    counts = torch.zeros(bsz, N, dtype=torch.int32, device=dev)
+    _native.call("tqb_sample_counts", _ptr(probs), n, bsz, _ptr(u_dev), n_shots, _ptr(cdf), _ptr(counts), stream)
+    STATS["launches"] += 3
+    counts = counts.cpu().numpy()
+    keys = gen_bitstrings(n)
+    distri_all = [OrderedDict(zip(keys, (int(c) for c in row))) for row in counts]
+    if draw_id is not None:
+        import matplotlib.pyplot as plt
+
+        plt.bar(distri_all[draw_id].keys(), distri_all[draw_id].values())
+        plt.xticks(rotation="vertical")
+        plt.xlabel("bitstring [qubit0, qubit1, ..., qubitN]")
+        plt.title("distribution of measured bitstrings")
+        plt.show()
+    return distri_all
+
+
+def _rotated_clone(qdev, observable):
+    from .device import QuantumDevice
+    from . import functional as tqf
+
+    clone = QuantumDevice(n_wires=qdev.n_wires, bsz=qdev.bsz, device=qdev.state.device)
+    clone.clone_states(qdev.states)
+    for wire, ch in enumerate(observable.upper()):
+        if ch == "X":
+            tqf.hadamard(clone, wires=wire)
+        elif ch == "Y":
+            tqf.pauliz(clone, wires=wire)
+            tqf.s(clone, wires=wire)
+            tqf.hadamard(clone, wires=wire)
+    return clone
+
+
+def _parity_expval(distributions, mask, n_shots):
+    out = []
+    for distri in distributions:
+        plus = minus = 0
+        for bitstring, count in distri.items():
+            par = sum(int(b) for b, m in zip(bitstring, mask) if m) % 2
+            if par == 0:
+                plus += count
+            else:
+                minus += count
+        out.append(plus / n_shots - minus / n_shots)
+    return out
+
+
+def expval_joint_sampling(qdev, observable: str, n_shots=1024):
+    """Shot-based estimate of a Pauli-string expectation (measurements.py:168-229)."""
+    observable = observable.upper()
+    clone = _rotated_clone(qdev, observable)
+    mask = [ch != "I" for ch in observable]
+    return torch.tensor(_parity_expval(measure(clone, n_shots=n_shots), mask, n_shots), dtype=torch.float32)
+
+
+def find_observable_groups(observables):
+    """Greedy grouping of qubit-wise compatible Pauli strings (measurements.py:77-110)."""
+    groups = {}
+    for observable in observables:
+        matched, new_name = None, None
+        for group in groups:
+            merged = list(group)
+            ok = True
+            for k, ch in enumerate(observable):
+                if ch == "I" or ch == group[k]:
+                    continue
+                if group[k] == "I":
+                    merged[k] = ch
+                else:
+                    ok = False
+                    break
+            if ok:
+                matched, new_name = group, "".join(merged)
+                break
+        if matched is None:
+            groups[observable] = [observable]
+        else:
+            elements = groups.pop(matched)
+            elements.append(observable)
+            groups[new_name] = elements
+    return groups
+
+
+def expval_joint_sampling_grouping(qdev, observables: List[str], n_shots_per_group=1024):
+    """One measurement per compatible group, shared by its members (measurements.py:113-165)."""
+    obs = [o.upper() for o in observables]
+    groups = find_observable_groups(obs)
+    result = {}
+    for group, elements in groups.items():
+        clone = _rotated_clone(qdev, group)
+        distributions = measure(clone, n_shots=n_shots_per_group)
+        for o in elements:
+            mask = [ch != "I" for ch in o]
+            result[o] = torch.tensor(_parity_expval(distributions, mask, n_shots_per_group), dtype=torch.float32)
+    return result

@@ -232,9 +232,12 @@ def _i32(v):
     return int(np.array(v & 0xFFFFFFFF, dtype=np.uint32).view(np.int32))
 
 
-def build_fused_stage(lops, n_local, n_total=None, t_single=T_SINGLE, t_multi=T_MULTI, l_min=L_MIN):
+def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, l_min=None):
     """lops: LOps in program order (targets < n_local; masks may use bits up to n_total)."""
     n_total = n_local if n_total is None else n_total
+    t_single = T_SINGLE if t_single is None else t_single
+    t_multi = T_MULTI if t_multi is None else t_multi
+    l_min = L_MIN if l_min is None else l_min
     st = FusedStage()
     st.n_ops = len(lops)
     # parameter slots in queue order
@@ -249,6 +252,7 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=T_SINGLE, t_multi=T_
             st.ps_recs.append(op.rec)
         st.any_grad |= op.grad
     # passes
+    t_single = max(t_single, min(t_multi, n_local))
     if n_local <= t_single:
         raw = [(set(), list(lops))]
         T, L = n_local, n_local
