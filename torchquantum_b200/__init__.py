@@ -6,7 +6,15 @@ gate-application API: `tq.QuantumDevice`, `tqf.<gate>` / `qdev.<gate>`, `tq.Oper
     import torchquantum_b200.functional as tqf
 """
 from .macro import *  # noqa: F401,F403
+from .module import QuantumModule, QuantumModuleList, QuantumModuleDict, QuantumGraph, static_support  # noqa: F401
 from .device import QuantumDevice  # noqa: F401
 from . import functional  # noqa: F401
+from . import operator  # noqa: F401
+from .operator import *  # noqa: F401,F403
+from .operator import op_name_dict  # noqa: F401
+from .measurement import *  # noqa: F401,F403
+from .measure_modules import MeasureAll, MeasureMultipleTimes, MeasureMultiPauliSum, MeasureMultiQubitPauliSum  # noqa: F401
+from .encoding import *  # noqa: F401,F403
+from .layer import *  # noqa: F401,F403
 
 __version__ = "0.1.0"

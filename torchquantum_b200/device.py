@@ -71,6 +71,10 @@ class QuantumDevice(nn.Module):
         self.device = self.state.device
         return self
 
+    @property
+    def compute_device(self):
+        return self._flat.device
+
     def flush(self):
         """Run every queued gate (fused) and materialise the state."""
         if self._queue:

@@ -69,8 +69,8 @@ def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, 
         else:
             params = params.squeeze(0)
         assert np.log2(params.shape[-1]) == len(wires_t)  # functional/gate_wrapper.py:433
-        if params.device != q_device.state.device:
-            params = params.to(q_device.state.device)
+        if params.device != q_device.compute_device:
+            params = params.to(q_device.compute_device)
         q_device.enqueue(cname, wires_t, params.to(C_DTYPE), bool(inverse))
         return
     expected = spec.n_wires if spec.n_wires is not None else len(wires_t)
@@ -79,8 +79,8 @@ def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, 
         raise TypeError(f"{name}: missing params")
     if spec.n_params == 0:
         params = None
-    elif params.device != q_device.state.device:
-        params = params.to(q_device.state.device)
+    elif params.device != q_device.compute_device:
+        params = params.to(q_device.compute_device)
     q_device.enqueue(cname, wires_t, params, bool(inverse))
 
 
