@@ -32,37 +32,44 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 1
+#define TQB_ABI_VERSION 2
 
 int tqb_abi_version(void);
 const char* tqb_last_error(void);
 
-/* Fill the per-sample gate-matrix rows mats[bsz][mat_stride] from parameters.
- * table_dev: n_records x 8 int32 (kind, flags, param offset, matrix offset, const offset, n floats,
- * n params, 0).  params_sh: [P_sh] shared parameters; params_ps: [bsz][ps_stride] per-sample. */
-int tqb_build_mats(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
-                   const float* params_ps, int ps_stride, const float* consts, float* mats,
-                   long long mat_stride, void* stream);
+/* Gate matrices live in one row shared by the batch (`msh`: constants and gates with shared
+ * parameters) and one row per sample (`mps[bsz][mps_stride]`: per-sample parameters).
+ * table_dev: n_records x 10 int32 (csrc/tqb_program.h, TQB_B_*); the first n_shared_records write
+ * `msh`, the others write every sample's `mps` row.  params_sh: [P_sh] shared parameters;
+ * params_ps: [bsz][ps_stride] per-sample parameters. */
+int tqb_build_mats(const int32_t* table_dev, int n_records, int n_shared_records, long long bsz,
+                   const float* params_sh, const float* params_ps, int ps_stride, const float* consts,
+                   float* msh, float* mps, long long mps_stride, void* stream);
 
-/* dL/dtheta from dL/dU rows (gmats): per-sample parameters -> gparams_ps[bsz][ps_stride];
- * shared parameters -> per-sample partials gparams_sh_partial[bsz][sh_stride] (caller sums over bsz). */
+/* dL/dtheta from the per-sample gradient rows gr[bsz][gr_stride] written by tqb_pass_backward:
+ * per-sample parameters -> gparams_ps[bsz][ps_stride]; shared parameters -> per-sample partials
+ * gparams_sh_partial[bsz][sh_stride] (caller sums over bsz). */
 int tqb_build_mats_bwd(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
-                       const float* params_ps, int ps_stride, const float* gmats, long long mat_stride,
+                       const float* params_ps, int ps_stride, const float* gr, long long gr_stride,
                        float* gparams_sh_partial, int sh_stride, float* gparams_ps, void* stream);
 
 /* One fused pass over the state: every tile of 2^T amplitudes is read from `src`, staged on chip,
  * the whole gate list of the pass applied to it, and written to `dst` (dst may equal src).
+ * desc_host: 8 ints on the HOST {T, R, L, n_seg, sh_max, ps_max, g_max, 0} copied from the program
+ * header (tile geometry and staging capacities).
  * ext_hi: bits OR-ed above the tile index when gates are controlled by / diagonal in qubits that
  * live on other ranks (sharded statevector). */
-int tqb_pass_forward(const float* src, float* dst, int n_qubits, long long bsz, const int32_t* prog_dev, int T, int R,
-                     int L, const float* mats, long long mat_stride, unsigned ext_hi, void* stream);
+int tqb_pass_forward(const float* src, float* dst, int n_qubits, long long bsz, const int32_t* prog_dev,
+                     const int* desc_host, const float* msh, const float* mps, long long mps_stride,
+                     unsigned ext_hi, void* stream);
 
 /* Adjoint sweep of the same pass: reads the pass OUTPUT psi and dL/dpsi_out, writes the pass INPUT
  * psi and dL/dpsi_in (dst may alias src); writes (single tile per sample) or atomically
- * accumulates (several tiles: pre-zero) the dL/dU rows. */
+ * accumulates (several tiles: pre-zero) the per-sample gradient rows gr[bsz][gr_stride]. */
 int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi_dst, float* lam_dst, int n_qubits,
-                      long long bsz, const int32_t* prog_dev, int T, int R, int L, const float* mats,
-                      float* gmats, long long mat_stride, unsigned ext_hi, void* stream);
+                      long long bsz, const int32_t* prog_dev, const int* desc_host, const float* msh,
+                      const float* mps, long long mps_stride, float* gr, long long gr_stride, unsigned ext_hi,
+                      void* stream);
 
 /* out = U_wires in (out of place); mats: complex64 [2^k][2^k] per sample with stride
  * mat_stride_complex (0 = shared); bitpos_dev: k bit positions, matrix MSB first;

@@ -25,67 +25,63 @@ static int fail_msg(const char* m) { snprintf(g_err, sizeof(g_err), "%s", m); re
 struct EmuExec {
   int nthreads;
   template <class F> void par(F f) { for (int t = 0; t < nthreads; ++t) f(t); }
+  template <class F> void par_nosync(F f) { for (int t = 0; t < nthreads; ++t) f(t); }
+  void async_copy8(float2* dst, const float2* src) { *dst = *src; }
+  void async_commit() {}
+  void async_wait_prev() {}
+  void async_wait_all() {}
   template <int N> void reduce_add(float* dst, float* v, int) { for (int i = 0; i < N; ++i) dst[i] += v[i]; }
   void global_add(float* p, float v) { *p += v; }
 };
 
 template <int R, bool BWD>
-static void emu_blocks(BlockCtx c, unsigned ntiles, long long grid, unsigned ext_hi) {
-  const SmemLayout l = smem_layout(c.T, c.L, c.S, BWD);
-  std::vector<unsigned char> smem(l.total + 16);
+static void emu_blocks(BlockCtx c, int n, const PassGeom& g, unsigned ext_hi) {
+  std::vector<unsigned char> smem(g.lay.total + 16);
   unsigned char* base = smem.data();
   base += (16 - ((uintptr_t)base & 15)) & 15;
-  c.s_psi = reinterpret_cast<float2*>(base + l.psi);
-  c.s_lam = reinterpret_cast<float2*>(base + l.lam);
-  c.s_mat = reinterpret_cast<float*>(base + l.mat);
-  c.s_grad = reinterpret_cast<float*>(base + l.grad);
-  c.s_prog = reinterpret_cast<int32_t*>(base + l.prog);
-  c.s_scat = reinterpret_cast<u64*>(base + l.scat);
+  c.s_psi = reinterpret_cast<float2*>(base + g.lay.psi);
+  c.s_lam = reinterpret_cast<float2*>(base + g.lay.lam);
+  c.s_msh = reinterpret_cast<float*>(base + g.lay.msh);
+  c.s_mps = reinterpret_cast<float*>(base + g.lay.mps);
+  c.s_grad = reinterpret_cast<float*>(base + g.lay.grad);
+  c.s_prog = reinterpret_cast<int32_t*>(base + g.lay.prog);
+  c.s_scat = reinterpret_cast<u64*>(base + g.lay.scat);
+  // a small "grid" of persistent blocks so the multi-item loop and the double buffering are exercised
+  const long long grid = g.n_items < 3 ? g.n_items : 3;
   for (long long blk = 0; blk < grid; ++blk) {
-    unsigned tile_id = 0;
-    if (ntiles > 1) { tile_id = (unsigned)(blk % ntiles); c.sample0 = (int)(blk / ntiles); }
-    else c.sample0 = (int)(blk * c.S);
-    c.tile_ext = tile_id | ext_hi;
-    c.outer_off = ntiles > 1 ? outer_offset(c.prog, c.n, tile_id) : 0ull;
     EmuExec ex{c.nthreads};
-    run_block<R, BWD>(ex, c);
+    BlockCtx cb = c;  // run_cta advances the staged-buffer pointers of its context
+    run_cta<R, BWD>(ex, cb, n, g.ntiles, ext_hi, blk, grid, g.n_items, g.nbuf, g.lay.buf_stride);
   }
 }
 
-static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz, const int32_t* prog, int T, int R,
-                    int L, const float* mats, float* gmats, long long mat_stride, unsigned ext_hi) {
-  if (T < 1 || T > TQB_MAX_T || T > n || R < 1 || R > TQB_MAX_R || R > T || L < 1 || L > T)
+static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz,
+                    const int32_t* prog, const int* desc, const float* msh, const float* mps, long long mps_stride,
+                    float* gr, long long gr_stride, unsigned ext_hi) {
+  const int T = desc[0], R = desc[1], L = desc[2], sh_max = desc[4], ps_max = desc[5], g_max = desc[6];
+  if (T < 1 || T > TQB_MAX_T || T > n || R < 1 || R > TQB_MAX_R || R > T || L < 0 || L > T)
     return fail_msg("tqb pass: bad tile geometry");
-  if (prog[TQB_H_MAGIC] != TQB_MAGIC || prog[TQB_H_T] != T || prog[TQB_H_R] != R || prog[TQB_H_L] != L)
+  if (prog[TQB_H_MAGIC] != TQB_MAGIC || prog[TQB_H_T] != T || prog[TQB_H_R] != R || prog[TQB_H_L] != L ||
+      prog[TQB_H_NSEG] != desc[3] || prog[TQB_H_SH_MAX] != sh_max || prog[TQB_H_PS_MAX] != ps_max ||
+      prog[TQB_H_G_MAX] != g_max)
     return fail_msg("tqb pass: program header mismatch");
+  if (sh_max > TQB_SEG_MAX_SH || ps_max > TQB_SEG_MAX_PS || g_max > TQB_SEG_MAX_G)
+    return fail_msg("tqb pass: segment exceeds staging capacity");
   if (bsz <= 0) return 0;
+  PassGeom g;
+  pass_geometry(n, bsz, T, R, L, bwd, sh_max, ps_max, g_max, 200 * 1024, g);
+  if (g.lay.total > 227 * 1024) return fail_msg("tqb pass: tile does not fit shared memory");
   BlockCtx c;
-  c.T = T; c.R = R; c.L = L; c.n = n; c.bsz = (int)bsz;
-  const int items = 1 << (T - R);
-  c.tps = items < 256 ? items : 256;
-  unsigned ntiles;
-  long long grid;
-  if (n == T) {
-    ntiles = 1;
-    int S = c.tps >= 128 ? 1 : 128 / c.tps;
-    const size_t budget = 160 * 1024;
-    while (S > 1 && smem_layout(T, L, S, bwd).total > budget) S >>= 1;
-    if (S * c.tps < 32) S = 32 / c.tps;
-    c.S = S;
-    grid = (bsz + S - 1) / S;
-  } else {
-    c.S = 1;
-    ntiles = 1u << (n - T);
-    grid = bsz * (long long)ntiles;
-  }
-  c.nthreads = c.S * c.tps;
-  c.multi_tile = ntiles > 1;
+  c.T = T; c.L = L; c.S = g.S; c.tps = g.tps; c.nthreads = g.S * g.tps; c.bsz = (int)bsz;
+  c.multi_tile = g.ntiles > 1;
+  c.sample0 = 0; c.tile_ext = 0; c.outer_off = 0;
   c.sample_stride = 1ull << n;
   c.prog = prog; c.psi = reinterpret_cast<float2*>(psi); c.lam = reinterpret_cast<float2*>(lam);
   c.psi_src = reinterpret_cast<const float2*>(psi_src); c.lam_src = reinterpret_cast<const float2*>(lam_src);
-  c.mats = mats; c.gmats = gmats; c.mat_stride = mat_stride;
+  c.msh = msh; c.mps = mps; c.gr = gr; c.mps_stride = mps_stride; c.gr_stride = gr_stride;
+  c.ps_cap = (ps_max + 3) & ~3; c.g_cap = (g_max + 3) & ~3;
 #define TQB_DISPATCH(RR) \
-  case RR: if (bwd) emu_blocks<RR, true>(c, ntiles, grid, ext_hi); else emu_blocks<RR, false>(c, ntiles, grid, ext_hi); return 0;
+  case RR: if (bwd) emu_blocks<RR, true>(c, n, g, ext_hi); else emu_blocks<RR, false>(c, n, g, ext_hi); return 0;
   switch (R) { TQB_DISPATCH(1) TQB_DISPATCH(2) TQB_DISPATCH(3) TQB_DISPATCH(4) }
 #undef TQB_DISPATCH
   return fail_msg("bad R");
@@ -99,29 +95,30 @@ extern "C" {
 int tqb_abi_version(void) { return TQB_ABI_VERSION; }
 const char* tqb_last_error(void) { return g_err; }
 
-int tqb_pass_forward(const float* src, float* dst, int n, long long bsz, const int32_t* prog, int T, int R, int L,
-                     const float* mats, long long mat_stride, unsigned ext_hi, void*) {
-  return run_pass(false, src, nullptr, dst, nullptr, n, bsz, prog, T, R, L, mats, nullptr, mat_stride, ext_hi);
+int tqb_pass_forward(const float* src, float* dst, int n, long long bsz, const int32_t* prog, const int* desc,
+                     const float* msh, const float* mps, long long mps_stride, unsigned ext_hi, void*) {
+  return run_pass(false, src, nullptr, dst, nullptr, n, bsz, prog, desc, msh, mps, mps_stride, nullptr, 0, ext_hi);
 }
 int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz,
-                      const int32_t* prog, int T, int R, int L, const float* mats, float* gmats, long long mat_stride,
-                      unsigned ext_hi, void*) {
-  return run_pass(true, psi_src, lam_src, psi, lam, n, bsz, prog, T, R, L, mats, gmats, mat_stride, ext_hi);
+                      const int32_t* prog, const int* desc, const float* msh, const float* mps, long long mps_stride,
+                      float* gr, long long gr_stride, unsigned ext_hi, void*) {
+  return run_pass(true, psi_src, lam_src, psi, lam, n, bsz, prog, desc, msh, mps, mps_stride, gr, gr_stride, ext_hi);
 }
 
-int tqb_build_mats(const int32_t* table, int nrec, long long bsz, const float* psh, const float* pps, int ps_stride,
-                   const float* consts, float* mats, long long mat_stride, void*) {
+int tqb_build_mats(const int32_t* table, int nrec, int n_sh, long long bsz, const float* psh, const float* pps,
+                   int ps_stride, const float* consts, float* msh, float* mps, long long mps_stride, void*) {
+  for (int r = 0; r < n_sh; ++r) build_one(table + r * TQB_B_WORDS, 0, psh, pps, ps_stride, consts, msh);
   for (long long b = 0; b < bsz; ++b)
-    for (int r = 0; r < nrec; ++r)
-      build_one(table + r * TQB_B_WORDS, (int)b, psh, pps, ps_stride, consts, mats + b * mat_stride);
+    for (int r = n_sh; r < nrec; ++r)
+      build_one(table + r * TQB_B_WORDS, b, psh, pps, ps_stride, consts, mps + b * mps_stride);
   return 0;
 }
 int tqb_build_mats_bwd(const int32_t* table, int nrec, long long bsz, const float* psh, const float* pps,
-                       int ps_stride, const float* gmats, long long mat_stride, float* gsh, int sh_stride, float* gps,
+                       int ps_stride, const float* gr, long long gr_stride, float* gsh, int sh_stride, float* gps,
                        void*) {
   for (long long b = 0; b < bsz; ++b)
     for (int r = 0; r < nrec; ++r)
-      build_one_bwd(table + r * TQB_B_WORDS, (int)b, psh, pps, ps_stride, gmats + b * mat_stride,
+      build_one_bwd(table + r * TQB_B_WORDS, b, psh, pps, ps_stride, gr + b * gr_stride,
                     gsh + b * sh_stride, gps + b * ps_stride);
   return 0;
 }

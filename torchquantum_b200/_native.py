@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtqb200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 _emulated = False
@@ -18,10 +18,10 @@ _vp, _i, _ll, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ui
 
 # name -> argtypes (all return int); mirrors include/tqb200.h
 SIGNATURES = {
-    "tqb_build_mats": [_vp, _i, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],
+    "tqb_build_mats": [_vp, _i, _i, _ll, _vp, _vp, _i, _vp, _vp, _vp, _ll, _vp],
     "tqb_build_mats_bwd": [_vp, _i, _ll, _vp, _vp, _i, _vp, _ll, _vp, _i, _vp, _vp],
-    "tqb_pass_forward": [_vp, _vp, _i, _ll, _vp, _i, _i, _i, _vp, _ll, _u, _vp],
-    "tqb_pass_backward": [_vp, _vp, _vp, _vp, _i, _ll, _vp, _i, _i, _i, _vp, _vp, _ll, _u, _vp],
+    "tqb_pass_forward": [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _u, _vp],
+    "tqb_pass_backward": [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _u, _vp],
     "tqb_apply_dense": [_vp, _vp, _i, _ll, _vp, _ll, _i, _vp, _i, _vp],
     "tqb_dense_grad": [_vp, _vp, _i, _ll, _i, _vp, _vp, _vp],
     "tqb_expval_pauli": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp],

@@ -13,12 +13,14 @@
 
 #if defined(__CUDACC__)
 #define TQB_FN __device__ __forceinline__
+#define TQB_FMA(a, b, c) fmaf((a), (b), (c))
 #else
 #include <cmath>
 #include <cstring>
 #define TQB_FN inline
+#define TQB_FMA(a, b, c) ((a) * (b) + (c))
 struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -29,21 +31,31 @@ namespace tqb {
 typedef unsigned int u32;
 typedef unsigned long long u64;
 
-TQB_FN float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+TQB_FN float2 cmul(float2 a, float2 b) { return make_float2(TQB_FMA(-a.y, b.y, a.x * b.x), TQB_FMA(a.y, b.x, a.x * b.y)); }
 // conj(a) * b
-TQB_FN float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+TQB_FN float2 cmulc(float2 a, float2 b) { return make_float2(TQB_FMA(a.y, b.y, a.x * b.x), TQB_FMA(-a.y, b.x, a.x * b.y)); }
 TQB_FN float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-TQB_FN float2 ld2(const float* m) { return make_float2(m[0], m[1]); }
+TQB_FN float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// m0 * a + m1 * b  (8 FMA-pipe instructions)
+TQB_FN float2 cfma2(float2 m0, float2 a, float2 m1, float2 b) {
+  float re = m0.x * a.x, im = m0.x * a.y;
+  re = TQB_FMA(-m0.y, a.y, re); im = TQB_FMA(m0.y, a.x, im);
+  re = TQB_FMA(m1.x, b.x, re);  im = TQB_FMA(m1.x, b.y, im);
+  re = TQB_FMA(-m1.y, b.y, re); im = TQB_FMA(m1.y, b.x, im);
+  return make_float2(re, im);
+}
+TQB_FN float4 ld4(const float* m) { return *reinterpret_cast<const float4*>(m); }
 
 // swizzled position of tile-local amplitude idx in the staged tile (8-byte slots):
 // xor the 4 low bits with the next 4 so that the 16 amplitudes a half-warp touches in one
 // 64-bit shared access fall in 16 distinct bank pairs for every run of consecutive register bits.
+// (GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b).)
 TQB_FN u32 swz(u32 idx) { return idx ^ ((idx >> 4) & 15u); }
 
 struct BlockCtx {
-  int T, R, L, n;          // tile bits, register bits, contiguous low bits, local qubits
+  int T, L;                // tile bits, contiguous low bits
   int S, tps, nthreads;    // samples per CTA, threads per sample, S * tps
-  int bsz, sample0;        // batch size, first sample handled by this CTA
+  int bsz, sample0;        // batch size, first sample handled by this work item
   int multi_tile;          // more than one tile per sample (gradients need atomics)
   u32 tile_ext;            // compressed outer index (+ rank bits in sharded mode)
   u64 outer_off;           // amplitude offset of the tile inside the sample
@@ -53,11 +65,13 @@ struct BlockCtx {
   const float2* lam_src;   // backward only: dL/dpsi read by the pass
   float2* psi;             // global state written by the pass
   float2* lam;             // backward only: lambda written by the pass
-  const float* mats;       // [bsz][mat_stride]
-  float* gmats;            // [bsz][mat_stride]
-  long long mat_stride;
+  const float* msh;        // shared matrix row
+  const float* mps;        // [bsz][mps_stride] per-sample matrix rows
+  float* gr;               // [bsz][gr_stride] gradient rows
+  long long mps_stride, gr_stride;
+  int ps_cap, g_cap;       // staged per-sample floats (stride of s_mps / s_grad per sample slot)
   // staged (shared) memory
-  float2* s_psi; float2* s_lam; float* s_mat; float* s_grad; int32_t* s_prog; u64* s_scat;
+  float2* s_psi; float2* s_lam; float* s_msh; float* s_mps; float* s_grad; int32_t* s_prog; u64* s_scat;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -73,19 +87,21 @@ TQB_FN void build_scatter(const BlockCtx& c, int tid) {
   }
 }
 
-TQB_FN void load_tile(const BlockCtx& c, int tid, const float2* g, float2* s) {
+// asynchronous (cp.async on the GPU) copy of the work item's tile(s) into the staged buffer
+template <class Exec>
+TQB_FN void load_tile_async(Exec& ex, const BlockCtx& c, int tid, const float2* g, float2* s) {
   const int slot = tid / c.tps, t = tid % c.tps;
   const int b = c.sample0 + slot;
   const u32 tile = 1u << c.T;
   float2* dst = s + (size_t)slot * tile;
   const u32 lowmask = (1u << c.L) - 1u;
-  const float2* src = g + (u64)b * c.sample_stride + c.outer_off;
-  for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < c.bsz) v = *reinterpret_cast<const float4*>(src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
-    dst[swz(idx)] = make_float2(v.x, v.y);
-    dst[swz(idx + 1)] = make_float2(v.z, v.w);
+  if (b >= c.bsz) {
+    for (u32 idx = t; idx < tile; idx += c.tps) dst[idx] = make_float2(0.f, 0.f);
+    return;
   }
+  const float2* src = g + (u64)b * c.sample_stride + c.outer_off;
+  for (u32 idx = t; idx < tile; idx += c.tps)
+    ex.async_copy8(dst + swz(idx), src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
 }
 
 TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
@@ -96,141 +112,141 @@ TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   const float2* src = s + (size_t)slot * tile;
   const u32 lowmask = (1u << c.L) - 1u;
   float2* dst = g + (u64)b * c.sample_stride + c.outer_off;
-  for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps) {
-    float2 a = src[swz(idx)], bq = src[swz(idx + 1)];
-    *reinterpret_cast<float4*>(dst + ((idx & lowmask) + c.s_scat[idx >> c.L])) = make_float4(a.x, a.y, bq.x, bq.y);
+  if (c.L >= 1) {
+    for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps) {
+      const float2 a = src[swz(idx)], bq = src[swz(idx + 1)];
+      *reinterpret_cast<float4*>(dst + ((idx & lowmask) + c.s_scat[idx >> c.L])) = make_float4(a.x, a.y, bq.x, bq.y);
+    }
+  } else {
+    for (u32 idx = t; idx < tile; idx += c.tps) dst[c.s_scat[idx]] = src[swz(idx)];
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// segment staging: op words, matrices (per sample), zeroed gradient accumulators
+// segment staging: op words + shared matrices (once per CTA and segment), per-sample matrices
+// and zeroed gradient accumulators (once per work item and segment)
 // ---------------------------------------------------------------------------------------
-template <bool BWD>
-TQB_FN void stage_segment(const BlockCtx& c, int tid, int soff) {
-  const int ng = c.prog[soff + 0], nops = c.prog[soff + 1];
-  const int mat_base = c.prog[soff + 2], mat_len = c.prog[soff + 3];
+TQB_FN void stage_segment_shared(const BlockCtx& c, int tid, int soff) {
+  const int ng = c.prog[soff + TQB_S_NGROUPS], nops = c.prog[soff + TQB_S_NOPS];
+  const int sh_base = c.prog[soff + TQB_S_SH_BASE], sh_len = c.prog[soff + TQB_S_SH_LEN];
   const int nwords = TQB_SEG_HDR_WORDS + ng * TQB_GROUP_WORDS + nops * TQB_OP_WORDS;
   for (int i = tid; i < nwords; i += c.nthreads) c.s_prog[i] = c.prog[soff + i];
-  for (int i = tid; i < c.S * mat_len; i += c.nthreads) {
-    const int slot = i / mat_len, k = i - slot * mat_len;
+  for (int i = tid; i < sh_len; i += c.nthreads) c.s_msh[i] = c.msh[sh_base + i];
+}
+
+template <bool BWD>
+TQB_FN void stage_segment_sample(const BlockCtx& c, int tid) {
+  const int ps_base = c.s_prog[TQB_S_PS_BASE], ps_len = c.s_prog[TQB_S_PS_LEN];
+  for (int i = tid; i < c.S * ps_len; i += c.nthreads) {
+    const int slot = i / ps_len, k = i - slot * ps_len;
     const int b = c.sample0 + slot;
-    c.s_mat[slot * TQB_SEG_MAX_FLOATS + k] = (b < c.bsz) ? c.mats[(long long)b * c.mat_stride + mat_base + k] : 0.f;
-    if (BWD) c.s_grad[slot * TQB_SEG_MAX_FLOATS + k] = 0.f;
+    c.s_mps[slot * c.ps_cap + k] = (b < c.bsz) ? c.mps[(long long)b * c.mps_stride + ps_base + k] : 0.f;
+  }
+  if (BWD) {
+    const int g_len = c.s_prog[TQB_S_G_LEN];
+    for (int i = tid; i < c.S * g_len; i += c.nthreads) {
+      const int slot = i / g_len, k = i - slot * g_len;
+      c.s_grad[slot * c.g_cap + k] = 0.f;
+    }
   }
 }
 
 template <class Exec>
 TQB_FN void flush_grads(Exec& ex, const BlockCtx& c, int tid) {
-  const int mat_base = c.s_prog[2], mat_len = c.s_prog[3];
-  for (int i = tid; i < c.S * mat_len; i += c.nthreads) {
-    const int slot = i / mat_len, k = i - slot * mat_len;
+  const int g_base = c.s_prog[TQB_S_G_BASE], g_len = c.s_prog[TQB_S_G_LEN];
+  for (int i = tid; i < c.S * g_len; i += c.nthreads) {
+    const int slot = i / g_len, k = i - slot * g_len;
     const int b = c.sample0 + slot;
     if (b >= c.bsz) continue;
-    const float v = c.s_grad[slot * TQB_SEG_MAX_FLOATS + k];
-    float* dst = c.gmats + (long long)b * c.mat_stride + mat_base + k;
+    const float v = c.s_grad[slot * c.g_cap + k];
+    float* dst = c.gr + (long long)b * c.gr_stride + g_base + k;
     if (c.multi_tile) ex.global_add(dst, v); else *dst = v;
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// register-resident op application
+// register-resident op application.  x[e]: the 2^R amplitudes of this thread, e = pattern of the
+// register bits.  `act`: bit e set when element e takes part (controls satisfied); only looked at
+// when MASKED.  ADJ applies the conjugate transpose (backward sweep).
 // ---------------------------------------------------------------------------------------
-template <int R>
-TQB_FN u32 dep(int e, const u32 (&pm)[R]) {
-  u32 d = 0;
+template <int R, int J, int KIND, bool MASKED, bool ADJ>
+TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
+  if constexpr (KIND == TQB_T_GEN) {
+    const float4 q0 = ld4(m), q1 = ld4(m + 4);
+    float2 m00 = make_float2(q0.x, q0.y), m01 = make_float2(q0.z, q0.w);
+    float2 m10 = make_float2(q1.x, q1.y), m11 = make_float2(q1.z, q1.w);
+    if (ADJ) {
+      const float2 t = m01;
+      m00 = cconj(m00); m01 = cconj(m10); m10 = cconj(t); m11 = cconj(m11);
+    }
 #pragma unroll
-  for (int j = 0; j < R; ++j) if (e & (1 << j)) d |= pm[j];
-  return d;
+    for (int e = 0; e < (1 << R); ++e) {
+      if (e & (1 << J)) continue;
+      if (!MASKED || ((act >> e) & 1u)) {
+        const float2 a = x[e], b = x[e | (1 << J)];
+        x[e] = cfma2(m00, a, m01, b);
+        x[e | (1 << J)] = cfma2(m10, a, m11, b);
+      }
+    }
+  } else if constexpr (KIND == TQB_T_REAL) {
+    const float4 q = ld4(m);
+    const float m00 = q.x, m01 = ADJ ? q.z : q.y, m10 = ADJ ? q.y : q.z, m11 = q.w;
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e) {
+      if (e & (1 << J)) continue;
+      if (!MASKED || ((act >> e) & 1u)) {
+        const float2 a = x[e], b = x[e | (1 << J)];
+        x[e] = make_float2(TQB_FMA(m01, b.x, m00 * a.x), TQB_FMA(m01, b.y, m00 * a.y));
+        x[e | (1 << J)] = make_float2(TQB_FMA(m11, b.x, m10 * a.x), TQB_FMA(m11, b.y, m10 * a.y));
+      }
+    }
+  } else {  // TQB_T_RX: [[c, -is], [-is, c]]
+    const float4 q = ld4(m);
+    const float cc = q.x, s = ADJ ? -q.y : q.y;
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e) {
+      if (e & (1 << J)) continue;
+      if (!MASKED || ((act >> e) & 1u)) {
+        const float2 a = x[e], b = x[e | (1 << J)];
+        x[e] = make_float2(TQB_FMA(s, b.y, cc * a.x), TQB_FMA(-s, b.x, cc * a.y));
+        x[e | (1 << J)] = make_float2(TQB_FMA(s, a.y, cc * b.x), TQB_FMA(-s, a.x, cc * b.y));
+      }
+    }
+  }
 }
 
 template <int R, int J>
-TQB_FN void u1q_fwd(float2 (&x)[1 << R], const float* m, u32 cm, u32 cv, u32 base, const u32 (&pm)[R]) {
-  const float2 m00 = ld2(m), m01 = ld2(m + 2), m10 = ld2(m + 4), m11 = ld2(m + 6);
+TQB_FN void perm(float2 (&x)[1 << R], u32 act) {
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if (e & (1 << J)) continue;
-    const u32 idx = base | dep<R>(e, pm);
-    if ((idx & cm) == cv) {
-      const float2 a = x[e], b = x[e | (1 << J)];
-      x[e] = cadd(cmul(m00, a), cmul(m01, b));
-      x[e | (1 << J)] = cadd(cmul(m10, a), cmul(m11, b));
-    }
+    const bool p = (act >> e) & 1u;
+    const float2 a = x[e], b = x[e | (1 << J)];
+    x[e] = p ? b : a;
+    x[e | (1 << J)] = p ? a : b;
   }
 }
 
-// backward of out = A in on one pair: x holds psi_out (unless NOUNAPPLY: psi_in), y holds
-// lambda_out.  Leaves psi_in / lambda_in = A^H lambda_out; accumulates g[2i+j] += lam_out_i conj(psi_in_j).
-template <int R, int J>
-TQB_FN void u1q_bwd(float2 (&x)[1 << R], float2 (&y)[1 << R], const float* m, u32 cm, u32 cv, u32 base,
-                    const u32 (&pm)[R], bool grad, bool unapply, float (&g)[8]) {
-  const float2 m00 = ld2(m), m01 = ld2(m + 2), m10 = ld2(m + 4), m11 = ld2(m + 6);
+// amp *= (element parity ? dB : dA) on active elements
+template <int R, bool MASKED>
+TQB_FN void diag(float2 (&x)[1 << R], float2 dA, float2 dB, u32 epar, u32 act) {
+  if (epar == 0u) {
 #pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & (1 << J)) continue;
-    const u32 idx = base | dep<R>(e, pm);
-    if ((idx & cm) == cv) {
-      float2 a = x[e], b = x[e | (1 << J)];
-      if (unapply) {
-        const float2 pa = cadd(cmulc(m00, a), cmulc(m10, b));
-        const float2 pb = cadd(cmulc(m01, a), cmulc(m11, b));
-        a = pa; b = pb;
-        x[e] = a; x[e | (1 << J)] = b;
-      }
-      const float2 la = y[e], lb = y[e | (1 << J)];
-      if (grad) {
-        float2 t;
-        t = cmulc(a, la); g[0] += t.x; g[1] += t.y;   // G00 = la conj(a)
-        t = cmulc(b, la); g[2] += t.x; g[3] += t.y;   // G01 = la conj(b)
-        t = cmulc(a, lb); g[4] += t.x; g[5] += t.y;   // G10
-        t = cmulc(b, lb); g[6] += t.x; g[7] += t.y;   // G11
-      }
-      y[e] = cadd(cmulc(m00, la), cmulc(m10, lb));
-      y[e | (1 << J)] = cadd(cmulc(m01, la), cmulc(m11, lb));
-    }
-  }
-}
-
-template <int R>
-TQB_FN void diag_fwd(float2 (&x)[1 << R], const float* m, u32 pmask, u32 opar, u32 cm, u32 cv, u32 base,
-                     const u32 (&pm)[R]) {
-  const float2 d0 = ld2(m), d1 = ld2(m + 2);
+    for (int e = 0; e < (1 << R); ++e)
+      if (!MASKED || ((act >> e) & 1u)) x[e] = cmul(dA, x[e]);
+  } else {
 #pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    const u32 idx = base | dep<R>(e, pm);
-    if ((idx & cm) == cv) {
-      const u32 p = (__popc(idx & pmask) + opar) & 1u;
-      x[e] = cmul(p ? d1 : d0, x[e]);
-    }
-  }
-}
-
-template <int R>
-TQB_FN void diag_bwd(float2 (&x)[1 << R], float2 (&y)[1 << R], const float* m, u32 pmask, u32 opar, u32 cm,
-                     u32 cv, u32 base, const u32 (&pm)[R], bool grad, bool unapply, float (&g)[8]) {
-  const float2 d0 = ld2(m), d1 = ld2(m + 2);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    const u32 idx = base | dep<R>(e, pm);
-    if ((idx & cm) == cv) {
-      const u32 p = (__popc(idx & pmask) + opar) & 1u;
-      const float2 d = p ? d1 : d0;
-      if (unapply) x[e] = cmulc(d, x[e]);
-      if (grad) {
-        const float2 t = cmulc(x[e], y[e]);  // lam_out conj(psi_in)
-        if (p) { g[2] += t.x; g[3] += t.y; } else { g[0] += t.x; g[1] += t.y; }
-      }
-      y[e] = cmulc(d, y[e]);
-    }
+    for (int e = 0; e < (1 << R); ++e)
+      if (!MASKED || ((act >> e) & 1u)) x[e] = cmul(((epar >> e) & 1u) ? dB : dA, x[e]);
   }
 }
 
 // 4x4 on register bits (1,0): quad index q = 2*bit1 + bit0
-template <int R>
-TQB_FN void u2q_fwd(float2 (&x)[1 << R], const float* m, u32 cm, u32 cv, u32 base, const u32 (&pm)[R]) {
+template <int R, bool ADJ>
+TQB_FN void u2q(float2 (&x)[1 << R], const float* m, u32 act) {
 #pragma unroll
   for (int e = 0; e < (1 << R); e += 4) {
-    const u32 idx = base | dep<R>(e, pm);
-    if ((idx & cm) == cv) {
+    if ((act >> e) & 1u) {
       float2 v[4], o[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) v[q] = x[e + q];
@@ -238,7 +254,11 @@ TQB_FN void u2q_fwd(float2 (&x)[1 << R], const float* m, u32 cm, u32 cv, u32 bas
       for (int i = 0; i < 4; ++i) {
         o[i] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[i] = cadd(o[i], cmul(ld2(m + 2 * (4 * i + j)), v[j]));
+        for (int j = 0; j < 4; ++j) {
+          const float* p = ADJ ? m + 2 * (4 * j + i) : m + 2 * (4 * i + j);
+          const float2 mv = make_float2(p[0], ADJ ? -p[1] : p[1]);
+          o[i] = cadd(o[i], cmul(mv, v[j]));
+        }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[e + q] = o[q];
@@ -246,43 +266,79 @@ TQB_FN void u2q_fwd(float2 (&x)[1 << R], const float* m, u32 cm, u32 cv, u32 bas
   }
 }
 
+// --- gradient accumulators (x = psi_in, y = lam_out unless noted) -------------------------
+// G[2i+j] += lam_out_i conj(psi_in_j) over active pairs of register bit J
+template <int R, int J, bool MASKED>
+TQB_FN void grad_full_1q(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 act, float (&g)[8]) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    if (!MASKED || ((act >> e) & 1u)) {
+      const float2 a = x[e], b = x[e | (1 << J)], la = y[e], lb = y[e | (1 << J)];
+      float2 t;
+      t = cmulc(a, la); g[0] += t.x; g[1] += t.y;
+      t = cmulc(b, la); g[2] += t.x; g[3] += t.y;
+      t = cmulc(a, lb); g[4] += t.x; g[5] += t.y;
+      t = cmulc(b, lb); g[6] += t.x; g[7] += t.y;
+    }
+  }
+}
+
+// generators X / Y of exp(-i theta P / 2) on register bit J (either side of the gate works: P commutes with it):
+//   GX: w += Im(conj(psi_b) lam_a + conj(psi_a) lam_b);  GY: w += Re(conj(psi_b) lam_a - conj(psi_a) lam_b)
+template <int R, int J, bool IS_Y, bool MASKED>
+TQB_FN float grad_gen_1q(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 act) {
+  float w = 0.f;
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    if (!MASKED || ((act >> e) & 1u)) {
+      const float2 a = x[e], b = x[e | (1 << J)], la = y[e], lb = y[e | (1 << J)];
+      if (IS_Y) {
+        w = TQB_FMA(b.x, la.x, w); w = TQB_FMA(b.y, la.y, w);
+        w = TQB_FMA(-a.x, lb.x, w); w = TQB_FMA(-a.y, lb.y, w);
+      } else {
+        w = TQB_FMA(b.x, la.y, w); w = TQB_FMA(-b.y, la.x, w);
+        w = TQB_FMA(a.x, lb.y, w); w = TQB_FMA(-a.y, lb.x, w);
+      }
+    }
+  }
+  return w;
+}
+
+// w[p] += Im(conj(psi_k) lam_k) over active elements of parity p (tp: thread parity, epar: element parity)
+template <int R, bool MASKED>
+TQB_FN void grad_dw(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 tp, u32 epar, u32 act, float (&w)[2]) {
+  float wa = 0.f, wb = 0.f;  // wa: elements with element parity 0, wb: parity 1
+  if (epar == 0u) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (!MASKED || ((act >> e) & 1u)) { wa = TQB_FMA(x[e].x, y[e].y, wa); wa = TQB_FMA(-x[e].y, y[e].x, wa); }
+  } else {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e) {
+      if (!MASKED || ((act >> e) & 1u)) {
+        const float v = TQB_FMA(x[e].x, y[e].y, -(x[e].y * y[e].x));
+        if ((epar >> e) & 1u) wb += v; else wa += v;
+      }
+    }
+  }
+  w[0] = tp ? wb : wa;
+  w[1] = tp ? wa : wb;
+}
+
 template <int R>
-TQB_FN void u2q_bwd(float2 (&x)[1 << R], float2 (&y)[1 << R], const float* m, u32 cm, u32 cv, u32 base,
-                    const u32 (&pm)[R], bool grad, bool unapply, float (&g)[32]) {
+TQB_FN void grad_full_2q(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 act, float (&g)[32]) {
 #pragma unroll
   for (int e = 0; e < (1 << R); e += 4) {
-    const u32 idx = base | dep<R>(e, pm);
-    if ((idx & cm) == cv) {
-      float2 v[4], l[4], o[4];
+    if ((act >> e) & 1u) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { v[q] = x[e + q]; l[q] = y[e + q]; }
-      if (unapply) {
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          o[j] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o[j] = cadd(o[j], cmulc(ld2(m + 2 * (4 * i + j)), v[i]));
+          const float2 t = cmulc(x[e + j], y[e + i]);
+          g[2 * (4 * i + j)] += t.x; g[2 * (4 * i + j) + 1] += t.y;
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { v[q] = o[q]; x[e + q] = o[q]; }
-      }
-      if (grad) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 t = cmulc(v[j], l[i]);
-            g[2 * (4 * i + j)] += t.x; g[2 * (4 * i + j) + 1] += t.y;
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o[j] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[j] = cadd(o[j], cmulc(ld2(m + 2 * (4 * i + j)), l[i]));
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) y[e + q] = o[q];
     }
   }
 }
@@ -307,115 +363,187 @@ TQB_FN void sort_positions(u32 (&sp)[R]) {
       if (sp[b] > sp[b + 1]) { const u32 t = sp[b]; sp[b] = sp[b + 1]; sp[b + 1] = t; }
 }
 
+#define TQB_DISPATCH_J(j, CALL)                               \
+  do {                                                        \
+    if ((j) == 0) { constexpr int JJ = 0; CALL; }             \
+    if constexpr (R > 1) { if ((j) == 1) { constexpr int JJ = 1; CALL; } } \
+    if constexpr (R > 2) { if ((j) == 2) { constexpr int JJ = 2; CALL; } } \
+    if constexpr (R > 3) { if ((j) == 3) { constexpr int JJ = 3; CALL; } } \
+  } while (0)
+
+template <int R, class Exec>
+TQB_FN void apply_op_fwd(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* op, u32 base, const float* smps) {
+  const u32 w0 = (u32)op[TQB_OP_W0];
+  if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;  // control on a non-tile bit: CTA-uniform
+  const u32 type = TQB_OP_TYPE(w0);
+  const int j = TQB_OP_J(w0);
+  const bool masked = w0 & (TQB_F_TCTRL | TQB_F_RCTRL);
+  u32 act = 0xffffu;
+  if (masked) {
+    act = (u32)op[TQB_OP_EMASK] & 0xffffu;
+    if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
+  }
+  const float* m = ((w0 & TQB_F_PS) ? smps : c.s_msh) + op[TQB_OP_SLOT];
+  if (type == TQB_T_REAL) {
+    TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)));
+  } else if (type == TQB_T_RX) {
+    TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_RX, false, false>(x, m, act)));
+  } else if (type == TQB_T_DIAG) {
+    const float4 q = ld4(m);
+    const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+    const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
+    const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
+    const u32 epar = (u32)op[TQB_OP_EMASK] >> 16;
+    if (masked) { if (act) diag<R, true>(x, dA, dB, epar, act); }
+    else diag<R, false>(x, dA, dB, epar, act);
+  } else if (type == TQB_T_PERM) {
+    if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act)));
+  } else if (type == TQB_T_GEN) {
+    if (masked) { if (act) TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, true, false>(x, m, act))); }
+    else TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, false, false>(x, m, act)));
+  } else {  // TQB_T_U2Q
+    if constexpr (R >= 2) { if (act) u2q<R, false>(x, m, act); }
+  }
+}
+
+// backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in
+template <int R, bool MASKED, class Exec>
+TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
+                     u32 w0, u32 act, u32 base, const float* smps, float* sgrad, int width) {
+  const u32 type = TQB_OP_TYPE(w0);
+  const int j = TQB_OP_J(w0);
+  const u32 gkind = TQB_OP_GKIND(w0);
+  const bool unapply = !(w0 & TQB_F_NOUNAPPLY);
+  const float* m = ((w0 & TQB_F_PS) ? smps : c.s_msh) + op[TQB_OP_SLOT];
+  float* gdst = sgrad + op[TQB_OP_GSLOT];
+  if (type == TQB_T_REAL || type == TQB_T_RX || type == TQB_T_GEN) {
+    float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float w = 0.f;
+    if (type == TQB_T_REAL) {
+      TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, true>(x, m, act), u1q<R, JJ, TQB_T_REAL, false, true>(y, m, act)));
+    } else if (type == TQB_T_RX) {
+      TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_RX, false, true>(x, m, act), u1q<R, JJ, TQB_T_RX, false, true>(y, m, act)));
+    } else if (!MASKED || act) {
+      if (unapply) TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, MASKED, true>(x, m, act)));
+      if (gkind == TQB_G_FULL) TQB_DISPATCH_J(j, (grad_full_1q<R, JJ, MASKED>(x, y, act, gacc)));
+      TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, MASKED, true>(y, m, act)));
+    }
+    if (gkind == TQB_G_X) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, false, MASKED>(x, y, act)));
+    if (gkind == TQB_G_Y) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, true, MASKED>(x, y, act)));
+    if (gkind == TQB_G_FULL) ex.template reduce_add<8>(gdst, gacc, width);
+    else if (gkind != TQB_G_NONE) { float w1[1] = {w}; ex.template reduce_add<1>(gdst, w1, width); }
+  } else if (type == TQB_T_DIAG) {
+    const float4 q = ld4(m);
+    const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+    const float2 d0 = make_float2(q.x, -q.y), d1 = make_float2(q.z, -q.w);  // conjugated
+    const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
+    const u32 epar = (u32)op[TQB_OP_EMASK] >> 16;
+    if (!MASKED || act) {
+      if (unapply) diag<R, MASKED>(x, dA, dB, epar, act);
+      diag<R, MASKED>(y, dA, dB, epar, act);
+    }
+    if (gkind == TQB_G_DW) {
+      float w2[2];
+      grad_dw<R, MASKED>(x, y, tp, epar, act, w2);
+      ex.template reduce_add<2>(gdst, w2, width);
+    }
+  } else if (type == TQB_T_PERM) {
+    if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act), perm<R, JJ>(y, act)));
+  } else {  // TQB_T_U2Q
+    if constexpr (R >= 2) {
+      float g32[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g32[i] = 0.f;
+      if (act) {
+        if (unapply) u2q<R, true>(x, m, act);
+        if (gkind == TQB_G_FULL) grad_full_2q<R>(x, y, act, g32);
+        u2q<R, true>(y, m, act);
+      }
+      if (gkind == TQB_G_FULL) ex.template reduce_add<32>(gdst, g32, width);
+    }
+  }
+}
+
+template <int R, class Exec>
+TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
+                         u32 base, const float* smps, float* sgrad, int width) {
+  const u32 w0 = (u32)op[TQB_OP_W0];
+  if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
+  if (w0 & (TQB_F_TCTRL | TQB_F_RCTRL)) {
+    u32 act = (u32)op[TQB_OP_EMASK] & 0xffffu;
+    if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
+    bwd_body<R, true, Exec>(ex, c, x, y, op, w0, act, base, smps, sgrad, width);
+  } else {
+    bwd_body<R, false, Exec>(ex, c, x, y, op, w0, 0xffffu, base, smps, sgrad, width);
+  }
+}
+
 template <int R, bool BWD, class Exec>
 TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
-  const int ng = c.s_prog[0];
+  const int ng = c.s_prog[TQB_S_NGROUPS];
   const int32_t* gh = c.s_prog + TQB_SEG_HDR_WORDS + g * TQB_GROUP_WORDS;
   const int slot = tid / c.tps, t = tid % c.tps;
-  u32 pos[R], sp[R], pm[R];
+  u32 sp[R], zp[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) { pos[j] = (u32)gh[j]; sp[j] = pos[j]; pm[j] = 1u << pos[j]; }
+  for (int j = 0; j < R; ++j) { sp[j] = (u32)gh[j]; zp[j] = swz(1u << sp[j]); }
   sort_positions<R>(sp);
   const int nops = gh[4];
   const int32_t* ops = c.s_prog + TQB_SEG_HDR_WORDS + ng * TQB_GROUP_WORDS + gh[5] * TQB_OP_WORDS;
   const int items = 1 << (c.T - R);
   float2* sps = c.s_psi + ((size_t)slot << c.T);
   float2* sla = BWD ? c.s_lam + ((size_t)slot << c.T) : nullptr;
-  const float* smat = c.s_mat + slot * TQB_SEG_MAX_FLOATS;
-  float* sgrad = BWD ? c.s_grad + slot * TQB_SEG_MAX_FLOATS : nullptr;
+  const float* smps = c.s_mps + slot * c.ps_cap;
+  float* sgrad = BWD ? c.s_grad + slot * c.g_cap : nullptr;
   const int width = c.tps < 32 ? c.tps : 32;
 
   for (int item = t; item < items; item += c.tps) {
     const u32 base = insert_zeros<R>((u32)item, sp);
+    const u32 sb = swz(base);
     float2 x[1 << R];
     float2 y[1 << R];
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
-      const u32 a = swz(base | dep<R>(e, pm));
+      u32 a = sb;
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (e & (1 << j)) a ^= zp[j];
       x[e] = sps[a];
       if constexpr (BWD) y[e] = sla[a];
     }
     for (int k = 0; k < nops; ++k) {
       const int32_t* op = ops + (BWD ? (nops - 1 - k) : k) * TQB_OP_WORDS;
-      const u32 w0 = (u32)op[TQB_OP_TYPE];
-      const u32 cmo = (u32)op[TQB_OP_CM_O], cvo = (u32)op[TQB_OP_CV_O];
-      if ((c.tile_ext & cmo) != cvo) continue;  // control on a non-tile (or global) bit: CTA-uniform
-      const u32 type = w0 & 0xffu;
-      const u32 cm = (u32)op[TQB_OP_CM_T], cv = (u32)op[TQB_OP_CV_T];
-      const float* m = smat + op[TQB_OP_SLOT];
-      const bool grad = BWD && (w0 & TQB_F_GRAD);
-      const bool unapply = !(w0 & TQB_F_NOUNAPPLY);
-      if (type == TQB_T_U1Q) {
-        const int j = op[TQB_OP_TGT];
-        if constexpr (!BWD) {
-          if (j == 0) u1q_fwd<R, 0>(x, m, cm, cv, base, pm);
-          if constexpr (R > 1) { if (j == 1) u1q_fwd<R, 1>(x, m, cm, cv, base, pm); }
-          if constexpr (R > 2) { if (j == 2) u1q_fwd<R, 2>(x, m, cm, cv, base, pm); }
-          if constexpr (R > 3) { if (j == 3) u1q_fwd<R, 3>(x, m, cm, cv, base, pm); }
-        } else {
-          float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (j == 0) u1q_bwd<R, 0>(x, y, m, cm, cv, base, pm, grad, unapply, gacc);
-          if constexpr (R > 1) { if (j == 1) u1q_bwd<R, 1>(x, y, m, cm, cv, base, pm, grad, unapply, gacc); }
-          if constexpr (R > 2) { if (j == 2) u1q_bwd<R, 2>(x, y, m, cm, cv, base, pm, grad, unapply, gacc); }
-          if constexpr (R > 3) { if (j == 3) u1q_bwd<R, 3>(x, y, m, cm, cv, base, pm, grad, unapply, gacc); }
-          if (grad) ex.template reduce_add<8>(sgrad + op[TQB_OP_SLOT], gacc, width);
-        }
-      } else if (type == TQB_T_DIAG) {
-        const u32 opar = (u32)__popc(c.tile_ext & (u32)op[TQB_OP_PM_O]) & 1u;
-        if constexpr (!BWD) {
-          diag_fwd<R>(x, m, (u32)op[TQB_OP_PM_T], opar, cm, cv, base, pm);
-        } else {
-          float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          diag_bwd<R>(x, y, m, (u32)op[TQB_OP_PM_T], opar, cm, cv, base, pm, grad, unapply, gacc);
-          if (grad) ex.template reduce_add<4>(sgrad + op[TQB_OP_SLOT], gacc, width);
-        }
-      } else {  // TQB_T_U2Q
-        if constexpr (R >= 2) {
-          if constexpr (!BWD) {
-            u2q_fwd<R>(x, m, cm, cv, base, pm);
-          } else {
-            float g32[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) g32[i] = 0.f;
-            u2q_bwd<R>(x, y, m, cm, cv, base, pm, grad, unapply, g32);
-            if (grad) ex.template reduce_add<32>(sgrad + op[TQB_OP_SLOT], g32, width);
-          }
-        }
-      }
+      if constexpr (BWD) apply_op_bwd<R, Exec>(ex, c, x, y, op, base, smps, sgrad, width);
+      else apply_op_fwd<R, Exec>(c, x, op, base, smps);
     }
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
-      const u32 a = swz(base | dep<R>(e, pm));
+      u32 a = sb;
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (e & (1 << j)) a ^= zp[j];
       sps[a] = x[e];
       if constexpr (BWD) sla[a] = y[e];
     }
   }
 }
 
-// whole block: load tile(s), run every segment/group, store tile(s)
+// all segments / groups of the pass on the tile staged in c.s_psi (and c.s_lam)
 template <int R, bool BWD, class Exec>
-TQB_FN void run_block(Exec& ex, const BlockCtx& c) {
-  ex.par([&](int tid) { build_scatter(c, tid); });
-  ex.par([&](int tid) {
-    load_tile(c, tid, c.psi_src, c.s_psi);
-    if (BWD) load_tile(c, tid, c.lam_src, c.s_lam);
-  });
+TQB_FN void run_tile(Exec& ex, const BlockCtx& c, bool shared_staged) {
   const int nseg = c.prog[TQB_H_NSEG];
   for (int si = 0; si < nseg; ++si) {
     const int s = BWD ? nseg - 1 - si : si;
-    const int soff = c.prog[TQB_H_SEGOFF + s];
-    ex.par([&](int tid) { stage_segment<BWD>(c, tid, soff); });
-    const int ng = c.s_prog[0];
+    if (!shared_staged) {
+      const int soff = c.prog[TQB_H_SEGOFF + s];
+      ex.par([&](int tid) { stage_segment_shared(c, tid, soff); });
+    }
+    if (c.s_prog[TQB_S_PS_LEN] > 0 || (BWD && c.s_prog[TQB_S_G_LEN] > 0))
+      ex.par([&](int tid) { stage_segment_sample<BWD>(c, tid); });
+    const int ng = c.s_prog[TQB_S_NGROUPS];
     for (int gi = 0; gi < ng; ++gi) {
       const int g = BWD ? ng - 1 - gi : gi;
       ex.par([&](int tid) { run_group<R, BWD>(ex, c, tid, g); });
     }
-    if (BWD) ex.par([&](int tid) { flush_grads(ex, c, tid); });
+    if (BWD && c.s_prog[TQB_S_G_LEN] > 0) ex.par([&](int tid) { flush_grads(ex, c, tid); });
   }
-  ex.par([&](int tid) {
-    store_tile(c, tid, c.psi, c.s_psi);
-    if (BWD) store_tile(c, tid, c.lam, c.s_lam);
-  });
 }
 
 // offset (in amplitudes) of tile `tile_id` inside a sample: deposit its bits into the non-tile positions
@@ -430,25 +558,107 @@ TQB_FN u64 outer_offset(const int32_t* prog, int n, u32 tile_id) {
   return off;
 }
 
-// shared-memory carve-up (bytes) for a block of S samples of 2^T amplitudes
-struct SmemLayout { size_t psi, lam, mat, grad, prog, scat, total; };
-inline
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-SmemLayout smem_layout(int T, int L, int S, bool bwd) {
+// persistent loop of one CTA over its work items (a work item = S samples of a single-tile state,
+// or one tile of one sample), with the next item's loads in flight while the current one computes
+// (c is taken by mutable reference on purpose: nvcc 12.9 mis-lowers a BlockCtx copy made here after
+// inlining into the kernel - the copy ends up aliased with the kernel's parameter space)
+template <int R, bool BWD, class Exec>
+TQB_FN void run_cta(Exec& ex, BlockCtx& c, int n, u32 ntiles, u32 ext_hi, long long item0, long long item_step,
+                    long long n_items, int nbuf, size_t buf_stride /* float2 elements between buffers */) {
+  float2* const psi_buf = c.s_psi;
+  float2* const lam_buf = c.s_lam;
+  const bool shared_once = c.prog[TQB_H_NSEG] == 1;
+  ex.par([&](int tid) {
+    build_scatter(c, tid);
+    if (shared_once) stage_segment_shared(c, tid, c.prog[TQB_H_SEGOFF]);
+  });
+  auto locate = [&](long long item) {
+    if (ntiles > 1) {
+      const u32 tile_id = (u32)(item % ntiles);
+      c.sample0 = (int)(item / ntiles);
+      c.tile_ext = tile_id | ext_hi;
+      c.outer_off = outer_offset(c.prog, n, tile_id);
+    } else {
+      c.sample0 = (int)(item * c.S);
+      c.tile_ext = ext_hi;
+      c.outer_off = 0ull;
+    }
+  };
+  auto issue = [&](long long item, int buf) {
+    locate(item);
+    ex.par_nosync([&](int tid) {
+      load_tile_async(ex, c, tid, c.psi_src, psi_buf + buf * buf_stride);
+      if (BWD) load_tile_async(ex, c, tid, c.lam_src, lam_buf + buf * buf_stride);
+      ex.async_commit();
+    });
+  };
+  if (item0 < n_items) issue(item0, 0);
+  int buf = 0;
+  for (long long item = item0; item < n_items; item += item_step) {
+    const long long next = item + item_step;
+    if (nbuf > 1 && next < n_items) {
+      issue(next, buf ^ 1);
+      ex.par([&](int) { ex.async_wait_prev(); });
+    } else {
+      ex.par([&](int) { ex.async_wait_all(); });
+    }
+    locate(item);
+    c.s_psi = psi_buf + buf * buf_stride;
+    c.s_lam = lam_buf + buf * buf_stride;
+    run_tile<R, BWD>(ex, c, shared_once);
+    ex.par([&](int tid) {
+      store_tile(c, tid, c.psi, c.s_psi);
+      if (BWD) store_tile(c, tid, c.lam, c.s_lam);
+    });
+    if (nbuf > 1) buf ^= 1;
+    else if (next < n_items) issue(next, 0);
+  }
+}
+
+// shared-memory carve-up (bytes)
+struct SmemLayout { size_t psi, lam, msh, mps, grad, prog, scat, total, buf_stride; };
+inline SmemLayout smem_layout(int T, int L, int S, bool bwd, int nbuf, int sh_max, int ps_max, int g_max) {
   SmemLayout l;
   size_t off = 0;
   const size_t tile = ((size_t)S << T) * sizeof(float2);
-  l.psi = off; off += tile;
-  l.lam = off; if (bwd) off += tile;
-  l.mat = off; off += (size_t)S * TQB_SEG_MAX_FLOATS * sizeof(float);
-  l.grad = off; if (bwd) off += (size_t)S * TQB_SEG_MAX_FLOATS * sizeof(float);
+  l.buf_stride = tile / sizeof(float2);
+  l.psi = off; off += tile * nbuf;
+  l.lam = off; if (bwd) off += tile * nbuf;
+  l.msh = off; off += (size_t)((sh_max + 3) & ~3) * sizeof(float);
+  l.mps = off; off += (size_t)S * ps_max * sizeof(float);
+  l.grad = off; if (bwd) off += (size_t)S * g_max * sizeof(float);
   l.prog = off; off += (size_t)TQB_SEG_MAX_WORDS * sizeof(int32_t);
   off = (off + 15) & ~(size_t)15;
   l.scat = off; off += ((size_t)1 << (T - L)) * sizeof(u64);
   l.total = (off + 15) & ~(size_t)15;
   return l;
+}
+
+// launch geometry shared by the CUDA launcher and the emulation
+struct PassGeom { int S, tps, nbuf; u32 ntiles; long long n_items; SmemLayout lay; };
+inline bool pass_geometry(int n, long long bsz, int T, int R, int L, bool bwd, int sh_max, int ps_max, int g_max,
+                          size_t smem_budget, PassGeom& g) {
+  const int items = 1 << (T - R);
+  g.tps = items < 256 ? items : 256;
+  ps_max = (ps_max + 3) & ~3;
+  g_max = (g_max + 3) & ~3;
+  if (n == T) {
+    g.ntiles = 1;
+    g.nbuf = 1;
+    int S = g.tps >= 128 ? 1 : 128 / g.tps;
+    while (S > 1 && smem_layout(T, L, S, bwd, 1, sh_max, ps_max, g_max).total > smem_budget) S >>= 1;
+    if (S * g.tps < 32) S = 32 / g.tps;  // whole warps for the shuffle reductions
+    g.S = S;
+    g.n_items = (bsz + S - 1) / S;
+  } else {
+    g.S = 1;
+    g.ntiles = 1u << (n - T);
+    g.n_items = bsz * (long long)g.ntiles;
+    g.nbuf = 2;
+    if (smem_layout(T, L, 1, bwd, 2, sh_max, ps_max, g_max).total > smem_budget) g.nbuf = 1;
+  }
+  g.lay = smem_layout(T, L, g.S, bwd, g.nbuf, sh_max, ps_max, g_max);
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -578,46 +788,72 @@ TQB_FN int build_gate(int kind, const T* th, Cx<T>* u) {
 
 TQB_FN int kind_dim(int nent) { return nent == 16 ? 4 : (nent == 4 ? 2 : 0); }  // 0: diagonal pair
 
-// one (op, sample): params -> applied matrix (inverse folded in) written to the sample's matrix row
-TQB_FN void build_one(const int32_t* rec, int b, const float* params_sh, const float* params_ps, int ps_stride,
-                      const float* consts, float* mats_row) {
+// one (op, sample): params -> applied matrix (inverse folded in), packed for the op type, written to
+// the shared row (b ignored) or the sample's row
+TQB_FN void build_one(const int32_t* rec, long long b, const float* params_sh, const float* params_ps, int ps_stride,
+                      const float* consts, float* row) {
   const int kind = rec[TQB_B_KIND];
-  float* out = mats_row + rec[TQB_B_MOFF];
+  float* out = row + rec[TQB_B_MOFF];
   if (kind == TQB_K_EXTERN) return;
   if (kind == TQB_K_CONST) {
     for (int i = 0; i < rec[TQB_B_NFLOAT]; ++i) out[i] = consts[rec[TQB_B_COFF] + i];
     return;
   }
   const bool inv = rec[TQB_B_FLAGS] & TQB_BF_INVERSE;
-  const float* p = (rec[TQB_B_FLAGS] & TQB_BF_PER_SAMPLE) ? params_ps + (long long)b * ps_stride + rec[TQB_B_POFF]
+  const float* p = (rec[TQB_B_FLAGS] & TQB_BF_PER_SAMPLE) ? params_ps + b * ps_stride + rec[TQB_B_POFF]
                                                           : params_sh + rec[TQB_B_POFF];
   float th[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = 0; i < rec[TQB_B_NPARAM]; ++i) th[i] = p[i];
   Cx<float> u[16];
   const int nent = build_gate<float>(kind, th, u);
   const int d = kind_dim(nent);
+  const int type = rec[TQB_B_TYPE];
   if (d == 0) {
     for (int i = 0; i < 2; ++i) { out[2 * i] = u[i].re; out[2 * i + 1] = inv ? -u[i].im : u[i].im; }
+    return;
+  }
+  Cx<float> a[16];  // applied matrix
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      const Cx<float> v = inv ? u[j * d + i] : u[i * d + j];
+      a[i * d + j] = Cx<float>{v.re, inv ? -v.im : v.im};
+    }
+  if (type == TQB_T_REAL) {
+    out[0] = a[0].re; out[1] = a[1].re; out[2] = a[2].re; out[3] = a[3].re;
+  } else if (type == TQB_T_RX) {
+    out[0] = a[0].re; out[1] = -a[1].im; out[2] = 0.f; out[3] = 0.f;
   } else {
-    for (int i = 0; i < d; ++i)
-      for (int j = 0; j < d; ++j) {
-        const Cx<float> v = inv ? u[j * d + i] : u[i * d + j];
-        out[2 * (i * d + j)] = v.re;
-        out[2 * (i * d + j) + 1] = inv ? -v.im : v.im;
-      }
+    for (int i = 0; i < d * d; ++i) { out[2 * i] = a[i].re; out[2 * i + 1] = a[i].im; }
   }
 }
 
-// one (op, sample): dL/dtheta_p = Re sum conj(dA_ij/dtheta_p) G_ij with A the applied matrix
-TQB_FN void build_one_bwd(const int32_t* rec, int b, const float* params_sh, const float* params_ps, int ps_stride,
-                          const float* gmats_row, float* gsh_row, float* gps_row) {
+// one (op, sample): dL/dtheta from the op's gradient accumulators
+//   FULL: Re sum conj(dA_ij/dtheta_p) G_ij with A the applied matrix
+//   X / Y: A = exp(-+ i theta P / 2)  ->  -+ w / 2
+//   DW:    A_k = exp(i phi_p(theta)) -> sum_p phi_p' w_p
+TQB_FN void build_one_bwd(const int32_t* rec, long long b, const float* params_sh, const float* params_ps,
+                          int ps_stride, const float* grow, float* gsh_row, float* gps_row) {
   const int kind = rec[TQB_B_KIND];
-  if (kind == TQB_K_EXTERN || kind == TQB_K_CONST) return;
+  const int gkind = rec[TQB_B_GKIND];
+  if (kind == TQB_K_EXTERN || kind == TQB_K_CONST || gkind == TQB_G_NONE) return;
   const bool inv = rec[TQB_B_FLAGS] & TQB_BF_INVERSE;
   const bool ps = rec[TQB_B_FLAGS] & TQB_BF_PER_SAMPLE;
-  const float* p = ps ? params_ps + (long long)b * ps_stride + rec[TQB_B_POFF] : params_sh + rec[TQB_B_POFF];
-  const float* G = gmats_row + rec[TQB_B_MOFF];
+  const float* p = ps ? params_ps + b * ps_stride + rec[TQB_B_POFF] : params_sh + rec[TQB_B_POFF];
+  const float* G = grow + rec[TQB_B_GOFF];
+  float* dst = (ps ? gps_row : gsh_row) + rec[TQB_B_POFF];
   const int np = rec[TQB_B_NPARAM];
+  if (gkind == TQB_G_X || gkind == TQB_G_Y) {
+    dst[0] = (inv ? 0.5f : -0.5f) * G[0];
+    return;
+  }
+  if (gkind == TQB_G_DW) {
+    float v;
+    if (kind == TQB_K_RZ) v = 0.5f * (G[1] - G[0]);
+    else if (kind == TQB_K_PHASE) v = G[1];   // d0 = 1 carries no phase
+    else v = G[0] + G[1];                     // global phase
+    dst[0] = inv ? -v : v;
+    return;
+  }
   for (int q = 0; q < np; ++q) {
     Dual th[4];
     for (int i = 0; i < 4; ++i) th[i] = Dual{i < np ? p[i] : 0.f, i == q ? 1.f : 0.f};
@@ -625,18 +861,13 @@ TQB_FN void build_one_bwd(const int32_t* rec, int b, const float* params_sh, con
     const int nent = build_gate<Dual>(kind, th, u);
     const int d = kind_dim(nent);
     float acc = 0.f;
-    if (d == 0) {
-      // applied a_p = d_p (or conj d_p when inverted): Re conj(da) G = dre*Gre + dim*Gim ; inverse flips dim
-      for (int i = 0; i < 2; ++i) acc += u[i].re.d * G[2 * i] + (inv ? -u[i].im.d : u[i].im.d) * G[2 * i + 1];
-    } else {
-      for (int i = 0; i < d; ++i)
-        for (int j = 0; j < d; ++j) {
-          // applied A_ij = U_ij, or conj(U_ji) when inverted
-          const Cx<Dual> v = inv ? u[j * d + i] : u[i * d + j];
-          acc += v.re.d * G[2 * (i * d + j)] + (inv ? -v.im.d : v.im.d) * G[2 * (i * d + j) + 1];
-        }
-    }
-    (ps ? gps_row : gsh_row)[rec[TQB_B_POFF] + q] = acc;
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) {
+        // applied A_ij = U_ij, or conj(U_ji) when inverted
+        const Cx<Dual> v = inv ? u[j * d + i] : u[i * d + j];
+        acc += v.re.d * G[2 * (i * d + j)] + (inv ? -v.im.d : v.im.d) * G[2 * (i * d + j) + 1];
+      }
+    dst[q] = acc;
   }
 }
 

@@ -33,16 +33,48 @@ struct CudaExec {
     f((int)threadIdx.x);
     __syncthreads();
   }
+  template <class F>
+  __device__ __forceinline__ void par_nosync(F f) { f((int)threadIdx.x); }
+  // global -> shared without a register round trip (LDGSTS); completion via commit/wait groups
+  __device__ __forceinline__ void async_copy8(float2* dst, const float2* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+  __device__ __forceinline__ void async_wait_prev() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+  __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
   // sum v[0..N) over the `width` consecutive lanes that share a sample, add into shared dst
   template <int N>
   __device__ __forceinline__ void reduce_add(float* dst, float* v, int width) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (width == 32 && N >= 8) {
+      // halving butterfly: every step each lane keeps one half of its values and ships the other
+      int off = 16;
+#pragma unroll
+      for (int half = N / 2; half >= 1; half >>= 1) {
+        const bool upper = lane & off;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? v[i] : v[i + half];
+          const float keep = upper ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+      }
+      // N == 8: offsets 16, 8, 4 consumed; N == 32: all five
+      float s = v[0];
+      for (; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (N == 8) { if ((lane & 3u) == 0u) atomicAdd(dst + (((lane >> 4) & 1u) * 4u + ((lane >> 3) & 1u) * 2u + ((lane >> 2) & 1u)), s); }
+      else atomicAdd(dst + lane, s);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       float s = v[i];
       for (int o = width >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       v[i] = s;
     }
-    if (((threadIdx.x & 31) & (width - 1)) == 0) {
+    if ((lane & (unsigned)(width - 1)) == 0u) {
 #pragma unroll
       for (int i = 0; i < N; ++i) atomicAdd(dst + i, v[i]);
     }
@@ -51,92 +83,102 @@ struct CudaExec {
 };
 
 struct PassArgs {
-  int T, R, L, n, S, tps, bsz;
+  int T, L, n, S, tps, bsz, nbuf, ps_cap, g_cap;
   unsigned ntiles, ext_hi;
+  long long n_items;
   const int32_t* prog;
   const float2* psi_src;
   const float2* lam_src;
   float2* psi;
   float2* lam;
-  const float* mats;
-  float* gmats;
-  long long mat_stride;
+  const float* msh;
+  const float* mps;
+  float* gr;
+  long long mps_stride, gr_stride;
+  unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_prog, o_scat, buf_stride;
 };
 
 template <int R, bool BWD>
-__global__ void __launch_bounds__(256) tqb_pass_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(256, BWD ? 2 : 3) tqb_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockCtx c;
-  c.T = a.T; c.R = R; c.L = a.L; c.n = a.n; c.S = a.S; c.tps = a.tps; c.nthreads = a.S * a.tps;
+  c.T = a.T; c.L = a.L; c.S = a.S; c.tps = a.tps; c.nthreads = a.S * a.tps;
   c.bsz = a.bsz;
   c.multi_tile = a.ntiles > 1;
-  unsigned tile_id = 0;
-  if (a.ntiles > 1) { tile_id = blockIdx.x % a.ntiles; c.sample0 = blockIdx.x / a.ntiles; }
-  else c.sample0 = blockIdx.x * a.S;
-  c.tile_ext = tile_id | a.ext_hi;
-  c.outer_off = a.ntiles > 1 ? outer_offset(a.prog, a.n, tile_id) : 0ull;
+  c.sample0 = 0; c.tile_ext = 0; c.outer_off = 0;
   c.sample_stride = 1ull << a.n;
-  c.prog = a.prog; c.psi_src = a.psi_src; c.lam_src = a.lam_src; c.psi = a.psi; c.lam = a.lam; c.mats = a.mats; c.gmats = a.gmats;
-  c.mat_stride = a.mat_stride;
-  const SmemLayout l = smem_layout(a.T, a.L, a.S, BWD);
-  c.s_psi = reinterpret_cast<float2*>(smem + l.psi);
-  c.s_lam = reinterpret_cast<float2*>(smem + l.lam);
-  c.s_mat = reinterpret_cast<float*>(smem + l.mat);
-  c.s_grad = reinterpret_cast<float*>(smem + l.grad);
-  c.s_prog = reinterpret_cast<int32_t*>(smem + l.prog);
-  c.s_scat = reinterpret_cast<u64*>(smem + l.scat);
+  c.prog = a.prog; c.psi_src = a.psi_src; c.lam_src = a.lam_src; c.psi = a.psi; c.lam = a.lam;
+  c.msh = a.msh; c.mps = a.mps; c.gr = a.gr; c.mps_stride = a.mps_stride; c.gr_stride = a.gr_stride;
+  c.ps_cap = a.ps_cap; c.g_cap = a.g_cap;
+  c.s_psi = reinterpret_cast<float2*>(smem + a.o_psi);
+  c.s_lam = reinterpret_cast<float2*>(smem + a.o_lam);
+  c.s_msh = reinterpret_cast<float*>(smem + a.o_msh);
+  c.s_mps = reinterpret_cast<float*>(smem + a.o_mps);
+  c.s_grad = reinterpret_cast<float*>(smem + a.o_grad);
+  c.s_prog = reinterpret_cast<int32_t*>(smem + a.o_prog);
+  c.s_scat = reinterpret_cast<u64*>(smem + a.o_scat);
   CudaExec ex;
-  run_block<R, BWD>(ex, c);
+  run_cta<R, BWD>(ex, c, a.n, a.ntiles, a.ext_hi, (long long)blockIdx.x, (long long)gridDim.x, a.n_items, a.nbuf,
+                  (size_t)a.buf_stride);
 }
 
+static int g_num_sms = 0;
+
 template <int R, bool BWD>
-static int launch_pass(const PassArgs& a, size_t smem, long long grid, cudaStream_t st) {
-  static int configured_smem = 0;  // per instantiation
+static int launch_pass(const PassArgs& a, size_t smem, cudaStream_t st) {
+  static int configured_smem = -1;  // per instantiation
+  static int occ_threads = 0, occ_smem = -1, occ_blocks = 0;
+  const int threads = a.S * a.tps;
   if ((int)smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(tqb_pass_kernel<R, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(pass)", e);
     configured_smem = (int)smem;
   }
-  tqb_pass_kernel<R, BWD><<<(unsigned)grid, a.S * a.tps, smem, st>>>(a);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  if (occ_threads != threads || occ_smem != (int)smem) {
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tqb_pass_kernel<R, BWD>, threads, smem);
+    if (e != cudaSuccess) return fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor(pass)", e);
+    occ_threads = threads; occ_smem = (int)smem; occ_blocks = nb < 1 ? 1 : nb;
+  }
+  long long grid = (long long)g_num_sms * occ_blocks;
+  if (grid > a.n_items) grid = a.n_items;
+  tqb_pass_kernel<R, BWD><<<(unsigned)grid, threads, smem, st>>>(a);
   TQB_CHECK_LAUNCH("tqb_pass_kernel");
   return 0;
 }
 
-static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz, const int32_t* prog, int T, int R,
-                    int L, const float* mats, float* gmats, long long mat_stride, unsigned ext_hi, void* stream) {
-  if (T < 1 || T > TQB_MAX_T || T > n || R < 1 || R > TQB_MAX_R || R > T || L < 1 || L > T)
+static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz,
+                    const int32_t* prog, const int* desc, const float* msh, const float* mps, long long mps_stride,
+                    float* gr, long long gr_stride, unsigned ext_hi, void* stream) {
+  const int T = desc[0], R = desc[1], L = desc[2], sh_max = desc[4], ps_max = desc[5], g_max = desc[6];
+  if (T < 1 || T > TQB_MAX_T || T > n || R < 1 || R > TQB_MAX_R || R > T || L < 0 || L > T)
     return fail_msg("tqb pass: bad tile geometry");
+  if (sh_max > TQB_SEG_MAX_SH || ps_max > TQB_SEG_MAX_PS || g_max > TQB_SEG_MAX_G)
+    return fail_msg("tqb pass: segment exceeds staging capacity");
   if (bsz <= 0) return 0;
+  PassGeom g;
+  pass_geometry(n, bsz, T, R, L, bwd, sh_max, ps_max, g_max, 200 * 1024, g);
+  if (g.lay.total > 227 * 1024) return fail_msg("tqb pass: tile does not fit shared memory");
   PassArgs a;
-  a.T = T; a.R = R; a.L = L; a.n = n; a.bsz = (int)bsz;
-  const int items = 1 << (T - R);
-  a.tps = items < 256 ? items : 256;
-  long long grid;
-  if (n == T) {
-    a.ntiles = 1;
-    // samples per CTA: fill 128 threads, bounded by what the staged segment matrices cost
-    int S = a.tps >= 128 ? 1 : 128 / a.tps;
-    const size_t budget = 160 * 1024;
-    while (S > 1 && smem_layout(T, L, S, bwd).total > budget) S >>= 1;
-    if (S * a.tps < 32) S = 32 / a.tps;  // whole warps for the shuffle reductions
-    a.S = S;
-    grid = (bsz + S - 1) / S;
-  } else {
-    a.S = 1;
-    a.ntiles = 1u << (n - T);
-    grid = bsz * (long long)a.ntiles;
-  }
-  if (grid > 0x7fffffffLL) return fail_msg("tqb pass: grid too large");
-  a.ext_hi = ext_hi;
+  a.T = T; a.L = L; a.n = n; a.S = g.S; a.tps = g.tps; a.bsz = (int)bsz; a.nbuf = g.nbuf;
+  a.ps_cap = (ps_max + 3) & ~3; a.g_cap = (g_max + 3) & ~3;
+  a.ntiles = g.ntiles; a.ext_hi = ext_hi; a.n_items = g.n_items;
   a.prog = prog; a.psi = reinterpret_cast<float2*>(psi); a.lam = reinterpret_cast<float2*>(lam);
   a.psi_src = reinterpret_cast<const float2*>(psi_src); a.lam_src = reinterpret_cast<const float2*>(lam_src);
-  a.mats = mats; a.gmats = gmats; a.mat_stride = mat_stride;
-  const size_t smem = smem_layout(T, L, a.S, bwd).total;
-  if (smem > 227 * 1024) return fail_msg("tqb pass: tile does not fit shared memory");
+  a.msh = msh; a.mps = mps; a.gr = gr; a.mps_stride = mps_stride; a.gr_stride = gr_stride;
+  a.o_psi = (unsigned)g.lay.psi; a.o_lam = (unsigned)g.lay.lam; a.o_msh = (unsigned)g.lay.msh; a.o_mps = (unsigned)g.lay.mps;
+  a.o_grad = (unsigned)g.lay.grad; a.o_prog = (unsigned)g.lay.prog; a.o_scat = (unsigned)g.lay.scat;
+  a.buf_stride = (unsigned)g.lay.buf_stride;
   cudaStream_t st = (cudaStream_t)stream;
 #define TQB_DISPATCH(RR)                                             \
   case RR:                                                           \
-    return bwd ? launch_pass<RR, true>(a, smem, grid, st) : launch_pass<RR, false>(a, smem, grid, st);
+    return bwd ? launch_pass<RR, true>(a, g.lay.total, st) : launch_pass<RR, false>(a, g.lay.total, st);
   switch (R) {
     TQB_DISPATCH(1)
     TQB_DISPATCH(2)
@@ -150,24 +192,31 @@ static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float*
 // ---------------------------------------------------------------------------------------
 // parameter -> matrix builder and its backward
 // ---------------------------------------------------------------------------------------
-__global__ void tqb_build_kernel(const int32_t* table, int nrec, long long bsz, const float* params_sh,
-                                 const float* params_ps, int ps_stride, const float* consts, float* mats,
-                                 long long mat_stride) {
+// records [0, n_sh) write the shared row once; records [n_sh, nrec) write every sample's row
+__global__ void tqb_build_kernel(const int32_t* table, int nrec, int n_sh, long long bsz, const float* params_sh,
+                                 const float* params_ps, int ps_stride, const float* consts, float* msh, float* mps,
+                                 long long mps_stride) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= bsz * nrec) return;
-  const int r = (int)(i % nrec);
-  const long long b = i / nrec;
-  build_one(table + r * TQB_B_WORDS, (int)b, params_sh, params_ps, ps_stride, consts, mats + b * mat_stride);
+  const int n_ps = nrec - n_sh;
+  if (i < n_sh) {
+    build_one(table + i * TQB_B_WORDS, 0, params_sh, params_ps, ps_stride, consts, msh);
+    return;
+  }
+  const long long k = i - n_sh;
+  if (k >= bsz * n_ps) return;
+  const int r = n_sh + (int)(k % n_ps);
+  const long long b = k / n_ps;
+  build_one(table + r * TQB_B_WORDS, b, params_sh, params_ps, ps_stride, consts, mps + b * mps_stride);
 }
 
 __global__ void tqb_build_bwd_kernel(const int32_t* table, int nrec, long long bsz, const float* params_sh,
-                                     const float* params_ps, int ps_stride, const float* gmats, long long mat_stride,
+                                     const float* params_ps, int ps_stride, const float* gr, long long gr_stride,
                                      float* gsh, int sh_stride, float* gps) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bsz * nrec) return;
   const int r = (int)(i % nrec);
   const long long b = i / nrec;
-  build_one_bwd(table + r * TQB_B_WORDS, (int)b, params_sh, params_ps, ps_stride, gmats + b * mat_stride,
+  build_one_bwd(table + r * TQB_B_WORDS, b, params_sh, params_ps, ps_stride, gr + b * gr_stride,
                 gsh + b * sh_stride, gps + b * ps_stride);
 }
 
@@ -421,35 +470,38 @@ extern "C" {
 int tqb_abi_version(void) { return TQB_ABI_VERSION; }
 const char* tqb_last_error(void) { return g_err; }
 
-int tqb_pass_forward(const float* src, float* dst, int n_qubits, long long bsz, const int32_t* prog_dev, int T, int R,
-                     int L, const float* mats, long long mat_stride, unsigned ext_hi, void* stream) {
-  return run_pass(false, src, nullptr, dst, nullptr, n_qubits, bsz, prog_dev, T, R, L, mats, nullptr, mat_stride, ext_hi, stream);
+int tqb_pass_forward(const float* src, float* dst, int n_qubits, long long bsz, const int32_t* prog_dev,
+                     const int* desc_host, const float* msh, const float* mps, long long mps_stride, unsigned ext_hi,
+                     void* stream) {
+  return run_pass(false, src, nullptr, dst, nullptr, n_qubits, bsz, prog_dev, desc_host, msh, mps, mps_stride, nullptr, 0,
+                  ext_hi, stream);
 }
 
 int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi_dst, float* lam_dst, int n_qubits,
-                      long long bsz, const int32_t* prog_dev, int T, int R, int L, const float* mats, float* gmats,
-                      long long mat_stride, unsigned ext_hi, void* stream) {
-  return run_pass(true, psi_src, lam_src, psi_dst, lam_dst, n_qubits, bsz, prog_dev, T, R, L, mats, gmats, mat_stride, ext_hi, stream);
+                      long long bsz, const int32_t* prog_dev, const int* desc_host, const float* msh, const float* mps,
+                      long long mps_stride, float* gr, long long gr_stride, unsigned ext_hi, void* stream) {
+  return run_pass(true, psi_src, lam_src, psi_dst, lam_dst, n_qubits, bsz, prog_dev, desc_host, msh, mps, mps_stride, gr,
+                  gr_stride, ext_hi, stream);
 }
 
-int tqb_build_mats(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
-                   const float* params_ps, int ps_stride, const float* consts, float* mats, long long mat_stride,
-                   void* stream) {
+int tqb_build_mats(const int32_t* table_dev, int n_records, int n_shared_records, long long bsz, const float* params_sh,
+                   const float* params_ps, int ps_stride, const float* consts, float* msh, float* mps,
+                   long long mps_stride, void* stream) {
   if (n_records <= 0 || bsz <= 0) return 0;
-  const long long total = bsz * n_records;
+  const long long total = n_shared_records + bsz * (long long)(n_records - n_shared_records);
   tqb_build_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      table_dev, n_records, bsz, params_sh, params_ps, ps_stride, consts, mats, mat_stride);
+      table_dev, n_records, n_shared_records, bsz, params_sh, params_ps, ps_stride, consts, msh, mps, mps_stride);
   TQB_CHECK_LAUNCH("tqb_build_kernel");
   return 0;
 }
 
 int tqb_build_mats_bwd(const int32_t* table_dev, int n_records, long long bsz, const float* params_sh,
-                       const float* params_ps, int ps_stride, const float* gmats, long long mat_stride,
+                       const float* params_ps, int ps_stride, const float* gr, long long gr_stride,
                        float* gparams_sh_partial, int sh_stride, float* gparams_ps, void* stream) {
   if (n_records <= 0 || bsz <= 0) return 0;
   const long long total = bsz * n_records;
   tqb_build_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      table_dev, n_records, bsz, params_sh, params_ps, ps_stride, gmats, mat_stride, gparams_sh_partial, sh_stride,
+      table_dev, n_records, bsz, params_sh, params_ps, ps_stride, gr, gr_stride, gparams_sh_partial, sh_stride,
       gparams_ps);
   TQB_CHECK_LAUNCH("tqb_build_bwd_kernel");
   return 0;

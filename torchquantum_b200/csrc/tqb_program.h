@@ -9,19 +9,25 @@
 // that differ in those bits and applies all ops of the group to them without touching shared
 // memory in between.
 //
+// Gate matrices live in two rows: one row shared by the whole batch (constants and gates whose
+// parameters are shared, `msh`) and one row per sample (`mps`, per-sample parameters).  Gradient
+// accumulators are one row per sample (`gr`).
+//
 // All words are int32.  Offsets are in words from the start of the program.
 #pragma once
 #include <stdint.h>
 
-#define TQB_MAGIC 0x54514231  // "TQB1"
-#define TQB_MAX_T 14          // largest tile (2^14 amplitudes = 128 KiB)
+#define TQB_MAGIC 0x54514232  // "TQB2"
+#define TQB_MAX_T 13          // largest tile (2^13 amplitudes = 64 KiB)
 #define TQB_MAX_R 4           // register bits per thread (16 amplitudes)
 #define TQB_OP_WORDS 10
 #define TQB_GROUP_WORDS 8
-#define TQB_SEG_HDR_WORDS 4
+#define TQB_SEG_HDR_WORDS 8
 #define TQB_SEG_MAX_OPS 64
-#define TQB_SEG_MAX_GROUPS 64
-#define TQB_SEG_MAX_FLOATS 768  // matrix floats staged per segment (per sample)
+#define TQB_SEG_MAX_GROUPS 32
+#define TQB_SEG_MAX_SH 768   // shared matrix floats staged per segment
+#define TQB_SEG_MAX_PS 256   // per-sample matrix floats staged per segment (per sample)
+#define TQB_SEG_MAX_G 256    // gradient floats per segment (per sample)
 #define TQB_SEG_MAX_WORDS (TQB_SEG_HDR_WORDS + TQB_SEG_MAX_GROUPS * TQB_GROUP_WORDS + TQB_SEG_MAX_OPS * TQB_OP_WORDS)
 
 // program header words
@@ -31,40 +37,72 @@
 #define TQB_H_NSEG 3
 #define TQB_H_L 4          // number of contiguous low bits in the tile
 #define TQB_H_WORDS 5      // total program length
-#define TQB_H_OUTER 6      // number of non-tile bits (n - T)
+#define TQB_H_OUTER 6      // number of non-tile bits (n_total - T)
+#define TQB_H_PS_MAX 7     // max per-sample matrix floats of any segment
 #define TQB_H_TBIT 8       // 16 words: global bit position of tile-local bit i
-#define TQB_H_SEGOFF 24    // n_seg words: offset of each segment
+#define TQB_H_G_MAX 24     // max gradient floats of any segment
+#define TQB_H_SH_MAX 25    // max shared matrix floats of any segment
+#define TQB_H_SEGOFF 32    // n_seg words: offset of each segment
 
-// segment header: [n_groups, n_ops, mat_base, mat_len]; then n_groups group records; then ops.
+// segment header (8 words); then n_groups group records; then the op records
+#define TQB_S_NGROUPS 0
+#define TQB_S_NOPS 1
+#define TQB_S_SH_BASE 2   // first float of this segment in the shared matrix row
+#define TQB_S_SH_LEN 3
+#define TQB_S_PS_BASE 4   // first float of this segment in every per-sample matrix row
+#define TQB_S_PS_LEN 5
+#define TQB_S_G_BASE 6    // first float of this segment in every gradient row
+#define TQB_S_G_LEN 7
+
 // group record: [regpos0..3, n_ops, first_op, 0, 0]  (regpos = tile-local bit of register bit j)
 // op record (10 words):
-#define TQB_OP_TYPE 0   // low 8 bits type, bits 8.. flags
-#define TQB_OP_TGT 1    // U1Q: register-bit index j.  U2Q: unused (targets are register bits 1,0)
-#define TQB_OP_PM_T 2   // DIAG: parity mask over tile-local bits
-#define TQB_OP_CM_T 3   // control mask over tile-local bits
-#define TQB_OP_CV_T 4   // required value of the controlled bits
-#define TQB_OP_SLOT 5   // float offset of this op's matrix inside the segment's staged matrices
-#define TQB_OP_PM_O 6   // DIAG: parity mask over the compressed outer (non-tile) index
-#define TQB_OP_CM_O 7   // control mask over the compressed outer index
-#define TQB_OP_CV_O 8
-#define TQB_OP_AUX 9
+#define TQB_OP_W0 0     // bits 0-3 type, 4-5 target register bit j, 8-15 flags, 16-19 gradient kind
+#define TQB_OP_SLOT 1   // float offset of this op's matrix in the staged shared / per-sample floats
+#define TQB_OP_EMASK 2  // low 16: elements e (register-bit patterns) whose register-bit controls hold;
+                        // high 16: DIAG parity of e over the parity bits that are register bits
+#define TQB_OP_CM_T 3   // control mask over the non-register tile-local bits
+#define TQB_OP_CV_T 4   // required value of those bits
+#define TQB_OP_PM_T 5   // DIAG: parity mask over the non-register tile-local bits
+#define TQB_OP_CM_O 6   // control mask over the compressed outer (non-tile) index
+#define TQB_OP_CV_O 7
+#define TQB_OP_PM_O 8   // DIAG: parity mask over the compressed outer index
+#define TQB_OP_GSLOT 9  // float offset of this op's gradient accumulators in the segment's gradient floats
 
-#define TQB_T_U1Q 0   // (controlled) 2x2 on one register bit; 8 floats row-major (re,im)
-#define TQB_T_DIAG 1  // (controlled) amp *= d[parity(idx & pm)]; 4 floats d0,d1
-#define TQB_T_U2Q 2   // (controlled) 4x4 on register bits (1,0) = (msb,lsb); 32 floats
+// op types.  Matrix slots are padded to a multiple of 4 floats (16-byte staged loads).
+#define TQB_T_GEN 0    // 2x2 complex on register bit j; 8 floats row-major (re,im)
+#define TQB_T_REAL 1   // real 2x2 on register bit j; 4 floats m00 m01 m10 m11       (ry, h, ...)
+#define TQB_T_RX 2     // [[c, -is], [-is, c]] on register bit j; floats c, s, 0, 0     (rx)
+#define TQB_T_DIAG 3   // amp *= d[parity]; 4 floats d0 (re,im), d1 (re,im)             (rz, cz, cu1, rzz ...)
+#define TQB_T_PERM 4   // swap the two amplitudes of register bit j; no floats           (x, cnot, toffoli ...)
+#define TQB_T_U2Q 5    // 4x4 complex on register bits (1,0) = (msb,lsb); 32 floats
 
-#define TQB_F_GRAD 0x100     // accumulate dL/dU for this op in the backward sweep
-#define TQB_F_NOUNAPPLY 0x200  // backward: psi already holds the op's INPUT (non-unitary single-op node)
+#define TQB_F_TCTRL 0x100      // has controls on non-register tile bits (CM_T/CV_T valid)
+#define TQB_F_RCTRL 0x200      // has controls on register bits (EMASK != 0xffff)
+#define TQB_F_PS 0x400         // matrix lives in the per-sample floats
+#define TQB_F_NOUNAPPLY 0x800  // backward: psi already holds the op's INPUT (non-unitary single-op node)
 
-// matrix-builder table: one record of 8 words per op (tqb_build_mats / tqb_build_mats_bwd)
-#define TQB_B_WORDS 8
+// gradient kinds (backward sweep): what is accumulated per sample for this op
+#define TQB_G_NONE 0
+#define TQB_G_FULL 1   // G = sum lam_out psi_in^H : 8 floats (GEN) / 32 floats (U2Q)
+#define TQB_G_X 2      // w = sum Im(conj((X psi)_k) lam_k)  over active pairs: 1 float   (rx, crx)
+#define TQB_G_Y 3      // w = sum Re(conj(psi_b) lam_a - conj(psi_a) lam_b):     1 float   (ry, cry)
+#define TQB_G_DW 4     // w_p = sum_{parity p} Im(conj(psi_k) lam_k):            2 floats  (phases)
+#define TQB_OP_TYPE(w0) ((w0) & 15)
+#define TQB_OP_J(w0) (((w0) >> 4) & 3)
+#define TQB_OP_GKIND(w0) (((w0) >> 16) & 15)
+
+// matrix-builder table: one record of 10 words per op (tqb_build_mats / tqb_build_mats_bwd)
+#define TQB_B_WORDS 10
 #define TQB_B_KIND 0      // builder kind (below)
-#define TQB_B_FLAGS 1     // bit0 inverse, bit1 per-sample params
+#define TQB_B_FLAGS 1     // bit0 inverse, bit1 per-sample params, bit2 matrix in per-sample row
 #define TQB_B_POFF 2      // first parameter column (in params_sh or params_ps)
-#define TQB_B_MOFF 3      // float offset in the matrix row
+#define TQB_B_MOFF 3      // float offset in the matrix row (shared or per-sample)
 #define TQB_B_COFF 4      // K_CONST: float offset into the constant pool
-#define TQB_B_NFLOAT 5    // floats written (8, 4 or 32)
+#define TQB_B_NFLOAT 5    // floats written
 #define TQB_B_NPARAM 6
+#define TQB_B_TYPE 7      // op type the matrix is packed for (TQB_T_*)
+#define TQB_B_GKIND 8     // gradient kind accumulated by the pass kernel
+#define TQB_B_GOFF 9      // float offset in the gradient row
 
 #define TQB_BF_INVERSE 1
 #define TQB_BF_PER_SAMPLE 2
@@ -73,9 +111,9 @@ enum {
   TQB_K_CONST = 0,   // copy NFLOAT floats from the constant pool (inverse already folded in)
   TQB_K_EXTERN = 1,  // matrix written by the host front end (explicit unitary); builder skips it
   TQB_K_RX = 2, TQB_K_RY = 3, TQB_K_ROT = 4, TQB_K_U2 = 5, TQB_K_U2RAW = 6, TQB_K_U3 = 7,
-  TQB_K_CU = 8, TQB_K_R = 9,                     // -> 2x2 (8 floats)
-  TQB_K_RZ = 10, TQB_K_PHASE = 11, TQB_K_GPHASE = 12,  // -> diagonal pair d0,d1 (4 floats)
+  TQB_K_CU = 8, TQB_K_R = 9,                     // -> 2x2
+  TQB_K_RZ = 10, TQB_K_PHASE = 11, TQB_K_GPHASE = 12,  // -> diagonal pair d0,d1
   TQB_K_RXX = 13, TQB_K_RYY = 14, TQB_K_RZX = 15, TQB_K_SEXC = 16, TQB_K_XXMYY = 17,
-  TQB_K_XXPYY = 18,                               // -> 4x4 (32 floats)
+  TQB_K_XXPYY = 18,                               // -> 4x4
   TQB_K_COUNT = 19
 };

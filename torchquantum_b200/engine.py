@@ -7,6 +7,8 @@ the backward, which un-applies the gates in reverse (tqb_pass_backward) while ac
 dL/dU, then maps dL/dU to dL/dtheta (tqb_build_mats_bwd): training memory is O(2^n) per sample
 instead of the reference's O(depth * 2^n) autograd tape.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -49,21 +51,32 @@ def _dev(obj, attr, device):
     return t[0]
 
 
+def _desc(pp):
+    if pp._desc_c is None:
+        pp._desc_c = (ctypes.c_int * 8)(*pp.desc)
+    return pp._desc_c
+
+
 def _build_mats(stage, bsz, psh, pps, externs, device):
-    mats = torch.empty(bsz, stage.M, dtype=torch.float32, device=device)
-    table = _dev(stage, "table", device)
-    consts = _dev(stage, "consts", device)
-    _native.call("tqb_build_mats", _ptr(table), table.shape[0], bsz, _ptr(psh), _ptr(pps),
-                 pps.shape[1] if pps is not None else 0, _ptr(consts), _ptr(mats), stage.M,
-                 _native.stream_ptr(mats))
-    STATS["launches"] += 1
-    for (rec, moff, dim, inverse), u in zip(stage.externs, externs):
+    msh = torch.empty(stage.M_sh, dtype=torch.float32, device=device)
+    mps = torch.empty(bsz, stage.M_ps, dtype=torch.float32, device=device)
+    if stage.table.shape[0]:
+        table = _dev(stage, "table", device)
+        consts = _dev(stage, "consts", device)
+        _native.call("tqb_build_mats", _ptr(table), table.shape[0], stage.n_sh_rec, bsz, _ptr(psh), _ptr(pps),
+                     pps.shape[1] if pps is not None else 0, _ptr(consts), _ptr(msh), _ptr(mps), stage.M_ps,
+                     _native.stream_ptr(msh))
+        STATS["launches"] += 1
+    for (rec, moff, dim, inverse, per_sample, goff), u in zip(stage.externs, externs):
         m = u.detach().to(torch.complex64)
         if inverse:
             m = m.conj().transpose(-1, -2)
         m = torch.view_as_real(m.contiguous()).reshape(-1, 2 * dim * dim)
-        mats[:, moff:moff + 2 * dim * dim] = m  # broadcasts a shared matrix over the batch
-    return mats
+        if per_sample:
+            mps[:, moff:moff + 2 * dim * dim] = m
+        else:
+            msh[moff:moff + 2 * dim * dim] = m[0]
+    return msh, mps
 
 
 class FusedFn(torch.autograd.Function):
@@ -75,34 +88,34 @@ class FusedFn(torch.autograd.Function):
         state = state.contiguous()
         bsz = state.shape[0]
         dev = state.device
-        mats = _build_mats(stage, bsz, psh, pps, externs, dev)
+        msh, mps = _build_mats(stage, bsz, psh, pps, externs, dev)
         out = torch.empty_like(state)
         src = state
         stream = _native.stream_ptr(state)
         for pp in stage.passes:
             prog = _dev(pp, "prog", dev)
-            _native.call("tqb_pass_forward", _ptr(src), _ptr(out), n, bsz, _ptr(prog), pp.T, pp.R, pp.L,
-                         _ptr(mats), stage.M, ext_hi, stream)
+            _native.call("tqb_pass_forward", _ptr(src), _ptr(out), n, bsz, _ptr(prog), _desc(pp), _ptr(msh),
+                         _ptr(mps), stage.M_ps, ext_hi, stream)
             STATS["launches"] += 1
             src = out
         if not stage.passes:
             out.copy_(state)
         ctx.stage, ctx.n, ctx.ext_hi = stage, n, ext_hi
         ctx.n_ext = len(externs)
-        ctx.save_for_backward(state if stage.save_input else out, psh, pps, mats, *externs)
+        ctx.save_for_backward(state if stage.save_input else out, psh, pps, msh, mps, *externs)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         stage, n, ext_hi = ctx.stage, ctx.n, ctx.ext_hi
         saved = ctx.saved_tensors
-        psi0, psh, pps, mats = saved[:4]
-        externs = saved[4:]
+        psi0, psh, pps, msh, mps = saved[:5]
+        externs = saved[5:]
         bsz = psi0.shape[0]
         dev = psi0.device
         grad_out = grad_out.contiguous()
         multi = any(pp.T < n for pp in stage.passes)
-        gmats = (torch.zeros if multi else torch.empty)(bsz, stage.M, dtype=torch.float32, device=dev)
+        gr = (torch.zeros if multi else torch.empty)(bsz, stage.G, dtype=torch.float32, device=dev)
         psi = torch.empty_like(psi0)
         lam = torch.empty_like(psi0)
         psrc, lsrc = psi0, grad_out
@@ -110,7 +123,7 @@ class FusedFn(torch.autograd.Function):
         for pp in reversed(stage.passes):
             prog = _dev(pp, "prog", dev)
             _native.call("tqb_pass_backward", _ptr(psrc), _ptr(lsrc), _ptr(psi), _ptr(lam), n, bsz, _ptr(prog),
-                         pp.T, pp.R, pp.L, _ptr(mats), _ptr(gmats), stage.M, ext_hi, stream)
+                         _desc(pp), _ptr(msh), _ptr(mps), stage.M_ps, _ptr(gr), stage.G, ext_hi, stream)
             STATS["launches"] += 1
             psrc, lsrc = psi, lam
         if not stage.passes:
@@ -121,7 +134,7 @@ class FusedFn(torch.autograd.Function):
             gsh_part = torch.zeros(bsz, max(stage.P_sh, 1), dtype=torch.float32, device=dev)
             gps_full = torch.zeros(bsz, max(stage.P_ps, 1), dtype=torch.float32, device=dev)
             _native.call("tqb_build_mats_bwd", _ptr(table), table.shape[0], bsz, _ptr(psh), _ptr(pps),
-                         pps.shape[1], _ptr(gmats), stage.M, _ptr(gsh_part), gsh_part.shape[1],
+                         pps.shape[1], _ptr(gr), stage.G, _ptr(gsh_part), gsh_part.shape[1],
                          _ptr(gps_full), stream)
             STATS["launches"] += 1
             if stage.P_sh and ctx.needs_input_grad[1]:
@@ -129,14 +142,16 @@ class FusedFn(torch.autograd.Function):
             if stage.P_ps and ctx.needs_input_grad[2]:
                 gps = gps_full
         gext = []
-        for i, ((rec, moff, dim, inverse), u) in enumerate(zip(stage.externs, externs)):
+        for i, ((rec, moff, dim, inverse, per_sample, goff), u) in enumerate(zip(stage.externs, externs)):
             if not ctx.needs_input_grad[6 + i]:
                 gext.append(None)
                 continue
-            g = torch.view_as_complex(gmats[:, moff:moff + 2 * dim * dim].reshape(bsz, dim, dim, 2).contiguous())
+            g = torch.view_as_complex(gr[:, goff:goff + 2 * dim * dim].reshape(bsz, dim, dim, 2).contiguous())
             if inverse:  # applied A = U^H  =>  dL/dU = (dL/dA)^H
                 g = g.conj().transpose(-1, -2)
-            gext.append(g.sum(0) if u.dim() == 2 else g)
+            if not per_sample:
+                g = g.sum(0, keepdim=True)
+            gext.append(g.reshape(u.shape))
         gstate = lam if ctx.needs_input_grad[0] else None
         return (gstate, gsh, gps, None, None, None, *gext)
 
@@ -211,7 +226,8 @@ def run_circuit(state, n, records, n_total=None, ext_hi=0):
         if params is not None:
             grad = grad_mode and params.requires_grad
             if name in G.UNITARY_LIKE:
-                pmode, ext_dim = "ext", params.shape[-1]
+                pmode, ext_dim = ("extps" if params.dim() == 3 and params.shape[0] == bsz and bsz > 1 else "ext"), \
+                    params.shape[-1]
             else:
                 if params.shape[0] == 1:
                     pmode = "sh"

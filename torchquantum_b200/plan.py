@@ -6,8 +6,14 @@ system instead: a *pass* is one HBM round trip of the state with a tile of 2^T a
 in shared memory; inside a pass, *groups* of gates whose targets fit R register bits are applied
 without touching shared memory.  Gates on disjoint qubits commute, so both levels use the same
 dependency-respecting greedy packing.  The output is the int32 program of csrc/tqb_program.h.
+
+Lowering picks the cheapest micro-op for every gate (csrc/tqb_program.h, TQB_T_*): X-like gates
+become register swaps (PERM), real matrices (ry, h) and rx get 4-instruction-per-amplitude forms,
+phase gates (z, s, t, cz, cu1 ...) only touch the amplitudes whose target bit is 1, and
+`cnot; diagonal; cnot` sandwiches (the QAOA cost layer) fold into one diagonal op.
 """
 import functools
+import itertools
 
 import numpy as np
 
@@ -18,44 +24,61 @@ T_SINGLE = 13   # largest state handled as one tile per sample (2^13 amplitudes 
 T_MULTI = 12    # tile bits when the state is streamed through HBM
 L_MIN = 5       # contiguous low bits always in the tile (2^5 amplitudes = 256 B runs)
 R_MAX = C.MAX_R
+R_GRAD = C.MAX_R  # register bits of programs that also run backward (two arrays live per thread)
+
+NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32}
+NGRAD = {C.G_NONE: 0, C.G_X: 1, C.G_Y: 1, C.G_DW: 2}
 
 
 class LOp:
     """A lowered micro-op on global bit positions."""
     __slots__ = ("type", "targets", "pmask", "cmask", "cval", "nfloat", "kind", "inverse", "pmode",
-                 "poff", "nparam", "const", "rec", "grad", "nounapply", "qmask", "ext_dim", "_lt")
+                 "poff", "nparam", "const", "rec", "grad", "gkind", "ngrad", "nounapply", "qmask", "ext_dim", "_lt")
 
     def __init__(self):
         self.pmask = self.cmask = self.cval = 0
         self.targets = ()
         self.kind, self.inverse, self.pmode, self.poff, self.nparam = C.K_CONST, False, None, 0, 0
         self.const, self.rec, self.grad, self.nounapply, self.ext_dim = None, -1, False, False, 0
+        self.gkind, self.ngrad = C.G_NONE, 0
+
+    @property
+    def per_sample(self):
+        return self.pmode in ("ps", "extps")
 
 
 def _bits(n, wires):
     return [n - 1 - int(w) for w in wires]
 
 
-def _const_floats(mat, inverse):
+def _applied(mat, inverse):
     m = np.asarray(mat, dtype=np.complex64)
     if inverse:
         m = m.conj().T if m.ndim == 2 else m.conj()
-    return np.ascontiguousarray(m).view(np.float32).reshape(-1)
+    return np.ascontiguousarray(m)
+
+
+def _pack_const(m, typ):
+    """Applied constant matrix -> the float packing of op type `typ`."""
+    if typ == C.T_REAL:
+        return np.ascontiguousarray(m.real.astype(np.float32)).reshape(-1)
+    return m.view(np.float32).reshape(-1)
 
 
 def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
     """One queue record -> LOp (fusable) or None for DENSE / RESET / NOP kinds.
-    pmode: None | 'sh' | 'ps' | 'ext' (explicit matrix supplied by the caller)."""
+    pmode: None | 'sh' | 'ps' | 'ext' / 'extps' (explicit matrix supplied by the caller)."""
     spec = G.SPECS[name]
     op = LOp()
     op.rec, op.grad, op.inverse, op.pmode = rec, grad, inverse, pmode
     bits = _bits(n, wires)
     kind = spec.kind
     const = spec.const
+    ext = pmode in ("ext", "extps")
     if name == "qft" and len(wires) <= 2:
         kind = G.U1Q if len(wires) == 1 else G.U2Q
         const = G.qft_matrix_np(len(wires))
-    if pmode == "ext":
+    if ext:
         if ext_dim == 2:
             kind = G.U1Q
         elif ext_dim == 4:
@@ -66,33 +89,86 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
     elif kind in (G.DENSE, G.RESET, G.NOP):
         return None
     n_ctrl = spec.n_ctrl if spec.n_ctrl >= 0 else len(wires) - 1
-    if pmode == "ext":
+    if ext:
         n_ctrl = 0
     for b in bits[:n_ctrl]:
         op.cmask |= 1 << b
     op.cval = 0 if spec.neg_ctrl else op.cmask
     rest = bits[n_ctrl:]
+    parametric = (not ext) and spec.builder is not None and pmode in ("sh", "ps")
+    applied = None if (ext or parametric) else _applied(const, inverse)
     if kind == G.U1Q:
         assert len(rest) == 1, f"{name}: expected one target wire"
-        op.type, op.targets, op.nfloat = C.T_U1Q, (rest[0],), 8
+        op.targets = (rest[0],)
+        if parametric:
+            if spec.builder == C.K_RX:
+                op.type, op.gkind = (C.T_GEN if op.cmask else C.T_RX), C.G_X
+            elif spec.builder == C.K_RY:
+                op.type, op.gkind = (C.T_GEN if op.cmask else C.T_REAL), C.G_Y
+            else:
+                op.type, op.gkind = C.T_GEN, C.G_FULL
+        elif ext:
+            op.type, op.gkind = C.T_GEN, C.G_FULL
+        else:
+            op.gkind = C.G_NONE
+            if np.array_equal(applied, np.array([[0, 1], [1, 0]], dtype=np.complex64)):
+                op.type = C.T_PERM
+            elif not op.cmask and not np.any(applied.imag):
+                op.type = C.T_REAL
+            else:
+                op.type = C.T_GEN
     elif kind == G.U2Q:
         assert len(rest) == 2, f"{name}: expected two target wires"
-        op.type, op.targets, op.nfloat = C.T_U2Q, (rest[0], rest[1]), 32
+        op.type, op.targets, op.gkind = C.T_U2Q, (rest[0], rest[1]), C.G_FULL
     else:
-        op.type, op.nfloat = C.T_DIAG, 4
+        op.type, op.gkind = C.T_DIAG, C.G_DW
         for b in rest:
             op.pmask |= 1 << b
-    if op.kind != C.K_EXTERN:
-        if spec.builder is not None and pmode in ("sh", "ps"):
+        phase_like = (spec.builder == C.K_PHASE) if parametric else (applied is not None and applied[0] == 1)
+        if phase_like and len(rest) == 1:
+            # d0 == 1: only amplitudes whose target bit is set change -> the target doubles as a control
+            op.cmask |= op.pmask
+            op.cval |= op.pmask
+    op.nfloat = NFLOAT[op.type]
+    if not grad:
+        op.gkind = C.G_NONE
+    op.ngrad = op.nfloat if op.gkind == C.G_FULL else NGRAD[op.gkind]
+    if not ext:
+        if parametric:
             op.kind, op.nparam = spec.builder, spec.n_params
         else:
-            op.kind, op.const = C.K_CONST, _const_floats(const, inverse)
+            op.kind, op.const = C.K_CONST, _pack_const(applied, op.type)
+            if op.type == C.T_PERM:
+                op.const = np.zeros(0, np.float32)
     tm = 0
     for t in op.targets:
         tm |= 1 << t
     op.qmask = tm | op.pmask | op.cmask
     assert bin(op.qmask).count("1") == len(set(bits)), f"{name}: repeated wires {wires}"
     return op
+
+
+def fold_cnot_sandwiches(lops):
+    """cnot(c,t); D; cnot(c,t) with D an uncontrolled parity-diagonal op acting on t (not on c)
+    == the same diagonal with c added to its parity mask.  Removes two of the three ops of every
+    `cx, rz, cx` edge term of a QAOA / ZZ-feature-map layer."""
+    out, i = [], 0
+    while i < len(lops):
+        a = lops[i]
+        if (i + 2 < len(lops) and a.type == C.T_PERM and bin(a.cmask).count("1") == 1 and a.cval == a.cmask):
+            d, b = lops[i + 1], lops[i + 2]
+            t, cbit = a.targets[0], a.cmask
+            if (b.type == C.T_PERM and b.cmask == a.cmask and b.cval == a.cval and b.targets == a.targets
+                    and d.type == C.T_DIAG and d.cmask == 0 and (d.pmask >> t) & 1 and not d.pmask & cbit
+                    and not d.nounapply):
+                d.pmask ^= cbit
+                d.qmask |= cbit
+                out.append(d)
+                i += 3
+                continue
+        out.append(a)
+        i += 1
+    return out
 
 
 # ---------------------------------------------------------------------------------------
@@ -125,19 +201,19 @@ def _pack_groups(ops, R):
         for op in remaining:
             ok = not (op.qmask & blocked)
             if ok:
-                if op.type == C.T_U1Q:
+                if op.type == C.T_U2Q:
+                    tm, tl = op._lt
+                    if not reg and R >= 2:
+                        reg.extend([tl, tm])
+                    elif not (len(reg) >= 2 and reg[0] == tl and reg[1] == tm):
+                        ok = False
+                elif op._lt:
                     t = op._lt[0]
                     if t not in reg:
                         if len(reg) < R:
                             reg.append(t)
                         else:
                             ok = False
-                elif op.type == C.T_U2Q:
-                    tm, tl = op._lt
-                    if not reg and R >= 2:
-                        reg.extend([tl, tm])
-                    elif not (len(reg) >= 2 and reg[0] == tl and reg[1] == tm):
-                        ok = False
             if ok:
                 part.append(op)
             else:
@@ -159,9 +235,8 @@ def _fill_registers(T, R, reg):
     reg = list(reg)
     free = [b for b in range(T) if b not in reg]
     missing = R - len(reg)
-    if missing == 0 and T - R < 4:
+    if missing == 0:
         return tuple(reg)
-    import itertools
 
     def degree(regset):
         if T - R < 4:
@@ -181,8 +256,6 @@ def _fill_registers(T, R, reg):
             worst = max(worst, max(banks.values()))
         return worst
 
-    if missing == 0:
-        return tuple(reg)
     best, best_deg = None, None
     for combo in itertools.combinations(free, missing):
         d = degree(reg + list(combo))
@@ -194,21 +267,22 @@ def _fill_registers(T, R, reg):
 
 
 class PassProgram:
-    __slots__ = ("T", "R", "L", "prog", "n_ops", "n_groups", "n_seg", "tile_bits")
+    __slots__ = ("T", "R", "L", "prog", "n_ops", "n_groups", "n_seg", "tile_bits", "desc", "_desc_c")
 
 
 class FusedStage:
-    """One autograd node: a list of passes sharing one matrix row layout."""
+    """One autograd node: a list of passes sharing one matrix / gradient row layout."""
     kind = "fused"
 
     def __init__(self):
         self.passes = []
-        self.table = None      # int32 [nrec, 8]
+        self.table = None      # int32 [nrec, B_WORDS], shared-row records first
+        self.n_sh_rec = 0
         self.consts = None     # float32
-        self.M = 0             # floats per matrix row
+        self.M_sh = self.M_ps = self.G = 0   # floats per shared matrix row / per-sample matrix row / gradient row
         self.P_sh = self.P_ps = 0
         self.sh_recs, self.ps_recs = [], []   # queue indices in parameter order
-        self.externs = []      # (rec, moff, dim, inverse)
+        self.externs = []      # (rec, moff, dim, inverse, per_sample_row, goff)
         self.save_input = False
         self.any_grad = False
         self.n_ops = 0
@@ -232,7 +306,67 @@ def _i32(v):
     return int(np.array(v & 0xFFFFFFFF, dtype=np.uint32).view(np.int32))
 
 
-def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, l_min=None):
+def _encode_op(op, regs, R, loc, oloc):
+    """Op record for a group whose register bit j is tile-local bit regs[j]."""
+    regidx = {b: j for j, b in enumerate(regs[:R])}
+    cm_t = cv_t = pm_t = cm_o = cv_o = pm_o = 0
+    reg_ctrl, reg_par = [], []
+
+    def walk(mask):
+        p = 0
+        while mask >> p:
+            if (mask >> p) & 1:
+                yield p
+            p += 1
+
+    for p in walk(op.cmask):
+        want = (op.cval >> p) & 1
+        if p in loc:
+            lb = loc[p]
+            if lb in regidx:
+                reg_ctrl.append((regidx[lb], want))
+            else:
+                cm_t |= 1 << lb
+                cv_t |= want << lb
+        else:
+            cm_o |= 1 << oloc[p]
+            cv_o |= want << oloc[p]
+    for p in walk(op.pmask):
+        if p in loc:
+            lb = loc[p]
+            if lb in regidx:
+                reg_par.append(regidx[lb])
+            else:
+                pm_t |= 1 << lb
+        else:
+            pm_o |= 1 << oloc[p]
+    emask = epar = 0
+    for e in range(16):
+        if all(((e >> j) & 1) == want for j, want in reg_ctrl):
+            emask |= 1 << e
+        if sum((e >> j) & 1 for j in reg_par) & 1:
+            epar |= 1 << e
+    flags = 0
+    if cm_t:
+        flags |= C.F_TCTRL
+    if emask != 0xFFFF:
+        flags |= C.F_RCTRL
+    if op.per_sample:
+        flags |= C.F_PS
+    if op.nounapply:
+        flags |= C.F_NOUNAPPLY
+    j = 0
+    if op.type == C.T_U2Q:
+        assert regs[0] == op._lt[1] and regs[1] == op._lt[0]
+    elif op._lt:
+        j = regidx[op._lt[0]]
+    if op.type in (C.T_REAL, C.T_RX):
+        assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
+    w0 = op.type | (j << 4) | flags | (op.gkind << 16)
+    return [w0, 0, emask | (epar << 16), cm_t, cv_t, pm_t, cm_o, cv_o, pm_o, 0]
+
+
+def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, l_min=None, r=None):
     """lops: LOps in program order (targets < n_local; masks may use bits up to n_total)."""
     n_total = n_local if n_total is None else n_total
     t_single = T_SINGLE if t_single is None else t_single
@@ -250,7 +384,7 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
             op.poff = st.P_ps
             st.P_ps += op.nparam
             st.ps_recs.append(op.rec)
-        st.any_grad |= op.grad
+        st.any_grad |= op.gkind != C.G_NONE
     # passes
     t_single = max(t_single, min(t_multi, n_local))
     if n_local <= t_single:
@@ -259,9 +393,10 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
     else:
         T, L = t_multi, l_min
         raw = _pack_passes(lops, L, T - L)
-    R = min(R_MAX, T)
-    consts, table, mat_off = [], [], 0
+    R = min(R_MAX if r is None else r, T)
+    consts, table_sh, table_ps = [], [], []
     const_off = 0
+    sh_off = ps_off = g_off = 0
     for chosen, ops in raw:
         if n_local <= t_single:
             tile_bits = list(range(n_local))
@@ -279,19 +414,6 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         loc = {g: i for i, g in enumerate(tile_bits)}
         outer = [p for p in range(n_total) if p not in loc]
         oloc = {g: i for i, g in enumerate(outer)}
-
-        def split(mask):
-            t = o = 0
-            p = 0
-            while mask >> p:
-                if (mask >> p) & 1:
-                    if p in loc:
-                        t |= 1 << loc[p]
-                    else:
-                        o |= 1 << oloc[p]
-                p += 1
-            return t, o
-
         for op in ops:
             op._lt = tuple(loc[t] for t in op.targets)
         groups = _pack_groups(ops, R)
@@ -301,16 +423,18 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
             regs = _fill_registers(T, R, tuple(reg))
             for i in range(0, max(len(part), 1), C.SEG_MAX_OPS):
                 flat.append((regs, part[i:i + C.SEG_MAX_OPS]))
-        segments, cur, cur_ops, cur_f = [], [], 0, 0
+        segments, cur, tot = [], [], [0, 0, 0, 0]
         for regs, part in flat:
-            f = sum(op.nfloat for op in part)
-            if cur and (cur_ops + len(part) > C.SEG_MAX_OPS or len(cur) + 1 > C.SEG_MAX_GROUPS
-                        or cur_f + f > C.SEG_MAX_FLOATS):
+            need = [len(part), sum(op.nfloat for op in part if not op.per_sample),
+                    sum(op.nfloat for op in part if op.per_sample), sum(op.ngrad for op in part)]
+            if cur and (tot[0] + need[0] > C.SEG_MAX_OPS or len(cur) + 1 > C.SEG_MAX_GROUPS
+                        or tot[1] + need[1] > C.SEG_MAX_SH or tot[2] + need[2] > C.SEG_MAX_PS
+                        or tot[3] + need[3] > C.SEG_MAX_G):
                 segments.append(cur)
-                cur, cur_ops, cur_f = [], 0, 0
+                cur, tot = [], [0, 0, 0, 0]
             cur.append((regs, part))
-            cur_ops += len(part)
-            cur_f += f
+            tot = [a + b for a, b in zip(tot, need)]
+            assert tot[1] <= C.SEG_MAX_SH and tot[2] <= C.SEG_MAX_PS and tot[3] <= C.SEG_MAX_G
         if cur:
             segments.append(cur)
         # encode
@@ -320,29 +444,36 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         for i, g in enumerate(tile_bits):
             hdr[C.H_TBIT + i] = g
         words = list(hdr)
+        sh_max = ps_max = g_max = 0
         for si, seg in enumerate(segments):
             words[C.H_SEGOFF + si] = len(words)
             nops = sum(len(p) for _, p in seg)
-            seg_floats = sum(op.nfloat for _, p in seg for op in p)
-            mat_len = (seg_floats + 3) & ~3
-            words += [len(seg), nops, mat_off, mat_len]
+            seg_ops = [op for _, p in seg for op in p]
+            sh_len = sum(op.nfloat for op in seg_ops if not op.per_sample)
+            ps_len = sum(op.nfloat for op in seg_ops if op.per_sample)
+            g_len = (sum(op.ngrad for op in seg_ops) + 3) & ~3
+            sh_max, ps_max, g_max = max(sh_max, sh_len), max(ps_max, ps_len), max(g_max, g_len)
+            words += [len(seg), nops, sh_off, sh_len, ps_off, ps_len, g_off, g_len]
             first = 0
             for regs, part in seg:
                 rp = list(regs) + [0] * (4 - len(regs))
                 words += rp + [len(part), first, 0, 0]
                 first += len(part)
-            slot = 0
+            sh_slot = ps_slot = g_slot = 0
             for regs, part in seg:
                 for op in part:
-                    pm_t, pm_o = split(op.pmask)
-                    cm_t, cm_o = split(op.cmask)
-                    cv_t, cv_o = split(op.cval)
-                    w0 = op.type | (C.F_GRAD if op.grad else 0) | (C.F_NOUNAPPLY if op.nounapply else 0)
-                    tgt = regs.index(op._lt[0]) if op.type == C.T_U1Q else 0
-                    if op.type == C.T_U2Q:
-                        assert regs[0] == op._lt[1] and regs[1] == op._lt[0]
-                    words += [w0, tgt, _i32(pm_t), _i32(cm_t), _i32(cv_t), slot, _i32(pm_o), _i32(cm_o),
-                              _i32(cv_o), 0]
+                    w = _encode_op(op, regs, R, loc, oloc)
+                    if op.per_sample:
+                        w[C.OP_SLOT], moff = ps_slot, ps_off + ps_slot
+                        ps_slot += op.nfloat
+                    else:
+                        w[C.OP_SLOT], moff = sh_slot, sh_off + sh_slot
+                        sh_slot += op.nfloat
+                    w[C.OP_GSLOT], goff = g_slot, g_off + g_slot
+                    g_slot += op.ngrad
+                    words += [_i32(v) for v in w]
+                    if op.nfloat == 0:
+                        continue
                     flags = (C.BF_INVERSE if op.inverse else 0) | (C.BF_PER_SAMPLE if op.pmode == "ps" else 0)
                     coff = 0
                     if op.kind == C.K_CONST:
@@ -351,19 +482,25 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
                         const_off += len(op.const)
                         assert len(op.const) == op.nfloat
                     if op.kind == C.K_EXTERN:
-                        st.externs.append((op.rec, mat_off + slot, op.ext_dim, op.inverse))
-                    table.append([op.kind, flags, op.poff, mat_off + slot, coff, op.nfloat, op.nparam, 0])
-                    slot += op.nfloat
-            mat_off += mat_len
+                        st.externs.append((op.rec, moff, op.ext_dim, op.inverse, op.per_sample, goff))
+                    rec = [op.kind, flags, op.poff, moff, coff, op.nfloat, op.nparam, op.type, op.gkind, goff]
+                    (table_ps if op.per_sample else table_sh).append(rec)
+            sh_off += sh_len
+            ps_off += ps_len
+            g_off += g_len
         words[C.H_WORDS] = len(words)
+        words[C.H_SH_MAX], words[C.H_PS_MAX], words[C.H_G_MAX] = sh_max, ps_max, g_max
         pp = PassProgram()
         pp.T, pp.R, pp.L = T, R, Lp
         pp.prog = np.array(words, dtype=np.int32)
         pp.n_ops, pp.n_groups, pp.n_seg, pp.tile_bits = len(ops), len(flat), len(segments), tile_bits
+        pp.desc = [T, R, Lp, len(segments), sh_max, ps_max, g_max, 0]
+        pp._desc_c = None
         st.passes.append(pp)
-    st.M = max(mat_off, 4)
-    st.table = np.array(table, dtype=np.int32).reshape(-1, C.B_WORDS)
-    st.consts = np.concatenate(consts).astype(np.float32) if consts else np.zeros(4, np.float32)
+    st.M_sh, st.M_ps, st.G = max(sh_off, 4), max(ps_off, 4), max(g_off, 4)
+    st.n_sh_rec = len(table_sh)
+    st.table = np.array(table_sh + table_ps, dtype=np.int32).reshape(-1, C.B_WORDS)
+    st.consts = np.concatenate(consts + [np.zeros(4, np.float32)]).astype(np.float32)
     return st
 
 
@@ -383,10 +520,12 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
     plan = CircuitPlan(n)
     plan.n_gates = len(key)
     cur = []
+    if grad_mode and "r" not in tile_kw:
+        tile_kw = dict(tile_kw, r=R_GRAD)
 
     def close():
         if cur:
-            plan.stages.append(build_fused_stage(list(cur), n, n_total, **tile_kw))
+            plan.stages.append(build_fused_stage(fold_cnot_sandwiches(cur), n, n_total, **tile_kw))
             cur.clear()
 
     for rec, (name, wires, inverse, pmode, grad, ext_dim) in enumerate(key):
