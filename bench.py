@@ -106,12 +106,39 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _time_passes(n, key, thetas, dev, reps=3):
+    """Per-launch CUDA-event times (ms) of tqb_pass_forward for every pass of the circuit `key`."""
+    from torchquantum_b200 import _native, engine
+    from torchquantum_b200.engine import _build_mats, _desc, _dev, _ptr
+
+    plan = engine.get_plan(n, tuple(key), False)
+    stage = plan.stages[0]
+    psh = torch.tensor(thetas or [0.0], dtype=torch.float32, device=dev)
+    pps = torch.zeros(1, 1, dtype=torch.float32, device=dev)
+    state = torch.zeros(1, 2 ** n, dtype=torch.complex64, device=dev)
+    state[0, 0] = 1
+    msh, mps = _build_mats(stage, 1, psh, pps, [], dev)
+    stream = _native.stream_ptr(state)
+    times = []
+    for rep in range(reps + 1):
+        for pp in stage.passes:
+            prog = _dev(pp, "prog", dev)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, 1, _ptr(prog), _desc(pp), _ptr(msh),
+                         _ptr(mps), stage.M_ps, 0, stream)
+            e.record()
+            if rep > 0:
+                times.append((s, e))
+    torch.cuda.synchronize()
+    norm = float(state.abs().pow(2).sum().item())
+    return [s.elapsed_time(e) for s, e in times], len(stage.passes), norm
+
+
 def gate_pass_roofline(dev, n=28, layers=4):
     """Time every launch of the fused gate-pass kernel on a config-4 style circuit (rx/ry/rz on every
-    wire + brickwork CNOTs) over a 2^n state (2 GiB at n=28: far larger than the 126 MB L2)."""
-    from torchquantum_b200 import _native, engine, plan as P
-    from torchquantum_b200.engine import _build_mats, _dev, _ptr
-
+    wire + brickwork CNOTs) over a 2^n state (2 GiB at n=28: far larger than the 126 MB L2), plus a
+    sweep of single passes holding k gates (k = 1: one HBM round trip per gate)."""
     rng = np.random.default_rng(0)
     key, thetas = [], []
     for layer in range(layers):
@@ -120,43 +147,39 @@ def gate_pass_roofline(dev, n=28, layers=4):
             thetas.append(rng.uniform(-np.pi, np.pi))
         for w in range(layer % 2, n - 1, 2):
             key.append(("cnot", (w, w + 1), False, None, False, 0))
-    plan = engine.get_plan(n, tuple(key), False)
-    stage = plan.stages[0]
-    psh = torch.tensor(thetas, dtype=torch.float32, device=dev)
-    pps = torch.zeros(1, 1, dtype=torch.float32, device=dev)
-    state = torch.zeros(1, 2 ** n, dtype=torch.complex64, device=dev)
-    state[0, 0] = 1
-    mats = _build_mats(stage, 1, psh, pps, [], dev)
-    stream = _native.stream_ptr(state)
-    times = []
-    for rep in range(3):
-        for pp in stage.passes:
-            prog = _dev(pp, "prog", dev)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, 1, _ptr(prog), pp.T, pp.R, pp.L,
-                         _ptr(mats), stage.M, 0, stream)
-            e.record()
-            if rep > 0:
-                times.append((s, e))
-    torch.cuda.synchronize()
-    ms = [s.elapsed_time(e) for s, e in times]
+    ms, n_pass, norm = _time_passes(n, key, thetas, dev)
     avg_ms = float(np.mean(ms))
     alg_bytes = 16.0 * 2 ** n
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    sweep = []
+    for k in (1, 4, 8, 16):  # k gates on the qubits of one tile -> exactly one pass
+        r2 = np.random.default_rng(k)
+        bits = list(range(5)) + list(range(n - 7, n))
+        key_k, th_k = [], []
+        for i in range(k):
+            b = bits[r2.integers(len(bits))]
+            key_k.append((["rx", "ry", "rz"][r2.integers(3)], (n - 1 - b,), False, "sh", False, 0))
+            th_k.append(r2.uniform(-np.pi, np.pi))
+        ms_k, np_k, _ = _time_passes(n, key_k, th_k, dev)
+        if np_k == 1:
+            t = float(np.mean(ms_k))
+            sweep.append({"gates_in_pass": k, "ms": round(t, 4), "GBps": round(alg_bytes / t / 1e6, 1),
+                          "frac": round(alg_bytes / t / 1e6 / peak, 4)})
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    norm = float(state.abs().pow(2).sum().item())
-    del state, mats
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
             "kernel": "tqb_pass_kernel<R=4,fwd>", "algorithmic_bytes_per_launch": alg_bytes,
             "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(ms),
-            "workload": f"cfg4 family: n={n} single statevector, {len(key)} gates in {len(stage.passes)} fused passes "
-                        f"({len(key) / len(stage.passes):.1f} gates/pass)", "state_norm_after": round(norm, 6)}
+            "workload": f"cfg4 family: n={n} single statevector, {len(key)} gates in {n_pass} fused passes "
+                        f"({len(key) / n_pass:.1f} gates/pass)", "state_norm_after": round(norm, 6),
+            "gate_amp_updates_per_s": round(len(key) * 2.0 ** n / (sum(ms) / (len(ms) / n_pass) * 1e-3), 1),
+            "single_pass_sweep": sweep,
+            "note": "a pass is HBM-bound up to ~2 gates and FP32-issue-bound beyond; the planner still fuses "
+                    "as deep as the tile allows because that minimises total time"}
 
 
 def cpu_reference_step(bsz, threads):

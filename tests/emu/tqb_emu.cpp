@@ -46,12 +46,13 @@ static void emu_blocks(BlockCtx c, int n, const PassGeom& g, unsigned ext_hi) {
   c.s_grad = reinterpret_cast<float*>(base + g.lay.grad);
   c.s_prog = reinterpret_cast<int32_t*>(base + g.lay.prog);
   c.s_scat = reinterpret_cast<u64*>(base + g.lay.scat);
+  c.s_olut = reinterpret_cast<u64*>(base + g.lay.olut);
   // a small "grid" of persistent blocks so the multi-item loop and the double buffering are exercised
   const long long grid = g.n_items < 3 ? g.n_items : 3;
   for (long long blk = 0; blk < grid; ++blk) {
     EmuExec ex{c.nthreads};
     BlockCtx cb = c;  // run_cta advances the staged-buffer pointers of its context
-    run_cta<R, BWD>(ex, cb, n, g.ntiles, ext_hi, blk, grid, g.n_items, g.nbuf, g.lay.buf_stride);
+    run_cta<R, BWD>(ex, cb, n, g.ntiles_log2, ext_hi, blk, grid, g.n_items, g.nbuf, g.lay.buf_stride);
   }
 }
 
@@ -73,7 +74,7 @@ static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float*
   if (g.lay.total > 227 * 1024) return fail_msg("tqb pass: tile does not fit shared memory");
   BlockCtx c;
   c.T = T; c.L = L; c.S = g.S; c.tps = g.tps; c.nthreads = g.S * g.tps; c.bsz = (int)bsz;
-  c.multi_tile = g.ntiles > 1;
+  c.multi_tile = g.ntiles_log2 > 0;
   c.sample0 = 0; c.tile_ext = 0; c.outer_off = 0;
   c.sample_stride = 1ull << n;
   c.prog = prog; c.psi = reinterpret_cast<float2*>(psi); c.lam = reinterpret_cast<float2*>(lam);

@@ -67,11 +67,14 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=28)
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--ks", type=int, nargs="*", default=[1, 2, 4, 8, 12, 16, 24, 32, 48, 64, 96])
+    ap.add_argument("--mix", default="both", choices=["both", "rot", "gen"])
     a = ap.parse_args()
     dev = "cuda:0"
     print(torch.cuda.get_device_name(0), "n =", a.n, "bwd" if a.bwd else "fwd")
     bytes_pass = (32.0 if a.bwd else 16.0) * 2 ** a.n
-    for kinds, label in ((("rx", "ry", "rz"), "rx/ry/rz+cnot"), (("u3like",), "general 2x2")):
+    mixes = [(("rx", "ry", "rz"), "rx/ry/rz+cnot"), (("u3like",), "general 2x2")]
+    mixes = [m for m in mixes if a.mix == "both" or (a.mix == "rot") == (m[0][0] == "rx")]
+    for kinds, label in mixes:
         for k in a.ks:
             rng = np.random.default_rng(k)
             if kinds[0] == "u3like":

@@ -11,6 +11,12 @@
 #pragma once
 #include "tqb_program.h"
 
+#define TQB_UNREACHABLE() __builtin_unreachable()
+#ifndef TQB_FWD_MODE
+// forward op dispatch: 0 = if-chain (default), 1 = switch / jump table.  Measured on B200 (n=28, 64-gate pass):
+// if-chain 6.99 ms, switch 7.80 ms, switch + two ping-pong register arrays 8.83 ms (profiles/r01_kernel_variants.txt)
+#define TQB_FWD_MODE 0
+#endif
 #if defined(__CUDACC__)
 #define TQB_FN __device__ __forceinline__
 #define TQB_FMA(a, b, c) fmaf((a), (b), (c))
@@ -72,6 +78,7 @@ struct BlockCtx {
   int ps_cap, g_cap;       // staged per-sample floats (stride of s_mps / s_grad per sample slot)
   // staged (shared) memory
   float2* s_psi; float2* s_lam; float* s_msh; float* s_mps; float* s_grad; int32_t* s_prog; u64* s_scat;
+  u64* s_olut;             // [3][256]: amplitude offset contributed by byte j of the tile id (streamed states only)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -84,6 +91,26 @@ TQB_FN void build_scatter(const BlockCtx& c, int tid) {
     for (int i = 0; i < c.T - c.L; ++i)
       if ((h >> i) & 1) off |= 1ull << c.prog[TQB_H_TBIT + c.L + i];
     c.s_scat[h] = off;
+  }
+}
+
+// per-CTA lookup tables: s_scat (tile-local high bits -> amplitude offset) and, for streamed states,
+// s_olut (byte j of the tile id -> amplitude offset of the non-tile bits it selects)
+TQB_FN void build_tables(const BlockCtx& c, int tid, int n, bool streamed) {
+  build_scatter(c, tid);
+  if (!streamed) return;
+  u64 tmask = 0;
+  for (int i = 0; i < c.T; ++i) tmask |= 1ull << c.prog[TQB_H_TBIT + i];
+  for (int e = tid; e < 3 * 256; e += c.nthreads) {
+    const int byte = e >> 8, v = e & 255;
+    u64 off = 0;
+    int k = 0;
+    for (int p = 0; p < n; ++p)
+      if (!((tmask >> p) & 1ull)) {
+        if ((k >> 3) == byte && ((v >> (k & 7)) & 1)) off |= 1ull << p;
+        ++k;
+      }
+    c.s_olut[e] = off;
   }
 }
 
@@ -100,6 +127,14 @@ TQB_FN void load_tile_async(Exec& ex, const BlockCtx& c, int tid, const float2* 
     return;
   }
   const float2* src = g + (u64)b * c.sample_stride + c.outer_off;
+  if (c.tps == 256) {
+    // idx = t + 256 k: the swizzle only mixes bits 0-7, so swz(idx) = swz(t) + 256 k
+    const float2* src_t = src + ((u32)t & lowmask);
+    float2* dst_t = dst + swz((u32)t);
+#pragma unroll 4
+    for (u32 k = 0; k < tile; k += 256u) ex.async_copy8(dst_t + k, src_t + ((k & lowmask) + c.s_scat[((u32)t + k) >> c.L]));
+    return;
+  }
   for (u32 idx = t; idx < tile; idx += c.tps)
     ex.async_copy8(dst + swz(idx), src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
 }
@@ -112,6 +147,19 @@ TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   const float2* src = s + (size_t)slot * tile;
   const u32 lowmask = (1u << c.L) - 1u;
   float2* dst = g + (u64)b * c.sample_stride + c.outer_off;
+  if (c.tps == 256 && c.L >= 1) {
+    // pair p = t + 256 k covers idx = 2p, 2p + 1 = 2t + 512 k (+1): swz(idx) = swz(2t) + 512 k
+    const u32 s0 = swz(2u * (u32)t);
+    const float2* src_a = src + s0;
+    const float2* src_b = src + (s0 ^ 1u);
+    float2* dst_t = dst + ((2u * (u32)t) & lowmask);
+#pragma unroll 4
+    for (u32 k = 0; k < tile; k += 512u) {
+      const float2 a = src_a[k], bq = src_b[k];
+      *reinterpret_cast<float4*>(dst_t + ((k & lowmask) + c.s_scat[(2u * (u32)t + k) >> c.L])) = make_float4(a.x, a.y, bq.x, bq.y);
+    }
+    return;
+  }
   if (c.L >= 1) {
     for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps) {
       const float2 a = src[swz(idx)], bq = src[swz(idx + 1)];
@@ -169,6 +217,53 @@ TQB_FN void flush_grads(Exec& ex, const BlockCtx& c, int tid) {
 // register bits.  `act`: bit e set when element e takes part (controls satisfied); only looked at
 // when MASKED.  ADJ applies the conjugate transpose (backward sweep).
 // ---------------------------------------------------------------------------------------
+// The pair updates below are written "in place": every output is produced by the instruction that
+// reads the last use of the register it replaces, so the register allocator needs no moves where
+// the op cases merge again (with the naive order the switch in apply_op_* costs ~2 MOV per amplitude).
+TQB_FN void pair_gen(float2& a, float2& b, float2 m00, float2 m01, float2 m10, float2 m11) {
+  // contribution of b to a'
+  float tr = m01.x * b.x, ti = m01.x * b.y;
+  tr = TQB_FMA(-m01.y, b.y, tr); ti = TQB_FMA(m01.y, b.x, ti);
+  // b' = m10 a + m11 b
+  const float p = m11.y * b.x;
+  float br = m11.x * b.x;
+  br = TQB_FMA(-m11.y, b.y, br);
+  float bi = TQB_FMA(m11.x, b.y, p);
+  br = TQB_FMA(m10.x, a.x, br); bi = TQB_FMA(m10.x, a.y, bi);
+  br = TQB_FMA(-m10.y, a.y, br); bi = TQB_FMA(m10.y, a.x, bi);
+  // a' = m00 a + t
+  const float q = TQB_FMA(m00.y, a.x, ti);
+  float ar = TQB_FMA(m00.x, a.x, tr);
+  ar = TQB_FMA(-m00.y, a.y, ar);
+  const float ai = TQB_FMA(m00.x, a.y, q);
+  a = make_float2(ar, ai);
+  b = make_float2(br, bi);
+}
+
+TQB_FN void pair_real(float2& a, float2& b, float m00, float m01, float m10, float m11) {
+  const float tr = m01 * b.x, ti = m01 * b.y;
+  float br = m11 * b.x, bi = m11 * b.y;
+  br = TQB_FMA(m10, a.x, br); bi = TQB_FMA(m10, a.y, bi);
+  a = make_float2(TQB_FMA(m00, a.x, tr), TQB_FMA(m00, a.y, ti));
+  b = make_float2(br, bi);
+}
+
+// [[c, -is], [-is, c]]
+TQB_FN void pair_rx(float2& a, float2& b, float cc, float s) {
+  const float t1 = s * b.y, t2 = -s * b.x;
+  float br = cc * b.x, bi = cc * b.y;
+  br = TQB_FMA(s, a.y, br); bi = TQB_FMA(-s, a.x, bi);
+  a = make_float2(TQB_FMA(cc, a.x, t1), TQB_FMA(cc, a.y, t2));
+  b = make_float2(br, bi);
+}
+
+TQB_FN void cmul_inplace(float2 d, float2& v) {
+  const float t = d.y * v.x;
+  float r = d.x * v.x;
+  r = TQB_FMA(-d.y, v.y, r);
+  v = make_float2(r, TQB_FMA(d.x, v.y, t));
+}
+
 template <int R, int J, int KIND, bool MASKED, bool ADJ>
 TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
   if constexpr (KIND == TQB_T_GEN) {
@@ -182,11 +277,7 @@ TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
       if (e & (1 << J)) continue;
-      if (!MASKED || ((act >> e) & 1u)) {
-        const float2 a = x[e], b = x[e | (1 << J)];
-        x[e] = cfma2(m00, a, m01, b);
-        x[e | (1 << J)] = cfma2(m10, a, m11, b);
-      }
+      if (!MASKED || ((act >> e) & 1u)) pair_gen(x[e], x[e | (1 << J)], m00, m01, m10, m11);
     }
   } else if constexpr (KIND == TQB_T_REAL) {
     const float4 q = ld4(m);
@@ -194,23 +285,15 @@ TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
       if (e & (1 << J)) continue;
-      if (!MASKED || ((act >> e) & 1u)) {
-        const float2 a = x[e], b = x[e | (1 << J)];
-        x[e] = make_float2(TQB_FMA(m01, b.x, m00 * a.x), TQB_FMA(m01, b.y, m00 * a.y));
-        x[e | (1 << J)] = make_float2(TQB_FMA(m11, b.x, m10 * a.x), TQB_FMA(m11, b.y, m10 * a.y));
-      }
+      if (!MASKED || ((act >> e) & 1u)) pair_real(x[e], x[e | (1 << J)], m00, m01, m10, m11);
     }
-  } else {  // TQB_T_RX: [[c, -is], [-is, c]]
+  } else {  // TQB_T_RX
     const float4 q = ld4(m);
     const float cc = q.x, s = ADJ ? -q.y : q.y;
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
       if (e & (1 << J)) continue;
-      if (!MASKED || ((act >> e) & 1u)) {
-        const float2 a = x[e], b = x[e | (1 << J)];
-        x[e] = make_float2(TQB_FMA(s, b.y, cc * a.x), TQB_FMA(-s, b.x, cc * a.y));
-        x[e | (1 << J)] = make_float2(TQB_FMA(s, a.y, cc * b.x), TQB_FMA(-s, a.x, cc * b.y));
-      }
+      if (!MASKED || ((act >> e) & 1u)) pair_rx(x[e], x[e | (1 << J)], cc, s);
     }
   }
 }
@@ -233,12 +316,20 @@ TQB_FN void diag(float2 (&x)[1 << R], float2 dA, float2 dB, u32 epar, u32 act) {
   if (epar == 0u) {
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e)
-      if (!MASKED || ((act >> e) & 1u)) x[e] = cmul(dA, x[e]);
+      if (!MASKED || ((act >> e) & 1u)) cmul_inplace(dA, x[e]);
   } else {
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e)
-      if (!MASKED || ((act >> e) & 1u)) x[e] = cmul(((epar >> e) & 1u) ? dB : dA, x[e]);
+      if (!MASKED || ((act >> e) & 1u)) cmul_inplace(((epar >> e) & 1u) ? dB : dA, x[e]);
   }
+}
+
+// DIAG whose element parity is bit J of e: no per-element selects
+template <int R, int J, bool MASKED>
+TQB_FN void diagj(float2 (&x)[1 << R], float2 dA, float2 dB, u32 act) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    if (!MASKED || ((act >> e) & 1u)) cmul_inplace((e & (1 << J)) ? dB : dA, x[e]);
 }
 
 // 4x4 on register bits (1,0): quad index q = 2*bit1 + bit0
@@ -327,6 +418,20 @@ TQB_FN void grad_dw(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 tp
   w[1] = tp ? wa : wb;
 }
 
+template <int R, int J, bool MASKED>
+TQB_FN void grad_dwj(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 tp, u32 act, float (&w)[2]) {
+  float wa = 0.f, wb = 0.f;
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (!MASKED || ((act >> e) & 1u)) {
+      if (e & (1 << J)) { wb = TQB_FMA(x[e].x, y[e].y, wb); wb = TQB_FMA(-x[e].y, y[e].x, wb); }
+      else { wa = TQB_FMA(x[e].x, y[e].y, wa); wa = TQB_FMA(-x[e].y, y[e].x, wa); }
+    }
+  }
+  w[0] = tp ? wb : wa;
+  w[1] = tp ? wa : wb;
+}
+
 template <int R>
 TQB_FN void grad_full_2q(const float2 (&x)[1 << R], const float2 (&y)[1 << R], u32 act, float (&g)[32]) {
 #pragma unroll
@@ -371,10 +476,19 @@ TQB_FN void sort_positions(u32 (&sp)[R]) {
     if constexpr (R > 3) { if ((j) == 3) { constexpr int JJ = 3; CALL; } } \
   } while (0)
 
+#define TQB_CASES_J(TYPE, CALL)                                                                   \
+  case TQB_OP_CODE(TYPE, 0): { constexpr int JJ = 0; CALL; } break;                                \
+  case TQB_OP_CODE(TYPE, 1): if constexpr (R > 1) { constexpr int JJ = 1; CALL; } break;           \
+  case TQB_OP_CODE(TYPE, 2): if constexpr (R > 2) { constexpr int JJ = 2; CALL; } break;           \
+  case TQB_OP_CODE(TYPE, 3): if constexpr (R > 3) { constexpr int JJ = 3; CALL; } break;
+
+// forward op, in place on the thread's register array (TQB_FWD_MODE 0: if-chain, 1: switch)
 template <int R, class Exec>
-TQB_FN void apply_op_fwd(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* op, u32 base, const float* smps) {
+TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* op, u32 base, const float* smps) {
   const u32 w0 = (u32)op[TQB_OP_W0];
-  if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;  // control on a non-tile bit: CTA-uniform
+  if (w0 & TQB_F_OCTRL) {
+    if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
+  }
   const u32 type = TQB_OP_TYPE(w0);
   const int j = TQB_OP_J(w0);
   const bool masked = w0 & (TQB_F_TCTRL | TQB_F_RCTRL);
@@ -384,6 +498,26 @@ TQB_FN void apply_op_fwd(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* 
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
   }
   const float* m = ((w0 & TQB_F_PS) ? smps : c.s_msh) + op[TQB_OP_SLOT];
+#if TQB_FWD_MODE == 1
+  switch (w0 & 63u) {
+    TQB_CASES_J(TQB_T_REAL, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)))
+    TQB_CASES_J(TQB_T_RX, (u1q<R, JJ, TQB_T_RX, false, false>(x, m, act)))
+    TQB_CASES_J(TQB_T_GEN, (masked ? u1q<R, JJ, TQB_T_GEN, true, false>(x, m, act) : u1q<R, JJ, TQB_T_GEN, false, false>(x, m, act)))
+    TQB_CASES_J(TQB_T_PERM, (perm<R, JJ>(x, act)))
+    case TQB_OP_CODE(TQB_T_DIAG, 0): case TQB_OP_CODE(TQB_T_DIAG, 1): case TQB_OP_CODE(TQB_T_DIAG, 2):
+    case TQB_OP_CODE(TQB_T_DIAG, 3): {
+      const float4 q = ld4(m);
+      const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+      const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
+      if (masked) diag<R, true>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)op[TQB_OP_EMASK] >> 16, act);
+      else diag<R, false>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)op[TQB_OP_EMASK] >> 16, act);
+    } break;
+    case TQB_OP_CODE(TQB_T_U2Q, 0):
+      if constexpr (R >= 2) u2q<R, false>(x, m, act);
+      break;
+    default: TQB_UNREACHABLE(); break;
+  }
+#else
   if (type == TQB_T_REAL) {
     TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)));
   } else if (type == TQB_T_RX) {
@@ -394,7 +528,10 @@ TQB_FN void apply_op_fwd(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* 
     const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
     const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
     const u32 epar = (u32)op[TQB_OP_EMASK] >> 16;
-    if (masked) { if (act) diag<R, true>(x, dA, dB, epar, act); }
+    if (w0 & TQB_F_DJ) {
+      if (masked) { if (act) TQB_DISPATCH_J(j, (diagj<R, JJ, true>(x, dA, dB, act))); }
+      else TQB_DISPATCH_J(j, (diagj<R, JJ, false>(x, dA, dB, act)));
+    } else if (masked) { if (act) diag<R, true>(x, dA, dB, epar, act); }
     else diag<R, false>(x, dA, dB, epar, act);
   } else if (type == TQB_T_PERM) {
     if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act)));
@@ -404,6 +541,7 @@ TQB_FN void apply_op_fwd(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* 
   } else {  // TQB_T_U2Q
     if constexpr (R >= 2) { if (act) u2q<R, false>(x, m, act); }
   }
+#endif
 }
 
 // backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in
@@ -438,14 +576,26 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
     const float2 d0 = make_float2(q.x, -q.y), d1 = make_float2(q.z, -q.w);  // conjugated
     const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
     const u32 epar = (u32)op[TQB_OP_EMASK] >> 16;
-    if (!MASKED || act) {
-      if (unapply) diag<R, MASKED>(x, dA, dB, epar, act);
-      diag<R, MASKED>(y, dA, dB, epar, act);
-    }
-    if (gkind == TQB_G_DW) {
-      float w2[2];
-      grad_dw<R, MASKED>(x, y, tp, epar, act, w2);
-      ex.template reduce_add<2>(gdst, w2, width);
+    if (w0 & TQB_F_DJ) {
+      if (!MASKED || act) {
+        if (unapply) TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(x, dA, dB, act)));
+        TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(y, dA, dB, act)));
+      }
+      if (gkind == TQB_G_DW) {
+        float w2[2] = {0.f, 0.f};
+        TQB_DISPATCH_J(j, (grad_dwj<R, JJ, MASKED>(x, y, tp, act, w2)));
+        ex.template reduce_add<2>(gdst, w2, width);
+      }
+    } else {
+      if (!MASKED || act) {
+        if (unapply) diag<R, MASKED>(x, dA, dB, epar, act);
+        diag<R, MASKED>(y, dA, dB, epar, act);
+      }
+      if (gkind == TQB_G_DW) {
+        float w2[2];
+        grad_dw<R, MASKED>(x, y, tp, epar, act, w2);
+        ex.template reduce_add<2>(gdst, w2, width);
+      }
     }
   } else if (type == TQB_T_PERM) {
     if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act), perm<R, JJ>(y, act)));
@@ -468,7 +618,9 @@ template <int R, class Exec>
 TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
                          u32 base, const float* smps, float* sgrad, int width) {
   const u32 w0 = (u32)op[TQB_OP_W0];
-  if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
+  if (w0 & TQB_F_OCTRL) {
+    if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
+  }
   if (w0 & (TQB_F_TCTRL | TQB_F_RCTRL)) {
     u32 act = (u32)op[TQB_OP_EMASK] & 0xffffu;
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
@@ -509,10 +661,11 @@ TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
       x[e] = sps[a];
       if constexpr (BWD) y[e] = sla[a];
     }
-    for (int k = 0; k < nops; ++k) {
-      const int32_t* op = ops + (BWD ? (nops - 1 - k) : k) * TQB_OP_WORDS;
-      if constexpr (BWD) apply_op_bwd<R, Exec>(ex, c, x, y, op, base, smps, sgrad, width);
-      else apply_op_fwd<R, Exec>(c, x, op, base, smps);
+    if constexpr (BWD) {
+      for (int k = nops - 1; k >= 0; --k)
+        apply_op_bwd<R, Exec>(ex, c, x, y, ops + k * TQB_OP_WORDS, base, smps, sgrad, width);
+    } else {
+      for (int k = 0; k < nops; ++k) apply_op_fwd_inplace<R, Exec>(c, x, ops + k * TQB_OP_WORDS, base, smps);
     }
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
@@ -546,38 +699,27 @@ TQB_FN void run_tile(Exec& ex, const BlockCtx& c, bool shared_staged) {
   }
 }
 
-// offset (in amplitudes) of tile `tile_id` inside a sample: deposit its bits into the non-tile positions
-TQB_FN u64 outer_offset(const int32_t* prog, int n, u32 tile_id) {
-  const int T = prog[TQB_H_T];
-  u64 tmask = 0;
-  for (int i = 0; i < T; ++i) tmask |= 1ull << prog[TQB_H_TBIT + i];
-  u64 off = 0;
-  int k = 0;
-  for (int p = 0; p < n; ++p)
-    if (!((tmask >> p) & 1ull)) { if ((tile_id >> k) & 1u) off |= 1ull << p; ++k; }
-  return off;
-}
-
 // persistent loop of one CTA over its work items (a work item = S samples of a single-tile state,
 // or one tile of one sample), with the next item's loads in flight while the current one computes
 // (c is taken by mutable reference on purpose: nvcc 12.9 mis-lowers a BlockCtx copy made here after
 // inlining into the kernel - the copy ends up aliased with the kernel's parameter space)
 template <int R, bool BWD, class Exec>
-TQB_FN void run_cta(Exec& ex, BlockCtx& c, int n, u32 ntiles, u32 ext_hi, long long item0, long long item_step,
+TQB_FN void run_cta(Exec& ex, BlockCtx& c, int n, u32 ntiles_log2, u32 ext_hi, long long item0, long long item_step,
                     long long n_items, int nbuf, size_t buf_stride /* float2 elements between buffers */) {
   float2* const psi_buf = c.s_psi;
   float2* const lam_buf = c.s_lam;
   const bool shared_once = c.prog[TQB_H_NSEG] == 1;
+  const bool streamed = ntiles_log2 > 0;
   ex.par([&](int tid) {
-    build_scatter(c, tid);
+    build_tables(c, tid, n, streamed);
     if (shared_once) stage_segment_shared(c, tid, c.prog[TQB_H_SEGOFF]);
   });
   auto locate = [&](long long item) {
-    if (ntiles > 1) {
-      const u32 tile_id = (u32)(item % ntiles);
-      c.sample0 = (int)(item / ntiles);
+    if (streamed) {
+      const u32 tile_id = (u32)item & ((1u << ntiles_log2) - 1u);
+      c.sample0 = (int)(item >> ntiles_log2);
       c.tile_ext = tile_id | ext_hi;
-      c.outer_off = outer_offset(c.prog, n, tile_id);
+      c.outer_off = c.s_olut[tile_id & 255u] + c.s_olut[256u + ((tile_id >> 8) & 255u)] + c.s_olut[512u + (tile_id >> 16)];
     } else {
       c.sample0 = (int)(item * c.S);
       c.tile_ext = ext_hi;
@@ -616,8 +758,8 @@ TQB_FN void run_cta(Exec& ex, BlockCtx& c, int n, u32 ntiles, u32 ext_hi, long l
 }
 
 // shared-memory carve-up (bytes)
-struct SmemLayout { size_t psi, lam, msh, mps, grad, prog, scat, total, buf_stride; };
-inline SmemLayout smem_layout(int T, int L, int S, bool bwd, int nbuf, int sh_max, int ps_max, int g_max) {
+struct SmemLayout { size_t psi, lam, msh, mps, grad, prog, scat, olut, total, buf_stride; };
+inline SmemLayout smem_layout(int T, int L, int S, bool bwd, int nbuf, int sh_max, int ps_max, int g_max, bool streamed) {
   SmemLayout l;
   size_t off = 0;
   const size_t tile = ((size_t)S << T) * sizeof(float2);
@@ -630,12 +772,13 @@ inline SmemLayout smem_layout(int T, int L, int S, bool bwd, int nbuf, int sh_ma
   l.prog = off; off += (size_t)TQB_SEG_MAX_WORDS * sizeof(int32_t);
   off = (off + 15) & ~(size_t)15;
   l.scat = off; off += ((size_t)1 << (T - L)) * sizeof(u64);
+  l.olut = off; if (streamed) off += 3 * 256 * sizeof(u64);
   l.total = (off + 15) & ~(size_t)15;
   return l;
 }
 
 // launch geometry shared by the CUDA launcher and the emulation
-struct PassGeom { int S, tps, nbuf; u32 ntiles; long long n_items; SmemLayout lay; };
+struct PassGeom { int S, tps, nbuf; u32 ntiles_log2; long long n_items; SmemLayout lay; };
 inline bool pass_geometry(int n, long long bsz, int T, int R, int L, bool bwd, int sh_max, int ps_max, int g_max,
                           size_t smem_budget, PassGeom& g) {
   const int items = 1 << (T - R);
@@ -643,21 +786,21 @@ inline bool pass_geometry(int n, long long bsz, int T, int R, int L, bool bwd, i
   ps_max = (ps_max + 3) & ~3;
   g_max = (g_max + 3) & ~3;
   if (n == T) {
-    g.ntiles = 1;
+    g.ntiles_log2 = 0;
     g.nbuf = 1;
     int S = g.tps >= 128 ? 1 : 128 / g.tps;
-    while (S > 1 && smem_layout(T, L, S, bwd, 1, sh_max, ps_max, g_max).total > smem_budget) S >>= 1;
+    while (S > 1 && smem_layout(T, L, S, bwd, 1, sh_max, ps_max, g_max, false).total > smem_budget) S >>= 1;
     if (S * g.tps < 32) S = 32 / g.tps;  // whole warps for the shuffle reductions
     g.S = S;
     g.n_items = (bsz + S - 1) / S;
   } else {
     g.S = 1;
-    g.ntiles = 1u << (n - T);
-    g.n_items = bsz * (long long)g.ntiles;
+    g.ntiles_log2 = (u32)(n - T);
+    g.n_items = bsz << (n - T);
     g.nbuf = 2;
-    if (smem_layout(T, L, 1, bwd, 2, sh_max, ps_max, g_max).total > smem_budget) g.nbuf = 1;
+    if (smem_layout(T, L, 1, bwd, 2, sh_max, ps_max, g_max, true).total > smem_budget) g.nbuf = 1;
   }
-  g.lay = smem_layout(T, L, g.S, bwd, g.nbuf, sh_max, ps_max, g_max);
+  g.lay = smem_layout(T, L, g.S, bwd, g.nbuf, sh_max, ps_max, g_max, n != T);
   return true;
 }
 

@@ -82,9 +82,17 @@ struct CudaExec {
   __device__ __forceinline__ void global_add(float* p, float v) { atomicAdd(p, v); }
 };
 
+// min CTAs/SM of the forward kernel: 2 (<= 128 registers, no spills) beat 3 (80 registers, spills) on every pass size
+#ifndef TQB_FWD_MINB
+#define TQB_FWD_MINB 2
+#endif
+// backward: 1 CTA/SM (255 registers, no spills) beat 2 (128 registers, 3.7 KB of spills): profiles/r01_kernel_variants.txt
+#ifndef TQB_BWD_MINB
+#define TQB_BWD_MINB 1
+#endif
 struct PassArgs {
   int T, L, n, S, tps, bsz, nbuf, ps_cap, g_cap;
-  unsigned ntiles, ext_hi;
+  unsigned ntiles_log2, ext_hi;
   long long n_items;
   const int32_t* prog;
   const float2* psi_src;
@@ -95,16 +103,16 @@ struct PassArgs {
   const float* mps;
   float* gr;
   long long mps_stride, gr_stride;
-  unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_prog, o_scat, buf_stride;
+  unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_prog, o_scat, o_olut, buf_stride;
 };
 
 template <int R, bool BWD>
-__global__ void __launch_bounds__(256, BWD ? 2 : 3) tqb_pass_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(256, BWD ? TQB_BWD_MINB : TQB_FWD_MINB) tqb_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockCtx c;
   c.T = a.T; c.L = a.L; c.S = a.S; c.tps = a.tps; c.nthreads = a.S * a.tps;
   c.bsz = a.bsz;
-  c.multi_tile = a.ntiles > 1;
+  c.multi_tile = a.ntiles_log2 > 0;
   c.sample0 = 0; c.tile_ext = 0; c.outer_off = 0;
   c.sample_stride = 1ull << a.n;
   c.prog = a.prog; c.psi_src = a.psi_src; c.lam_src = a.lam_src; c.psi = a.psi; c.lam = a.lam;
@@ -117,8 +125,9 @@ __global__ void __launch_bounds__(256, BWD ? 2 : 3) tqb_pass_kernel(const PassAr
   c.s_grad = reinterpret_cast<float*>(smem + a.o_grad);
   c.s_prog = reinterpret_cast<int32_t*>(smem + a.o_prog);
   c.s_scat = reinterpret_cast<u64*>(smem + a.o_scat);
+  c.s_olut = reinterpret_cast<u64*>(smem + a.o_olut);
   CudaExec ex;
-  run_cta<R, BWD>(ex, c, a.n, a.ntiles, a.ext_hi, (long long)blockIdx.x, (long long)gridDim.x, a.n_items, a.nbuf,
+  run_cta<R, BWD>(ex, c, a.n, a.ntiles_log2, a.ext_hi, (long long)blockIdx.x, (long long)gridDim.x, a.n_items, a.nbuf,
                   (size_t)a.buf_stride);
 }
 
@@ -168,12 +177,12 @@ static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float*
   PassArgs a;
   a.T = T; a.L = L; a.n = n; a.S = g.S; a.tps = g.tps; a.bsz = (int)bsz; a.nbuf = g.nbuf;
   a.ps_cap = (ps_max + 3) & ~3; a.g_cap = (g_max + 3) & ~3;
-  a.ntiles = g.ntiles; a.ext_hi = ext_hi; a.n_items = g.n_items;
+  a.ntiles_log2 = g.ntiles_log2; a.ext_hi = ext_hi; a.n_items = g.n_items;
   a.prog = prog; a.psi = reinterpret_cast<float2*>(psi); a.lam = reinterpret_cast<float2*>(lam);
   a.psi_src = reinterpret_cast<const float2*>(psi_src); a.lam_src = reinterpret_cast<const float2*>(lam_src);
   a.msh = msh; a.mps = mps; a.gr = gr; a.mps_stride = mps_stride; a.gr_stride = gr_stride;
   a.o_psi = (unsigned)g.lay.psi; a.o_lam = (unsigned)g.lay.lam; a.o_msh = (unsigned)g.lay.msh; a.o_mps = (unsigned)g.lay.mps;
-  a.o_grad = (unsigned)g.lay.grad; a.o_prog = (unsigned)g.lay.prog; a.o_scat = (unsigned)g.lay.scat;
+  a.o_grad = (unsigned)g.lay.grad; a.o_prog = (unsigned)g.lay.prog; a.o_scat = (unsigned)g.lay.scat; a.o_olut = (unsigned)g.lay.olut;
   a.buf_stride = (unsigned)g.lay.buf_stride;
   cudaStream_t st = (cudaStream_t)stream;
 #define TQB_DISPATCH(RR)                                             \

@@ -56,7 +56,7 @@
 
 // group record: [regpos0..3, n_ops, first_op, 0, 0]  (regpos = tile-local bit of register bit j)
 // op record (10 words):
-#define TQB_OP_W0 0     // bits 0-3 type, 4-5 target register bit j, 8-15 flags, 16-19 gradient kind
+#define TQB_OP_W0 0     // bits 0-1 target register bit j, 2-5 type, 8-15 flags, 16-19 gradient kind
 #define TQB_OP_SLOT 1   // float offset of this op's matrix in the staged shared / per-sample floats
 #define TQB_OP_EMASK 2  // low 16: elements e (register-bit patterns) whose register-bit controls hold;
                         // high 16: DIAG parity of e over the parity bits that are register bits
@@ -80,6 +80,8 @@
 #define TQB_F_RCTRL 0x200      // has controls on register bits (EMASK != 0xffff)
 #define TQB_F_PS 0x400         // matrix lives in the per-sample floats
 #define TQB_F_NOUNAPPLY 0x800  // backward: psi already holds the op's INPUT (non-unitary single-op node)
+#define TQB_F_OCTRL 0x1000     // has controls on outer (non-tile) bits (CM_O/CV_O valid)
+#define TQB_F_DJ 0x2000        // DIAG whose only register-resident parity bit is register bit j (element parity = bit j of e)
 
 // gradient kinds (backward sweep): what is accumulated per sample for this op
 #define TQB_G_NONE 0
@@ -87,8 +89,9 @@
 #define TQB_G_X 2      // w = sum Im(conj((X psi)_k) lam_k)  over active pairs: 1 float   (rx, crx)
 #define TQB_G_Y 3      // w = sum Re(conj(psi_b) lam_a - conj(psi_a) lam_b):     1 float   (ry, cry)
 #define TQB_G_DW 4     // w_p = sum_{parity p} Im(conj(psi_k) lam_k):            2 floats  (phases)
-#define TQB_OP_TYPE(w0) ((w0) & 15)
-#define TQB_OP_J(w0) (((w0) >> 4) & 3)
+#define TQB_OP_TYPE(w0) (((w0) >> 2) & 15)
+#define TQB_OP_J(w0) ((w0) & 3)
+#define TQB_OP_CODE(type, j) (((type) << 2) | (j))
 #define TQB_OP_GKIND(w0) (((w0) >> 16) & 15)
 
 // matrix-builder table: one record of 10 words per op (tqb_build_mats / tqb_build_mats_bwd)

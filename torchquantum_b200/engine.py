@@ -244,7 +244,10 @@ def run_circuit(state, n, records, n_total=None, ext_hi=0):
         if stage.kind == "fused":
             dev = state.device
             if stage.sh_recs:
-                psh = torch.cat([records[r][2].reshape(1, -1) for r in stage.sh_recs], dim=1).reshape(-1)
+                # (2-D [1, p] parameters are concatenated as they are: a reshape per gate would add one autograd
+                # node per parameter to every step)
+                psh = torch.cat([records[r][2] if records[r][2].dim() == 2 else records[r][2].reshape(1, -1)
+                                 for r in stage.sh_recs], dim=1).reshape(-1)
                 psh = psh.to(device=dev, dtype=torch.float32)
             else:
                 psh = torch.zeros(1, dtype=torch.float32, device=dev)

@@ -86,9 +86,33 @@ def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, 
 
 def _make(name):
     cname = G.canonical(name)
+    spec = G.SPECS.get(cname)
+    simple = spec is not None and cname not in G.UNITARY_LIKE and spec.kind not in (G.RESET,)
+    n_wires_fixed = spec.n_wires if spec is not None else None
+    n_params = spec.n_params if spec is not None else 0
 
     def gate(q_device, wires, params=None, n_wires=None, static=False, parent_graph=None, inverse=False,
              comp_method="bmm"):
+        if simple and not q_device.record_op:
+            # hot path of gate_wrapper for catalogue gates (same checks, no per-call dictionary lookups)
+            if isinstance(wires, (int, np.integer)):
+                wires_t = (int(wires),)
+            else:
+                wires_t = tuple([int(w) for w in wires])
+            if n_wires_fixed is not None and n_wires_fixed != len(wires_t):
+                raise AssertionError(f"{name}: expected {n_wires_fixed} wires, got {len(wires_t)}")
+            if n_params == 0:
+                params = None
+            else:
+                if params is None:
+                    raise TypeError(f"{name}: missing params")
+                if not isinstance(params, torch.Tensor) or params.dim() != 2:
+                    params = _normalize_params(cname, params)
+                dev = q_device._flat.device
+                if params.device != dev:
+                    params = params.to(dev)
+            q_device._queue.append((cname, wires_t, params, bool(inverse)))
+            return
         gate_wrapper(name=cname, mat=mat_dict.get(cname), method=comp_method, q_device=q_device, wires=wires,
                      params=params, n_wires=n_wires, static=static, parent_graph=parent_graph, inverse=inverse)
 

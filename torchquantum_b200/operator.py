@@ -92,37 +92,47 @@ class Operator(QuantumModule):
 
     def forward(self, q_device, wires=None, params=None, inverse=None):
         """operator/op_types.py:182-266: external `params` overwrite self.params; wires update;
-        then the functional queues the gate."""
-        if inverse is not None:
+        then the functional queues the gate.  (Attributes are only re-assigned when they change:
+        nn.Module.__setattr__ costs more than queueing the gate.)"""
+        if inverse is not None and inverse != self.inverse:
             self.inverse = inverse
         if params is not None:
             self.params = params
-        if self.params is not None:
-            self.params = self.params.unsqueeze(-1) if self.params.dim() == 1 else self.params
+        p = self.params
+        if p is not None and p.dim() == 1:
+            p = p.unsqueeze(-1)
+            self.params = p
         if wires is not None:
-            self.wires = [wires] if isinstance(wires, (int, np.integer)) else wires
-        if self.params is None:
+            wires = [wires] if isinstance(wires, (int, np.integer)) else wires
+            if wires is not self.wires:
+                self.wires = wires
+        noise = self.noise_model_tq
+        if p is None:
             if self.n_wires is None:
                 self.func(q_device, self.wires, inverse=self.inverse)
             else:
                 self.func(q_device, self.wires, n_wires=self.n_wires, inverse=self.inverse)
         else:
-            p = self.params
-            if self.noise_model_tq is not None and hasattr(self.noise_model_tq, "add_noise"):
-                p = self.noise_model_tq.add_noise(p)
+            if noise is not None and hasattr(noise, "add_noise"):
+                p = noise.add_noise(p)
             if self.n_wires is None:
                 self.func(q_device, self.wires, params=p, inverse=self.inverse)
             else:
                 self.func(q_device, self.wires, params=p, n_wires=self.n_wires, inverse=self.inverse)
-        if self.noise_model_tq is not None and getattr(self.noise_model_tq, "is_add_noise", False):
-            for noise_op in self.noise_model_tq.sample_noise_op(self):
+        if noise is not None and getattr(noise, "is_add_noise", False):
+            for noise_op in noise.sample_noise_op(self):
                 noise_op(q_device)
 
     def __repr__(self):
         return f" class: {self.name} \n parameters: {self.params} \n wires: {self.wires} \n inverse: {self.inverse}"
 
-    # nn.Module would refuse to overwrite a registered Parameter with a plain tensor
+    _PLAIN_ATTRS = frozenset(("wires", "inverse", "n_wires", "static_matrix", "clifford_quantization"))
+
     def __setattr__(self, name, value):
+        if name in Operator._PLAIN_ATTRS:  # plain python state: skip nn.Module's type dispatch
+            self.__dict__[name] = value
+            return
+        # nn.Module would refuse to overwrite a registered Parameter with a plain tensor
         if name == "params" and "_parameters" in self.__dict__ and "params" in self._parameters \
                 and not isinstance(value, nn.Parameter):
             del self._parameters["params"]

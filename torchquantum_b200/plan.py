@@ -14,6 +14,7 @@ phase gates (z, s, t, cz, cu1 ...) only touch the amplitudes whose target bit is
 """
 import functools
 import itertools
+import os
 
 import numpy as np
 
@@ -23,8 +24,8 @@ from . import gates as G
 T_SINGLE = 13   # largest state handled as one tile per sample (2^13 amplitudes = 64 KiB)
 T_MULTI = 12    # tile bits when the state is streamed through HBM
 L_MIN = 5       # contiguous low bits always in the tile (2^5 amplitudes = 256 B runs)
-R_MAX = C.MAX_R
-R_GRAD = C.MAX_R  # register bits of programs that also run backward (two arrays live per thread)
+R_MAX = int(os.environ.get("TQB200_R", C.MAX_R))   # register bits per thread (env: kernel experiments)
+R_GRAD = int(os.environ.get("TQB200_RGRAD", C.MAX_R))  # register bits of programs that also run backward (two arrays live per thread)
 
 NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32}
 NGRAD = {C.G_NONE: 0, C.G_X: 1, C.G_Y: 1, C.G_DW: 2}
@@ -355,14 +356,19 @@ def _encode_op(op, regs, R, loc, oloc):
         flags |= C.F_PS
     if op.nounapply:
         flags |= C.F_NOUNAPPLY
+    if cm_o:
+        flags |= C.F_OCTRL
     j = 0
+    if op.type == C.T_DIAG and len(reg_par) == 1:
+        flags |= C.F_DJ
+        j = reg_par[0]
     if op.type == C.T_U2Q:
         assert regs[0] == op._lt[1] and regs[1] == op._lt[0]
     elif op._lt:
         j = regidx[op._lt[0]]
     if op.type in (C.T_REAL, C.T_RX):
         assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
-    w0 = op.type | (j << 4) | flags | (op.gkind << 16)
+    w0 = (op.type << 2) | j | flags | (op.gkind << 16)
     return [w0, 0, emask | (epar << 16), cm_t, cv_t, pm_t, cm_o, cv_o, pm_o, 0]
 
 
