@@ -90,6 +90,8 @@ struct CudaExec {
 #ifndef TQB_BWD_MINB
 #define TQB_BWD_MINB 1
 #endif
+static int g_num_sms = 0;
+
 struct PassArgs {
   int T, L, n, S, tps, bsz, nbuf, ps_cap, g_cap;
   unsigned ntiles_log2, ext_hi;
@@ -106,8 +108,13 @@ struct PassArgs {
   unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_prog, o_scat, o_olut, buf_stride;
 };
 
-template <int R, bool BWD>
-__global__ void __launch_bounds__(256, BWD ? TQB_BWD_MINB : TQB_FWD_MINB) tqb_pass_kernel(const PassArgs a) {
+// SMALL: CTAs of <= 128 threads (states of <= 11 qubits held whole in shared memory, several samples per CTA)
+#ifndef TQB_BWD_MINB_SMALL
+#define TQB_BWD_MINB_SMALL 3
+#endif
+template <int R, bool BWD, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 128 : 256, SMALL ? (BWD ? TQB_BWD_MINB_SMALL : 2 * TQB_FWD_MINB) : (BWD ? TQB_BWD_MINB : TQB_FWD_MINB))
+tqb_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockCtx c;
   c.T = a.T; c.L = a.L; c.S = a.S; c.tps = a.tps; c.nthreads = a.S * a.tps;
@@ -131,15 +138,13 @@ __global__ void __launch_bounds__(256, BWD ? TQB_BWD_MINB : TQB_FWD_MINB) tqb_pa
                   (size_t)a.buf_stride);
 }
 
-static int g_num_sms = 0;
-
-template <int R, bool BWD>
-static int launch_pass(const PassArgs& a, size_t smem, cudaStream_t st) {
+template <int R, bool BWD, bool SMALL>
+static int launch_pass_t(const PassArgs& a, size_t smem, cudaStream_t st) {
   static int configured_smem = -1;  // per instantiation
   static int occ_threads = 0, occ_smem = -1, occ_blocks = 0;
   const int threads = a.S * a.tps;
   if ((int)smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tqb_pass_kernel<R, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tqb_pass_kernel<R, BWD, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(pass)", e);
     configured_smem = (int)smem;
   }
@@ -151,15 +156,20 @@ static int launch_pass(const PassArgs& a, size_t smem, cudaStream_t st) {
   }
   if (occ_threads != threads || occ_smem != (int)smem) {
     int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tqb_pass_kernel<R, BWD>, threads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tqb_pass_kernel<R, BWD, SMALL>, threads, smem);
     if (e != cudaSuccess) return fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor(pass)", e);
     occ_threads = threads; occ_smem = (int)smem; occ_blocks = nb < 1 ? 1 : nb;
   }
   long long grid = (long long)g_num_sms * occ_blocks;
   if (grid > a.n_items) grid = a.n_items;
-  tqb_pass_kernel<R, BWD><<<(unsigned)grid, threads, smem, st>>>(a);
+  tqb_pass_kernel<R, BWD, SMALL><<<(unsigned)grid, threads, smem, st>>>(a);
   TQB_CHECK_LAUNCH("tqb_pass_kernel");
   return 0;
+}
+
+template <int R, bool BWD>
+static int launch_pass(const PassArgs& a, size_t smem, cudaStream_t st) {
+  return a.S * a.tps <= 128 ? launch_pass_t<R, BWD, true>(a, smem, st) : launch_pass_t<R, BWD, false>(a, smem, st);
 }
 
 static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float* psi, float* lam, int n, long long bsz,

@@ -28,8 +28,8 @@ class Op1QAllLayer(QuantumModule):
 
     @static_support
     def forward(self, q_device):
-        for k in range(self.n_wires):
-            self.ops_all[k](q_device, wires=k)
+        for k, op_k in enumerate(self.ops_all):
+            op_k.queue_on(q_device, k)
 
 
 class Op2QAllLayer(QuantumModule):
@@ -50,11 +50,11 @@ class Op2QAllLayer(QuantumModule):
 
     @static_support
     def forward(self, q_device):
-        for k in range(len(self.ops_all)):
+        for k, op_k in enumerate(self.ops_all):
             wires = [k, (k + self.jump) % self.n_wires]
             if self.wire_reverse:
                 wires.reverse()
-            self.ops_all[k](q_device, wires=wires)
+            op_k.queue_on(q_device, wires)
 
 
 class Op2QDenseLayer(QuantumModule):

@@ -123,6 +123,35 @@ class Operator(QuantumModule):
             for noise_op in noise.sample_noise_op(self):
                 noise_op(q_device)
 
+    def queue_on(self, q_device, wires):
+        """Hot path for this package's own layer templates: same effect as `self(q_device, wires=wires)`
+        for a catalogue gate with 2-D (or no) parameters when no noise model, static graph or op
+        recording is involved; anything else goes through the full `forward`."""
+        p = self.params
+        cname = self._fast_cname
+        if (cname is None or self.noise_model_tq is not None or q_device.record_op
+                or (p is not None and (p.dim() != 2 or p.device != q_device._flat.device))):
+            self(q_device, wires=wires)
+            return
+        if wires is not self.wires:
+            self.__dict__["wires"] = wires
+        wires_t = (int(wires),) if isinstance(wires, (int, np.integer)) else tuple([int(w) for w in wires])
+        q_device._queue.append((cname, wires_t, p, bool(self.inverse)))
+
+    @property
+    def _fast_cname(self):
+        cls = type(self)
+        c = cls.__dict__.get("_fast_cname_cache", 0)
+        if c == 0:
+            name = G.canonical(getattr(self.func, "__name__", ""))
+            spec = G.SPECS.get(name)
+            ok = (spec is not None and name not in G.UNITARY_LIKE and spec.kind != G.RESET
+                  and spec.n_wires is not None and type(cls.forward) is type(Operator.forward)
+                  and cls.forward is Operator.forward)
+            c = name if ok else None
+            cls._fast_cname_cache = c
+        return c
+
     def __repr__(self):
         return f" class: {self.name} \n parameters: {self.params} \n wires: {self.wires} \n inverse: {self.inverse}"
 
