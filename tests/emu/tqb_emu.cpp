@@ -181,7 +181,7 @@ int tqb_expval_pauli(const float* state, int n, long long bsz, const unsigned lo
     for (int t = 0; t < nt; ++t) {
       double acc = 0;
       for (u64 k = 0; k < (1ull << n); ++k) acc += (std::conj(s[(b << n) + k]) * pauli_apply(s + (b << n), k, xm[t], zm[t], ny[t])).real();
-      out[b * nt + t] += (float)acc;
+      if (n > 12) out[b * nt + t] += (float)acc; else out[b * nt + t] = (float)acc;  // same contract as the CUDA build
     }
   return 0;
 }
@@ -206,7 +206,7 @@ int tqb_expval_z(const float* state, int n, long long bsz, float* out, void*) {
       acc[n] += p;
       for (int j = 0; j < n; ++j) acc[j] += ((k >> j) & 1) ? -p : p;
     }
-    for (int j = 0; j <= n; ++j) out[b * (n + 1) + j] += (float)acc[j];
+    for (int j = 0; j <= n; ++j) { if (n > 12) out[b * (n + 1) + j] += (float)acc[j]; else out[b * (n + 1) + j] = (float)acc[j]; }
   }
   return 0;
 }

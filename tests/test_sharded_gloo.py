@@ -1,0 +1,82 @@
+"""Sharded statevector (amplitude axis) on CPU: world_size-2 and -4 `gloo` process groups
+driving the host-emulation build of the kernel source; every rank checks its slab against the
+single-process CPU oracle.  (The GPU suite repeats this over NCCL on real B200s.)"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _ops_qft_brick(n, seed):
+    """config-5 family: X-prepared basis state, QFT (H + CU1 ladder + swaps), brickwork layers."""
+    from tests import cases
+
+    rng = np.random.default_rng(seed)
+    ops = [{"name": "paulix", "wires": [w]} for w in range(n) if rng.integers(2)]
+    for top in range(n):
+        ops.append({"name": "hadamard", "wires": [top]})
+        for d, w in enumerate(range(top + 1, n)):
+            ops.append({"name": "cu1", "wires": [w, top], "params": torch.tensor([[np.pi / 2 ** (d + 1)]], dtype=torch.float32)})
+    for w in range(n // 2):
+        ops.append({"name": "swap", "wires": [w, n - 1 - w]})
+    return ops + cases.brickwork_ops(n, 3, seed=seed + 1)
+
+
+def _worker(rank, world, port, n, seed, emu_path, tiles):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torchquantum_b200 as tq
+        import torchquantum_b200.functional as tqf
+        from oracle import tq_oracle as O
+        from tests import cases
+        from tests.helpers import assert_close
+        from torchquantum_b200 import _native
+        from torchquantum_b200.measurement import expval, expval_joint_analytical_multi
+
+        _native.use_library_for_testing(emu_path)
+        if tiles is not None:  # force several tiles per slab: the rank bits sit above the tile index
+            from torchquantum_b200 import plan as P
+            P.T_SINGLE, P.T_MULTI, P.L_MIN = tiles
+        ops = _ops_qft_brick(n, seed)
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device="cpu")
+        cases.apply_ops(q, ops, "cpu")
+        obs = ["".join("ZXYI"[(i + s) % 4] for i in range(n)) for s in range(3)] + ["Z" * n]
+        ev = expval_joint_analytical_multi(q, obs)
+        want = O.run_ops(n, 1, ops)
+        ev_want = torch.stack([O.expval_joint_rotated(want, o) for o in obs], dim=-1)
+        assert_close(ev, ev_want, rtol=1e-4, what=f"rank {rank} expvals")
+        nl = q.nl
+        assert q.stats["exchanges"] >= 1
+        slab = q.get_states_1d()
+        assert_close(slab, want[:, rank << nl:(rank + 1) << nl], rtol=2e-5, what=f"rank {rank} slab")
+        full = q.gather_states_1d()
+        assert_close(full, want, rtol=2e-5, what="gathered state")
+        # per-wire <Z> after a few more gates that leave qubits in the rank index
+        tqf.rx(q, wires=0, params=torch.tensor([[0.3]]))
+        tqf.cnot(q, wires=[n - 1, 0])
+        z = expval(q, list(range(n)), [cases._Obs("Z")] * n)
+        want2 = O.run_ops(n, 1, [{"name": "rx", "wires": [0], "params": torch.tensor([[0.3]])},
+                                 {"name": "cnot", "wires": [n - 1, 0]}], want.reshape([1] + [2] * n))
+        zw, _ = O.expval(want2.reshape([1] + [2] * n), list(range(n)), ["Z"] * n)
+        assert_close(z, zw, rtol=1e-4, what="per-wire Z")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,tiles", [(2, 8, None), (4, 9, None), (2, 9, (4, 5, 2)), (4, 10, (5, 6, 3))])
+def test_sharded_qft_brickwork_matches_oracle(world, n, tiles):
+    emu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libtqb200_emu.so")
+    if not os.path.exists(emu):
+        pytest.skip("host emulation library not built (run __graft_entry__.build())")
+    mp.spawn(_worker, args=(world, _free_port(), n, 3, emu, tiles), nprocs=world, join=True)

@@ -8,6 +8,7 @@ gate-application API: `tq.QuantumDevice`, `tqf.<gate>` / `qdev.<gate>`, `tq.Oper
 from .macro import *  # noqa: F401,F403
 from .module import QuantumModule, QuantumModuleList, QuantumModuleDict, QuantumGraph, static_support  # noqa: F401
 from .device import QuantumDevice  # noqa: F401
+from .sharded import ShardedQuantumDevice  # noqa: F401
 from . import functional  # noqa: F401
 from . import operator  # noqa: F401
 from .operator import *  # noqa: F401,F403

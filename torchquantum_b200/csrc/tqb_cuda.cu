@@ -317,6 +317,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 #define TQB_TERM_BATCH 8
 // out[b][t] (+)= <psi_b| P_t |psi_b>,  P|k> = i^ny (-1)^popc(k&z) |k^x>
+// TB terms share every load of psi[k]; TB = 1 serves the reference API (one call per Pauli string)
+template <int TB>
 __global__ void __launch_bounds__(256) tqb_expval_pauli_kernel(const float2* state, int n, const u64* xm,
                                                                 const u64* zm, const int* ny, int nterms,
                                                                 float* out, int chunk_log2, int use_atomic) {
@@ -324,13 +326,13 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_kernel(const float2* sta
   const float2* psi = state + (b << n);
   const u64 k0 = (u64)blockIdx.x << chunk_log2;
   const u64 k1 = k0 + (1ull << chunk_log2);
-  __shared__ float red[8][TQB_TERM_BATCH];
-  for (int t0 = 0; t0 < nterms; t0 += TQB_TERM_BATCH) {
-    float acc[TQB_TERM_BATCH];
-    u64 x[TQB_TERM_BATCH], z[TQB_TERM_BATCH];
-    int ph[TQB_TERM_BATCH];
+  __shared__ float red[8][TB];
+  for (int t0 = 0; t0 < nterms; t0 += TB) {
+    float acc[TB];
+    u64 x[TB], z[TB];
+    int ph[TB];
 #pragma unroll
-    for (int t = 0; t < TQB_TERM_BATCH; ++t) {
+    for (int t = 0; t < TB; ++t) {
       acc[t] = 0.f;
       const int tt = t0 + t < nterms ? t0 + t : nterms - 1;
       x[t] = xm[tt]; z[t] = zm[tt]; ph[t] = ny[tt] & 3;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_kernel(const float2* sta
     for (u64 k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
       const float2 a = psi[k];
 #pragma unroll
-      for (int t = 0; t < TQB_TERM_BATCH; ++t) {
+      for (int t = 0; t < TB; ++t) {
         const float2 c = x[t] ? psi[k ^ x[t]] : a;
         float2 w = cmulc(c, a);  // conj(psi[k^x]) psi[k]
         float v = (ph[t] == 0) ? w.x : (ph[t] == 1) ? -w.y : (ph[t] == 2) ? -w.x : w.y;
@@ -347,12 +349,12 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_kernel(const float2* sta
       }
     }
 #pragma unroll
-    for (int t = 0; t < TQB_TERM_BATCH; ++t) {
+    for (int t = 0; t < TB; ++t) {
       const float s = warp_sum(acc[t]);
       if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = s;
     }
     __syncthreads();
-    if (threadIdx.x < TQB_TERM_BATCH && t0 + (int)threadIdx.x < nterms) {
+    if (threadIdx.x < TB && t0 + (int)threadIdx.x < nterms) {
       float s = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
       float* dst = out + b * nterms + t0 + threadIdx.x;
@@ -557,9 +559,14 @@ int tqb_expval_pauli(const float* state, int n_qubits, long long bsz, const unsi
   const int cl = expval_chunk_log2(n_qubits);
   dim3 grid(1u << (n_qubits - cl), (unsigned)bsz);
   if (bsz > 65535) return fail_msg("tqb_expval_pauli: bsz > 65535");
-  tqb_expval_pauli_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(state), n_qubits,
-                                                                 xmask_dev, zmask_dev, ny_dev, n_terms, out, cl,
-                                                                 grid.x > 1);
+  const float2* st2 = reinterpret_cast<const float2*>(state);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_terms == 1)
+    tqb_expval_pauli_kernel<1><<<grid, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, cl, grid.x > 1);
+  else if (n_terms <= 4)
+    tqb_expval_pauli_kernel<4><<<grid, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, cl, grid.x > 1);
+  else
+    tqb_expval_pauli_kernel<TQB_TERM_BATCH><<<grid, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, cl, grid.x > 1);
   TQB_CHECK_LAUNCH("tqb_expval_pauli_kernel");
   return 0;
 }

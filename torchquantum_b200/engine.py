@@ -79,11 +79,34 @@ def _build_mats(stage, bsz, psh, pps, externs, device):
     return msh, mps
 
 
+def _ext_hi(rank, n, pp):
+    """Sharded statevector: the rank index supplies the index bits above the local 2^n amplitudes; the
+    kernel sees them as the top bits of the compressed non-tile index (csrc/tqb_program.h, CM_O / PM_O)."""
+    return (rank << (n - pp.T)) & 0xFFFFFFFF
+
+
+def run_fused_inplace(state, stage, n, rank, psh, pps, externs):
+    """No-grad execution of a fused stage IN PLACE on `state` (every pass reads and writes the same
+    buffer: a tile is fully staged on chip before it is written back).  Used by the sharded device,
+    where a second copy of a 16-64 GiB shard is not affordable."""
+    _native.check_device(state)
+    assert state.is_contiguous()
+    bsz, dev = state.shape[0], state.device
+    msh, mps = _build_mats(stage, bsz, psh, pps, externs, dev)
+    stream = _native.stream_ptr(state)
+    for pp in stage.passes:
+        prog = _dev(pp, "prog", dev)
+        _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, bsz, _ptr(prog), _desc(pp), _ptr(msh),
+                     _ptr(mps), stage.M_ps, _ext_hi(rank, n, pp), stream)
+        STATS["launches"] += 1
+    return state
+
+
 class FusedFn(torch.autograd.Function):
     """state [bsz, 2^n] complex64 -> state, through all passes of one fused stage."""
 
     @staticmethod
-    def forward(ctx, state, psh, pps, stage, n, ext_hi, *externs):
+    def forward(ctx, state, psh, pps, stage, n, rank, *externs):
         _native.check_device(state)
         state = state.contiguous()
         bsz = state.shape[0]
@@ -95,19 +118,19 @@ class FusedFn(torch.autograd.Function):
         for pp in stage.passes:
             prog = _dev(pp, "prog", dev)
             _native.call("tqb_pass_forward", _ptr(src), _ptr(out), n, bsz, _ptr(prog), _desc(pp), _ptr(msh),
-                         _ptr(mps), stage.M_ps, ext_hi, stream)
+                         _ptr(mps), stage.M_ps, _ext_hi(rank, n, pp), stream)
             STATS["launches"] += 1
             src = out
         if not stage.passes:
             out.copy_(state)
-        ctx.stage, ctx.n, ctx.ext_hi = stage, n, ext_hi
+        ctx.stage, ctx.n, ctx.rank = stage, n, rank
         ctx.n_ext = len(externs)
         ctx.save_for_backward(state if stage.save_input else out, psh, pps, msh, mps, *externs)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        stage, n, ext_hi = ctx.stage, ctx.n, ctx.ext_hi
+        stage, n, rank = ctx.stage, ctx.n, ctx.rank
         saved = ctx.saved_tensors
         psi0, psh, pps, msh, mps = saved[:5]
         externs = saved[5:]
@@ -123,7 +146,7 @@ class FusedFn(torch.autograd.Function):
         for pp in reversed(stage.passes):
             prog = _dev(pp, "prog", dev)
             _native.call("tqb_pass_backward", _ptr(psrc), _ptr(lsrc), _ptr(psi), _ptr(lam), n, bsz, _ptr(prog),
-                         _desc(pp), _ptr(msh), _ptr(mps), stage.M_ps, _ptr(gr), stage.G, ext_hi, stream)
+                         _desc(pp), _ptr(msh), _ptr(mps), stage.M_ps, _ptr(gr), stage.G, _ext_hi(rank, n, pp), stream)
             STATS["launches"] += 1
             psrc, lsrc = psi, lam
         if not stage.passes:
@@ -214,9 +237,10 @@ def _reset(state, n, wires):
     return flat * torch.sqrt(1 / (flat.abs() ** 2).sum(-1)).unsqueeze(-1)
 
 
-def run_circuit(state, n, records, n_total=None, ext_hi=0):
+def run_circuit(state, n, records, n_total=None, rank=0, inplace=False):
     """state: [bsz, 2^n] complex64; records: list of (name, wires, params, inverse) with canonical
-    names and normalised params (2-D float tensors, or complex matrices for unitary-like gates)."""
+    names and normalised params (2-D float tensors, or complex matrices for unitary-like gates).
+    n_total / rank: sharded statevector (plan.build_plan); inplace: overwrite `state` (no-grad only)."""
     bsz = state.shape[0]
     grad_mode = torch.is_grad_enabled() and (
         state.requires_grad or any(r[2] is not None and r[2].requires_grad for r in records))
@@ -257,7 +281,10 @@ def run_circuit(state, n, records, n_total=None, ext_hi=0):
             else:
                 pps = torch.zeros(bsz, 1, dtype=torch.float32, device=dev)
             externs = [records[e[0]][2].to(dev) for e in stage.externs]
-            state = FusedFn.apply(state, psh, pps, stage, n, ext_hi, *externs)
+            if inplace and not grad_mode:
+                state = run_fused_inplace(state, stage, n, rank, psh, pps, externs)
+            else:
+                state = FusedFn.apply(state, psh, pps, stage, n, rank, *externs)
         elif stage.kind == "dense":
             name, wires, params, inverse = records[stage.rec]
             if stage.const is not None:

@@ -71,7 +71,8 @@ class _ExpvalPauliFn(torch.autograd.Function):
         _native.check_device(state)
         state = state.contiguous()
         bsz, nt = state.shape[0], xm.shape[0]
-        out = torch.zeros(bsz, nt, dtype=torch.float32, device=state.device)
+        # blocks of one sample accumulate atomically only when the state spans several chunks (n > 12)
+        out = (torch.zeros if n > 12 else torch.empty)(bsz, nt, dtype=torch.float32, device=state.device)
         _native.call("tqb_expval_pauli", _ptr(state), n, bsz, _ptr(xm), _ptr(zm), _ptr(ny), nt, _ptr(out),
                      _native.stream_ptr(state))
         STATS["launches"] += 1
@@ -96,7 +97,7 @@ class _ExpvalZFn(torch.autograd.Function):
         _native.check_device(state)
         state = state.contiguous()
         bsz = state.shape[0]
-        out = torch.zeros(bsz, n + 1, dtype=torch.float32, device=state.device)
+        out = (torch.zeros if n > 12 else torch.empty)(bsz, n + 1, dtype=torch.float32, device=state.device)
         _native.call("tqb_expval_z", _ptr(state), n, bsz, _ptr(out), _native.stream_ptr(state))
         STATS["launches"] += 1
         ctx.save_for_backward(state)
@@ -118,6 +119,8 @@ def expval_joint_analytical_multi(qdev, observables: List[str]):
     """All Pauli strings in one kernel launch -> [bsz, len(observables)] float32."""
     for o in observables:
         assert len(o) == qdev.n_wires
+    if getattr(qdev, "is_sharded", False):
+        return qdev.expval_pauli(list(observables))
     states = qdev.get_states_1d()
     xm, zm, ny = _mask_tensors(observables, states.device)
     return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny)
@@ -125,7 +128,7 @@ def expval_joint_analytical_multi(qdev, observables: List[str]):
 
 def expval_joint_analytical(qdev, observable: str):
     """<psi_b| P |psi_b> for the Pauli string `observable` (char j acts on wire j) -> [bsz] float32."""
-    return expval_joint_analytical_multi(qdev, [observable])[:, 0]
+    return expval_joint_analytical_multi(qdev, [observable]).reshape(-1)
 
 
 def expval(qdev, wires: Union[int, List[int]], observables):
@@ -137,7 +140,10 @@ def expval(qdev, wires: Union[int, List[int]], observables):
         for rotation in observable.diagonalizing_gates():
             rotation(qdev, wires=wire)
     n = qdev.n_wires
-    z = _ExpvalZFn.apply(qdev.get_states_1d(), n)
+    if getattr(qdev, "is_sharded", False):
+        z = qdev.expval_z_all()
+    else:
+        z = _ExpvalZFn.apply(qdev.get_states_1d(), n)
     norm = z[:, n]
     cols = []
     for wire, observable in zip(wires, observables):
@@ -151,7 +157,12 @@ def measure(qdev, n_shots=1024, draw_id=None):
     """Sample bitstrings (measurements.py:37-74) -> list[OrderedDict[bitstring -> count]] with all
     2^n keys.  Bit-exact with the reference under the shared global `random` stream."""
     n = qdev.n_wires
-    states = qdev.get_states_1d().detach().contiguous()
+    if getattr(qdev, "is_sharded", False):
+        if n > 24:
+            raise NotImplementedError("measure() enumerates all 2^n bitstrings (as the reference does): n <= 24 only")
+        states = qdev.gather_states_1d().detach().contiguous()
+    else:
+        states = qdev.get_states_1d().detach().contiguous()
     _native.check_device(states)
     bsz, N = states.shape
     dev = states.device

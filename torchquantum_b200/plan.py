@@ -522,8 +522,13 @@ class CircuitPlan:
 
 
 def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
-    """key: tuple of (name, wires, inverse, pmode, grad, ext_dim) in queue order."""
+    """key: tuple of (name, wires, inverse, pmode, grad, ext_dim) in queue order.
+
+    Sharded statevector (n_total > n): this rank holds the n low index bits, `wires` count from the
+    most significant of all n_total bits (wire w = bit n_total-1-w); wires 0 .. n_total-n-1 live in
+    the rank index and may only be controls or parity bits of diagonal gates (K11: no traffic)."""
     plan = CircuitPlan(n)
+    nb = n if n_total is None else n_total
     plan.n_gates = len(key)
     cur = []
     if grad_mode and "r" not in tile_kw:
@@ -542,12 +547,15 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
             close()
             plan.stages.append(ResetStage(tuple(int(w) for w in wires)))
             continue
-        op = lower(n, name, wires, inverse, pmode, grad, rec, ext_dim)
+        op = lower(nb, name, wires, inverse, pmode, grad, rec, ext_dim)
         if op is None:  # dense
             close()
             const = G.qft_matrix_np(len(wires)) if name == "qft" else None
-            plan.stages.append(DenseStage(rec, _bits(n, wires), const, inverse, grad_mode))
+            bits = _bits(nb, wires)
+            assert max(bits) < n, f"{name}: dense gates need all their wires on this rank"
+            plan.stages.append(DenseStage(rec, bits, const, inverse, grad_mode))
             continue
+        assert all(t < n for t in op.targets), f"{name}: target wire lives in the rank index (swap it in first)"
         if grad_mode and not spec.unitary:
             # non-unitary in-tile op: its own node, keeps its input instead of un-applying
             close()

@@ -1,0 +1,413 @@
+"""Sharded statevector device (north_star item 4; SURVEY §8 row (e), kernels K10 / K11).
+
+The reference has no multi-GPU code at all (README.md:52 only claims "30+ qubits with multiple
+GPUs"); this is the drop-in's extension of `tq.QuantumDevice` (device/devices.py:36-136) to states
+that do not fit one GPU.  One process per GPU (`torch.distributed`, NCCL over NVLink 5):
+
+* rank r of 2^g holds the amplitudes whose g top *physical* index bits equal r: a contiguous
+  slab of 2^(n-g) amplitudes per batch element (TorchQuantum is big-endian, so with the initial
+  layout these are wires 0..g-1);
+* a table `pos[logical bit] -> physical bit` tracks where every qubit currently lives;
+* gates whose targets are local run through the same fused gate-pass kernels as on one GPU;
+  controls and parity bits of diagonal gates may sit in the rank index at no cost (the rank
+  supplies the missing index bits to the kernel: K11, no traffic);
+* a gate with a non-diagonal target on a global qubit triggers ONE exchange of all g global
+  qubits with g local qubits that are not needed for the longest time: victims are moved to
+  the top local bits by a fused local pass, then a zero-copy `all_to_all_single` of 2^g equal
+  chunks swaps physical bits [nl-g, nl) <-> [nl, n).  Every rank sends (1 - 2^-g) of its shard;
+* gates commute when they share no qubit, so before paying for an exchange the queue is scanned
+  for everything that can still run in the current layout (same dependency-respecting greedy
+  as the pass packer in plan.py);
+* SWAP gates are free: they only relabel `pos`.
+
+Forward only (no autograd through the exchange yet): circuits of this size are simulated, not
+trained, in BASELINE configs 4-5.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native, engine
+from . import gates as G
+from .engine import STATS, _ptr
+from .macro import C_DTYPE
+
+__all__ = ["ShardedQuantumDevice"]
+
+
+def _local_bits_needed(name, wires, params):
+    """Wires (as given) that must be local for the gate to run without communication."""
+    spec = G.SPECS[name]
+    if spec.kind in (G.DIAG, G.NOP):
+        return ()
+    if spec.kind == G.RESET:
+        raise NotImplementedError("reset is not supported on a sharded device")
+    if spec.kind == G.DENSE:
+        return tuple(wires)
+    n_ctrl = spec.n_ctrl if spec.n_ctrl >= 0 else len(wires) - 1
+    return tuple(wires[n_ctrl:])
+
+
+class ShardedQuantumDevice:
+    """`QuantumDevice` whose statevector is partitioned over the ranks of a process group."""
+
+    is_sharded = True
+
+    def __init__(self, n_wires, device_name="default", bsz=1, device="cuda", record_op=False, process_group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedQuantumDevice needs torch.distributed to be initialised")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.g = int(np.log2(self.world))
+        if 1 << self.g != self.world:
+            raise ValueError("the number of ranks must be a power of two")
+        self.n_wires, self.device_name, self.bsz = n_wires, device_name, bsz
+        self.nl = n_wires - self.g
+        if self.nl < max(self.g, 1):
+            raise ValueError("too few qubits for this many ranks")
+        self.device = torch.device(device)
+        self.record_op = record_op
+        self._op_history, self._history_pending = [], []
+        self._queue = []
+        self.stats = {"exchanges": 0, "exchange_bytes_sent": 0, "exchange_ms": [], "local_permute_passes": 0}
+        self.time_exchanges = False
+        self.reset_states(bsz)
+
+    # --- state container ------------------------------------------------------------------
+    def reset_states(self, bsz):
+        self.bsz = bsz
+        flat = torch.zeros(bsz, 1 << self.nl, dtype=C_DTYPE, device=self.device)
+        if self.rank == 0:
+            flat[:, 0] = 1
+        self._flat = flat
+        self._queue = []
+        self.pos = list(range(self.n_wires))  # logical bit -> physical bit
+
+    def set_local_states(self, flat):
+        """Install this rank's slab (canonical layout: global index = rank * 2^nl + local index)."""
+        self._flat = flat.reshape(flat.shape[0], 1 << self.nl).to(C_DTYPE).contiguous()
+        self.bsz = self._flat.shape[0]
+        self._queue = []
+        self.pos = list(range(self.n_wires))
+
+    @property
+    def compute_device(self):
+        return self._flat.device
+
+    def enqueue(self, name, wires, params, inverse):
+        self._queue.append((name, wires, params, inverse))
+
+    def reset_op_history(self):
+        self._op_history, self._history_pending = [], []
+
+    @property
+    def op_history(self):
+        for entry in self._history_pending:
+            p = entry["params"]
+            if p is not None:
+                entry["params"] = p.squeeze().detach().cpu().numpy().tolist()
+        self._history_pending = []
+        return self._op_history
+
+    def _record(self, entry):
+        self._op_history.append(entry)
+        self._history_pending.append(entry)
+
+    # --- execution ------------------------------------------------------------------------
+    def _pwire(self, logical_bit, pos=None):
+        return self.n_wires - 1 - (self.pos if pos is None else pos)[logical_bit]
+
+    def _run_local(self, records):
+        if records:
+            self._flat = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank,
+                                            inplace=True)
+
+    def flush(self):
+        if not self._queue:
+            return
+        remaining, self._queue = self._queue, []
+        n, nl = self.n_wires, self.nl
+        with torch.no_grad():
+            while remaining:
+                runnable, rest, blocked = [], [], 0
+                pos = list(self.pos)
+                for rec in remaining:
+                    name, wires, params, inverse = rec
+                    lbits = [n - 1 - w for w in wires]
+                    qm = 0
+                    for b in lbits:
+                        qm |= 1 << b
+                    need = _local_bits_needed(name, wires, params)
+                    if name == "swap" and not (qm & blocked):
+                        pos[lbits[0]], pos[lbits[1]] = pos[lbits[1]], pos[lbits[0]]  # relabel: no data moves
+                        continue
+                    if (qm & blocked) or any(pos[n - 1 - w] >= nl for w in need):
+                        blocked |= qm
+                        rest.append(rec)
+                        continue
+                    runnable.append((name, tuple(n - 1 - pos[b] for b in lbits), params, inverse))
+                self.pos = pos
+                self._run_local(runnable)
+                if rest:
+                    self._exchange(rest)
+                remaining = rest
+
+    def _next_need(self, rest):
+        """logical bit -> index of the first record of `rest` that needs it local (inf if none)."""
+        nxt = {}
+        for i, (name, wires, params, inverse) in enumerate(rest):
+            for w in _local_bits_needed(name, wires, params):
+                nxt.setdefault(self.n_wires - 1 - w, i)
+        return nxt
+
+    def _exchange(self, rest):
+        """Bring every global qubit on chip: pick the g local qubits needed last as victims, move them
+        to the top local bits (fused local pass), all-to-all."""
+        n, nl, g = self.n_wires, self.nl, self.g
+        nxt = self._next_need(rest)
+        inv = {p: l for l, p in enumerate(self.pos)}
+        local_logical = [inv[p] for p in range(nl)]
+        order = sorted(local_logical, key=lambda l: (-nxt.get(l, 1 << 60), -self.pos[l]))
+        victims = order[:g]
+        self._move_to_top(victims)
+        self._all_to_all()
+
+    def _move_to_top(self, victims):
+        """Local bit permutation so that `victims` (logical bits) occupy physical bits [nl-g, nl)."""
+        n, nl, g = self.n_wires, self.nl, self.g
+        top = list(range(nl - g, nl))
+        inv = {p: l for l, p in enumerate(self.pos)}
+        vict = set(victims)
+        free_top = [p for p in top if inv[p] not in vict]
+        movers = [v for v in victims if self.pos[v] < nl - g]
+        recs = []
+        for v, p in zip(movers, free_top):
+            a, b = self.pos[v], p                      # exchange the contents of physical bits a and b
+            wa, wb = n - 1 - a, n - 1 - b
+            recs += [("cnot", (wa, wb), None, False), ("cnot", (wb, wa), None, False), ("cnot", (wa, wb), None, False)]
+            other = inv[p]
+            self.pos[v], self.pos[other] = b, a
+            inv[a], inv[b] = other, v
+        if recs:
+            self.stats["local_permute_passes"] += 1
+            self._run_local(recs)
+
+    def _all_to_all(self):
+        """Swap physical bits [nl-g, nl) <-> [nl, n): chunk j of the slab goes to rank j and the chunk
+        received from rank i lands at chunk position i (K10)."""
+        nl, g, W = self.nl, self.g, self.world
+        flat = self._flat
+        bsz = flat.shape[0]
+        chunk = 1 << (nl - g)
+        if bsz == 1:
+            send = flat.view(W, chunk)
+        else:
+            send = flat.view(bsz, W, chunk).transpose(0, 1).contiguous()
+        recv = torch.empty_like(send)
+        timed = self.time_exchanges and flat.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+        if timed:
+            e1.record()
+            self.stats["exchange_ms"].append((e0, e1))
+        self.stats["exchanges"] += 1
+        self.stats["exchange_bytes_sent"] += (W - 1) * chunk * bsz * 8
+        if bsz == 1:
+            self._flat = recv.view(1, -1)
+        else:
+            self._flat = recv.view(W, bsz, chunk).transpose(0, 1).contiguous().view(bsz, -1)
+        for l, p in enumerate(self.pos):
+            if nl - g <= p < nl:
+                self.pos[l] = p + g
+            elif p >= nl:
+                self.pos[l] = p - g
+
+    def exchange_times_ms(self):
+        out = [a.elapsed_time(b) for a, b in self.stats["exchange_ms"]]
+        return out
+
+    # --- layout ---------------------------------------------------------------------------
+    def canonicalize(self):
+        """Restore the identity layout (logical bit l at physical bit l)."""
+        self.flush()
+        n, nl, g = self.n_wires, self.nl, self.g
+        with torch.no_grad():
+            target_global = list(range(nl, n))
+            if any(self.pos[l] != l for l in target_global):
+                if any(self.pos[l] >= nl for l in target_global):
+                    # some rank qubits are in the rank index at the wrong place (or stay there): first
+                    # bring ALL of them on chip, parking g qubits that belong on chip in the rank index
+                    inv = {p: l for l, p in enumerate(self.pos)}
+                    park = [inv[p] for p in range(nl) if inv[p] < nl][:g]
+                    self._move_to_top(park)
+                    self._all_to_all()
+                self._move_to_top_ordered(target_global)
+                self._all_to_all()
+            self._permute_local_to_identity()
+        assert self.pos == list(range(n))
+
+    def _move_to_top_ordered(self, logical):
+        """logical[i] -> physical bit nl-g+i (all of them currently local)."""
+        n, nl, g = self.n_wires, self.nl, self.g
+        self._apply_local_permutation({l: nl - g + i for i, l in enumerate(logical)})
+
+    def _permute_local_to_identity(self):
+        self._apply_local_permutation({l: l for l in range(self.nl)})
+
+    def _apply_local_permutation(self, want):
+        """want: logical bit -> physical local bit it must end at (other local qubits fill what is left)."""
+        n, nl = self.n_wires, self.nl
+        recs = []
+        inv = {p: l for l, p in enumerate(self.pos)}
+        for l, dst in want.items():
+            a = self.pos[l]
+            assert a < nl and dst < nl
+            if a == dst:
+                continue
+            wa, wb = n - 1 - a, n - 1 - dst
+            recs += [("cnot", (wa, wb), None, False), ("cnot", (wb, wa), None, False), ("cnot", (wa, wb), None, False)]
+            other = inv[dst]
+            self.pos[l], self.pos[other] = dst, a
+            inv[a], inv[dst] = other, l
+        if recs:
+            self.stats["local_permute_passes"] += 1
+            self._run_local(recs)
+
+    # --- reading the state ----------------------------------------------------------------
+    def get_states_1d(self):
+        """This rank's slab [bsz, 2^(n-g)] in the canonical layout (amplitude rank * 2^nl + k)."""
+        self.canonicalize()
+        return self._flat
+
+    def gather_states_1d(self):
+        """Full [bsz, 2^n] state on every rank (tests / small n only)."""
+        local = self.get_states_1d().contiguous()
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
+        return torch.cat(parts, dim=1)
+
+    @property
+    def states(self):
+        raise RuntimeError("a sharded device exposes get_states_1d() (local slab) / gather_states_1d()")
+
+    # --- measurement (dispatched from torchquantum_b200.measurement) -----------------------
+    def _all_reduce(self, t):
+        dist.all_reduce(t, group=self.group)
+        return t
+
+    def expval_pauli(self, observables):
+        """[bsz, n_terms] <psi|P_t|psi>: X / Y factors on rank-index qubits are rotated to Z first
+        (the rotation is undone lazily by queued inverse gates), Z factors there only flip the sign of
+        this rank's partial sum; one all-reduce of bsz * n_terms floats."""
+        from . import functional as tqf
+        from .measurement import pauli_masks
+
+        n, nl = self.n_wires, self.nl
+        self.flush()
+        out_cols = []
+        # group terms that need no rotation
+        direct, rotated = [], []
+        for t, o in enumerate(observables):
+            assert len(o) == n
+            needs = any(ch in "XY" and self.pos[n - 1 - w] >= nl for w, ch in enumerate(o.upper()))
+            (rotated if needs else direct).append(t)
+        result = torch.zeros(self.bsz, len(observables), dtype=torch.float32, device=self._flat.device)
+        if direct:
+            result[:, direct] = self._expval_local([observables[t] for t in direct])
+        for t in rotated:
+            o = observables[t].upper()
+            undo = []
+            zs = []
+            for w, ch in enumerate(o):
+                if ch == "X":
+                    tqf.hadamard(self, wires=w)
+                    undo.append(("hadamard", w))
+                elif ch == "Y":
+                    tqf.sdg(self, wires=w)
+                    tqf.hadamard(self, wires=w)
+                    undo += [("s", w), ("hadamard", w)]
+                zs.append("I" if ch == "I" else "Z")
+            self.flush()
+            result[:, t] = self._expval_local(["".join(zs)])[:, 0]
+            for name, w in reversed(undo):
+                getattr(tqf, name)(self, wires=w)
+        return self._all_reduce(result)
+
+    def _expval_local(self, observables):
+        from .measurement import pauli_masks
+
+        n, nl = self.n_wires, self.nl
+        xs, zs, nys, signs = [], [], [], []
+        for o in observables:
+            x = z = ny = 0
+            sign = 1.0
+            for w, ch in enumerate(o.upper()):
+                p = self.pos[n - 1 - w]
+                if ch == "I":
+                    continue
+                if p >= nl:
+                    assert ch == "Z"
+                    if (self.rank >> (p - nl)) & 1:
+                        sign = -sign
+                    continue
+                if ch in "XY":
+                    x |= 1 << p
+                if ch in "YZ":
+                    z |= 1 << p
+                if ch == "Y":
+                    ny += 1
+            xs.append(x); zs.append(z); nys.append(ny); signs.append(sign)
+        dev = self._flat.device
+        xm = torch.tensor(xs, dtype=torch.int64, device=dev)
+        zm = torch.tensor(zs, dtype=torch.int64, device=dev)
+        ny = torch.tensor(nys, dtype=torch.int32, device=dev)
+        state = self._flat
+        _native.check_device(state)
+        out = torch.zeros(self.bsz, len(observables), dtype=torch.float32, device=dev)
+        _native.call("tqb_expval_pauli", _ptr(state), nl, self.bsz, _ptr(xm), _ptr(zm), _ptr(ny), len(observables),
+                     _ptr(out), _native.stream_ptr(state))
+        STATS["launches"] += 1
+        return out * torch.tensor(signs, dtype=torch.float32, device=dev)
+
+    def expval_z_all(self):
+        """[bsz, n+1]: column l = <Z> of LOGICAL bit l, column n = squared norm (all-reduced)."""
+        n, nl = self.n_wires, self.nl
+        self.flush()
+        state = self._flat
+        dev = state.device
+        loc = torch.zeros(self.bsz, nl + 1, dtype=torch.float32, device=dev)
+        _native.call("tqb_expval_z", _ptr(state), nl, self.bsz, _ptr(loc), _native.stream_ptr(state))
+        STATS["launches"] += 1
+        out = torch.empty(self.bsz, n + 1, dtype=torch.float32, device=dev)
+        norm = loc[:, nl]
+        out[:, n] = norm
+        for l in range(n):
+            p = self.pos[l]
+            if p < nl:
+                out[:, l] = loc[:, p]
+            else:
+                out[:, l] = -norm if (self.rank >> (p - nl)) & 1 else norm
+        return self._all_reduce(out)
+
+    @property
+    def name(self):
+        return self.__class__.__name__
+
+    def __repr__(self):
+        return (f" class: {self.name} \n number of qubits: {self.n_wires} ({self.nl} local + {self.g} in the rank index)\n"
+                f" batch size: {self.bsz} \n rank {self.rank} of {self.world} \n layout: {self.pos}")
+
+
+def _bind_functionals():
+    from .functional import func_name_dict, func_name_dict_collect
+
+    for name, func in func_name_dict.items():
+        setattr(ShardedQuantumDevice, name, func)
+    for name, func in func_name_dict_collect.items():
+        setattr(ShardedQuantumDevice, name, func)
+
+
+_bind_functionals()
