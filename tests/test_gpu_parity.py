@@ -91,3 +91,20 @@ def test_full_size_properties_n24():
     s0 = q.get_states_1d()
     assert abs(s0[0, 0].abs().item() - 1.0) < 1e-4
     assert s0[0, 1:].abs().max().item() < 1e-4
+
+
+def test_sharded_statevector_two_gpus():
+    """Amplitude-sharded device over NCCL vs the same circuit on one GPU (needs >= 2 visible GPUs;
+    the world_size-2/4 gloo suite in tests/test_sharded_gloo.py covers the logic on CPU)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tools", "dist_sharded.py"), "--check", "20"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

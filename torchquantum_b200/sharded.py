@@ -289,6 +289,21 @@ class ShardedQuantumDevice:
         dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
         return torch.cat(parts, dim=1)
 
+    def read_amplitudes(self, indices):
+        """Amplitudes at the given canonical flat indices (python ints) in whatever layout the state is
+        in right now: the owner rank looks each one up, one all-reduce shares them -> [bsz, len]."""
+        self.flush()
+        n, nl = self.n_wires, self.nl
+        out = torch.zeros(self.bsz, len(indices), 2, dtype=torch.float32, device=self._flat.device)
+        for i, k in enumerate(indices):
+            phys = 0
+            for l in range(n):
+                if (k >> l) & 1:
+                    phys |= 1 << self.pos[l]
+            if phys >> nl == self.rank:
+                out[:, i] = torch.view_as_real(self._flat[:, phys & ((1 << nl) - 1)])
+        return torch.view_as_complex(self._all_reduce(out))
+
     @property
     def states(self):
         raise RuntimeError("a sharded device exposes get_states_1d() (local slab) / gather_states_1d()")
