@@ -11,7 +11,7 @@ import torchquantum_b200.functional as tqf
 from oracle import tq_oracle as O
 from torchquantum_b200.measurement import (expval, expval_joint_analytical, expval_joint_analytical_multi,
                                            measure)
-from tests.helpers import assert_close, load, op_params
+from tests.helpers import assert_close, load, op_params  # noqa: F401
 
 
 def apply_ops(qdev, ops, device, requires_grad=False):
@@ -187,3 +187,102 @@ def check_against_oracle(device, n, bsz, ops, grad=False, rtol=1e-5):
         assert_close(torch.cat([a.reshape(-1) for a in g]), torch.cat([a.reshape(-1) for a in g_cpu]), rtol=1e-4,
                      what=f"grads n={n}")
     return states
+
+
+def check_cfg2_vqe(device, n=5, reps=3, bsz=6, graphed=False):
+    """BASELINE config 2 through the class API (GeneralEncoder + EfficientSU2 'linear' + one
+    expval_joint_analytical call per Hamiltonian term, loss = mean energy) vs the oracle; three steps so
+    that the layers' record caches and the shared read-out backward are exercised, the last one after
+    flipping an operator's `inverse` flag (cache invalidation)."""
+    torch.manual_seed(3)
+    enc = tq.GeneralEncoder([{"input_idx": [w], "func": "ry", "wires": [w]} for w in range(n)])
+    ansatz = tq.EfficientSU2(n_wires=n, reps=reps, entanglement_layer="linear").to(device)
+    terms = ["I" * i + "ZZ" + "I" * (n - 2 - i) for i in range(n - 1)] + ["I" * i + "X" + "I" * (n - 1 - i) for i in range(n)]
+    params = [p for p in ansatz.parameters()]
+    ops_mods = [m for m in ansatz.modules() if isinstance(m, tq.Operator)]
+
+    def ours(x):
+        q = tq.QuantumDevice(n_wires=n, bsz=x.shape[0], device=device)
+        enc(q, x)
+        ansatz(q)
+        e = 0
+        for t in terms:
+            e = e + expval_joint_analytical(q, t)
+        return e.mean()
+
+    def oracle(x_cpu):
+        leaves = [p.detach().cpu().clone().requires_grad_(True) for p in params]
+        by_id = {id(p): l for p, l in zip(params, leaves)}
+        ops = [{"name": "ry", "wires": [w], "params": x_cpu[:, [w]]} for w in range(n)]
+        for layer in ansatz.layers_all:
+            for k, o in enumerate(layer.ops_all):
+                if o.params is not None:
+                    ops.append({"name": o.name.lower(), "wires": [k], "params": by_id[id(o.params)], "inverse": o.inverse})
+                else:
+                    ops.append({"name": "cnot", "wires": [k, k + 1], "inverse": o.inverse})
+        st = O.run_ops(n, x_cpu.shape[0], ops)
+        e = sum(O.expval_joint_analytical(st, t) for t in terms).mean()
+        g = torch.autograd.grad(e, leaves + [x_cpu])
+        return e, g
+
+    step = None
+    for it in range(3):
+        if it == 2:
+            ops_mods[1].inverse = True
+        x = (torch.rand(bsz, n) * np.pi).to(device).requires_grad_(True)
+        for p in params:
+            p.grad = None
+        if graphed and it < 2:
+            if step is None:
+                step = tq.GraphedStep(ours, [x.detach().requires_grad_(True)], params)
+            loss = step(x.detach())
+            gx = step.static_inputs[0].grad
+        else:
+            loss = ours(x)
+            loss.backward()
+            gx = x.grad
+        e, g = oracle(x.detach().cpu().clone().requires_grad_(True))
+        assert_close(loss, e, what=f"cfg2 energy step {it}")
+        assert_close(torch.cat([p.grad.reshape(-1) for p in params]), torch.cat([a.reshape(-1) for a in g[:-1]]),
+                     rtol=1e-4, what=f"cfg2 param grads step {it}")
+        if gx is not None:
+            assert_close(gx, g[-1], rtol=1e-4, what=f"cfg2 grad x step {it}")
+
+
+QAOA_EDGES_8 = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 0), (0, 4), (1, 5), (2, 6), (3, 7)]
+
+
+def check_cfg3_qaoa(device, n=8, p=3, bsz=4, edges=QAOA_EDGES_8):
+    """BASELINE config 3 (examples/qaoa/max_cut_backprop.py:59-109): H on every wire, per layer an rx(beta)
+    mixer on every wire and cx-rz(gamma)-cx per edge, per-sample betas/gammas; cost = sum 0.5 <Z_i Z_j>."""
+    g = torch.Generator().manual_seed(11)
+    betas = (0.5 * torch.rand(bsz, p, generator=g))
+    gammas = (0.5 * torch.rand(bsz, p, generator=g))
+
+    def circuit(b, gm):
+        ops = [{"name": "hadamard", "wires": [w]} for w in range(n)]
+        for layer in range(p):
+            for w in range(n):
+                ops.append({"name": "rx", "wires": [w], "params": b[:, [layer]]})
+            for (i, j) in edges:
+                ops.append({"name": "cnot", "wires": [i, j]})
+                ops.append({"name": "rz", "wires": [j], "params": gm[:, [layer]]})
+                ops.append({"name": "cnot", "wires": [i, j]})
+        return ops
+
+    def zz(i, j):
+        return "".join("Z" if w in (i, j) else "I" for w in range(n))
+
+    bd, gd = betas.to(device).requires_grad_(True), gammas.to(device).requires_grad_(True)
+    q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+    apply_ops(q, circuit(bd, gd), device)
+    cost = sum(0.5 * expval_joint_analytical(q, zz(i, j)) for (i, j) in edges)
+    bc, gc = betas.clone().requires_grad_(True), gammas.clone().requires_grad_(True)
+    st = O.run_ops(n, bsz, circuit(bc, gc))
+    assert_close(q.get_states_1d(), st, what="cfg3 states")
+    cost_cpu = sum(0.5 * O.expval_joint_analytical(st, zz(i, j)) for (i, j) in edges)
+    assert_close(cost, cost_cpu, rtol=1e-4, what="cfg3 cost")
+    gb, gg = torch.autograd.grad(cost.sum(), [bd, gd])
+    gbc, ggc = torch.autograd.grad(cost_cpu.sum(), [bc, gc])
+    assert_close(gb, gbc, rtol=1e-4, what="cfg3 grad beta")
+    assert_close(gg, ggc, rtol=1e-4, what="cfg3 grad gamma")

@@ -30,7 +30,6 @@ struct EmuExec {
   void async_commit() {}
   void async_wait_prev() {}
   void async_wait_all() {}
-  template <int N> void reduce_add(float* dst, float* v, int) { for (int i = 0; i < N; ++i) dst[i] += v[i]; }
   void global_add(float* p, float v) { *p += v; }
 };
 
@@ -44,6 +43,7 @@ static void emu_blocks(BlockCtx c, int n, const PassGeom& g, unsigned ext_hi) {
   c.s_msh = reinterpret_cast<float*>(base + g.lay.msh);
   c.s_mps = reinterpret_cast<float*>(base + g.lay.mps);
   c.s_grad = reinterpret_cast<float*>(base + g.lay.grad);
+  c.s_part = reinterpret_cast<float*>(base + g.lay.part);
   c.s_prog = reinterpret_cast<int32_t*>(base + g.lay.prog);
   c.s_scat = reinterpret_cast<u64*>(base + g.lay.scat);
   c.s_olut = reinterpret_cast<u64*>(base + g.lay.olut);

@@ -99,3 +99,11 @@ def test_errors_match_reference_behaviour():
     tqf.rx(q, wires=0, params=torch.rand(5))  # batch mismatch: bmm raises RuntimeError in the reference
     with pytest.raises(RuntimeError):
         q.get_states_1d()
+
+
+def test_cfg2_vqe_class_api_record_cache():
+    cases.check_cfg2_vqe("cpu")
+
+
+def test_cfg3_qaoa_per_sample_params():
+    cases.check_cfg3_qaoa("cpu", n=6, p=2, bsz=3, edges=[(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 0), (0, 3)])

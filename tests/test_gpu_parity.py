@@ -66,6 +66,53 @@ def test_brickwork_vs_oracle(n, bsz, depth):
     cases.check_against_oracle(DEV, n, bsz, cases.brickwork_ops(n, depth, seed=n), grad=(n <= 16))
 
 
+def test_cfg2_vqe_class_api():
+    cases.check_cfg2_vqe(DEV, n=6, reps=4, bsz=40)
+
+
+def test_cfg2_vqe_cuda_graph_step():
+    """tq.GraphedStep (whole fwd+bwd step replayed as a CUDA graph) gives the same energy and gradients."""
+    cases.check_cfg2_vqe(DEV, n=6, reps=4, bsz=40, graphed=True)
+
+
+def test_cfg2_full_shape_readout_kernels():
+    """Warp-per-sample Pauli read-out at the config-2 shape (n=10, bsz=4096) vs the multi-term launch and the
+    per-wire marginals; shared backward of 19 single-string read-outs vs one multi-string read-out."""
+    import torchquantum_b200 as tq
+    from torchquantum_b200.measurement import expval_joint_analytical, expval_joint_analytical_multi
+
+    n, bsz = 10, 4096
+    torch.manual_seed(0)
+    terms = ["I" * i + "ZZ" + "I" * (n - 2 - i) for i in range(n - 1)] + ["I" * i + "X" + "I" * (n - 1 - i) for i in range(n)] \
+        + ["XYZIIZYXII", "YYIIIIIIZZ"]
+    st = torch.randn(bsz, 2 ** n, dtype=torch.complex64, device=DEV)
+    st = (st / st.norm(dim=1, keepdim=True)).requires_grad_(True)
+    q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=DEV)
+    q.set_states(st)
+    multi = expval_joint_analytical_multi(q, terms)
+    singles = torch.stack([expval_joint_analytical(q, t) for t in terms], dim=1)
+    cases.assert_close(singles, multi, what="single-string vs multi-string read-out")
+    # dense check of a few samples against the oracle's Kronecker form
+    from oracle import tq_oracle as O
+    want = torch.stack([O.expval_joint_analytical(st[:4].detach().cpu(), t) for t in terms], dim=1)
+    cases.assert_close(multi[:4], want, what="read-out vs oracle")
+    w = torch.randn(bsz, len(terms), device=DEV)
+    (g1,) = torch.autograd.grad((singles * w).sum(), st, retain_graph=True)
+    (g2,) = torch.autograd.grad((multi * w).sum(), st)
+    cases.assert_close(g1, g2, rtol=1e-4, what="shared backward of single-string read-outs")
+
+
+def test_cfg3_qaoa_per_sample_params():
+    cases.check_cfg3_qaoa(DEV)
+
+
+def test_cfg3_qaoa_n14_streamed():
+    """Same family on a state that streams through HBM in tiles (n=14), 3-regular ring-with-chords graph."""
+    n = 14
+    edges = [(i, (i + 1) % n) for i in range(n)] + [(i, i + n // 2) for i in range(n // 2)]
+    cases.check_cfg3_qaoa(DEV, n=n, p=2, bsz=2, edges=edges)
+
+
 def test_per_sample_params_large_batch():
     ops = cases.brickwork_ops(6, 6, seed=1, per_sample_bsz=300)
     cases.check_against_oracle(DEV, 6, 300, ops, grad=True)

@@ -17,5 +17,6 @@ from .measurement import *  # noqa: F401,F403
 from .measure_modules import MeasureAll, MeasureMultipleTimes, MeasureMultiPauliSum, MeasureMultiQubitPauliSum  # noqa: F401
 from .encoding import *  # noqa: F401,F403
 from .layer import *  # noqa: F401,F403
+from .graphs import GraphedStep  # noqa: F401
 
 __version__ = "0.1.0"

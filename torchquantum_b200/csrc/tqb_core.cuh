@@ -78,6 +78,7 @@ struct BlockCtx {
   int ps_cap, g_cap;       // staged per-sample floats (stride of s_mps / s_grad per sample slot)
   // staged (shared) memory
   float2* s_psi; float2* s_lam; float* s_msh; float* s_mps; float* s_grad; int32_t* s_prog; u64* s_scat;
+  float* s_part;           // backward: per-thread gradient partials [g_cap][nthreads + 1]
   u64* s_olut;             // [3][256]: amplitude offset contributed by byte j of the tile id (streamed states only)
 };
 
@@ -191,11 +192,33 @@ TQB_FN void stage_segment_sample(const BlockCtx& c, int tid) {
     c.s_mps[slot * c.ps_cap + k] = (b < c.bsz) ? c.mps[(long long)b * c.mps_stride + ps_base + k] : 0.f;
   }
   if (BWD) {
+    // every thread owns column `tid` of the partial-gradient matrix: zero it without any synchronisation
     const int g_len = c.s_prog[TQB_S_G_LEN];
-    for (int i = tid; i < c.S * g_len; i += c.nthreads) {
-      const int slot = i / g_len, k = i - slot * g_len;
-      c.s_grad[slot * c.g_cap + k] = 0.f;
-    }
+    float* col = c.s_part + tid;
+    for (int k = 0; k < g_len; ++k) col[k * (c.nthreads + 1)] = 0.f;
+  }
+}
+
+// The backward sweep accumulates every op's gradient partials per THREAD (stash) and sums them over the threads
+// of a sample once per segment: thread (slot, k) adds the tps partials of float k in thread order.  (One warp-
+// shuffle reduction + shared atomics per op and item cost more than the op's arithmetic on the small batched
+// states: 5 dependent shuffle steps with 3 warps per scheduler to hide them.)  Row stride nthreads + 1: both
+// the stash (consecutive tid) and this sum (consecutive k) are bank-conflict free; the order is deterministic.
+template <int N>
+TQB_FN void stash(float* col, int pstride, int gslot, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) col[(gslot + i) * pstride] += v[i];
+}
+
+TQB_FN void reduce_partials(const BlockCtx& c, int tid) {
+  const int g_len = c.s_prog[TQB_S_G_LEN];
+  const int pstride = c.nthreads + 1;
+  for (int i = tid; i < c.S * g_len; i += c.nthreads) {
+    const int slot = i / g_len, k = i - slot * g_len;
+    const float* row = c.s_part + k * pstride + slot * c.tps;
+    float acc = 0.f;
+    for (int t = 0; t < c.tps; ++t) acc += row[t];
+    c.s_grad[slot * c.g_cap + k] = acc;
   }
 }
 
@@ -547,13 +570,13 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
 // backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in
 template <int R, bool MASKED, class Exec>
 TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
-                     u32 w0, u32 act, u32 base, const float* smps, float* sgrad, int width) {
+                     u32 w0, u32 act, u32 base, const float* smps, float* spart, int pstride) {
   const u32 type = TQB_OP_TYPE(w0);
   const int j = TQB_OP_J(w0);
   const u32 gkind = TQB_OP_GKIND(w0);
   const bool unapply = !(w0 & TQB_F_NOUNAPPLY);
   const float* m = ((w0 & TQB_F_PS) ? smps : c.s_msh) + op[TQB_OP_SLOT];
-  float* gdst = sgrad + op[TQB_OP_GSLOT];
+  const int gslot = op[TQB_OP_GSLOT];
   if (type == TQB_T_REAL || type == TQB_T_RX || type == TQB_T_GEN) {
     float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float w = 0.f;
@@ -568,8 +591,8 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
     }
     if (gkind == TQB_G_X) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, false, MASKED>(x, y, act)));
     if (gkind == TQB_G_Y) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, true, MASKED>(x, y, act)));
-    if (gkind == TQB_G_FULL) ex.template reduce_add<8>(gdst, gacc, width);
-    else if (gkind != TQB_G_NONE) { float w1[1] = {w}; ex.template reduce_add<1>(gdst, w1, width); }
+    if (gkind == TQB_G_FULL) stash<8>(spart, pstride, gslot, gacc);
+    else if (gkind != TQB_G_NONE) { float w1[1] = {w}; stash<1>(spart, pstride, gslot, w1); }
   } else if (type == TQB_T_DIAG) {
     const float4 q = ld4(m);
     const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
@@ -584,7 +607,7 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
       if (gkind == TQB_G_DW) {
         float w2[2] = {0.f, 0.f};
         TQB_DISPATCH_J(j, (grad_dwj<R, JJ, MASKED>(x, y, tp, act, w2)));
-        ex.template reduce_add<2>(gdst, w2, width);
+        stash<2>(spart, pstride, gslot, w2);
       }
     } else {
       if (!MASKED || act) {
@@ -594,7 +617,7 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
       if (gkind == TQB_G_DW) {
         float w2[2];
         grad_dw<R, MASKED>(x, y, tp, epar, act, w2);
-        ex.template reduce_add<2>(gdst, w2, width);
+        stash<2>(spart, pstride, gslot, w2);
       }
     }
   } else if (type == TQB_T_PERM) {
@@ -609,14 +632,14 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
         if (gkind == TQB_G_FULL) grad_full_2q<R>(x, y, act, g32);
         u2q<R, true>(y, m, act);
       }
-      if (gkind == TQB_G_FULL) ex.template reduce_add<32>(gdst, g32, width);
+      if (gkind == TQB_G_FULL) stash<32>(spart, pstride, gslot, g32);
     }
   }
 }
 
 template <int R, class Exec>
 TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
-                         u32 base, const float* smps, float* sgrad, int width) {
+                         u32 base, const float* smps, float* spart, int pstride) {
   const u32 w0 = (u32)op[TQB_OP_W0];
   if (w0 & TQB_F_OCTRL) {
     if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
@@ -624,9 +647,9 @@ TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float
   if (w0 & (TQB_F_TCTRL | TQB_F_RCTRL)) {
     u32 act = (u32)op[TQB_OP_EMASK] & 0xffffu;
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
-    bwd_body<R, true, Exec>(ex, c, x, y, op, w0, act, base, smps, sgrad, width);
+    bwd_body<R, true, Exec>(ex, c, x, y, op, w0, act, base, smps, spart, pstride);
   } else {
-    bwd_body<R, false, Exec>(ex, c, x, y, op, w0, 0xffffu, base, smps, sgrad, width);
+    bwd_body<R, false, Exec>(ex, c, x, y, op, w0, 0xffffu, base, smps, spart, pstride);
   }
 }
 
@@ -645,8 +668,8 @@ TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
   float2* sps = c.s_psi + ((size_t)slot << c.T);
   float2* sla = BWD ? c.s_lam + ((size_t)slot << c.T) : nullptr;
   const float* smps = c.s_mps + slot * c.ps_cap;
-  float* sgrad = BWD ? c.s_grad + slot * c.g_cap : nullptr;
-  const int width = c.tps < 32 ? c.tps : 32;
+  float* spart = BWD ? c.s_part + tid : nullptr;
+  const int pstride = c.nthreads + 1;
 
   for (int item = t; item < items; item += c.tps) {
     const u32 base = insert_zeros<R>((u32)item, sp);
@@ -663,7 +686,7 @@ TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
     }
     if constexpr (BWD) {
       for (int k = nops - 1; k >= 0; --k)
-        apply_op_bwd<R, Exec>(ex, c, x, y, ops + k * TQB_OP_WORDS, base, smps, sgrad, width);
+        apply_op_bwd<R, Exec>(ex, c, x, y, ops + k * TQB_OP_WORDS, base, smps, spart, pstride);
     } else {
       for (int k = 0; k < nops; ++k) apply_op_fwd_inplace<R, Exec>(c, x, ops + k * TQB_OP_WORDS, base, smps);
     }
@@ -695,7 +718,10 @@ TQB_FN void run_tile(Exec& ex, const BlockCtx& c, bool shared_staged) {
       const int g = BWD ? ng - 1 - gi : gi;
       ex.par([&](int tid) { run_group<R, BWD>(ex, c, tid, g); });
     }
-    if (BWD && c.s_prog[TQB_S_G_LEN] > 0) ex.par([&](int tid) { flush_grads(ex, c, tid); });
+    if (BWD && c.s_prog[TQB_S_G_LEN] > 0) {
+      ex.par([&](int tid) { reduce_partials(c, tid); });
+      ex.par([&](int tid) { flush_grads(ex, c, tid); });
+    }
   }
 }
 
@@ -758,8 +784,8 @@ TQB_FN void run_cta(Exec& ex, BlockCtx& c, int n, u32 ntiles_log2, u32 ext_hi, l
 }
 
 // shared-memory carve-up (bytes)
-struct SmemLayout { size_t psi, lam, msh, mps, grad, prog, scat, olut, total, buf_stride; };
-inline SmemLayout smem_layout(int T, int L, int S, bool bwd, int nbuf, int sh_max, int ps_max, int g_max, bool streamed) {
+struct SmemLayout { size_t psi, lam, msh, mps, grad, part, prog, scat, olut, total, buf_stride; };
+inline SmemLayout smem_layout(int T, int L, int S, int tps, bool bwd, int nbuf, int sh_max, int ps_max, int g_max, bool streamed) {
   SmemLayout l;
   size_t off = 0;
   const size_t tile = ((size_t)S << T) * sizeof(float2);
@@ -769,6 +795,7 @@ inline SmemLayout smem_layout(int T, int L, int S, bool bwd, int nbuf, int sh_ma
   l.msh = off; off += (size_t)((sh_max + 3) & ~3) * sizeof(float);
   l.mps = off; off += (size_t)S * ps_max * sizeof(float);
   l.grad = off; if (bwd) off += (size_t)S * g_max * sizeof(float);
+  l.part = off; if (bwd) off += (size_t)g_max * (S * tps + 1) * sizeof(float);
   l.prog = off; off += (size_t)TQB_SEG_MAX_WORDS * sizeof(int32_t);
   off = (off + 15) & ~(size_t)15;
   l.scat = off; off += ((size_t)1 << (T - L)) * sizeof(u64);
@@ -789,7 +816,7 @@ inline bool pass_geometry(int n, long long bsz, int T, int R, int L, bool bwd, i
     g.ntiles_log2 = 0;
     g.nbuf = 1;
     int S = g.tps >= 128 ? 1 : 128 / g.tps;
-    while (S > 1 && smem_layout(T, L, S, bwd, 1, sh_max, ps_max, g_max, false).total > smem_budget) S >>= 1;
+    while (S > 1 && smem_layout(T, L, S, g.tps, bwd, 1, sh_max, ps_max, g_max, false).total > smem_budget) S >>= 1;
     if (S * g.tps < 32) S = 32 / g.tps;  // whole warps for the shuffle reductions
     g.S = S;
     g.n_items = (bsz + S - 1) / S;
@@ -798,9 +825,9 @@ inline bool pass_geometry(int n, long long bsz, int T, int R, int L, bool bwd, i
     g.ntiles_log2 = (u32)(n - T);
     g.n_items = bsz << (n - T);
     g.nbuf = 2;
-    if (smem_layout(T, L, 1, bwd, 2, sh_max, ps_max, g_max, true).total > smem_budget) g.nbuf = 1;
+    if (smem_layout(T, L, 1, g.tps, bwd, 2, sh_max, ps_max, g_max, true).total > smem_budget) g.nbuf = 1;
   }
-  g.lay = smem_layout(T, L, g.S, bwd, g.nbuf, sh_max, ps_max, g_max, n != T);
+  g.lay = smem_layout(T, L, g.S, g.tps, bwd, g.nbuf, sh_max, ps_max, g_max, n != T);
   return true;
 }
 

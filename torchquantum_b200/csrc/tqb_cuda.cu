@@ -43,42 +43,6 @@ struct CudaExec {
   __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
   __device__ __forceinline__ void async_wait_prev() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
   __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-  // sum v[0..N) over the `width` consecutive lanes that share a sample, add into shared dst
-  template <int N>
-  __device__ __forceinline__ void reduce_add(float* dst, float* v, int width) {
-    const unsigned lane = threadIdx.x & 31u;
-    if (width == 32 && N >= 8) {
-      // halving butterfly: every step each lane keeps one half of its values and ships the other
-      int off = 16;
-#pragma unroll
-      for (int half = N / 2; half >= 1; half >>= 1) {
-        const bool upper = lane & off;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-          const float send = upper ? v[i] : v[i + half];
-          const float keep = upper ? v[i + half] : v[i];
-          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-        off >>= 1;
-      }
-      // N == 8: offsets 16, 8, 4 consumed; N == 32: all five
-      float s = v[0];
-      for (; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-      if (N == 8) { if ((lane & 3u) == 0u) atomicAdd(dst + (((lane >> 4) & 1u) * 4u + ((lane >> 3) & 1u) * 2u + ((lane >> 2) & 1u)), s); }
-      else atomicAdd(dst + lane, s);
-      return;
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float s = v[i];
-      for (int o = width >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      v[i] = s;
-    }
-    if ((lane & (unsigned)(width - 1)) == 0u) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) atomicAdd(dst + i, v[i]);
-    }
-  }
   __device__ __forceinline__ void global_add(float* p, float v) { atomicAdd(p, v); }
 };
 
@@ -105,7 +69,7 @@ struct PassArgs {
   const float* mps;
   float* gr;
   long long mps_stride, gr_stride;
-  unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_prog, o_scat, o_olut, buf_stride;
+  unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_part, o_prog, o_scat, o_olut, buf_stride;
 };
 
 // SMALL: CTAs of <= 128 threads (states of <= 11 qubits held whole in shared memory, several samples per CTA)
@@ -130,6 +94,7 @@ tqb_pass_kernel(const PassArgs a) {
   c.s_msh = reinterpret_cast<float*>(smem + a.o_msh);
   c.s_mps = reinterpret_cast<float*>(smem + a.o_mps);
   c.s_grad = reinterpret_cast<float*>(smem + a.o_grad);
+  c.s_part = reinterpret_cast<float*>(smem + a.o_part);
   c.s_prog = reinterpret_cast<int32_t*>(smem + a.o_prog);
   c.s_scat = reinterpret_cast<u64*>(smem + a.o_scat);
   c.s_olut = reinterpret_cast<u64*>(smem + a.o_olut);
@@ -192,7 +157,7 @@ static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float*
   a.psi_src = reinterpret_cast<const float2*>(psi_src); a.lam_src = reinterpret_cast<const float2*>(lam_src);
   a.msh = msh; a.mps = mps; a.gr = gr; a.mps_stride = mps_stride; a.gr_stride = gr_stride;
   a.o_psi = (unsigned)g.lay.psi; a.o_lam = (unsigned)g.lay.lam; a.o_msh = (unsigned)g.lay.msh; a.o_mps = (unsigned)g.lay.mps;
-  a.o_grad = (unsigned)g.lay.grad; a.o_prog = (unsigned)g.lay.prog; a.o_scat = (unsigned)g.lay.scat; a.o_olut = (unsigned)g.lay.olut;
+  a.o_grad = (unsigned)g.lay.grad; a.o_part = (unsigned)g.lay.part; a.o_prog = (unsigned)g.lay.prog; a.o_scat = (unsigned)g.lay.scat; a.o_olut = (unsigned)g.lay.olut;
   a.buf_stride = (unsigned)g.lay.buf_stride;
   cudaStream_t st = (cudaStream_t)stream;
 #define TQB_DISPATCH(RR)                                             \
@@ -361,6 +326,54 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_kernel(const float2* sta
       if (use_atomic) atomicAdd(dst, s); else *dst = s;
     }
     __syncthreads();
+  }
+}
+
+// Small states (n <= 13: a sample is at most 64 KiB): one WARP per sample, 128-bit loads of amplitude pairs, no
+// block-level synchronisation.  The batched configs (cfg 1/2: thousands of 4-10 qubit samples) spend their read-out
+// here; the block-per-chunk kernel above leaves most lanes idle on them.
+template <int TB>
+__global__ void __launch_bounds__(256) tqb_expval_pauli_warp_kernel(const float2* state, int n, const u64* xm,
+                                                                     const u64* zm, const int* ny, int nterms,
+                                                                     float* out, long long bsz) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (b >= bsz) return;
+  const float4* psi4 = reinterpret_cast<const float4*>(state + (b << n));
+  const u32 npairs = 1u << (n - 1);
+  for (int t0 = 0; t0 < nterms; t0 += TB) {
+    float acc[TB];
+    u32 x[TB], z[TB];
+    int ph[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+      acc[t] = 0.f;
+      const int tt = t0 + t < nterms ? t0 + t : nterms - 1;
+      x[t] = (u32)xm[tt]; z[t] = (u32)zm[tt]; ph[t] = ny[tt] & 3;
+    }
+#pragma unroll 4
+    for (u32 p = lane; p < npairs; p += 32u) {
+      const float4 a = psi4[p];
+#pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        float4 c = x[t] ? psi4[p ^ (x[t] >> 1)] : a;
+        if (x[t] & 1u) c = make_float4(c.z, c.w, c.x, c.y);
+        // w = conj(psi[k^x]) psi[k] for k = 2p, 2p+1
+        const float w0x = fmaf(c.y, a.y, c.x * a.x), w0y = fmaf(-c.y, a.x, c.x * a.y);
+        const float w1x = fmaf(c.w, a.w, c.z * a.z), w1y = fmaf(-c.w, a.z, c.z * a.w);
+        float v0 = (ph[t] == 0) ? w0x : (ph[t] == 1) ? -w0y : (ph[t] == 2) ? -w0x : w0y;
+        float v1 = (ph[t] == 0) ? w1x : (ph[t] == 1) ? -w1y : (ph[t] == 2) ? -w1x : w1y;
+        const u32 par = (u32)__popc((2u * p) & z[t]);
+        if (par & 1u) v0 = -v0;
+        if ((par + (z[t] & 1u)) & 1u) v1 = -v1;
+        acc[t] += v0 + v1;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+      const float s = warp_sum(acc[t]);
+      if (lane == 0 && t0 + t < nterms) out[b * nterms + t0 + t] = s;
+    }
   }
 }
 
@@ -561,6 +574,17 @@ int tqb_expval_pauli(const float* state, int n_qubits, long long bsz, const unsi
   if (bsz > 65535) return fail_msg("tqb_expval_pauli: bsz > 65535");
   const float2* st2 = reinterpret_cast<const float2*>(state);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_qubits >= 1 && n_qubits <= 13 && bsz >= 64) {  // one warp per sample
+    const unsigned blocks = (unsigned)((bsz * 32 + 255) / 256);
+    if (n_terms == 1)
+      tqb_expval_pauli_warp_kernel<1><<<blocks, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, bsz);
+    else if (n_terms <= 4)
+      tqb_expval_pauli_warp_kernel<4><<<blocks, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, bsz);
+    else
+      tqb_expval_pauli_warp_kernel<TQB_TERM_BATCH><<<blocks, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, bsz);
+    TQB_CHECK_LAUNCH("tqb_expval_pauli_warp_kernel");
+    return 0;
+  }
   if (n_terms == 1)
     tqb_expval_pauli_kernel<1><<<grid, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, cl, grid.x > 1);
   else if (n_terms <= 4)

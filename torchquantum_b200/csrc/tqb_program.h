@@ -27,7 +27,7 @@
 #define TQB_SEG_MAX_GROUPS 32
 #define TQB_SEG_MAX_SH 768   // shared matrix floats staged per segment
 #define TQB_SEG_MAX_PS 256   // per-sample matrix floats staged per segment (per sample)
-#define TQB_SEG_MAX_G 256    // gradient floats per segment (per sample)
+#define TQB_SEG_MAX_G 48     // gradient floats per segment (per sample): the backward stages [G][threads + 1] partials
 #define TQB_SEG_MAX_WORDS (TQB_SEG_HDR_WORDS + TQB_SEG_MAX_GROUPS * TQB_GROUP_WORDS + TQB_SEG_MAX_OPS * TQB_OP_WORDS)
 
 // program header words

@@ -18,6 +18,8 @@ __all__ = ["QuantumDevice"]
 
 
 class QuantumDevice(nn.Module):
+    accepts_record_chunks = True  # the queue may hold engine.RecordChunk items (layer templates)
+
     def __init__(self, n_wires: int, device_name: str = "default", bsz: int = 1,
                  device: Union[torch.device, str] = "cpu", record_op: bool = False):
         super().__init__()
@@ -25,9 +27,9 @@ class QuantumDevice(nn.Module):
         self.device_name = device_name
         self.bsz = bsz
         self.device = device
-        _state = torch.zeros(2 ** n_wires, dtype=C_DTYPE)
-        _state[0] = 1 + 0j
-        _state = torch.reshape(_state, [2] * n_wires).to(device)
+        _state = torch.zeros(2 ** n_wires, dtype=C_DTYPE, device=device)  # built on the device: no H2D copy
+        _state[:1].fill_(1)
+        _state = torch.reshape(_state, [2] * n_wires)
         self.register_buffer("state", _state)
         self._queue = []
         self._flat = None
@@ -116,7 +118,7 @@ class QuantumDevice(nn.Module):
 
     def reset_states(self, bsz: int):
         flat = torch.zeros(bsz, 2 ** self.n_wires, dtype=C_DTYPE, device=self.state.device)
-        flat[:, 0] = 1
+        flat[:, 0].fill_(1)  # (a fill kernel; `flat[:, 0] = 1` uploads a host scalar, which a CUDA-graph capture rejects)
         self._set_flat(flat)
 
     def reset_identity_states(self):

@@ -24,11 +24,26 @@ class GeneralEncoder(Encoder):
         super().__init__()
         self.func_list = func_list
 
+    def _columns(self, x, idx):
+        """x[:, idx] without a host->device index upload per call: a consecutive run of columns is a
+        view; any other list goes through a device index tensor cached per device (also keeps the
+        step capturable in a CUDA graph)."""
+        if isinstance(idx, (list, tuple)) and len(idx) > 0 and all(isinstance(i, int) for i in idx):
+            if all(idx[k + 1] == idx[k] + 1 for k in range(len(idx) - 1)) and idx[0] >= 0:
+                return x[:, idx[0]:idx[-1] + 1]
+            cache = self.__dict__.setdefault("_idx_cache", {})
+            key = (tuple(idx), x.device)
+            t = cache.get(key)
+            if t is None:
+                t = cache[key] = torch.tensor(idx, dtype=torch.long, device=x.device)
+            return x.index_select(1, t)
+        return x[:, idx]
+
     @static_support
     def forward(self, qdev, x):
         for info in self.func_list:
             if op_name_dict[info["func"]].num_params > 0:
-                params = x[:, info["input_idx"]]
+                params = self._columns(x, info["input_idx"])
             else:
                 params = None
             func_name_dict[info["func"]](qdev, wires=info["wires"], params=params, static=self.static_mode,

@@ -237,32 +237,71 @@ def _reset(state, n, wires):
     return flat * torch.sqrt(1 / (flat.abs() ** 2).sum(-1)).unsqueeze(-1)
 
 
-def run_circuit(state, n, records, n_total=None, rank=0, inplace=False):
-    """state: [bsz, 2^n] complex64; records: list of (name, wires, params, inverse) with canonical
-    names and normalised params (2-D float tensors, or complex matrices for unitary-like gates).
+class RecordChunk(list):
+    """A run of gate records that a layer template queues unchanged step after step (same Parameter
+    objects, same wires).  The per-record plan keys are cached on the chunk, so a step only re-checks
+    the `requires_grad` flags instead of rebuilding several hundred key tuples."""
+
+    def __init__(self, records):
+        super().__init__(records)
+        self.params = [r[2] for r in records if r[2] is not None]
+        self._keys = {}
+
+    def key_for(self, bsz, grad_mode):
+        flags = [p.requires_grad for p in self.params]
+        hit = self._keys.get((bsz, grad_mode))
+        if hit is not None and hit[0] == flags:
+            return hit[1]
+        key = tuple([_record_key(r, bsz, grad_mode) for r in self])
+        self._keys[(bsz, grad_mode)] = (flags, key)
+        return key
+
+
+def _record_key(record, bsz, grad_mode):
+    name, wires, params, inverse = record
+    pmode, grad, ext_dim = None, False, 0
+    if params is not None:
+        grad = grad_mode and params.requires_grad
+        if name in G.UNITARY_LIKE:
+            pmode, ext_dim = ("extps" if params.dim() == 3 and params.shape[0] == bsz and bsz > 1 else "ext"), \
+                params.shape[-1]
+        else:
+            if params.shape[0] == 1:
+                pmode = "sh"
+            elif params.shape[0] == bsz:
+                pmode = "ps"
+            else:
+                raise RuntimeError(
+                    f"{name}: parameter batch {params.shape[0]} does not match state batch {bsz}")
+            if G.SPECS[name].n_params != params.shape[1]:
+                raise RuntimeError(f"{name}: expected {G.SPECS[name].n_params} parameters, got {params.shape[1]}")
+    return (name, wires, inverse, pmode, grad, ext_dim)
+
+
+def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False):
+    """state: [bsz, 2^n] complex64; queue: list of records (name, wires, params, inverse) with canonical
+    names and normalised params (2-D float tensors, or complex matrices for unitary-like gates), or
+    RecordChunks of such records.
     n_total / rank: sharded statevector (plan.build_plan); inplace: overwrite `state` (no-grad only)."""
     bsz = state.shape[0]
+    chunked = any(type(item) is RecordChunk for item in queue)
+    if chunked:
+        records = []
+        for item in queue:
+            if type(item) is RecordChunk:
+                records.extend(item)
+            else:
+                records.append(item)
+    else:
+        records = queue
     grad_mode = torch.is_grad_enabled() and (
         state.requires_grad or any(r[2] is not None and r[2].requires_grad for r in records))
-    key = []
-    for name, wires, params, inverse in records:
-        pmode, grad, ext_dim = None, False, 0
-        if params is not None:
-            grad = grad_mode and params.requires_grad
-            if name in G.UNITARY_LIKE:
-                pmode, ext_dim = ("extps" if params.dim() == 3 and params.shape[0] == bsz and bsz > 1 else "ext"), \
-                    params.shape[-1]
-            else:
-                if params.shape[0] == 1:
-                    pmode = "sh"
-                elif params.shape[0] == bsz:
-                    pmode = "ps"
-                else:
-                    raise RuntimeError(
-                        f"{name}: parameter batch {params.shape[0]} does not match state batch {bsz}")
-                if G.SPECS[name].n_params != params.shape[1]:
-                    raise RuntimeError(f"{name}: expected {G.SPECS[name].n_params} parameters, got {params.shape[1]}")
-        key.append((name, wires, inverse, pmode, grad, ext_dim))
+    if chunked:
+        key = ()
+        for item in queue:
+            key += item.key_for(bsz, grad_mode) if type(item) is RecordChunk else (_record_key(item, bsz, grad_mode),)
+    else:
+        key = [_record_key(r, bsz, grad_mode) for r in records]
     plan = get_plan(n, tuple(key), grad_mode, n_total)
     for stage in plan.stages:
         if stage.kind == "fused":

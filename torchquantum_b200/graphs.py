@@ -1,0 +1,54 @@
+"""CUDA-graph capture of a whole training step.
+
+A step of a small-qubit batched workload (config 1/2) is a few dozen short kernels; the Python that
+queues 600 gates, walks autograd and accumulates 420 parameter gradients costs more than the kernels
+run.  `GraphedStep` records one forward + backward of `loss_fn` into a CUDA graph (the plan, the gate
+programs and the Pauli masks are already resident after the warm-up steps) and replays it per step:
+inputs are copied into the captured buffers, the loss and the parameters' `.grad` tensors are the
+captured outputs (and `static_inputs[i].grad` for inputs that require grad).  Gate parameters are read from the live `nn.Parameter` storage at replay time, so an
+optimizer stepping them in place between replays works as usual.
+
+The circuit structure, batch size and parameter set must not change between replays (the same
+restriction as `torch.cuda.make_graphed_callables`)."""
+import torch
+
+__all__ = ["GraphedStep"]
+
+
+class GraphedStep:
+    def __init__(self, loss_fn, example_inputs, params, warmup=3):
+        self.params = [p for p in params if p.requires_grad]
+        self.static_inputs = [x.detach().clone().requires_grad_(x.requires_grad) for x in example_inputs]
+        dev = self.static_inputs[0].device
+        assert dev.type == "cuda", "GraphedStep needs CUDA tensors"
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._zero()
+                loss_fn(*self.static_inputs).backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._zero()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = loss_fn(*self.static_inputs)
+            self.loss.backward()
+        self._leaves = self.params + [x for x in self.static_inputs if x.requires_grad]
+        self._grads = [p.grad for p in self._leaves]   # the captured gradient buffers
+
+    def _zero(self):
+        for p in self.params + self.static_inputs:
+            p.grad = None
+
+    def __call__(self, *inputs):
+        """Copy `inputs` (device or pinned host tensors) into the captured buffers, replay the step and
+        return the captured loss tensor; gradients are in the parameters' `.grad`."""
+        with torch.no_grad():
+            for s, x in zip(self.static_inputs, inputs):
+                if x is not s:
+                    s.copy_(x, non_blocking=True)
+        self.graph.replay()
+        for p, g in zip(self._leaves, self._grads):   # survive `zero_grad(set_to_none=True)` between steps
+            if p.grad is not g:
+                p.grad = g
+        return self.loss

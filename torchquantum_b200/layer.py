@@ -15,7 +15,42 @@ __all__ = ["RandomLayer", "RandomLayerAllTypes", "Op1QAllLayer", "Op2QAllLayer",
            "LayerTemplate0", "NLocal", "TwoLocal", "EfficientSU2", "RealAmplitudes", "QFTLayer"]
 
 
-class Op1QAllLayer(QuantumModule):
+class _RecordCache:
+    """Template layers queue the same records (same Parameter objects, wires, inverse flags) every step.
+    `records(q_device)` returns them from a cache that is re-validated by the operators' version
+    counters (any attribute write on an operator bumps its version) and the parameters' device; it
+    returns None whenever some operator needs its full `forward` (noise model, op recording, ...)."""
+
+    def _layer_ops_wires(self):
+        raise NotImplementedError
+
+    def records(self, q_device):
+        if q_device.record_op or not getattr(q_device, "accepts_record_chunks", False):
+            return None
+        dev = q_device._flat.device
+        c = self.__dict__.get("_rec_cache")
+        if c is not None and c[0] == dev:
+            ver = 0
+            for o in c[2]:
+                ver += o.__dict__["_ver"]
+            if ver == c[1] and all(p.device == dev for p in c[4]):
+                return c[3]
+        ops, recs, ver = [], [], 0
+        for o, wires in self._layer_ops_wires():
+            r = o.fast_record(q_device, wires)
+            if r is None:
+                self.__dict__["_rec_cache"] = None
+                return None
+            if wires is not o.wires:
+                o.__dict__["wires"] = wires
+            ops.append(o)
+            recs.append(r)
+            ver += o.__dict__["_ver"]
+        self.__dict__["_rec_cache"] = (dev, ver, ops, recs, [r[2] for r in recs if r[2] is not None])
+        return recs
+
+
+class Op1QAllLayer(QuantumModule, _RecordCache):
     """The same one-qubit operation on every wire (layer/layers/layers.py:71-97)."""
 
     def __init__(self, op, n_wires: int, has_params=False, trainable=False):
@@ -26,13 +61,20 @@ class Op1QAllLayer(QuantumModule):
         for _ in range(n_wires):
             self.ops_all.append(op(has_params=has_params, trainable=trainable))
 
+    def _layer_ops_wires(self):
+        return [(op_k, k) for k, op_k in enumerate(self.ops_all)]
+
     @static_support
     def forward(self, q_device):
+        recs = self.records(q_device)
+        if recs is not None:
+            q_device._queue.extend(recs)
+            return
         for k, op_k in enumerate(self.ops_all):
             op_k.queue_on(q_device, k)
 
 
-class Op2QAllLayer(QuantumModule):
+class Op2QAllLayer(QuantumModule, _RecordCache):
     """The same two-qubit operation on wire pairs [k, k+jump] (layer/entanglement/op2_layer.py:43-110)."""
 
     def __init__(self, op, n_wires: int, has_params=False, trainable=False, wire_reverse=False, jump=1,
@@ -48,12 +90,22 @@ class Op2QAllLayer(QuantumModule):
         for _ in range(n_ops):
             self.ops_all.append(op(has_params=has_params, trainable=trainable))
 
-    @static_support
-    def forward(self, q_device):
+    def _layer_ops_wires(self):
+        out = []
         for k, op_k in enumerate(self.ops_all):
             wires = [k, (k + self.jump) % self.n_wires]
             if self.wire_reverse:
                 wires.reverse()
+            out.append((op_k, wires))
+        return out
+
+    @static_support
+    def forward(self, q_device):
+        recs = self.records(q_device)
+        if recs is not None:
+            q_device._queue.extend(recs)
+            return
+        for op_k, wires in self._layer_ops_wires():
             op_k.queue_on(q_device, wires)
 
 
@@ -181,9 +233,32 @@ class LayerTemplate0(QuantumModule):
     def build_layers(self):
         raise NotImplementedError
 
+    def _chunk(self, q_device):
+        """All layers' records as one engine.RecordChunk when every layer is a cacheable template."""
+        parts = []
+        for layer in self.layers_all:
+            if not isinstance(layer, _RecordCache) or layer._forward_hooks or layer._forward_pre_hooks:
+                return None
+            recs = layer.records(q_device)
+            if recs is None:
+                return None
+            parts.append(recs)
+        c = self.__dict__.get("_chunk_cache")
+        if c is not None and len(c[0]) == len(parts) and all(a is b for a, b in zip(c[0], parts)):
+            return c[1]
+        from .engine import RecordChunk
+
+        chunk = RecordChunk([r for recs in parts for r in recs])
+        self.__dict__["_chunk_cache"] = (parts, chunk)
+        return chunk
+
     @static_support
     def forward(self, q_device):
         self.q_device = q_device
+        chunk = self._chunk(q_device)
+        if chunk is not None:
+            q_device._queue.append(chunk)
+            return
         for k in range(len(self.layers_all)):
             self.layers_all[k](q_device)
 

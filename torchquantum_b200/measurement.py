@@ -51,7 +51,7 @@ _MASK_CACHE = {}
 
 
 def _mask_tensors(observables, device):
-    key = (tuple(observables), str(device))
+    key = (tuple(observables), device)
     t = _MASK_CACHE.get(key)
     if t is None:
         ms = [pauli_masks(o) for o in observables]
@@ -65,9 +65,46 @@ def _mask_tensors(observables, device):
     return t
 
 
+class _Pending:
+    """Backward work shared by every Pauli read-out of one state tensor: each read-out's backward only
+    files its (observables, dL/d<P>) here; the state's hub node then produces dL/dpsi for all of them in
+    ONE kernel launch (instead of one launch, one 2^n-sized temporary and one autograd add per string)."""
+    __slots__ = ("obs", "gouts")
+
+    def __init__(self):
+        self.obs, self.gouts = [], []
+
+
+class _StateHubFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, n, pending):
+        ctx.n, ctx.pending = n, pending
+        ctx.save_for_backward(state)
+        ctx.set_materialize_grads(False)
+        return state.view_as(state)
+
+    @staticmethod
+    def backward(ctx, g):
+        pend = ctx.pending
+        if not pend.obs:
+            return g, None, None
+        (state,) = ctx.saved_tensors
+        obs, gouts = pend.obs, pend.gouts
+        pend.obs, pend.gouts = [], []
+        xm, zm, ny = _mask_tensors(obs, state.device)
+        gout = (gouts[0] if len(gouts) == 1 else torch.cat(gouts, dim=1)).contiguous()
+        grad = torch.empty_like(state)
+        _native.call("tqb_expval_pauli_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(xm), _ptr(zm), _ptr(ny),
+                     xm.shape[0], _ptr(gout), _ptr(grad), _native.stream_ptr(state))
+        STATS["launches"] += 1
+        if g is not None:
+            grad += g
+        return grad, None, None
+
+
 class _ExpvalPauliFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, state, n, xm, zm, ny):
+    def forward(ctx, state, n, xm, zm, ny, observables, pending):
         _native.check_device(state)
         state = state.contiguous()
         bsz, nt = state.shape[0], xm.shape[0]
@@ -76,19 +113,34 @@ class _ExpvalPauliFn(torch.autograd.Function):
         _native.call("tqb_expval_pauli", _ptr(state), n, bsz, _ptr(xm), _ptr(zm), _ptr(ny), nt, _ptr(out),
                      _native.stream_ptr(state))
         STATS["launches"] += 1
-        ctx.save_for_backward(state, xm, zm, ny)
-        ctx.n = n
+        ctx.n, ctx.pending, ctx.observables = n, pending, observables
+        if pending is None:
+            ctx.save_for_backward(state, xm, zm, ny)
         return out
 
     @staticmethod
     def backward(ctx, gout):
+        if ctx.pending is not None:  # the state's hub node runs the kernel for all read-outs at once
+            ctx.pending.obs.extend(ctx.observables)
+            ctx.pending.gouts.append(gout)
+            return None, None, None, None, None, None, None
         state, xm, zm, ny = ctx.saved_tensors
         gout = gout.contiguous()
         grad = torch.empty_like(state)
         _native.call("tqb_expval_pauli_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(xm), _ptr(zm), _ptr(ny),
                      xm.shape[0], _ptr(gout), _ptr(grad), _native.stream_ptr(state))
         STATS["launches"] += 1
-        return grad, None, None, None, None
+        return grad, None, None, None, None, None, None
+
+
+def _hub(qdev, states):
+    """(view of `states`, pending list) of the hub node of this state tensor (one per tensor)."""
+    h = qdev.__dict__.get("_expval_hub")
+    if h is None or h[0] is not states:
+        pend = _Pending()
+        h = (states, _StateHubFn.apply(states, qdev.n_wires, pend), pend)
+        qdev.__dict__["_expval_hub"] = h
+    return h[1], h[2]
 
 
 class _ExpvalZFn(torch.autograd.Function):
@@ -123,7 +175,10 @@ def expval_joint_analytical_multi(qdev, observables: List[str]):
         return qdev.expval_pauli(list(observables))
     states = qdev.get_states_1d()
     xm, zm, ny = _mask_tensors(observables, states.device)
-    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny)
+    pending = None
+    if torch.is_grad_enabled() and states.requires_grad:
+        states, pending = _hub(qdev, states)
+    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny, tuple(o.upper() for o in observables), pending)
 
 
 def expval_joint_analytical(qdev, observable: str):

@@ -123,20 +123,28 @@ class Operator(QuantumModule):
             for noise_op in noise.sample_noise_op(self):
                 noise_op(q_device)
 
-    def queue_on(self, q_device, wires):
-        """Hot path for this package's own layer templates: same effect as `self(q_device, wires=wires)`
-        for a catalogue gate with 2-D (or no) parameters when no noise model, static graph or op
-        recording is involved; anything else goes through the full `forward`."""
+    def fast_record(self, q_device, wires):
+        """The queue record `(name, wires, params, inverse)` of this operator on `wires`, or None when the
+        full `forward` has to run (noise model, op recording, unusual parameters, non-catalogue gate)."""
         p = self.params
         cname = self._fast_cname
         if (cname is None or self.noise_model_tq is not None or q_device.record_op
                 or (p is not None and (p.dim() != 2 or p.device != q_device._flat.device))):
+            return None
+        wires_t = (int(wires),) if isinstance(wires, (int, np.integer)) else tuple([int(w) for w in wires])
+        return (cname, wires_t, p, bool(self.inverse))
+
+    def queue_on(self, q_device, wires):
+        """Hot path for this package's own layer templates: same effect as `self(q_device, wires=wires)`
+        for a catalogue gate with 2-D (or no) parameters when no noise model, static graph or op
+        recording is involved; anything else goes through the full `forward`."""
+        rec = self.fast_record(q_device, wires)
+        if rec is None:
             self(q_device, wires=wires)
             return
         if wires is not self.wires:
             self.__dict__["wires"] = wires
-        wires_t = (int(wires),) if isinstance(wires, (int, np.integer)) else tuple([int(w) for w in wires])
-        q_device._queue.append((cname, wires_t, p, bool(self.inverse)))
+        q_device._queue.append(rec)
 
     @property
     def _fast_cname(self):
@@ -155,11 +163,20 @@ class Operator(QuantumModule):
     def __repr__(self):
         return f" class: {self.name} \n parameters: {self.params} \n wires: {self.wires} \n inverse: {self.inverse}"
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() may swap Parameter objects without going through __setattr__
+        self.__dict__["_ver"] = self.__dict__.get("_ver", 0) + 1
+        return super()._apply(fn, *args, **kwargs)
+
     _PLAIN_ATTRS = frozenset(("wires", "inverse", "n_wires", "static_matrix", "clifford_quantization"))
 
     def __setattr__(self, name, value):
+        # every attribute write bumps the operator's version: layer templates cache the records they queue
+        # and re-validate them by version (layer._RecordCache)
+        d = self.__dict__
+        d["_ver"] = d.get("_ver", 0) + 1
         if name in Operator._PLAIN_ATTRS:  # plain python state: skip nn.Module's type dispatch
-            self.__dict__[name] = value
+            d[name] = value
             return
         # nn.Module would refuse to overwrite a registered Parameter with a plain tensor
         if name == "params" and "_parameters" in self.__dict__ and "params" in self._parameters \

@@ -427,8 +427,17 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         flat = []
         for reg, part in groups:
             regs = _fill_registers(T, R, tuple(reg))
-            for i in range(0, max(len(part), 1), C.SEG_MAX_OPS):
-                flat.append((regs, part[i:i + C.SEG_MAX_OPS]))
+            # a chunk of a group must fit one segment's staging capacity on its own
+            chunk, use = [], [0, 0, 0, 0]
+            for op in part:
+                need = [1, 0 if op.per_sample else op.nfloat, op.nfloat if op.per_sample else 0, op.ngrad]
+                if chunk and (use[0] + 1 > C.SEG_MAX_OPS or use[1] + need[1] > C.SEG_MAX_SH
+                              or use[2] + need[2] > C.SEG_MAX_PS or use[3] + need[3] > C.SEG_MAX_G):
+                    flat.append((regs, chunk))
+                    chunk, use = [], [0, 0, 0, 0]
+                chunk.append(op)
+                use = [a + b for a, b in zip(use, need)]
+            flat.append((regs, chunk))
         segments, cur, tot = [], [], [0, 0, 0, 0]
         for regs, part in flat:
             need = [len(part), sum(op.nfloat for op in part if not op.per_sample),
