@@ -286,3 +286,56 @@ def check_cfg3_qaoa(device, n=8, p=3, bsz=4, edges=QAOA_EDGES_8):
     gbc, ggc = torch.autograd.grad(cost_cpu.sum(), [bc, gc])
     assert_close(gb, gbc, rtol=1e-4, what="cfg3 grad beta")
     assert_close(gg, ggc, rtol=1e-4, what="cfg3 grad gamma")
+
+
+def special_angle_ops(n, bsz):
+    """rx / ry / rz / h / cnot mix with the angles where the scaled forms switch mode (|cos| vs |sin| of theta/2):
+    0, pi/2, pi, 3pi/2, 2pi, negative, per-sample columns mixing both modes."""
+    angles = [0.0, np.pi / 2, np.pi, 1.5 * np.pi, 2 * np.pi, -np.pi, -0.5 * np.pi, 1e-4, np.pi - 1e-4, 3.0]
+    rng = np.random.default_rng(4)
+    ops = []
+    for k, a in enumerate(angles * 3):
+        name = ["rx", "ry", "rz"][k % 3]
+        w = int(rng.integers(n))
+        if k % 4 == 3 and bsz > 1:
+            col = np.array([angles[(k + j) % len(angles)] for j in range(bsz)], dtype=np.float32).reshape(bsz, 1)
+            ops.append({"name": name, "wires": [w], "params": torch.tensor(col)})
+        else:
+            ops.append({"name": name, "wires": [w], "params": torch.tensor([[a]], dtype=torch.float32),
+                        "inverse": bool(k % 5 == 4)})
+        if k % 2:
+            ops.append({"name": "hadamard", "wires": [int(rng.integers(n))]})
+        c, t = rng.choice(n, size=2, replace=False)
+        ops.append({"name": "cnot", "wires": [int(c), int(t)]})
+        if k % 3 == 0:
+            ops.append({"name": ["s", "t", "pauliz", "u1"][k % 4], "wires": [int(t)],
+                        **({"params": torch.tensor([[0.3 * k]], dtype=torch.float32)} if k % 4 == 3 else {})})
+    return ops
+
+
+def check_forward_only_forms(device, n=7, bsz=3):
+    """Forward-only programs (scaled rx/ry/h/one-bit diagonals, CNOTs folded into the preceding gate) vs the oracle."""
+    from torchquantum_b200 import engine
+
+    for ops in (special_angle_ops(n, bsz), brickwork_ops(n, 6, seed=9), brickwork_ops(n, 4, seed=10, per_sample_bsz=bsz)):
+        with torch.no_grad():
+            check_against_oracle(device, n, bsz, ops, grad=False)
+    # the planner really emitted the forms under test
+    from torchquantum_b200 import _codes as C
+    key = tuple((o["name"], tuple(o["wires"]), False, "sh" if "params" in o else None, False, 0)
+                for o in brickwork_ops(n, 6, seed=9))
+    plan = engine.get_plan(n, key, False)
+    types, postx = set(), 0
+    for st in plan.stages:
+        for pp in st.passes:
+            w = pp.prog
+            for si in range(w[C.H_NSEG]):
+                off = w[C.H_SEGOFF + si]
+                ng, nops = w[off + C.S_NGROUPS], w[off + C.S_NOPS]
+                base = off + C.SEG_HDR_WORDS + ng * C.GROUP_WORDS
+                for k in range(nops):
+                    w0 = int(w[base + k * C.OP_WORDS]) & 0xFFFFFFFF
+                    types.add((w0 >> 2) & 15)
+                    postx += bool(w0 & C.F_POSTX)
+    assert {C.T_RXS, C.T_RYS, C.T_DIAGS} <= types, types
+    assert postx > 0, "no CNOT was folded"

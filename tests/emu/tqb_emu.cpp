@@ -81,6 +81,7 @@ static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float*
   c.psi_src = reinterpret_cast<const float2*>(psi_src); c.lam_src = reinterpret_cast<const float2*>(lam_src);
   c.msh = msh; c.mps = mps; c.gr = gr; c.mps_stride = mps_stride; c.gr_stride = gr_stride;
   c.ps_cap = (ps_max + 3) & ~3; c.g_cap = (g_max + 3) & ~3;
+  c.scale_sh = prog[TQB_H_SCALE_SH]; c.scale_ps = prog[TQB_H_SCALE_PS];
 #define TQB_DISPATCH(RR) \
   case RR: if (bwd) emu_blocks<RR, true>(c, n, g, ext_hi); else emu_blocks<RR, false>(c, n, g, ext_hi); return 0;
   switch (R) { TQB_DISPATCH(1) TQB_DISPATCH(2) TQB_DISPATCH(3) TQB_DISPATCH(4) }
@@ -108,10 +109,10 @@ int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi, fl
 
 int tqb_build_mats(const int32_t* table, int nrec, int n_sh, long long bsz, const float* psh, const float* pps,
                    int ps_stride, const float* consts, float* msh, float* mps, long long mps_stride, void*) {
-  for (int r = 0; r < n_sh; ++r) build_one(table + r * TQB_B_WORDS, 0, psh, pps, ps_stride, consts, msh);
+  for (int r = 0; r < n_sh; ++r) build_one(table + r * TQB_B_WORDS, 0, psh, pps, ps_stride, consts, msh, table);
   for (long long b = 0; b < bsz; ++b)
     for (int r = n_sh; r < nrec; ++r)
-      build_one(table + r * TQB_B_WORDS, b, psh, pps, ps_stride, consts, mps + b * mps_stride);
+      build_one(table + r * TQB_B_WORDS, b, psh, pps, ps_stride, consts, mps + b * mps_stride, table);
   return 0;
 }
 int tqb_build_mats_bwd(const int32_t* table, int nrec, long long bsz, const float* psh, const float* pps,

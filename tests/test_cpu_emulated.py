@@ -107,3 +107,13 @@ def test_cfg2_vqe_class_api_record_cache():
 
 def test_cfg3_qaoa_per_sample_params():
     cases.check_cfg3_qaoa("cpu", n=6, p=2, bsz=3, edges=[(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 0), (0, 3)])
+
+
+def test_forward_only_forms():
+    cases.check_forward_only_forms("cpu")
+
+
+@pytest.mark.parametrize("tiles", [(4, 5, 2), (5, 6, 3)])
+def test_forward_only_forms_multi_tile(tiles):
+    P.T_SINGLE, P.T_MULTI, P.L_MIN = tiles
+    cases.check_forward_only_forms("cpu", n=8, bsz=2)

@@ -113,6 +113,21 @@ def test_cfg3_qaoa_n14_streamed():
     cases.check_cfg3_qaoa(DEV, n=n, p=2, bsz=2, edges=edges)
 
 
+def test_forward_only_forms():
+    """Scaled rx/ry/h/one-bit diagonals + folded CNOTs (programs without a backward) vs the oracle: one tile per
+    sample, forced small tiles, and a really streamed state (n=15, T=12)."""
+    from torchquantum_b200 import plan as P
+
+    cases.check_forward_only_forms(DEV)
+    cases.check_forward_only_forms(DEV, n=15, bsz=2)
+    saved = (P.T_SINGLE, P.T_MULTI, P.L_MIN)
+    try:
+        P.T_SINGLE, P.T_MULTI, P.L_MIN = 5, 6, 3
+        cases.check_forward_only_forms(DEV, n=9, bsz=2)
+    finally:
+        P.T_SINGLE, P.T_MULTI, P.L_MIN = saved
+
+
 def test_per_sample_params_large_batch():
     ops = cases.brickwork_ops(6, 6, seed=1, per_sample_bsz=300)
     cases.check_against_oracle(DEV, 6, 300, ops, grad=True)

@@ -27,6 +27,7 @@
 #define TQB_FMA(a, b, c) ((a) * (b) + (c))
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -51,6 +52,8 @@ TQB_FN float2 cfma2(float2 m0, float2 a, float2 m1, float2 b) {
   return make_float2(re, im);
 }
 TQB_FN float4 ld4(const float* m) { return *reinterpret_cast<const float4*>(m); }
+// an op's staged matrix: pointer + its first four floats, fetched one op ahead of use (run_group)
+struct Mat { const float* p; float4 q0; };
 
 // swizzled position of tile-local amplitude idx in the staged tile (8-byte slots):
 // xor the 4 low bits with the next 4 so that the 16 amplitudes a half-warp touches in one
@@ -79,6 +82,7 @@ struct BlockCtx {
   // staged (shared) memory
   float2* s_psi; float2* s_lam; float* s_msh; float* s_mps; float* s_grad; int32_t* s_prog; u64* s_scat;
   float* s_part;           // backward: per-thread gradient partials [g_cap][nthreads + 1]
+  int scale_sh, scale_ps;  // float offsets of the pass's deferred scale factor in msh / mps rows (-1: none)
   u64* s_olut;             // [3][256]: amplitude offset contributed by byte j of the tile id (streamed states only)
 };
 
@@ -140,6 +144,18 @@ TQB_FN void load_tile_async(Exec& ex, const BlockCtx& c, int tid, const float2* 
     ex.async_copy8(dst + swz(idx), src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
 }
 
+// deferred scale factor of the pass for sample b (scaled op forms, csrc/tqb_program.h)
+TQB_FN bool pass_scale(const BlockCtx& c, int b, float2& f) {
+  if (c.scale_sh < 0 && c.scale_ps < 0) return false;
+  f = make_float2(1.f, 0.f);
+  if (c.scale_sh >= 0) f = make_float2(c.msh[c.scale_sh], c.msh[c.scale_sh + 1]);
+  if (c.scale_ps >= 0) {
+    const float* p = c.mps + (long long)b * c.mps_stride + c.scale_ps;
+    f = cmul(f, make_float2(p[0], p[1]));
+  }
+  return true;
+}
+
 TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   const int slot = tid / c.tps, t = tid % c.tps;
   const int b = c.sample0 + slot;
@@ -148,12 +164,22 @@ TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   const float2* src = s + (size_t)slot * tile;
   const u32 lowmask = (1u << c.L) - 1u;
   float2* dst = g + (u64)b * c.sample_stride + c.outer_off;
+  float2 f;
+  const bool scaled = pass_scale(c, b, f);
   if (c.tps == 256 && c.L >= 1) {
     // pair p = t + 256 k covers idx = 2p, 2p + 1 = 2t + 512 k (+1): swz(idx) = swz(2t) + 512 k
     const u32 s0 = swz(2u * (u32)t);
     const float2* src_a = src + s0;
     const float2* src_b = src + (s0 ^ 1u);
     float2* dst_t = dst + ((2u * (u32)t) & lowmask);
+    if (scaled) {
+#pragma unroll 4
+      for (u32 k = 0; k < tile; k += 512u) {
+        const float2 a = cmul(f, src_a[k]), bq = cmul(f, src_b[k]);
+        *reinterpret_cast<float4*>(dst_t + ((k & lowmask) + c.s_scat[(2u * (u32)t + k) >> c.L])) = make_float4(a.x, a.y, bq.x, bq.y);
+      }
+      return;
+    }
 #pragma unroll 4
     for (u32 k = 0; k < tile; k += 512u) {
       const float2 a = src_a[k], bq = src_b[k];
@@ -163,11 +189,16 @@ TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   }
   if (c.L >= 1) {
     for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps) {
-      const float2 a = src[swz(idx)], bq = src[swz(idx + 1)];
+      float2 a = src[swz(idx)], bq = src[swz(idx + 1)];
+      if (scaled) { a = cmul(f, a); bq = cmul(f, bq); }
       *reinterpret_cast<float4*>(dst + ((idx & lowmask) + c.s_scat[idx >> c.L])) = make_float4(a.x, a.y, bq.x, bq.y);
     }
   } else {
-    for (u32 idx = t; idx < tile; idx += c.tps) dst[c.s_scat[idx]] = src[swz(idx)];
+    for (u32 idx = t; idx < tile; idx += c.tps) {
+      float2 a = src[swz(idx)];
+      if (scaled) a = cmul(f, a);
+      dst[c.s_scat[idx]] = a;
+    }
   }
 }
 
@@ -287,10 +318,82 @@ TQB_FN void cmul_inplace(float2 d, float2& v) {
   v = make_float2(r, TQB_FMA(d.x, v.y, t));
 }
 
+// ---- scaled forms: one FMA per float; the common factor goes to the pass's deferred scale -------------
+// mode 0: [[1, -ir], [-ir, 1]]   mode 1: [[ir, 1], [1, ir]]
+template <int MODE>
+TQB_FN void pair_rxs(float2& a, float2& b, float r) {
+  if (MODE == 0) {
+    const float ax = TQB_FMA(r, b.y, a.x), ay = TQB_FMA(-r, b.x, a.y);
+    b = make_float2(TQB_FMA(r, a.y, b.x), TQB_FMA(-r, a.x, b.y));
+    a = make_float2(ax, ay);
+  } else {
+    const float ax = TQB_FMA(-r, a.y, b.x), ay = TQB_FMA(r, a.x, b.y);
+    b = make_float2(TQB_FMA(-r, b.y, a.x), TQB_FMA(r, b.x, a.y));
+    a = make_float2(ax, ay);
+  }
+}
+// mode 0: [[1, -r], [r, 1]]   mode 1: [[r, -1], [1, r]]
+template <int MODE>
+TQB_FN void pair_rys(float2& a, float2& b, float r) {
+  if (MODE == 0) {
+    const float ax = TQB_FMA(-r, b.x, a.x), ay = TQB_FMA(-r, b.y, a.y);
+    b = make_float2(TQB_FMA(r, a.x, b.x), TQB_FMA(r, a.y, b.y));
+    a = make_float2(ax, ay);
+  } else {
+    const float ax = TQB_FMA(r, a.x, -b.x), ay = TQB_FMA(r, a.y, -b.y);
+    b = make_float2(TQB_FMA(r, b.x, a.x), TQB_FMA(r, b.y, a.y));
+    a = make_float2(ax, ay);
+  }
+}
+TQB_FN void pair_hs(float2& a, float2& b) {
+  const float2 t = a;
+  a = make_float2(t.x + b.x, t.y + b.y);
+  b = make_float2(t.x - b.x, t.y - b.y);
+}
+
+// f(a, b) on every pair of register bit J; JC >= 0: a CNOT controlled by register bit JC on this bit is folded
+// in, i.e. the pair's outputs are exchanged where bit JC of e is set (compile-time: pure register renaming)
+template <int R, int J, int JC, class F>
+TQB_FN void for_pairs(float2 (&x)[1 << R], F f) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    float2 a = x[e], b = x[e | (1 << J)];
+    f(a, b);
+    const bool sw = JC >= 0 && ((e >> (JC >= 0 ? JC : 0)) & 1);
+    x[e] = sw ? b : a;
+    x[e | (1 << J)] = sw ? a : b;
+  }
+}
+
+// scaled / CNOT-folding forward ops (KIND: TQB_T_RXS, TQB_T_RYS, TQB_T_HS, TQB_T_DIAGS with F_DJ, TQB_T_REAL)
+template <int R, int J, int JC, int KIND>
+TQB_FN void fast1q(float2 (&x)[1 << R], const Mat& m) {
+  if constexpr (KIND == TQB_T_HS) {
+    for_pairs<R, J, JC>(x, [](float2& a, float2& b) { pair_hs(a, b); });
+  } else {
+    const float4 q = m.q0;
+    if constexpr (KIND == TQB_T_RXS) {
+      const float r = q.z;
+      if (q.w == 0.f) for_pairs<R, J, JC>(x, [r](float2& a, float2& b) { pair_rxs<0>(a, b, r); });
+      else for_pairs<R, J, JC>(x, [r](float2& a, float2& b) { pair_rxs<1>(a, b, r); });
+    } else if constexpr (KIND == TQB_T_RYS) {
+      const float r = q.z;
+      if (q.w == 0.f) for_pairs<R, J, JC>(x, [r](float2& a, float2& b) { pair_rys<0>(a, b, r); });
+      else for_pairs<R, J, JC>(x, [r](float2& a, float2& b) { pair_rys<1>(a, b, r); });
+    } else if constexpr (KIND == TQB_T_DIAGS) {
+      const float2 rel = make_float2(q.x, q.y);
+      for_pairs<R, J, JC>(x, [rel](float2&, float2& b) { cmul_inplace(rel, b); });
+    } else {  // TQB_T_REAL
+      for_pairs<R, J, JC>(x, [q](float2& a, float2& b) { pair_real(a, b, q.x, q.y, q.z, q.w); });
+    }
+  }
+}
+
 template <int R, int J, int KIND, bool MASKED, bool ADJ>
-TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
+TQB_FN void u1q(float2 (&x)[1 << R], const Mat& m, u32 act) {
   if constexpr (KIND == TQB_T_GEN) {
-    const float4 q0 = ld4(m), q1 = ld4(m + 4);
+    const float4 q0 = m.q0, q1 = ld4(m.p + 4);
     float2 m00 = make_float2(q0.x, q0.y), m01 = make_float2(q0.z, q0.w);
     float2 m10 = make_float2(q1.x, q1.y), m11 = make_float2(q1.z, q1.w);
     if (ADJ) {
@@ -303,7 +406,7 @@ TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
       if (!MASKED || ((act >> e) & 1u)) pair_gen(x[e], x[e | (1 << J)], m00, m01, m10, m11);
     }
   } else if constexpr (KIND == TQB_T_REAL) {
-    const float4 q = ld4(m);
+    const float4 q = m.q0;
     const float m00 = q.x, m01 = ADJ ? q.z : q.y, m10 = ADJ ? q.y : q.z, m11 = q.w;
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
@@ -311,7 +414,7 @@ TQB_FN void u1q(float2 (&x)[1 << R], const float* m, u32 act) {
       if (!MASKED || ((act >> e) & 1u)) pair_real(x[e], x[e | (1 << J)], m00, m01, m10, m11);
     }
   } else {  // TQB_T_RX
-    const float4 q = ld4(m);
+    const float4 q = m.q0;
     const float cc = q.x, s = ADJ ? -q.y : q.y;
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
@@ -357,7 +460,8 @@ TQB_FN void diagj(float2 (&x)[1 << R], float2 dA, float2 dB, u32 act) {
 
 // 4x4 on register bits (1,0): quad index q = 2*bit1 + bit0
 template <int R, bool ADJ>
-TQB_FN void u2q(float2 (&x)[1 << R], const float* m, u32 act) {
+TQB_FN void u2q(float2 (&x)[1 << R], const Mat& mm, u32 act) {
+  const float* m = mm.p;
 #pragma unroll
   for (int e = 0; e < (1 << R); e += 4) {
     if ((act >> e) & 1u) {
@@ -499,6 +603,18 @@ TQB_FN void sort_positions(u32 (&sp)[R]) {
     if constexpr (R > 3) { if ((j) == 3) { constexpr int JJ = 3; CALL; } } \
   } while (0)
 
+// JJ from j, then CC from the folded CNOT's control register bit (CC = -1: none); j == jc never occurs
+#define TQB_DISPATCH_JC(j, postx, jc, CALL)                                                          \
+  TQB_DISPATCH_J(j, do {                                                                             \
+    if (!(postx)) { constexpr int CC = -1; CALL; }                                                   \
+    else {                                                                                           \
+      if constexpr (JJ != 0) { if ((jc) == 0) { constexpr int CC = 0; CALL; } }                      \
+      if constexpr (R > 1 && JJ != 1) { if ((jc) == 1) { constexpr int CC = 1; CALL; } }             \
+      if constexpr (R > 2 && JJ != 2) { if ((jc) == 2) { constexpr int CC = 2; CALL; } }             \
+      if constexpr (R > 3 && JJ != 3) { if ((jc) == 3) { constexpr int CC = 3; CALL; } }             \
+    }                                                                                                \
+  } while (0))
+
 #define TQB_CASES_J(TYPE, CALL)                                                                   \
   case TQB_OP_CODE(TYPE, 0): { constexpr int JJ = 0; CALL; } break;                                \
   case TQB_OP_CODE(TYPE, 1): if constexpr (R > 1) { constexpr int JJ = 1; CALL; } break;           \
@@ -507,8 +623,8 @@ TQB_FN void sort_positions(u32 (&sp)[R]) {
 
 // forward op, in place on the thread's register array (TQB_FWD_MODE 0: if-chain, 1: switch)
 template <int R, class Exec>
-TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const int32_t* op, u32 base, const float* smps) {
-  const u32 w0 = (u32)op[TQB_OP_W0];
+TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const int4 h, const Mat& m, const int32_t* op, u32 base) {
+  const u32 w0 = (u32)h.x;
   if (w0 & TQB_F_OCTRL) {
     if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
   }
@@ -517,10 +633,9 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
   const bool masked = w0 & (TQB_F_TCTRL | TQB_F_RCTRL);
   u32 act = 0xffffu;
   if (masked) {
-    act = (u32)op[TQB_OP_EMASK] & 0xffffu;
+    act = (u32)h.z & 0xffffu;
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
   }
-  const float* m = ((w0 & TQB_F_PS) ? smps : c.s_msh) + op[TQB_OP_SLOT];
 #if TQB_FWD_MODE == 1
   switch (w0 & 63u) {
     TQB_CASES_J(TQB_T_REAL, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)))
@@ -529,11 +644,11 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
     TQB_CASES_J(TQB_T_PERM, (perm<R, JJ>(x, act)))
     case TQB_OP_CODE(TQB_T_DIAG, 0): case TQB_OP_CODE(TQB_T_DIAG, 1): case TQB_OP_CODE(TQB_T_DIAG, 2):
     case TQB_OP_CODE(TQB_T_DIAG, 3): {
-      const float4 q = ld4(m);
-      const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+      const float4 q = m.q0;
+      const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
       const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
-      if (masked) diag<R, true>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)op[TQB_OP_EMASK] >> 16, act);
-      else diag<R, false>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)op[TQB_OP_EMASK] >> 16, act);
+      if (masked) diag<R, true>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)h.z >> 16, act);
+      else diag<R, false>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)h.z >> 16, act);
     } break;
     case TQB_OP_CODE(TQB_T_U2Q, 0):
       if constexpr (R >= 2) u2q<R, false>(x, m, act);
@@ -541,16 +656,44 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
     default: TQB_UNREACHABLE(); break;
   }
 #else
+  if (type >= TQB_T_RXS || (w0 & TQB_F_POSTX)) {
+    // scaled forms and ops with a folded CNOT (programs without a backward)
+    const bool postx = w0 & TQB_F_POSTX;
+    const int jc = TQB_OP_JC(w0);
+    if (type == TQB_T_RXS) {
+      TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_RXS>(x, m)));
+    } else if (type == TQB_T_RYS) {
+      TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_RYS>(x, m)));
+    } else if (type == TQB_T_DIAGS) {
+      if (w0 & TQB_F_DJ) {
+        TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_DIAGS>(x, m)));
+      } else {
+        // the bit lives outside the registers: the thread's 2^R amplitudes all share its value
+        const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+        if (tp) {
+          const float4 q = m.q0;
+          const float2 rel = make_float2(q.x, q.y);
+#pragma unroll
+          for (int e = 0; e < (1 << R); ++e) cmul_inplace(rel, x[e]);
+        }
+      }
+    } else if (type == TQB_T_HS) {
+      TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_HS>(x, m)));
+    } else {  // TQB_T_REAL with a folded CNOT
+      TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_REAL>(x, m)));
+    }
+    return;
+  }
   if (type == TQB_T_REAL) {
     TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)));
   } else if (type == TQB_T_RX) {
     TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_RX, false, false>(x, m, act)));
   } else if (type == TQB_T_DIAG) {
-    const float4 q = ld4(m);
-    const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+    const float4 q = m.q0;
+    const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
     const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
     const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
-    const u32 epar = (u32)op[TQB_OP_EMASK] >> 16;
+    const u32 epar = (u32)h.z >> 16;
     if (w0 & TQB_F_DJ) {
       if (masked) { if (act) TQB_DISPATCH_J(j, (diagj<R, JJ, true>(x, dA, dB, act))); }
       else TQB_DISPATCH_J(j, (diagj<R, JJ, false>(x, dA, dB, act)));
@@ -569,13 +712,12 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
 
 // backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in
 template <int R, bool MASKED, class Exec>
-TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
-                     u32 w0, u32 act, u32 base, const float* smps, float* spart, int pstride) {
+TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int4 h, const Mat& m,
+                     const int32_t* op, u32 w0, u32 act, u32 base, float* spart, int pstride) {
   const u32 type = TQB_OP_TYPE(w0);
   const int j = TQB_OP_J(w0);
   const u32 gkind = TQB_OP_GKIND(w0);
   const bool unapply = !(w0 & TQB_F_NOUNAPPLY);
-  const float* m = ((w0 & TQB_F_PS) ? smps : c.s_msh) + op[TQB_OP_SLOT];
   const int gslot = op[TQB_OP_GSLOT];
   if (type == TQB_T_REAL || type == TQB_T_RX || type == TQB_T_GEN) {
     float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -594,11 +736,11 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
     if (gkind == TQB_G_FULL) stash<8>(spart, pstride, gslot, gacc);
     else if (gkind != TQB_G_NONE) { float w1[1] = {w}; stash<1>(spart, pstride, gslot, w1); }
   } else if (type == TQB_T_DIAG) {
-    const float4 q = ld4(m);
-    const u32 tp = (u32)(__popc(base & (u32)op[TQB_OP_PM_T]) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+    const float4 q = m.q0;
+    const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
     const float2 d0 = make_float2(q.x, -q.y), d1 = make_float2(q.z, -q.w);  // conjugated
     const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
-    const u32 epar = (u32)op[TQB_OP_EMASK] >> 16;
+    const u32 epar = (u32)h.z >> 16;
     if (w0 & TQB_F_DJ) {
       if (!MASKED || act) {
         if (unapply) TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(x, dA, dB, act)));
@@ -638,18 +780,18 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
 }
 
 template <int R, class Exec>
-TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int32_t* op,
-                         u32 base, const float* smps, float* spart, int pstride) {
-  const u32 w0 = (u32)op[TQB_OP_W0];
+TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int4 h, const Mat& m,
+                         const int32_t* op, u32 base, float* spart, int pstride) {
+  const u32 w0 = (u32)h.x;
   if (w0 & TQB_F_OCTRL) {
     if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
   }
   if (w0 & (TQB_F_TCTRL | TQB_F_RCTRL)) {
-    u32 act = (u32)op[TQB_OP_EMASK] & 0xffffu;
+    u32 act = (u32)h.z & 0xffffu;
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
-    bwd_body<R, true, Exec>(ex, c, x, y, op, w0, act, base, smps, spart, pstride);
+    bwd_body<R, true, Exec>(ex, c, x, y, h, m, op, w0, act, base, spart, pstride);
   } else {
-    bwd_body<R, false, Exec>(ex, c, x, y, op, w0, 0xffffu, base, smps, spart, pstride);
+    bwd_body<R, false, Exec>(ex, c, x, y, h, m, op, w0, 0xffffu, base, spart, pstride);
   }
 }
 
@@ -684,11 +826,18 @@ TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
       x[e] = sps[a];
       if constexpr (BWD) y[e] = sla[a];
     }
-    if constexpr (BWD) {
-      for (int k = nops - 1; k >= 0; --k)
-        apply_op_bwd<R, Exec>(ex, c, x, y, ops + k * TQB_OP_WORDS, base, smps, spart, pstride);
-    } else {
-      for (int k = 0; k < nops; ++k) apply_op_fwd_inplace<R, Exec>(c, x, ops + k * TQB_OP_WORDS, base, smps);
+    // op header (w0, slot, emask, pm_t) in one 128-bit shared read, then the first four matrix floats.
+    // (Fetching them one / two ops ahead was tried: the register rotation costs more ALU-pipe MOVs than the
+    // latency it hides - profiles/r01_v3_notes.txt.)
+    for (int i = 0; i < nops; ++i) {
+      const int k = BWD ? nops - 1 - i : i;
+      const int32_t* op = ops + k * TQB_OP_WORDS;
+      const int4 h = *reinterpret_cast<const int4*>(op);
+      Mat m;
+      m.p = ((h.x & TQB_F_PS) ? smps : c.s_msh) + h.y;
+      m.q0 = ld4(m.p);
+      if constexpr (BWD) apply_op_bwd<R, Exec>(ex, c, x, y, h, m, op, base, spart, pstride);
+      else apply_op_fwd_inplace<R, Exec>(c, x, h, m, op, base);
     }
 #pragma unroll
     for (int e = 0; e < (1 << R); ++e) {
@@ -796,6 +945,7 @@ inline SmemLayout smem_layout(int T, int L, int S, int tps, bool bwd, int nbuf, 
   l.mps = off; off += (size_t)S * ps_max * sizeof(float);
   l.grad = off; if (bwd) off += (size_t)S * g_max * sizeof(float);
   l.part = off; if (bwd) off += (size_t)g_max * (S * tps + 1) * sizeof(float);
+  off = (off + 15) & ~(size_t)15;  // op headers are read as 128-bit words
   l.prog = off; off += (size_t)TQB_SEG_MAX_WORDS * sizeof(int32_t);
   off = (off + 15) & ~(size_t)15;
   l.scat = off; off += ((size_t)1 << (T - L)) * sizeof(u64);
@@ -958,10 +1108,29 @@ TQB_FN int build_gate(int kind, const T* th, Cx<T>* u) {
 
 TQB_FN int kind_dim(int nent) { return nent == 16 ? 4 : (nent == 4 ? 2 : 0); }  // 0: diagonal pair
 
+// scaled rotation (c, s) -> packed (c, s, r, mode) and the factor left out of the per-amplitude arithmetic
+TQB_FN void pack_scaled_rot(int type, float cc, float ss, float* out, float2& f) {
+  const bool m1 = fabsf(cc) < fabsf(ss);
+  out[0] = cc; out[1] = ss; out[2] = m1 ? cc / ss : ss / cc; out[3] = m1 ? 1.f : 0.f;
+  if (type == TQB_T_RXS) f = m1 ? make_float2(0.f, -ss) : make_float2(cc, 0.f);
+  else f = m1 ? make_float2(ss, 0.f) : make_float2(cc, 0.f);
+}
+// one-bit diagonal (d0, d1) -> packed (rel, d0) with rel = d1 / d0 (|d0| = 1 for every catalogue gate)
+TQB_FN void pack_scaled_diag(float2 d0, float2 d1, float* out, float2& f) {
+  const float n2 = d0.x * d0.x + d0.y * d0.y;
+  const float2 rel = make_float2((d1.x * d0.x + d1.y * d0.y) / n2, (d1.y * d0.x - d1.x * d0.y) / n2);
+  out[0] = rel.x; out[1] = rel.y; out[2] = d0.x; out[3] = d0.y;
+  f = d0;
+}
+
 // one (op, sample): params -> applied matrix (inverse folded in), packed for the op type, written to
 // the shared row (b ignored) or the sample's row
+// matrix floats of one parametric record and, for the scaled forms, the factor they leave out (returns true then)
+TQB_FN bool build_param(const int32_t* rec, long long b, const float* params_sh, const float* params_ps, int ps_stride,
+                        float* out, float2& f);
+
 TQB_FN void build_one(const int32_t* rec, long long b, const float* params_sh, const float* params_ps, int ps_stride,
-                      const float* consts, float* row) {
+                      const float* consts, float* row, const int32_t* table) {
   const int kind = rec[TQB_B_KIND];
   float* out = row + rec[TQB_B_MOFF];
   if (kind == TQB_K_EXTERN) return;
@@ -969,6 +1138,28 @@ TQB_FN void build_one(const int32_t* rec, long long b, const float* params_sh, c
     for (int i = 0; i < rec[TQB_B_NFLOAT]; ++i) out[i] = consts[rec[TQB_B_COFF] + i];
     return;
   }
+  if (kind == TQB_K_SCALE) {
+    // constant part (folded by the planner) times the factors of the scaled parametric records of this pass
+    float2 acc = make_float2(consts[rec[TQB_B_POFF]], consts[rec[TQB_B_POFF] + 1]);
+    for (int r = rec[TQB_B_COFF]; r < rec[TQB_B_COFF] + rec[TQB_B_NFLOAT]; ++r) {
+      const int32_t* q = table + r * TQB_B_WORDS;
+      const int t = q[TQB_B_TYPE];
+      if (q[TQB_B_KIND] < TQB_K_RX || q[TQB_B_KIND] >= TQB_K_SCALE || (t != TQB_T_RXS && t != TQB_T_RYS && t != TQB_T_DIAGS))
+        continue;
+      float tmp[4];
+      float2 f;
+      if (build_param(q, b, params_sh, params_ps, ps_stride, tmp, f)) acc = cmul(acc, f);
+    }
+    out[0] = acc.x; out[1] = acc.y; out[2] = 0.f; out[3] = 0.f;
+    return;
+  }
+  float2 f;
+  build_param(rec, b, params_sh, params_ps, ps_stride, out, f);
+}
+
+TQB_FN bool build_param(const int32_t* rec, long long b, const float* params_sh, const float* params_ps, int ps_stride,
+                        float* out, float2& f) {
+  const int kind = rec[TQB_B_KIND];
   const bool inv = rec[TQB_B_FLAGS] & TQB_BF_INVERSE;
   const float* p = (rec[TQB_B_FLAGS] & TQB_BF_PER_SAMPLE) ? params_ps + b * ps_stride + rec[TQB_B_POFF]
                                                           : params_sh + rec[TQB_B_POFF];
@@ -979,8 +1170,12 @@ TQB_FN void build_one(const int32_t* rec, long long b, const float* params_sh, c
   const int d = kind_dim(nent);
   const int type = rec[TQB_B_TYPE];
   if (d == 0) {
+    if (type == TQB_T_DIAGS) {
+      pack_scaled_diag(make_float2(u[0].re, inv ? -u[0].im : u[0].im), make_float2(u[1].re, inv ? -u[1].im : u[1].im), out, f);
+      return true;
+    }
     for (int i = 0; i < 2; ++i) { out[2 * i] = u[i].re; out[2 * i + 1] = inv ? -u[i].im : u[i].im; }
-    return;
+    return false;
   }
   Cx<float> a[16];  // applied matrix
   for (int i = 0; i < d; ++i)
@@ -992,9 +1187,16 @@ TQB_FN void build_one(const int32_t* rec, long long b, const float* params_sh, c
     out[0] = a[0].re; out[1] = a[1].re; out[2] = a[2].re; out[3] = a[3].re;
   } else if (type == TQB_T_RX) {
     out[0] = a[0].re; out[1] = -a[1].im; out[2] = 0.f; out[3] = 0.f;
+  } else if (type == TQB_T_RXS) {
+    pack_scaled_rot(type, a[0].re, -a[1].im, out, f);
+    return true;
+  } else if (type == TQB_T_RYS) {
+    pack_scaled_rot(type, a[0].re, a[2].re, out, f);
+    return true;
   } else {
     for (int i = 0; i < d * d; ++i) { out[2 * i] = a[i].re; out[2 * i + 1] = a[i].im; }
   }
+  return false;
 }
 
 // one (op, sample): dL/dtheta from the op's gradient accumulators

@@ -72,9 +72,11 @@ struct PassArgs {
   unsigned o_psi, o_lam, o_msh, o_mps, o_grad, o_part, o_prog, o_scat, o_olut, buf_stride;
 };
 
-// SMALL: CTAs of <= 128 threads (states of <= 11 qubits held whole in shared memory, several samples per CTA)
+// SMALL: CTAs of <= 128 threads (states of <= 11 qubits held whole in shared memory, several samples per CTA).
+// Backward: 2 CTAs/SM (255 registers, no spills) beat 3 (168 registers, 270 B of spills) and 4 (128 registers):
+// 3.17 / 3.51 / 4.19 ms on the config-2 adjoint pass (profiles/r01_v3_notes.txt)
 #ifndef TQB_BWD_MINB_SMALL
-#define TQB_BWD_MINB_SMALL 3
+#define TQB_BWD_MINB_SMALL 2
 #endif
 template <int R, bool BWD, bool SMALL>
 __global__ void __launch_bounds__(SMALL ? 128 : 256, SMALL ? (BWD ? TQB_BWD_MINB_SMALL : 2 * TQB_FWD_MINB) : (BWD ? TQB_BWD_MINB : TQB_FWD_MINB))
@@ -89,6 +91,7 @@ tqb_pass_kernel(const PassArgs a) {
   c.prog = a.prog; c.psi_src = a.psi_src; c.lam_src = a.lam_src; c.psi = a.psi; c.lam = a.lam;
   c.msh = a.msh; c.mps = a.mps; c.gr = a.gr; c.mps_stride = a.mps_stride; c.gr_stride = a.gr_stride;
   c.ps_cap = a.ps_cap; c.g_cap = a.g_cap;
+  c.scale_sh = a.prog[TQB_H_SCALE_SH]; c.scale_ps = a.prog[TQB_H_SCALE_PS];
   c.s_psi = reinterpret_cast<float2*>(smem + a.o_psi);
   c.s_lam = reinterpret_cast<float2*>(smem + a.o_lam);
   c.s_msh = reinterpret_cast<float*>(smem + a.o_msh);
@@ -183,14 +186,14 @@ __global__ void tqb_build_kernel(const int32_t* table, int nrec, int n_sh, long 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_ps = nrec - n_sh;
   if (i < n_sh) {
-    build_one(table + i * TQB_B_WORDS, 0, params_sh, params_ps, ps_stride, consts, msh);
+    build_one(table + i * TQB_B_WORDS, 0, params_sh, params_ps, ps_stride, consts, msh, table);
     return;
   }
   const long long k = i - n_sh;
   if (k >= bsz * n_ps) return;
   const int r = n_sh + (int)(k % n_ps);
   const long long b = k / n_ps;
-  build_one(table + r * TQB_B_WORDS, b, params_sh, params_ps, ps_stride, consts, mps + b * mps_stride);
+  build_one(table + r * TQB_B_WORDS, b, params_sh, params_ps, ps_stride, consts, mps + b * mps_stride, table);
 }
 
 __global__ void tqb_build_bwd_kernel(const int32_t* table, int nrec, long long bsz, const float* params_sh,

@@ -20,7 +20,7 @@
 #define TQB_MAGIC 0x54514232  // "TQB2"
 #define TQB_MAX_T 13          // largest tile (2^13 amplitudes = 64 KiB)
 #define TQB_MAX_R 4           // register bits per thread (16 amplitudes)
-#define TQB_OP_WORDS 10
+#define TQB_OP_WORDS 12
 #define TQB_GROUP_WORDS 8
 #define TQB_SEG_HDR_WORDS 8
 #define TQB_SEG_MAX_OPS 64
@@ -42,6 +42,8 @@
 #define TQB_H_TBIT 8       // 16 words: global bit position of tile-local bit i
 #define TQB_H_G_MAX 24     // max gradient floats of any segment
 #define TQB_H_SH_MAX 25    // max shared matrix floats of any segment
+#define TQB_H_SCALE_SH 26  // float offset (shared matrix row) of the pass's deferred complex scale factor, -1: none
+#define TQB_H_SCALE_PS 27  // float offset (per-sample matrix rows) of the per-sample part of that factor, -1: none
 #define TQB_H_SEGOFF 32    // n_seg words: offset of each segment
 
 // segment header (8 words); then n_groups group records; then the op records
@@ -55,18 +57,19 @@
 #define TQB_S_G_LEN 7
 
 // group record: [regpos0..3, n_ops, first_op, 0, 0]  (regpos = tile-local bit of register bit j)
-// op record (10 words):
-#define TQB_OP_W0 0     // bits 0-1 target register bit j, 2-5 type, 8-15 flags, 16-19 gradient kind
+// op record (12 words = 48 bytes; words 0-3 are read as one 128-bit word, two ops ahead of use):
+#define TQB_OP_W0 0     // bits 0-1 target register bit j, 2-5 type, 8-15 flags, 16-19 gradient kind, 20-21 jc
 #define TQB_OP_SLOT 1   // float offset of this op's matrix in the staged shared / per-sample floats
 #define TQB_OP_EMASK 2  // low 16: elements e (register-bit patterns) whose register-bit controls hold;
                         // high 16: DIAG parity of e over the parity bits that are register bits
-#define TQB_OP_CM_T 3   // control mask over the non-register tile-local bits
-#define TQB_OP_CV_T 4   // required value of those bits
-#define TQB_OP_PM_T 5   // DIAG: parity mask over the non-register tile-local bits
+#define TQB_OP_PM_T 3   // DIAG: parity mask over the non-register tile-local bits
+#define TQB_OP_CM_T 4   // control mask over the non-register tile-local bits
+#define TQB_OP_CV_T 5   // required value of those bits
 #define TQB_OP_CM_O 6   // control mask over the compressed outer (non-tile) index
 #define TQB_OP_CV_O 7
 #define TQB_OP_PM_O 8   // DIAG: parity mask over the compressed outer index
 #define TQB_OP_GSLOT 9  // float offset of this op's gradient accumulators in the segment's gradient floats
+                        // (words 10-11: padding)
 
 // op types.  Matrix slots are padded to a multiple of 4 floats (16-byte staged loads).
 #define TQB_T_GEN 0    // 2x2 complex on register bit j; 8 floats row-major (re,im)
@@ -75,6 +78,13 @@
 #define TQB_T_DIAG 3   // amp *= d[parity]; 4 floats d0 (re,im), d1 (re,im)             (rz, cz, cu1, rzz ...)
 #define TQB_T_PERM 4   // swap the two amplitudes of register bit j; no floats           (x, cnot, toffoli ...)
 #define TQB_T_U2Q 5    // 4x4 complex on register bits (1,0) = (msb,lsb); 32 floats
+// "Scaled" forms (programs that never run backward): the gate's common factor is left out of the per-amplitude
+// arithmetic (one FMA per float instead of two FP instructions) and multiplied into the pass's deferred scale factor
+// (TQB_H_SCALE_*), which is applied once when the tile is written back.  4 floats (c, s, r, mode):
+#define TQB_T_RXS 6    // rx:  mode 0 (|c| >= |s|): c [[1, -ir], [-ir, 1]], r = s/c;  mode 1: -is [[ir, 1], [1, ir]], r = c/s
+#define TQB_T_RYS 7    // ry:  mode 0: c [[1, -r], [r, 1]], r = s/c;                  mode 1: s [[r, -1], [1, r]], r = c/s
+#define TQB_T_HS 8     // hadamard: a' = a + b, b' = a - b, factor 1/sqrt(2); no floats
+#define TQB_T_DIAGS 9  // one-bit diagonal d0 diag(1, rel): amplitudes whose bit is set *= rel, factor d0; floats rel (re,im), d0 (re,im)
 
 #define TQB_F_TCTRL 0x100      // has controls on non-register tile bits (CM_T/CV_T valid)
 #define TQB_F_RCTRL 0x200      // has controls on register bits (EMASK != 0xffff)
@@ -82,6 +92,8 @@
 #define TQB_F_NOUNAPPLY 0x800  // backward: psi already holds the op's INPUT (non-unitary single-op node)
 #define TQB_F_OCTRL 0x1000     // has controls on outer (non-tile) bits (CM_O/CV_O valid)
 #define TQB_F_DJ 0x2000        // DIAG whose only register-resident parity bit is register bit j (element parity = bit j of e)
+#define TQB_F_POSTX 0x4000     // a CNOT (control = register bit JC, target = this op's bit j) is folded in: the two outputs
+                               // of every pair whose control bit is set are exchanged (costs nothing: register renaming)
 
 // gradient kinds (backward sweep): what is accumulated per sample for this op
 #define TQB_G_NONE 0
@@ -93,6 +105,7 @@
 #define TQB_OP_J(w0) ((w0) & 3)
 #define TQB_OP_CODE(type, j) (((type) << 2) | (j))
 #define TQB_OP_GKIND(w0) (((w0) >> 16) & 15)
+#define TQB_OP_JC(w0) (((w0) >> 20) & 3)   // TQB_F_POSTX: register bit of the folded CNOT's control
 
 // matrix-builder table: one record of 10 words per op (tqb_build_mats / tqb_build_mats_bwd)
 #define TQB_B_WORDS 10
@@ -109,6 +122,7 @@
 
 #define TQB_BF_INVERSE 1
 #define TQB_BF_PER_SAMPLE 2
+// K_SCALE records: product of the scale factors of the scaled ops among table records [COFF, COFF + NFLOAT) -> 2 floats at MOFF
 
 enum {
   TQB_K_CONST = 0,   // copy NFLOAT floats from the constant pool (inverse already folded in)
@@ -118,5 +132,6 @@ enum {
   TQB_K_RZ = 10, TQB_K_PHASE = 11, TQB_K_GPHASE = 12,  // -> diagonal pair d0,d1
   TQB_K_RXX = 13, TQB_K_RYY = 14, TQB_K_RZX = 15, TQB_K_SEXC = 16, TQB_K_XXMYY = 17,
   TQB_K_XXPYY = 18,                               // -> 4x4
-  TQB_K_COUNT = 19
+  TQB_K_SCALE = 19,  // deferred scale factor of one pass (see TQB_BF_* above)
+  TQB_K_COUNT = 20
 };

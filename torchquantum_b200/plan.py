@@ -25,16 +25,22 @@ T_SINGLE = 13   # largest state handled as one tile per sample (2^13 amplitudes 
 T_MULTI = 12    # tile bits when the state is streamed through HBM
 L_MIN = 5       # contiguous low bits always in the tile (2^5 amplitudes = 256 B runs)
 R_MAX = int(os.environ.get("TQB200_R", C.MAX_R))   # register bits per thread (env: kernel experiments)
-R_GRAD = int(os.environ.get("TQB200_RGRAD", C.MAX_R))  # register bits of programs that also run backward (two arrays live per thread)
+R_GRAD = int(os.environ.get("TQB200_RGRAD", C.MAX_R))
+FAST_FWD = os.environ.get("TQB200_FAST_FWD", "1") != "0"   # scaled op forms + CNOT folding in forward-only programs  # register bits of programs that also run backward (two arrays live per thread)
 
-NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32}
+NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32,
+          C.T_RXS: 4, C.T_RYS: 4, C.T_HS: 0, C.T_DIAGS: 4}
+SCALED = (C.T_RXS, C.T_RYS, C.T_HS, C.T_DIAGS)       # forms whose common factor is deferred to the end of the pass
+FOLDS_CNOT = (C.T_RXS, C.T_RYS, C.T_HS, C.T_REAL)    # 1-qubit forms that can absorb a following CNOT on their target
+_H = (np.array([[1, 1], [1, -1]]) / np.sqrt(2)).astype(np.complex64)
 NGRAD = {C.G_NONE: 0, C.G_X: 1, C.G_Y: 1, C.G_DW: 2}
 
 
 class LOp:
     """A lowered micro-op on global bit positions."""
     __slots__ = ("type", "targets", "pmask", "cmask", "cval", "nfloat", "kind", "inverse", "pmode",
-                 "poff", "nparam", "const", "rec", "grad", "gkind", "ngrad", "nounapply", "qmask", "ext_dim", "_lt")
+                 "poff", "nparam", "const", "rec", "grad", "gkind", "ngrad", "nounapply", "qmask", "ext_dim", "_lt",
+                 "_lc", "_soft", "postx", "scale_const")
 
     def __init__(self):
         self.pmask = self.cmask = self.cval = 0
@@ -42,6 +48,7 @@ class LOp:
         self.kind, self.inverse, self.pmode, self.poff, self.nparam = C.K_CONST, False, None, 0, 0
         self.const, self.rec, self.grad, self.nounapply, self.ext_dim = None, -1, False, False, 0
         self.gkind, self.ngrad = C.G_NONE, 0
+        self._lc, self._soft, self.postx, self.scale_const = None, (), None, None
 
     @property
     def per_sample(self):
@@ -66,9 +73,11 @@ def _pack_const(m, typ):
     return m.view(np.float32).reshape(-1)
 
 
-def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
+def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0, fast=False):
     """One queue record -> LOp (fusable) or None for DENSE / RESET / NOP kinds.
-    pmode: None | 'sh' | 'ps' | 'ext' / 'extps' (explicit matrix supplied by the caller)."""
+    pmode: None | 'sh' | 'ps' | 'ext' / 'extps' (explicit matrix supplied by the caller).
+    fast: the program never runs backward -> uncontrolled rx / ry / h / one-bit diagonals take the scaled
+    forms of csrc/tqb_program.h (TQB_T_RXS ...)."""
     spec = G.SPECS[name]
     op = LOp()
     op.rec, op.grad, op.inverse, op.pmode = rec, grad, inverse, pmode
@@ -103,9 +112,9 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
         op.targets = (rest[0],)
         if parametric:
             if spec.builder == C.K_RX:
-                op.type, op.gkind = (C.T_GEN if op.cmask else C.T_RX), C.G_X
+                op.type, op.gkind = (C.T_GEN if op.cmask else (C.T_RXS if fast else C.T_RX)), C.G_X
             elif spec.builder == C.K_RY:
-                op.type, op.gkind = (C.T_GEN if op.cmask else C.T_REAL), C.G_Y
+                op.type, op.gkind = (C.T_GEN if op.cmask else (C.T_RYS if fast else C.T_REAL)), C.G_Y
             else:
                 op.type, op.gkind = C.T_GEN, C.G_FULL
         elif ext:
@@ -114,6 +123,8 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
             op.gkind = C.G_NONE
             if np.array_equal(applied, np.array([[0, 1], [1, 0]], dtype=np.complex64)):
                 op.type = C.T_PERM
+            elif fast and not op.cmask and np.allclose(applied, _H, atol=1e-7):
+                op.type, op.scale_const = C.T_HS, complex(np.float32(1 / np.sqrt(2)))
             elif not op.cmask and not np.any(applied.imag):
                 op.type = C.T_REAL
             else:
@@ -126,7 +137,11 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
         for b in rest:
             op.pmask |= 1 << b
         phase_like = (spec.builder == C.K_PHASE) if parametric else (applied is not None and applied[0] == 1)
-        if phase_like and len(rest) == 1:
+        if fast and len(rest) == 1 and not op.cmask and (parametric or (applied is not None and abs(applied[0]) > 0.5)):
+            op.type = C.T_DIAGS   # d0 diag(1, d1/d0): half the amplitudes are touched, d0 joins the pass's scale factor
+            if not parametric:
+                op.scale_const = complex(applied[0])
+        elif phase_like and len(rest) == 1:
             # d0 == 1: only amplitudes whose target bit is set change -> the target doubles as a control
             op.cmask |= op.pmask
             op.cval |= op.pmask
@@ -139,8 +154,11 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0):
             op.kind, op.nparam = spec.builder, spec.n_params
         else:
             op.kind, op.const = C.K_CONST, _pack_const(applied, op.type)
-            if op.type == C.T_PERM:
+            if op.type in (C.T_PERM, C.T_HS):
                 op.const = np.zeros(0, np.float32)
+            elif op.type == C.T_DIAGS:
+                rel = np.complex64(applied[1] / applied[0])
+                op.const = np.array([rel.real, rel.imag, applied[0].real, applied[0].imag], dtype=np.float32)
     tm = 0
     for t in op.targets:
         tm |= 1 << t
@@ -160,8 +178,14 @@ def fold_cnot_sandwiches(lops):
             d, b = lops[i + 1], lops[i + 2]
             t, cbit = a.targets[0], a.cmask
             if (b.type == C.T_PERM and b.cmask == a.cmask and b.cval == a.cval and b.targets == a.targets
-                    and d.type == C.T_DIAG and d.cmask == 0 and (d.pmask >> t) & 1 and not d.pmask & cbit
+                    and d.type in (C.T_DIAG, C.T_DIAGS) and d.cmask == 0 and (d.pmask >> t) & 1 and not d.pmask & cbit
                     and not d.nounapply):
+                if d.type == C.T_DIAGS:   # two parity bits now: back to the (d0, d1) form
+                    d.type, d.scale_const = C.T_DIAG, None
+                    if d.kind == C.K_CONST:
+                        rel, d0 = complex(d.const[0], d.const[1]), complex(d.const[2], d.const[3])
+                        d1 = rel * d0
+                        d.const = np.array([d0.real, d0.imag, d1.real, d1.imag], dtype=np.float32)
                 d.pmask ^= cbit
                 d.qmask |= cbit
                 out.append(d)
@@ -198,7 +222,7 @@ def _pack_groups(ops, R):
     U2Q ops need their targets at register indices (1, 0)."""
     remaining, groups = list(ops), []
     while remaining:
-        reg, blocked, part, rest = [], 0, [], []
+        reg, blocked, part, rest, soft = [], 0, [], [], []
         for op in remaining:
             ok = not (op.qmask & blocked)
             if ok:
@@ -216,13 +240,43 @@ def _pack_groups(ops, R):
                         else:
                             ok = False
             if ok:
+                soft.extend(op._soft)
                 part.append(op)
             else:
                 blocked |= op.qmask
                 rest.append(op)
+        for b in soft:   # bits that are cheaper as register bits but need not be (fast programs): spare slots only
+            if b not in reg and len(reg) < R:
+                reg.append(b)
         groups.append((reg, part))
         remaining = rest
     return groups
+
+
+def _fold_cnots(part, regs):
+    """Fast programs: `G on t; cnot(c -> t)` with c and t both register bits of the group and G an uncontrolled
+    one-qubit op on t becomes G with TQB_F_POSTX (the kernel exchanges the pair's outputs where c is set, which
+    is register renaming).  G may be moved up to the CNOT: everything between acts on other bits."""
+    regset = set(regs)
+    out = []
+    for op in part:
+        if (op.type == C.T_PERM and op._lc is not None and op._lc in regset and op._lt[0] in regset
+                and op._lc != op._lt[0]):
+            tg = op.targets[0]
+            for k in range(len(out) - 1, -1, -1):
+                g = out[k]
+                if (g.qmask >> tg) & 1:
+                    one_bit = (g.type in FOLDS_CNOT and g.targets == (tg,) and not g.cmask) or \
+                        (g.type == C.T_DIAGS and g.pmask == 1 << tg)
+                    if one_bit and g.postx is None:
+                        out.pop(k)
+                        g.postx = op._lc
+                        out.append(g)
+                        op = None
+                    break
+        if op is not None:
+            out.append(op)
+    return out
 
 
 def _swz(idx):
@@ -359,7 +413,7 @@ def _encode_op(op, regs, R, loc, oloc):
     if cm_o:
         flags |= C.F_OCTRL
     j = 0
-    if op.type == C.T_DIAG and len(reg_par) == 1:
+    if op.type in (C.T_DIAG, C.T_DIAGS) and len(reg_par) == 1:
         flags |= C.F_DJ
         j = reg_par[0]
     if op.type == C.T_U2Q:
@@ -369,11 +423,19 @@ def _encode_op(op, regs, R, loc, oloc):
     if op.type in (C.T_REAL, C.T_RX):
         assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
     w0 = (op.type << 2) | j | flags | (op.gkind << 16)
-    return [w0, 0, emask | (epar << 16), cm_t, cv_t, pm_t, cm_o, cv_o, pm_o, 0]
+    if op.postx is not None:
+        assert op.postx in regidx and regidx[op.postx] != j and (op.type != C.T_DIAGS or flags & C.F_DJ)
+        w0 |= C.F_POSTX | (regidx[op.postx] << 20)
+    w = [0] * C.OP_WORDS
+    w[C.OP_W0], w[C.OP_EMASK] = w0, emask | (epar << 16)
+    w[C.OP_CM_T], w[C.OP_CV_T], w[C.OP_PM_T] = cm_t, cv_t, pm_t
+    w[C.OP_CM_O], w[C.OP_CV_O], w[C.OP_PM_O] = cm_o, cv_o, pm_o
+    return w
 
 
-def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, l_min=None, r=None):
-    """lops: LOps in program order (targets < n_local; masks may use bits up to n_total)."""
+def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, l_min=None, r=None, fast=False):
+    """lops: LOps in program order (targets < n_local; masks may use bits up to n_total).
+    fast: forward-only program (scaled op forms, CNOT folding)."""
     n_total = n_local if n_total is None else n_total
     t_single = T_SINGLE if t_single is None else t_single
     t_multi = T_MULTI if t_multi is None else t_multi
@@ -422,11 +484,21 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         oloc = {g: i for i, g in enumerate(outer)}
         for op in ops:
             op._lt = tuple(loc[t] for t in op.targets)
+            op._lc, op._soft = None, ()
+            if fast and op.type == C.T_PERM and bin(op.cmask).count("1") == 1 and op.cval == op.cmask:
+                cb = op.cmask.bit_length() - 1
+                if cb in loc:
+                    op._lc, op._soft = loc[cb], (loc[cb],)
+            elif fast and op.type == C.T_DIAGS and (op.pmask.bit_length() - 1) in loc:
+                op._soft = (loc[op.pmask.bit_length() - 1],)
         groups = _pack_groups(ops, R)
+        sh_rec0, ps_rec0 = len(table_sh), len(table_ps)
         # split oversize groups, then cut into segments
         flat = []
         for reg, part in groups:
             regs = _fill_registers(T, R, tuple(reg))
+            if fast:
+                part = _fold_cnots(part, regs)
             # a chunk of a group must fit one segment's staging capacity on its own
             chunk, use = [], [0, 0, 0, 0]
             for op in part:
@@ -456,6 +528,7 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         hdr = [0] * (C.H_SEGOFF + len(segments))
         hdr[C.H_MAGIC], hdr[C.H_T], hdr[C.H_R], hdr[C.H_NSEG] = _i32(C.MAGIC), T, R, len(segments)
         hdr[C.H_L], hdr[C.H_OUTER] = Lp, n_total - T
+        hdr[C.H_SCALE_SH] = hdr[C.H_SCALE_PS] = -1
         for i, g in enumerate(tile_bits):
             hdr[C.H_TBIT + i] = g
         words = list(hdr)
@@ -503,6 +576,28 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
             sh_off += sh_len
             ps_off += ps_len
             g_off += g_len
+        # deferred scale factor of the pass (scaled op forms): constant part folded here, parametric part by the
+        # matrix builder (K_SCALE records scan this pass's records)
+        scaled = [op for op in ops if op.type in SCALED]
+        if scaled:
+            pre = complex(1.0)
+            for op in scaled:
+                if op.scale_const is not None:
+                    pre *= op.scale_const
+            if pre != 1.0 or any(op.scale_const is None and not op.per_sample for op in scaled):
+                consts.append(np.array([pre.real, pre.imag], dtype=np.float32))
+                table_sh.append([C.K_SCALE, 0, const_off, sh_off, sh_rec0, len(table_sh) - sh_rec0, 0, 0, C.G_NONE, 0])
+                const_off += 2
+                words[C.H_SCALE_SH] = sh_off
+                sh_off += 4
+            if any(op.per_sample for op in scaled):
+                consts.append(np.array([1.0, 0.0], dtype=np.float32))
+                # COFF is local to the per-sample table here; made absolute once the shared table is complete
+                table_ps.append([C.K_SCALE, C.BF_PER_SAMPLE, const_off, ps_off, ps_rec0, len(table_ps) - ps_rec0, 0, 0,
+                                 C.G_NONE, 0])
+                const_off += 2
+                words[C.H_SCALE_PS] = ps_off
+                ps_off += 4
         words[C.H_WORDS] = len(words)
         words[C.H_SH_MAX], words[C.H_PS_MAX], words[C.H_G_MAX] = sh_max, ps_max, g_max
         pp = PassProgram()
@@ -514,6 +609,9 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         st.passes.append(pp)
     st.M_sh, st.M_ps, st.G = max(sh_off, 4), max(ps_off, 4), max(g_off, 4)
     st.n_sh_rec = len(table_sh)
+    for rec in table_ps:
+        if rec[C.B_KIND] == C.K_SCALE:
+            rec[C.B_COFF] += len(table_sh)
     st.table = np.array(table_sh + table_ps, dtype=np.int32).reshape(-1, C.B_WORDS)
     st.consts = np.concatenate(consts + [np.zeros(4, np.float32)]).astype(np.float32)
     return st
@@ -542,6 +640,9 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
     cur = []
     if grad_mode and "r" not in tile_kw:
         tile_kw = dict(tile_kw, r=R_GRAD)
+    fast = FAST_FWD and not grad_mode
+    if fast:
+        tile_kw = dict(tile_kw, fast=True)
 
     def close():
         if cur:
@@ -556,7 +657,7 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
             close()
             plan.stages.append(ResetStage(tuple(int(w) for w in wires)))
             continue
-        op = lower(nb, name, wires, inverse, pmode, grad, rec, ext_dim)
+        op = lower(nb, name, wires, inverse, pmode, grad, rec, ext_dim, fast=fast)
         if op is None:  # dense
             close()
             const = G.qft_matrix_np(len(wires)) if name == "qft" else None
