@@ -339,3 +339,46 @@ def check_forward_only_forms(device, n=7, bsz=3):
                     postx += bool(w0 & C.F_POSTX)
     assert {C.T_RXS, C.T_RYS, C.T_DIAGS} <= types, types
     assert postx > 0, "no CNOT was folded"
+
+
+def qft_ops(n, do_swaps=True, with_params=True):
+    ops = []
+    for top in range(n):
+        ops.append({"name": "hadamard", "wires": [top]})
+        for w in range(top + 1, n):
+            ops.append({"name": "cu1", "wires": [w, top], "params": torch.tensor([[np.pi / 2 ** (w - top)]], dtype=torch.float32)})
+    if do_swaps:
+        ops += [{"name": "swap", "wires": [w, n - 1 - w]} for w in range(n // 2)]
+    return ops
+
+
+def check_qft_phase_ladders(device, n=8, bsz=2):
+    """QFT (H + cu1 ladders + swaps) in a forward-only program: the cu1 runs fold into TQB_T_LADDER ops; vs the
+    oracle on a random initial state, the inverse QFT (negated angles / inverse flag), and constant cz / cs rungs."""
+    from torchquantum_b200 import engine, _codes as C
+
+    g = torch.Generator().manual_seed(5)
+    init = torch.randn(bsz, 2 ** n, 2, generator=g)
+    init = torch.view_as_complex(init / init.flatten(1).norm(dim=1).reshape(bsz, 1, 1)).contiguous()
+    extra = [{"name": "cz", "wires": [0, 2]}, {"name": "cz", "wires": [0, 3]}, {"name": "cz", "wires": [0, 1]},
+             {"name": "cu1", "wires": [4, 0], "params": torch.tensor([[0.7]], dtype=torch.float32), "inverse": True}]
+    for ops in (qft_ops(n), qft_ops(n, do_swaps=False) + extra,
+                [dict(o, inverse=True) for o in reversed(qft_ops(n))]):
+        q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+        q.set_states(init.clone().to(device))
+        with torch.no_grad():
+            apply_ops(q, [dict(o, params=o["params"].to(device)) if "params" in o else o for o in ops], device)
+            got = q.get_states_1d()
+        want = O.run_ops(n, bsz, ops, init_states=init.clone())
+        assert_close(got, want, what=f"qft-like circuit n={n}")
+    key = tuple((o["name"], tuple(o["wires"]), False, "sh" if "params" in o else None, False, 0) for o in qft_ops(n))
+    plan = engine.get_plan(n, key, False)
+    types = []
+    for st in plan.stages:
+        for pp in st.passes:
+            w = pp.prog
+            for si in range(w[C.H_NSEG]):
+                off = w[C.H_SEGOFF + si]
+                base = off + C.SEG_HDR_WORDS + w[off + C.S_NGROUPS] * C.GROUP_WORDS
+                types += [(int(w[base + k * C.OP_WORDS]) >> 2) & 15 for k in range(w[off + C.S_NOPS])]
+    assert types.count(C.T_LADDER) >= n - 3, types

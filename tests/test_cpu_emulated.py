@@ -117,3 +117,12 @@ def test_forward_only_forms():
 def test_forward_only_forms_multi_tile(tiles):
     P.T_SINGLE, P.T_MULTI, P.L_MIN = tiles
     cases.check_forward_only_forms("cpu", n=8, bsz=2)
+
+
+def test_qft_phase_ladders():
+    cases.check_qft_phase_ladders("cpu")
+
+
+def test_qft_phase_ladders_multi_tile():
+    P.T_SINGLE, P.T_MULTI, P.L_MIN = 4, 5, 2
+    cases.check_qft_phase_ladders("cpu", n=8, bsz=1)

@@ -128,6 +128,14 @@ def test_forward_only_forms():
         P.T_SINGLE, P.T_MULTI, P.L_MIN = saved
 
 
+def test_qft_phase_ladders():
+    """QFT / inverse QFT / constant rungs through the folded controlled-phase ladders vs the oracle, on-chip (n=8, 12)
+    and streamed (n=15: ladder bits in the outer index)."""
+    cases.check_qft_phase_ladders(DEV)
+    cases.check_qft_phase_ladders(DEV, n=12, bsz=1)
+    cases.check_qft_phase_ladders(DEV, n=15, bsz=1)
+
+
 def test_per_sample_params_large_batch():
     ops = cases.brickwork_ops(6, 6, seed=1, per_sample_bsz=300)
     cases.check_against_oracle(DEV, 6, 300, ops, grad=True)
@@ -153,6 +161,31 @@ def test_full_size_properties_n24():
     s0 = q.get_states_1d()
     assert abs(s0[0, 0].abs().item() - 1.0) < 1e-4
     assert s0[0, 1:].abs().max().item() < 1e-4
+
+
+def test_cfg3_full_size_properties():
+    """Config 3 at its full size (n=20, p=8, bsz=64, 900 gates; no reference can run it): unit norm and adjoint
+    gradients vs a 4th-order finite difference of forward runs."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import configs
+
+    r = configs.run_cfg3(torch.device(DEV), timing=False)
+    assert r["ok"], r
+
+
+def test_cfg4_full_size_properties():
+    """Config 4 at its full size (n=28, depth 100, ~4150 gates): unit norm, |<Z>| <= 1, circuit . circuit^-1 = 1."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import configs
+
+    r = configs.run_cfg4(torch.device(DEV), timing=False)
+    assert r["ok"], r
 
 
 def test_sharded_statevector_two_gpus():

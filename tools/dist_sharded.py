@@ -98,7 +98,7 @@ def main():
         q.time_exchanges = True
         for rep in range(2):   # rep 0 warms up (plan build, NCCL channels)
             q.reset_states(1)
-            q.stats.update(exchanges=0, exchange_bytes_sent=0, exchange_ms=[], local_permute_passes=0)
+            q.stats.update(exchanges=0, exchange_bytes_sent=0, exchange_ms=[], local_permute_passes=0, local_runs=[])
             dist.barrier(); torch.cuda.synchronize()
             l0 = engine.STATS["launches"]
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -132,6 +132,7 @@ def main():
             "nvlink_peak_GBps_per_direction": 900.0,
             "exchange_frac_of_nvlink": round(sent / max(t[2].item(), 1e-9) / 1e6 / 900.0, 4),
             "kernel_launches": engine.STATS["launches"] - l0,
+            "local_runs_gates_launches_ms": q.local_run_times(),
             "gate_amp_updates_per_s": round(n_gates * 2.0 ** n / ((t[0].item() + t[1].item()) * 1e-3), 1),
             "qft_amp_rel_err_max": amp_err, "norm_after": norm,
             "ok": bool(amp_err < 1e-4 and abs(norm - 1) < 1e-3),

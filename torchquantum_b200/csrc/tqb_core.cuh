@@ -31,6 +31,7 @@ struct alignas(16) int4 { int x, y, z, w; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 #endif
 
 namespace tqb {
@@ -679,6 +680,35 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
       }
     } else if (type == TQB_T_HS) {
       TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_HS>(x, m)));
+    } else if (type == TQB_T_LADDER) {
+      if (act) {
+        // phase of this thread's amplitudes from the ladder bits outside the registers ...
+        const float* tab = m.p;
+        float2 ph = make_float2(1.f, 0.f);
+        u32 mt = base & (u32)h.w;
+        while (mt) {
+          const int b = __ffs((int)mt) - 1;
+          mt &= mt - 1u;
+          ph = cmul(ph, *reinterpret_cast<const float2*>(tab + 2 * b));
+        }
+        ph = cmul(ph, *reinterpret_cast<const float2*>(op + TQB_OP_LPH));  // outer bits: once per tile (ladder_outer)
+        // ... times, per register bit of the ladder, that bit's phase on the elements where it is set
+        // (in place: no second 2^R-entry array in registers)
+        const u32 lreg = TQB_OP_LREG(w0), rp = (u32)h.z >> 16;
+#pragma unroll
+        for (int e = 0; e < (1 << R); ++e)
+          if ((act >> e) & 1u) cmul_inplace(ph, x[e]);
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          if ((lreg >> jj) & 1u) {
+            const float2 t = *reinterpret_cast<const float2*>(tab + 2 * ((rp >> (4 * jj)) & 15u));
+#pragma unroll
+            for (int e = 0; e < (1 << R); ++e)
+              if ((e >> jj) & 1)
+                if ((act >> e) & 1u) cmul_inplace(t, x[e]);
+          }
+        }
+      }
     } else {  // TQB_T_REAL with a folded CNOT
       TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_REAL>(x, m)));
     }
@@ -795,6 +825,26 @@ TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float
   }
 }
 
+// TQB_T_LADDER: the phase contributed by the ladder bits in the outer (non-tile) index is the same for the whole
+// tile: one thread per ladder op multiplies it up and parks it in the op's staged record (TQB_OP_LPH)
+TQB_FN void ladder_outer(const BlockCtx& c, int tid) {
+  const int ng = c.s_prog[TQB_S_NGROUPS], nops = c.s_prog[TQB_S_NOPS];
+  int32_t* ops = c.s_prog + TQB_SEG_HDR_WORDS + ng * TQB_GROUP_WORDS;
+  for (int k = tid; k < nops; k += c.nthreads) {
+    int32_t* op = ops + k * TQB_OP_WORDS;
+    if (TQB_OP_TYPE((u32)op[TQB_OP_W0]) != TQB_T_LADDER) continue;
+    const float* tab = c.s_msh + op[TQB_OP_SLOT];
+    float2 ph = make_float2(1.f, 0.f);
+    u32 mo = c.tile_ext & (u32)op[TQB_OP_PM_O];
+    while (mo) {
+      const int b = __ffs((int)mo) - 1;
+      mo &= mo - 1u;
+      ph = cmul(ph, *reinterpret_cast<const float2*>(tab + 2 * (c.T + b)));
+    }
+    *reinterpret_cast<float2*>(op + TQB_OP_LPH) = ph;
+  }
+}
+
 template <int R, bool BWD, class Exec>
 TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
   const int ng = c.s_prog[TQB_S_NGROUPS];
@@ -863,6 +913,7 @@ TQB_FN void run_tile(Exec& ex, const BlockCtx& c, bool shared_staged) {
     if (c.s_prog[TQB_S_PS_LEN] > 0 || (BWD && c.s_prog[TQB_S_G_LEN] > 0))
       ex.par([&](int tid) { stage_segment_sample<BWD>(c, tid); });
     const int ng = c.s_prog[TQB_S_NGROUPS];
+    if (!BWD && c.s_prog[TQB_SEG_HDR_WORDS + 6] > 0) ex.par([&](int tid) { ladder_outer(c, tid); });
     for (int gi = 0; gi < ng; ++gi) {
       const int g = BWD ? ng - 1 - gi : gi;
       ex.par([&](int tid) { run_group<R, BWD>(ex, c, tid, g); });
@@ -1170,6 +1221,10 @@ TQB_FN bool build_param(const int32_t* rec, long long b, const float* params_sh,
   const int d = kind_dim(nent);
   const int type = rec[TQB_B_TYPE];
   if (d == 0) {
+    if (type == TQB_T_LADDER) {  // one rung: the phase applied where both bits are set
+      out[0] = u[1].re; out[1] = inv ? -u[1].im : u[1].im;
+      return false;
+    }
     if (type == TQB_T_DIAGS) {
       pack_scaled_diag(make_float2(u[0].re, inv ? -u[0].im : u[0].im), make_float2(u[1].re, inv ? -u[1].im : u[1].im), out, f);
       return true;

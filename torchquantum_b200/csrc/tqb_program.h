@@ -56,7 +56,8 @@
 #define TQB_S_G_BASE 6    // first float of this segment in every gradient row
 #define TQB_S_G_LEN 7
 
-// group record: [regpos0..3, n_ops, first_op, 0, 0]  (regpos = tile-local bit of register bit j)
+// group record: [regpos0..3, n_ops, first_op, n_ladders, 0]  (regpos = tile-local bit of register bit j;
+// n_ladders: TQB_T_LADDER ops in the whole segment, first group record only)
 // op record (12 words = 48 bytes; words 0-3 are read as one 128-bit word, two ops ahead of use):
 #define TQB_OP_W0 0     // bits 0-1 target register bit j, 2-5 type, 8-15 flags, 16-19 gradient kind, 20-21 jc
 #define TQB_OP_SLOT 1   // float offset of this op's matrix in the staged shared / per-sample floats
@@ -69,7 +70,9 @@
 #define TQB_OP_CV_O 7
 #define TQB_OP_PM_O 8   // DIAG: parity mask over the compressed outer index
 #define TQB_OP_GSLOT 9  // float offset of this op's gradient accumulators in the segment's gradient floats
-                        // (words 10-11: padding)
+#define TQB_OP_LPH 10   // TQB_T_LADDER: words 10-11 are SCRATCH in the staged copy: the kernel writes the tile's outer-bit phase
+                        // (re, im as float bits) here once per tile, every thread reads it back
+#define TQB_OP_LREG(w0) (((w0) >> 22) & 15)
 
 // op types.  Matrix slots are padded to a multiple of 4 floats (16-byte staged loads).
 #define TQB_T_GEN 0    // 2x2 complex on register bit j; 8 floats row-major (re,im)
@@ -85,6 +88,11 @@
 #define TQB_T_RYS 7    // ry:  mode 0: c [[1, -r], [r, 1]], r = s/c;                  mode 1: s [[r, -1], [1, r]], r = c/s
 #define TQB_T_HS 8     // hadamard: a' = a + b, b' = a - b, factor 1/sqrt(2); no floats
 #define TQB_T_DIAGS 9  // one-bit diagonal d0 diag(1, rel): amplitudes whose bit is set *= rel, factor d0; floats rel (re,im), d0 (re,im)
+#define TQB_T_LADDER 10 // controlled phase ladder (a run of cu1 / cphase gates sharing one qubit, e.g. one rung set of a QFT):
+                        // where the controls hold, amp *= prod over the ladder bits that are set of that bit's phase.
+                        // floats: one (re, im) per tile-local bit position [T], then one per compressed outer bit;
+                        // PM_T / PM_O: ladder bits outside the registers; w0 bits 22-25: register bits in the ladder;
+                        // EMASK high 16: tile-local position of register bit j (table index), 4 bits each
 
 #define TQB_F_TCTRL 0x100      // has controls on non-register tile bits (CM_T/CV_T valid)
 #define TQB_F_RCTRL 0x200      // has controls on register bits (EMASK != 0xffff)

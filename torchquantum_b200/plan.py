@@ -40,7 +40,7 @@ class LOp:
     """A lowered micro-op on global bit positions."""
     __slots__ = ("type", "targets", "pmask", "cmask", "cval", "nfloat", "kind", "inverse", "pmode",
                  "poff", "nparam", "const", "rec", "grad", "gkind", "ngrad", "nounapply", "qmask", "ext_dim", "_lt",
-                 "_lc", "_soft", "postx", "scale_const")
+                 "_lc", "_soft", "postx", "scale_const", "rungs")
 
     def __init__(self):
         self.pmask = self.cmask = self.cval = 0
@@ -49,6 +49,7 @@ class LOp:
         self.const, self.rec, self.grad, self.nounapply, self.ext_dim = None, -1, False, False, 0
         self.gkind, self.ngrad = C.G_NONE, 0
         self._lc, self._soft, self.postx, self.scale_const = None, (), None, None
+        self.rungs = None   # T_LADDER: [(global bit, source LOp)]
 
     @property
     def per_sample(self):
@@ -196,6 +197,56 @@ def fold_cnot_sandwiches(lops):
     return out
 
 
+LADDER_MIN = 3   # shortest run of controlled phases worth a ladder op
+
+
+def _is_rung(op):
+    """cu1 / cphase-like: phase e^{i theta} where two bits are both set, nothing else; shared or constant angle."""
+    if op.type != C.T_DIAG or op.grad or op.nounapply or op.pmode not in (None, "sh"):
+        return False
+    if bin(op.cmask).count("1") != 2 or op.cval != op.cmask or (op.pmask & ~op.cmask) or bin(op.pmask).count("1") != 1:
+        return False
+    if op.kind == C.K_CONST:
+        return op.const is not None and op.const[0] == 1 and op.const[1] == 0
+    return op.kind == C.K_PHASE
+
+
+def fold_phase_ladders(lops):
+    """Forward-only programs: a run of >= LADDER_MIN consecutive controlled phases that share one qubit c and hit
+    distinct partners (the rungs H_c, cu1(c+1, c), cu1(c+2, c), ... of a QFT) becomes ONE TQB_T_LADDER op:
+    where bit c is set, the amplitude is multiplied by the product of the phases of the partner bits that are set.
+    One op record and ~200 instructions per thread instead of one masked diagonal op per rung."""
+    out, i = [], 0
+    while i < len(lops):
+        a = lops[i]
+        if _is_rung(a) and i + 1 < len(lops) and _is_rung(lops[i + 1]) and (a.cmask & lops[i + 1].cmask):
+            common = a.cmask & lops[i + 1].cmask
+            if bin(common).count("1") == 1:
+                run, seen, k = [], 0, i
+                while k < len(lops) and _is_rung(lops[k]) and (lops[k].cmask & common):
+                    partner = lops[k].cmask & ~common
+                    if partner == 0 or (partner & seen):
+                        break
+                    seen |= partner
+                    run.append(lops[k])
+                    k += 1
+                if len(run) >= LADDER_MIN:
+                    lad = LOp()
+                    lad.type, lad.rec, lad.pmode = C.T_LADDER, run[0].rec, None
+                    lad.cmask = lad.cval = common
+                    lad.pmask = seen
+                    lad.qmask = common | seen
+                    lad.rungs = [((r.cmask & ~common).bit_length() - 1, r) for r in run]
+                    lad.nfloat = 0   # sized per pass (2 floats per tile-local and per outer bit position)
+                    lad.kind = C.K_CONST
+                    out.append(lad)
+                    i = k
+                    continue
+        out.append(a)
+        i += 1
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 # greedy, dependency-respecting packing
 # ---------------------------------------------------------------------------------------
@@ -308,7 +359,8 @@ def _fill_registers(T, R, reg):
                     w = ((w >> p) << (p + 1)) | (w & ((1 << p) - 1))
                 k = _swz(w) & 15
                 banks[k] = banks.get(k, 0) + 1
-            worst = max(worst, max(banks.values()))
+            if banks:
+                worst = max(worst, max(banks.values()))
         return worst
 
     best, best_deg = None, None
@@ -423,6 +475,11 @@ def _encode_op(op, regs, R, loc, oloc):
     if op.type in (C.T_REAL, C.T_RX):
         assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
     w0 = (op.type << 2) | j | flags | (op.gkind << 16)
+    if op.type == C.T_LADDER:
+        lreg = 0
+        for jj in reg_par:
+            lreg |= 1 << jj
+        w0 |= lreg << 22
     if op.postx is not None:
         assert op.postx in regidx and regidx[op.postx] != j and (op.type != C.T_DIAGS or flags & C.F_DJ)
         w0 |= C.F_POSTX | (regidx[op.postx] << 20)
@@ -443,16 +500,17 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
     st = FusedStage()
     st.n_ops = len(lops)
     # parameter slots in queue order
-    for op in lops:
-        if op.pmode == "sh":
-            op.poff = st.P_sh
-            st.P_sh += op.nparam
-            st.sh_recs.append(op.rec)
-        elif op.pmode == "ps":
-            op.poff = st.P_ps
-            st.P_ps += op.nparam
-            st.ps_recs.append(op.rec)
-        st.any_grad |= op.gkind != C.G_NONE
+    for top in lops:
+        for op in ([r for _, r in top.rungs] if top.rungs else [top]):
+            if op.pmode == "sh":
+                op.poff = st.P_sh
+                st.P_sh += op.nparam
+                st.sh_recs.append(op.rec)
+            elif op.pmode == "ps":
+                op.poff = st.P_ps
+                st.P_ps += op.nparam
+                st.ps_recs.append(op.rec)
+            st.any_grad |= op.gkind != C.G_NONE
     # passes
     t_single = max(t_single, min(t_multi, n_local))
     if n_local <= t_single:
@@ -491,6 +549,8 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
                     op._lc, op._soft = loc[cb], (loc[cb],)
             elif fast and op.type == C.T_DIAGS and (op.pmask.bit_length() - 1) in loc:
                 op._soft = (loc[op.pmask.bit_length() - 1],)
+            if op.type == C.T_LADDER:
+                op.nfloat = (2 * (T + len(outer)) + 3) & ~3
         groups = _pack_groups(ops, R)
         sh_rec0, ps_rec0 = len(table_sh), len(table_ps)
         # split oversize groups, then cut into segments
@@ -543,9 +603,10 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
             sh_max, ps_max, g_max = max(sh_max, sh_len), max(ps_max, ps_len), max(g_max, g_len)
             words += [len(seg), nops, sh_off, sh_len, ps_off, ps_len, g_off, g_len]
             first = 0
+            n_ladders = sum(op.type == C.T_LADDER for op in seg_ops)
             for regs, part in seg:
                 rp = list(regs) + [0] * (4 - len(regs))
-                words += rp + [len(part), first, 0, 0]
+                words += rp + [len(part), first, n_ladders if first == 0 else 0, 0]
                 first += len(part)
             sh_slot = ps_slot = g_slot = 0
             for regs, part in seg:
@@ -559,8 +620,39 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
                         sh_slot += op.nfloat
                     w[C.OP_GSLOT], goff = g_slot, g_off + g_slot
                     g_slot += op.ngrad
+                    if op.type == C.T_LADDER:
+                        rp = 0
+                        for jj, b in enumerate(regs[:R]):
+                            rp |= (b & 15) << (4 * jj)
+                        w[C.OP_EMASK] = (w[C.OP_EMASK] & 0xFFFF) | (rp << 16)
                     words += [_i32(v) for v in w]
                     if op.nfloat == 0:
+                        continue
+                    if op.type == C.T_LADDER:
+                        # one 2-float record per rung at its bit's table position, identity (1, 0) in the gaps
+                        # (records are evaluated concurrently: no two may write the same floats)
+                        rung_at = {(loc[bit] if bit in loc else T + oloc[bit]): r for bit, r in op.rungs}
+                        npos, pos = op.nfloat // 2, 0
+                        while pos < npos:
+                            r = rung_at.get(pos)
+                            if r is None:
+                                end = pos
+                                while end < npos and end not in rung_at:
+                                    end += 1
+                                consts.append(np.tile(np.array([1.0, 0.0], dtype=np.float32), end - pos))
+                                table_sh.append([C.K_CONST, 0, 0, moff + 2 * pos, const_off, 2 * (end - pos), 0, C.T_LADDER,
+                                                 C.G_NONE, 0])
+                                const_off += 2 * (end - pos)
+                                pos = end
+                                continue
+                            if r.kind == C.K_CONST:
+                                consts.append(np.asarray(r.const[2:4], dtype=np.float32))
+                                table_sh.append([C.K_CONST, 0, 0, moff + 2 * pos, const_off, 2, 0, C.T_LADDER, C.G_NONE, 0])
+                                const_off += 2
+                            else:
+                                table_sh.append([r.kind, C.BF_INVERSE if r.inverse else 0, r.poff, moff + 2 * pos, 0, 2,
+                                                 r.nparam, C.T_LADDER, C.G_NONE, 0])
+                            pos += 1
                         continue
                     flags = (C.BF_INVERSE if op.inverse else 0) | (C.BF_PER_SAMPLE if op.pmode == "ps" else 0)
                     coff = 0
@@ -646,7 +738,10 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
 
     def close():
         if cur:
-            plan.stages.append(build_fused_stage(fold_cnot_sandwiches(cur), n, n_total, **tile_kw))
+            ops = fold_cnot_sandwiches(cur)
+            if fast:
+                ops = fold_phase_ladders(ops)
+            plan.stages.append(build_fused_stage(ops, n, n_total, **tile_kw))
             cur.clear()
 
     for rec, (name, wires, inverse, pmode, grad, ext_dim) in enumerate(key):

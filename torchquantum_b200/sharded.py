@@ -120,8 +120,16 @@ class ShardedQuantumDevice:
 
     def _run_local(self, records):
         if records:
+            timed = self.time_exchanges and self._flat.is_cuda
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = engine.STATS["launches"]
+                e0.record()
             self._flat = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank,
                                             inplace=True)
+            if timed:
+                e1.record()
+                self.stats.setdefault("local_runs", []).append((len(records), engine.STATS["launches"] - l0, e0, e1))
 
     def flush(self):
         if not self._queue:
@@ -224,6 +232,10 @@ class ShardedQuantumDevice:
                 self.pos[l] = p + g
             elif p >= nl:
                 self.pos[l] = p - g
+
+    def local_run_times(self):
+        """[(gates, kernel launches, ms)] of every local fused run since the stats were reset (time_exchanges)."""
+        return [(n, l, round(a.elapsed_time(b), 3)) for n, l, a, b in self.stats.get("local_runs", [])]
 
     def exchange_times_ms(self):
         out = [a.elapsed_time(b) for a, b in self.stats["exchange_ms"]]
