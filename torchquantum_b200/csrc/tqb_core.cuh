@@ -12,6 +12,10 @@
 #include "tqb_program.h"
 
 #define TQB_UNREACHABLE() __builtin_unreachable()
+#ifndef TQB_TYPES
+#define TQB_TYPES 0xffffu
+#endif
+#define TQB_HAS(T) (((TQB_TYPES) >> (T)) & 1u)
 #ifndef TQB_FWD_MODE
 // forward op dispatch: 0 = if-chain (default), 1 = switch / jump table.  Measured on B200 (n=28, 64-gate pass):
 // if-chain 6.99 ms, switch 7.80 ms, switch + two ping-pong register arrays 8.83 ms (profiles/r01_kernel_variants.txt)
@@ -19,11 +23,13 @@
 #endif
 #if defined(__CUDACC__)
 #define TQB_FN __device__ __forceinline__
+#define TQB_COLD __device__ __noinline__
 #define TQB_FMA(a, b, c) fmaf((a), (b), (c))
 #else
 #include <cmath>
 #include <cstring>
 #define TQB_FN inline
+#define TQB_COLD static
 #define TQB_FMA(a, b, c) ((a) * (b) + (c))
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
@@ -437,6 +443,19 @@ TQB_FN void perm(float2 (&x)[1 << R], u32 act) {
   }
 }
 
+// CNOT whose control is register bit JC and target register bit J: exchange the pair where the control is set.
+// Compile-time pattern: the compiler emits plain moves for the 2^(R-2) pairs concerned instead of 2^R selects.
+template <int R, int J, int JC>
+TQB_FN void perm_c(float2 (&x)[1 << R]) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if ((e & (1 << J)) || !((e >> (JC >= 0 ? JC : 0)) & 1)) continue;
+    const float2 a = x[e];
+    x[e] = x[e | (1 << J)];
+    x[e | (1 << J)] = a;
+  }
+}
+
 // amp *= (element parity ? dB : dA) on active elements
 template <int R, bool MASKED>
 TQB_FN void diag(float2 (&x)[1 << R], float2 dA, float2 dB, u32 epar, u32 act) {
@@ -661,11 +680,11 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
     // scaled forms and ops with a folded CNOT (programs without a backward)
     const bool postx = w0 & TQB_F_POSTX;
     const int jc = TQB_OP_JC(w0);
-    if (type == TQB_T_RXS) {
+    if (TQB_HAS(TQB_T_RXS) && type == TQB_T_RXS) {
       TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_RXS>(x, m)));
-    } else if (type == TQB_T_RYS) {
+    } else if (TQB_HAS(TQB_T_RYS) && type == TQB_T_RYS) {
       TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_RYS>(x, m)));
-    } else if (type == TQB_T_DIAGS) {
+    } else if (TQB_HAS(TQB_T_DIAGS) && type == TQB_T_DIAGS) {
       if (w0 & TQB_F_DJ) {
         TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_DIAGS>(x, m)));
       } else {
@@ -678,47 +697,18 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
           for (int e = 0; e < (1 << R); ++e) cmul_inplace(rel, x[e]);
         }
       }
-    } else if (type == TQB_T_HS) {
+    } else if (TQB_HAS(TQB_T_HS) && type == TQB_T_HS) {
       TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_HS>(x, m)));
-    } else if (type == TQB_T_LADDER) {
-      if (act) {
-        // phase of this thread's amplitudes from the ladder bits outside the registers ...
-        const float* tab = m.p;
-        float2 ph = make_float2(1.f, 0.f);
-        u32 mt = base & (u32)h.w;
-        while (mt) {
-          const int b = __ffs((int)mt) - 1;
-          mt &= mt - 1u;
-          ph = cmul(ph, *reinterpret_cast<const float2*>(tab + 2 * b));
-        }
-        ph = cmul(ph, *reinterpret_cast<const float2*>(op + TQB_OP_LPH));  // outer bits: once per tile (ladder_outer)
-        // ... times, per register bit of the ladder, that bit's phase on the elements where it is set
-        // (in place: no second 2^R-entry array in registers)
-        const u32 lreg = TQB_OP_LREG(w0), rp = (u32)h.z >> 16;
-#pragma unroll
-        for (int e = 0; e < (1 << R); ++e)
-          if ((act >> e) & 1u) cmul_inplace(ph, x[e]);
-#pragma unroll
-        for (int jj = 0; jj < R; ++jj) {
-          if ((lreg >> jj) & 1u) {
-            const float2 t = *reinterpret_cast<const float2*>(tab + 2 * ((rp >> (4 * jj)) & 15u));
-#pragma unroll
-            for (int e = 0; e < (1 << R); ++e)
-              if ((e >> jj) & 1)
-                if ((act >> e) & 1u) cmul_inplace(t, x[e]);
-          }
-        }
-      }
-    } else {  // TQB_T_REAL with a folded CNOT
+    } else if (TQB_HAS(TQB_T_RXS)) {  // TQB_T_REAL with a folded CNOT (forward-only programs)
       TQB_DISPATCH_JC(j, postx, jc, (fast1q<R, JJ, CC, TQB_T_REAL>(x, m)));
     }
     return;
   }
-  if (type == TQB_T_REAL) {
+  if (TQB_HAS(TQB_T_REAL) && type == TQB_T_REAL) {
     TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)));
-  } else if (type == TQB_T_RX) {
+  } else if (TQB_HAS(TQB_T_RX) && type == TQB_T_RX) {
     TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_RX, false, false>(x, m, act)));
-  } else if (type == TQB_T_DIAG) {
+  } else if (TQB_HAS(TQB_T_DIAG) && type == TQB_T_DIAG) {
     const float4 q = m.q0;
     const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
     const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
@@ -729,12 +719,12 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
       else TQB_DISPATCH_J(j, (diagj<R, JJ, false>(x, dA, dB, act)));
     } else if (masked) { if (act) diag<R, true>(x, dA, dB, epar, act); }
     else diag<R, false>(x, dA, dB, epar, act);
-  } else if (type == TQB_T_PERM) {
+  } else if (TQB_HAS(TQB_T_PERM) && type == TQB_T_PERM) {
     if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act)));
-  } else if (type == TQB_T_GEN) {
+  } else if (TQB_HAS(TQB_T_GEN) && type == TQB_T_GEN) {
     if (masked) { if (act) TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, true, false>(x, m, act))); }
     else TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, false, false>(x, m, act)));
-  } else {  // TQB_T_U2Q
+  } else if (TQB_HAS(TQB_T_U2Q)) {  // TQB_T_U2Q
     if constexpr (R >= 2) { if (act) u2q<R, false>(x, m, act); }
   }
 #endif
@@ -793,7 +783,10 @@ TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&
       }
     }
   } else if (type == TQB_T_PERM) {
-    if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act), perm<R, JJ>(y, act)));
+    if (w0 & TQB_F_POSTX) {
+      const int jc = TQB_OP_JC(w0);
+      TQB_DISPATCH_JC(j, true, jc, (perm_c<R, JJ, CC>(x), perm_c<R, JJ, CC>(y)));
+    } else if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act), perm<R, JJ>(y, act)));
   } else {  // TQB_T_U2Q
     if constexpr (R >= 2) {
       float g32[32];
@@ -842,6 +835,63 @@ TQB_FN void ladder_outer(const BlockCtx& c, int tid) {
       ph = cmul(ph, *reinterpret_cast<const float2*>(tab + 2 * (c.T + b)));
     }
     *reinterpret_cast<float2*>(op + TQB_OP_LPH) = ph;
+  }
+}
+
+// A ladder group (group record word 7 == 1) holds only TQB_T_LADDER ops and no register bits: it is applied
+// straight on the staged tile, 16 amplitudes (tile-local bits 0-3) per thread and item.  It lives outside the
+// register interpreter on purpose: with its data-dependent loops inside apply_op_fwd_inplace every other op of the
+// forward kernel ran 35-40 % slower (profiles/r01_v3_notes.txt).
+// Separate function (not inlined): with this body inlined into the pass kernel, ptxas produced ~20 % slower code
+// for the whole kernel (every op type), although the group is never executed by those programs.
+TQB_COLD void ladder_group(const int32_t* s_prog, float2* s_psi, const float* s_msh, int T, int tps, u32 tile_ext, int tid,
+                           int g) {
+  struct { const int32_t* s_prog; float2* s_psi; const float* s_msh; int T, tps; u32 tile_ext; } c = {s_prog, s_psi, s_msh, T, tps, tile_ext};
+  const int ng = c.s_prog[TQB_S_NGROUPS];
+  const int32_t* gh = c.s_prog + TQB_SEG_HDR_WORDS + g * TQB_GROUP_WORDS;
+  const int nops = gh[4];
+  const int32_t* ops = c.s_prog + TQB_SEG_HDR_WORDS + ng * TQB_GROUP_WORDS + gh[5] * TQB_OP_WORDS;
+  const int slot = tid / c.tps, t = tid % c.tps;
+  float2* sps = c.s_psi + ((size_t)slot << c.T);
+  const u32 tile = 1u << c.T;
+  const u32 ne = tile < 16u ? tile : 16u;         // amplitudes per item
+  const u32 items = tile < 16u ? 1u : tile >> 4;
+  for (int k = 0; k < nops; ++k) {
+    const int32_t* op = ops + k * TQB_OP_WORDS;
+    const u32 w0 = (u32)op[TQB_OP_W0];
+    if ((w0 & TQB_F_OCTRL) && (c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) continue;
+    const float* tab = c.s_msh + op[TQB_OP_SLOT];
+    const float2 lph = *reinterpret_cast<const float2*>(op + TQB_OP_LPH);
+    const u32 pm = (u32)op[TQB_OP_PM_T];
+    const u32 cm = (w0 & TQB_F_TCTRL) ? (u32)op[TQB_OP_CM_T] : 0u, cv = (w0 & TQB_F_TCTRL) ? (u32)op[TQB_OP_CV_T] : 0u;
+    // phases of the 16 patterns of tile-local bits 0-3
+    float2 P[16];
+    P[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float2 tj = make_float2(1.f, 0.f);
+      if ((pm >> jj) & 1u) tj = *reinterpret_cast<const float2*>(tab + 2 * jj);
+#pragma unroll
+      for (int e = (1 << jj); e < (2 << jj); ++e) P[e] = cmul(P[e ^ (1 << jj)], tj);
+    }
+    for (u32 item = (u32)t; item < items; item += (u32)c.tps) {
+      const u32 hi = item << 4;
+      if ((hi & cm & ~15u) != (cv & ~15u)) continue;
+      float2 ph = lph;
+      u32 mt = hi & pm;
+      while (mt) {
+        const int b = __ffs((int)mt) - 1;
+        mt &= mt - 1u;
+        ph = cmul(ph, *reinterpret_cast<const float2*>(tab + 2 * b));
+      }
+#pragma unroll
+      for (u32 e = 0; e < 16u; ++e) {
+        if (e < ne && (e & cm) == (cv & 15u)) {
+          const u32 a = swz(hi | e);
+          sps[a] = cmul(cmul(ph, P[e]), sps[a]);
+        }
+      }
+    }
   }
 }
 
@@ -916,7 +966,8 @@ TQB_FN void run_tile(Exec& ex, const BlockCtx& c, bool shared_staged) {
     if (!BWD && c.s_prog[TQB_SEG_HDR_WORDS + 6] > 0) ex.par([&](int tid) { ladder_outer(c, tid); });
     for (int gi = 0; gi < ng; ++gi) {
       const int g = BWD ? ng - 1 - gi : gi;
-      ex.par([&](int tid) { run_group<R, BWD>(ex, c, tid, g); });
+      if (!BWD && c.s_prog[TQB_SEG_HDR_WORDS + g * TQB_GROUP_WORDS + 7] == 1) ex.par([&](int tid) { ladder_group(c.s_prog, c.s_psi, c.s_msh, c.T, c.tps, c.tile_ext, tid, g); });
+      else ex.par([&](int tid) { run_group<R, BWD>(ex, c, tid, g); });
     }
     if (BWD && c.s_prog[TQB_S_G_LEN] > 0) {
       ex.par([&](int tid) { reduce_partials(c, tid); });

@@ -56,8 +56,9 @@
 #define TQB_S_G_BASE 6    // first float of this segment in every gradient row
 #define TQB_S_G_LEN 7
 
-// group record: [regpos0..3, n_ops, first_op, n_ladders, 0]  (regpos = tile-local bit of register bit j;
-// n_ladders: TQB_T_LADDER ops in the whole segment, first group record only)
+// group record: [regpos0..3, n_ops, first_op, n_ladders, kind]  (regpos = tile-local bit of register bit j;
+// n_ladders: TQB_T_LADDER ops in the whole segment, first group record only; kind 1: ladder group - only
+// TQB_T_LADDER ops, no register bits, applied directly on the staged tile)
 // op record (12 words = 48 bytes; words 0-3 are read as one 128-bit word, two ops ahead of use):
 #define TQB_OP_W0 0     // bits 0-1 target register bit j, 2-5 type, 8-15 flags, 16-19 gradient kind, 20-21 jc
 #define TQB_OP_SLOT 1   // float offset of this op's matrix in the staged shared / per-sample floats
@@ -91,8 +92,8 @@
 #define TQB_T_LADDER 10 // controlled phase ladder (a run of cu1 / cphase gates sharing one qubit, e.g. one rung set of a QFT):
                         // where the controls hold, amp *= prod over the ladder bits that are set of that bit's phase.
                         // floats: one (re, im) per tile-local bit position [T], then one per compressed outer bit;
-                        // PM_T / PM_O: ladder bits outside the registers; w0 bits 22-25: register bits in the ladder;
-                        // EMASK high 16: tile-local position of register bit j (table index), 4 bits each
+                        // PM_T / PM_O: the ladder's tile-local / outer bits; controls in CM_T / CV_T / CM_O / CV_O
+                        // (ladders run in groups of their own, without register bits)
 
 #define TQB_F_TCTRL 0x100      // has controls on non-register tile bits (CM_T/CV_T valid)
 #define TQB_F_RCTRL 0x200      // has controls on register bits (EMASK != 0xffff)

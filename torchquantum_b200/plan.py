@@ -26,6 +26,7 @@ T_MULTI = 12    # tile bits when the state is streamed through HBM
 L_MIN = 5       # contiguous low bits always in the tile (2^5 amplitudes = 256 B runs)
 R_MAX = int(os.environ.get("TQB200_R", C.MAX_R))   # register bits per thread (env: kernel experiments)
 R_GRAD = int(os.environ.get("TQB200_RGRAD", C.MAX_R))
+PERM_C = os.environ.get("TQB200_PERM_C", "0") != "0"       # CNOT between register bits as a compile-time exchange (slower: A/B notes)
 FAST_FWD = os.environ.get("TQB200_FAST_FWD", "1") != "0"   # scaled op forms + CNOT folding in forward-only programs  # register bits of programs that also run backward (two arrays live per thread)
 
 NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32,
@@ -273,9 +274,13 @@ def _pack_groups(ops, R):
     U2Q ops need their targets at register indices (1, 0)."""
     remaining, groups = list(ops), []
     while remaining:
-        reg, blocked, part, rest, soft = [], 0, [], [], []
+        reg, blocked, part, rest, soft, ladder_group = [], 0, [], [], [], False
         for op in remaining:
             ok = not (op.qmask & blocked)
+            if ok and (op.type == C.T_LADDER) != ladder_group and part:
+                ok = False   # ladders run in groups of their own (applied on the staged tile, no register bits)
+            if ok and not part:
+                ladder_group = op.type == C.T_LADDER
             if ok:
                 if op.type == C.T_U2Q:
                     tm, tl = op._lt
@@ -475,11 +480,10 @@ def _encode_op(op, regs, R, loc, oloc):
     if op.type in (C.T_REAL, C.T_RX):
         assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
     w0 = (op.type << 2) | j | flags | (op.gkind << 16)
-    if op.type == C.T_LADDER:
-        lreg = 0
-        for jj in reg_par:
-            lreg |= 1 << jj
-        w0 |= lreg << 22
+    if (PERM_C and op.type == C.T_PERM and len(reg_ctrl) == 1 and reg_ctrl[0][1] == 1 and not cm_t and not cm_o
+            and op._lt and reg_ctrl[0][0] != j):
+        # CNOT between two register bits: compile-time exchange pattern in the kernel (perm_c)
+        w0 |= C.F_POSTX | (reg_ctrl[0][0] << 20)
     if op.postx is not None:
         assert op.postx in regidx and regidx[op.postx] != j and (op.type != C.T_DIAGS or flags & C.F_DJ)
         w0 |= C.F_POSTX | (regidx[op.postx] << 20)
@@ -606,12 +610,13 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
             n_ladders = sum(op.type == C.T_LADDER for op in seg_ops)
             for regs, part in seg:
                 rp = list(regs) + [0] * (4 - len(regs))
-                words += rp + [len(part), first, n_ladders if first == 0 else 0, 0]
+                is_lad = 1 if part and part[0].type == C.T_LADDER else 0
+                words += rp + [len(part), first, n_ladders if first == 0 else 0, is_lad]
                 first += len(part)
             sh_slot = ps_slot = g_slot = 0
             for regs, part in seg:
                 for op in part:
-                    w = _encode_op(op, regs, R, loc, oloc)
+                    w = _encode_op(op, () if op.type == C.T_LADDER else regs, R, loc, oloc)
                     if op.per_sample:
                         w[C.OP_SLOT], moff = ps_slot, ps_off + ps_slot
                         ps_slot += op.nfloat
@@ -620,11 +625,6 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
                         sh_slot += op.nfloat
                     w[C.OP_GSLOT], goff = g_slot, g_off + g_slot
                     g_slot += op.ngrad
-                    if op.type == C.T_LADDER:
-                        rp = 0
-                        for jj, b in enumerate(regs[:R]):
-                            rp |= (b & 15) << (4 * jj)
-                        w[C.OP_EMASK] = (w[C.OP_EMASK] & 0xFFFF) | (rp << 16)
                     words += [_i32(v) for v in w]
                     if op.nfloat == 0:
                         continue
