@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 2
+#define TQB_ABI_VERSION 3
 
 int tqb_abi_version(void);
 const char* tqb_last_error(void);

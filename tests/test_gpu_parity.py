@@ -25,7 +25,7 @@ def test_native_library_loaded():
     from torchquantum_b200 import _native
 
     assert not _native.is_emulated()
-    assert _native.lib().tqb_abi_version() == 2
+    assert _native.lib().tqb_abi_version() == 3
 
 
 def test_every_gate():

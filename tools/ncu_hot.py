@@ -7,6 +7,7 @@ import sys
 
 rep, kre = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+# function names on the source page look like `void tqb_pass_kernel<(int)4, (bool)1, (bool)1>(PassArgs)`
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 allrows = list(csv.reader(out.splitlines()))

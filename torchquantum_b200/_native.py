@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TQB200_LIB") or os.path.join(_HERE, "lib", "libtqb200.so")  # env: kernel A/B experiments
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 _emulated = False

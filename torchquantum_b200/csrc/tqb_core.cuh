@@ -443,19 +443,6 @@ TQB_FN void perm(float2 (&x)[1 << R], u32 act) {
   }
 }
 
-// CNOT whose control is register bit JC and target register bit J: exchange the pair where the control is set.
-// Compile-time pattern: the compiler emits plain moves for the 2^(R-2) pairs concerned instead of 2^R selects.
-template <int R, int J, int JC>
-TQB_FN void perm_c(float2 (&x)[1 << R]) {
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if ((e & (1 << J)) || !((e >> (JC >= 0 ? JC : 0)) & 1)) continue;
-    const float2 a = x[e];
-    x[e] = x[e | (1 << J)];
-    x[e | (1 << J)] = a;
-  }
-}
-
 // amp *= (element parity ? dB : dA) on active elements
 template <int R, bool MASKED>
 TQB_FN void diag(float2 (&x)[1 << R], float2 dA, float2 dB, u32 epar, u32 act) {
@@ -730,74 +717,48 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
 #endif
 }
 
-// backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in
-template <int R, bool MASKED, class Exec>
-TQB_FN void bwd_body(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float2 (&y)[1 << R], const int4 h, const Mat& m,
-                     const int32_t* op, u32 w0, u32 act, u32 base, float* spart, int pstride) {
-  const u32 type = TQB_OP_TYPE(w0);
-  const int j = TQB_OP_J(w0);
-  const u32 gkind = TQB_OP_GKIND(w0);
-  const bool unapply = !(w0 & TQB_F_NOUNAPPLY);
-  const int gslot = op[TQB_OP_GSLOT];
-  if (type == TQB_T_REAL || type == TQB_T_RX || type == TQB_T_GEN) {
-    float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float w = 0.f;
-    if (type == TQB_T_REAL) {
-      TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, true>(x, m, act), u1q<R, JJ, TQB_T_REAL, false, true>(y, m, act)));
-    } else if (type == TQB_T_RX) {
-      TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_RX, false, true>(x, m, act), u1q<R, JJ, TQB_T_RX, false, true>(y, m, act)));
-    } else if (!MASKED || act) {
-      if (unapply) TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, MASKED, true>(x, m, act)));
-      if (gkind == TQB_G_FULL) TQB_DISPATCH_J(j, (grad_full_1q<R, JJ, MASKED>(x, y, act, gacc)));
-      TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, MASKED, true>(y, m, act)));
+// backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in.
+// The masked (controlled) and unmasked variants are split per op TYPE, never around the whole dispatcher: two
+// instantiations of the full dispatcher made the compiler permute the 64 live amplitude registers at every op
+// (ncu: 27 % of the adjoint kernel's instructions were MOVs, 19 % on the line of that split).
+template <int R, bool MASKED>
+TQB_FN void bwd_gen(float2 (&x)[1 << R], float2 (&y)[1 << R], const Mat& m, int j, u32 act, u32 gkind, bool unapply,
+                    float* spart, int pstride, int gslot) {
+  float gacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float w = 0.f;
+  if (!MASKED || act) {
+    if (unapply) TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, MASKED, true>(x, m, act)));
+    if (gkind == TQB_G_FULL) TQB_DISPATCH_J(j, (grad_full_1q<R, JJ, MASKED>(x, y, act, gacc)));
+    TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_GEN, MASKED, true>(y, m, act)));
+  }
+  if (gkind == TQB_G_X) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, false, MASKED>(x, y, act)));
+  if (gkind == TQB_G_Y) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, true, MASKED>(x, y, act)));
+  if (gkind == TQB_G_FULL) stash<8>(spart, pstride, gslot, gacc);
+  else if (gkind != TQB_G_NONE) { float w1[1] = {w}; stash<1>(spart, pstride, gslot, w1); }
+}
+
+template <int R, bool MASKED>
+TQB_FN void bwd_diag(float2 (&x)[1 << R], float2 (&y)[1 << R], float2 dA, float2 dB, u32 w0, int j, u32 epar, u32 tp,
+                     u32 act, u32 gkind, bool unapply, float* spart, int pstride, int gslot) {
+  if (w0 & TQB_F_DJ) {
+    if (!MASKED || act) {
+      if (unapply) TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(x, dA, dB, act)));
+      TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(y, dA, dB, act)));
     }
-    if (gkind == TQB_G_X) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, false, MASKED>(x, y, act)));
-    if (gkind == TQB_G_Y) TQB_DISPATCH_J(j, (w = grad_gen_1q<R, JJ, true, MASKED>(x, y, act)));
-    if (gkind == TQB_G_FULL) stash<8>(spart, pstride, gslot, gacc);
-    else if (gkind != TQB_G_NONE) { float w1[1] = {w}; stash<1>(spart, pstride, gslot, w1); }
-  } else if (type == TQB_T_DIAG) {
-    const float4 q = m.q0;
-    const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
-    const float2 d0 = make_float2(q.x, -q.y), d1 = make_float2(q.z, -q.w);  // conjugated
-    const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
-    const u32 epar = (u32)h.z >> 16;
-    if (w0 & TQB_F_DJ) {
-      if (!MASKED || act) {
-        if (unapply) TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(x, dA, dB, act)));
-        TQB_DISPATCH_J(j, (diagj<R, JJ, MASKED>(y, dA, dB, act)));
-      }
-      if (gkind == TQB_G_DW) {
-        float w2[2] = {0.f, 0.f};
-        TQB_DISPATCH_J(j, (grad_dwj<R, JJ, MASKED>(x, y, tp, act, w2)));
-        stash<2>(spart, pstride, gslot, w2);
-      }
-    } else {
-      if (!MASKED || act) {
-        if (unapply) diag<R, MASKED>(x, dA, dB, epar, act);
-        diag<R, MASKED>(y, dA, dB, epar, act);
-      }
-      if (gkind == TQB_G_DW) {
-        float w2[2];
-        grad_dw<R, MASKED>(x, y, tp, epar, act, w2);
-        stash<2>(spart, pstride, gslot, w2);
-      }
+    if (gkind == TQB_G_DW) {
+      float w2[2] = {0.f, 0.f};
+      TQB_DISPATCH_J(j, (grad_dwj<R, JJ, MASKED>(x, y, tp, act, w2)));
+      stash<2>(spart, pstride, gslot, w2);
     }
-  } else if (type == TQB_T_PERM) {
-    if (w0 & TQB_F_POSTX) {
-      const int jc = TQB_OP_JC(w0);
-      TQB_DISPATCH_JC(j, true, jc, (perm_c<R, JJ, CC>(x), perm_c<R, JJ, CC>(y)));
-    } else if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act), perm<R, JJ>(y, act)));
-  } else {  // TQB_T_U2Q
-    if constexpr (R >= 2) {
-      float g32[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) g32[i] = 0.f;
-      if (act) {
-        if (unapply) u2q<R, true>(x, m, act);
-        if (gkind == TQB_G_FULL) grad_full_2q<R>(x, y, act, g32);
-        u2q<R, true>(y, m, act);
-      }
-      if (gkind == TQB_G_FULL) stash<32>(spart, pstride, gslot, g32);
+  } else {
+    if (!MASKED || act) {
+      if (unapply) diag<R, MASKED>(x, dA, dB, epar, act);
+      diag<R, MASKED>(y, dA, dB, epar, act);
+    }
+    if (gkind == TQB_G_DW) {
+      float w2[2];
+      grad_dw<R, MASKED>(x, y, tp, epar, act, w2);
+      stash<2>(spart, pstride, gslot, w2);
     }
   }
 }
@@ -809,12 +770,56 @@ TQB_FN void apply_op_bwd(Exec& ex, const BlockCtx& c, float2 (&x)[1 << R], float
   if (w0 & TQB_F_OCTRL) {
     if ((c.tile_ext & (u32)op[TQB_OP_CM_O]) != (u32)op[TQB_OP_CV_O]) return;
   }
-  if (w0 & (TQB_F_TCTRL | TQB_F_RCTRL)) {
-    u32 act = (u32)h.z & 0xffffu;
+  const bool masked = w0 & (TQB_F_TCTRL | TQB_F_RCTRL);
+  u32 act = 0xffffu;
+  if (masked) {
+    act = (u32)h.z & 0xffffu;
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
-    bwd_body<R, true, Exec>(ex, c, x, y, h, m, op, w0, act, base, spart, pstride);
-  } else {
-    bwd_body<R, false, Exec>(ex, c, x, y, h, m, op, w0, 0xffffu, base, spart, pstride);
+  }
+  const u32 type = TQB_OP_TYPE(w0);
+  const int j = TQB_OP_J(w0);
+  const u32 gkind = TQB_OP_GKIND(w0);
+  const bool unapply = !(w0 & TQB_F_NOUNAPPLY);
+  const int gslot = op[TQB_OP_GSLOT];
+  if (type == TQB_T_REAL) {          // never controlled (planner): ry, h, ...
+    TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_REAL, false, true>(x, m, act), u1q<R, JJ, TQB_T_REAL, false, true>(y, m, act)));
+    if (gkind == TQB_G_Y) {
+      float w1[1] = {0.f};
+      TQB_DISPATCH_J(j, (w1[0] = grad_gen_1q<R, JJ, true, false>(x, y, act)));
+      stash<1>(spart, pstride, gslot, w1);
+    }
+  } else if (type == TQB_T_RX) {     // never controlled
+    TQB_DISPATCH_J(j, (u1q<R, JJ, TQB_T_RX, false, true>(x, m, act), u1q<R, JJ, TQB_T_RX, false, true>(y, m, act)));
+    if (gkind == TQB_G_X) {
+      float w1[1] = {0.f};
+      TQB_DISPATCH_J(j, (w1[0] = grad_gen_1q<R, JJ, false, false>(x, y, act)));
+      stash<1>(spart, pstride, gslot, w1);
+    }
+  } else if (type == TQB_T_DIAG) {
+    const float4 q = m.q0;
+    const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
+    const float2 d0 = make_float2(q.x, -q.y), d1 = make_float2(q.z, -q.w);  // conjugated
+    const float2 dA = tp ? d1 : d0, dB = tp ? d0 : d1;
+    const u32 epar = (u32)h.z >> 16;
+    if (masked) bwd_diag<R, true>(x, y, dA, dB, w0, j, epar, tp, act, gkind, unapply, spart, pstride, gslot);
+    else bwd_diag<R, false>(x, y, dA, dB, w0, j, epar, tp, act, gkind, unapply, spart, pstride, gslot);
+  } else if (type == TQB_T_PERM) {
+    if (act) TQB_DISPATCH_J(j, (perm<R, JJ>(x, act), perm<R, JJ>(y, act)));
+  } else if (TQB_HAS(TQB_T_GEN) && type == TQB_T_GEN) {
+    if (masked) bwd_gen<R, true>(x, y, m, j, act, gkind, unapply, spart, pstride, gslot);
+    else bwd_gen<R, false>(x, y, m, j, act, gkind, unapply, spart, pstride, gslot);
+  } else if (TQB_HAS(TQB_T_U2Q)) {  // TQB_T_U2Q
+    if constexpr (R >= 2) {
+      float g32[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g32[i] = 0.f;
+      if (act) {
+        if (unapply) u2q<R, true>(x, m, act);
+        if (gkind == TQB_G_FULL) grad_full_2q<R>(x, y, act, g32);
+        u2q<R, true>(y, m, act);
+      }
+      if (gkind == TQB_G_FULL) stash<32>(spart, pstride, gslot, g32);
+    }
   }
 }
 

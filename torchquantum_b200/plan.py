@@ -26,7 +26,6 @@ T_MULTI = 12    # tile bits when the state is streamed through HBM
 L_MIN = 5       # contiguous low bits always in the tile (2^5 amplitudes = 256 B runs)
 R_MAX = int(os.environ.get("TQB200_R", C.MAX_R))   # register bits per thread (env: kernel experiments)
 R_GRAD = int(os.environ.get("TQB200_RGRAD", C.MAX_R))
-PERM_C = os.environ.get("TQB200_PERM_C", "0") != "0"       # CNOT between register bits as a compile-time exchange (slower: A/B notes)
 FAST_FWD = os.environ.get("TQB200_FAST_FWD", "1") != "0"   # scaled op forms + CNOT folding in forward-only programs  # register bits of programs that also run backward (two arrays live per thread)
 
 NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32,
@@ -480,10 +479,6 @@ def _encode_op(op, regs, R, loc, oloc):
     if op.type in (C.T_REAL, C.T_RX):
         assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
     w0 = (op.type << 2) | j | flags | (op.gkind << 16)
-    if (PERM_C and op.type == C.T_PERM and len(reg_ctrl) == 1 and reg_ctrl[0][1] == 1 and not cm_t and not cm_o
-            and op._lt and reg_ctrl[0][0] != j):
-        # CNOT between two register bits: compile-time exchange pattern in the kernel (perm_c)
-        w0 |= C.F_POSTX | (reg_ctrl[0][0] << 20)
     if op.postx is not None:
         assert op.postx in regidx and regidx[op.postx] != j and (op.type != C.T_DIAGS or flags & C.F_DJ)
         w0 |= C.F_POSTX | (regidx[op.postx] << 20)
