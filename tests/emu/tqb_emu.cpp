@@ -27,6 +27,7 @@ struct EmuExec {
   template <class F> void par(F f) { for (int t = 0; t < nthreads; ++t) f(t); }
   template <class F> void par_nosync(F f) { for (int t = 0; t < nthreads; ++t) f(t); }
   void async_copy8(float2* dst, const float2* src) { *dst = *src; }
+  void async_copy16(float2* dst, const float2* src) { dst[0] = src[0]; dst[1] = src[1]; }
   void async_commit() {}
   void async_wait_prev() {}
   void async_wait_all() {}

@@ -62,17 +62,21 @@ TQB_FN float4 ld4(const float* m) { return *reinterpret_cast<const float4*>(m); 
 // an op's staged matrix: pointer + its first four floats, fetched one op ahead of use (run_group)
 struct Mat { const float* p; float4 q0; };
 
-// swizzled position of tile-local amplitude idx in the staged tile (8-byte slots):
-// xor the 4 low bits with the next 4 so that the 16 amplitudes a half-warp touches in one
-// 64-bit shared access fall in 16 distinct bank pairs for every run of consecutive register bits.
-// (GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b).)
-TQB_FN u32 swz(u32 idx) { return idx ^ ((idx >> 4) & 15u); }
+// swizzled position of tile-local amplitude idx in the staged tile (8-byte slots); two layouts, chosen per launch:
+// pair = true  (states streamed through HBM): xor index bits 4-6 into bits 1-3.  Bit 0 stays, so the amplitude pair
+//   (2p, 2p+1) is one aligned 16-byte slot pair: tiles are filled with 16-byte cp.async and drained with 128-bit
+//   shared loads (half the copy instructions: a 1-gate pass went from 4.9 to 6.1 TB/s); the 64-bit accesses of a
+//   half-warp fall in >= 8 distinct bank pairs for runs of consecutive register bits.
+// pair = false (a whole sample staged per CTA, hundreds of gates per load): xor bits 4-7 into bits 0-3, 16 distinct
+//   bank pairs (the on-chip config-2 passes are 2 % faster with it; their tile IO does not matter).
+// (GF(2)-linear either way: swz(a ^ b) == swz(a) ^ swz(b).)
+TQB_FN u32 swz(u32 idx, bool pair) { return pair ? idx ^ (((idx >> 4) & 7u) << 1) : idx ^ ((idx >> 4) & 15u); }
 
 struct BlockCtx {
   int T, L;                // tile bits, contiguous low bits
   int S, tps, nthreads;    // samples per CTA, threads per sample, S * tps
   int bsz, sample0;        // batch size, first sample handled by this work item
-  int multi_tile;          // more than one tile per sample (gradients need atomics)
+  int multi_tile;          // more than one tile per sample (gradients need atomics; pair swizzle)
   u32 tile_ext;            // compressed outer index (+ rank bits in sharded mode)
   u64 outer_off;           // amplitude offset of the tile inside the sample
   u64 sample_stride;       // 2^n
@@ -139,16 +143,31 @@ TQB_FN void load_tile_async(Exec& ex, const BlockCtx& c, int tid, const float2* 
     return;
   }
   const float2* src = g + (u64)b * c.sample_stride + c.outer_off;
-  if (c.tps == 256) {
+  const bool pair = c.multi_tile;
+  if (pair && c.L >= 1) {
+    if (c.tps == 256 && tile >= 512u) {
+      // pair p = t + 256 k covers idx = 2t + 512 k (+1): the swizzle only mixes bits 1-6, so swz(idx) = swz(2t) + 512 k
+      const float2* src_t = src + ((2u * (u32)t) & lowmask);
+      float2* dst_t = dst + swz(2u * (u32)t, true);
+#pragma unroll 4
+      for (u32 k = 0; k < tile; k += 512u)
+        ex.async_copy16(dst_t + k, src_t + ((k & lowmask) + c.s_scat[(2u * (u32)t + k) >> c.L]));
+      return;
+    }
+    for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps)
+      ex.async_copy16(dst + swz(idx, true), src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
+    return;
+  }
+  if (!pair && c.tps == 256) {
     // idx = t + 256 k: the swizzle only mixes bits 0-7, so swz(idx) = swz(t) + 256 k
     const float2* src_t = src + ((u32)t & lowmask);
-    float2* dst_t = dst + swz((u32)t);
+    float2* dst_t = dst + swz((u32)t, false);
 #pragma unroll 4
     for (u32 k = 0; k < tile; k += 256u) ex.async_copy8(dst_t + k, src_t + ((k & lowmask) + c.s_scat[((u32)t + k) >> c.L]));
     return;
   }
   for (u32 idx = t; idx < tile; idx += c.tps)
-    ex.async_copy8(dst + swz(idx), src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
+    ex.async_copy8(dst + swz(idx, pair), src + ((idx & lowmask) + c.s_scat[idx >> c.L]));
 }
 
 // deferred scale factor of the pass for sample b (scaled op forms, csrc/tqb_program.h)
@@ -175,10 +194,18 @@ TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   const bool scaled = pass_scale(c, b, f);
   if (c.tps == 256 && c.L >= 1) {
     // pair p = t + 256 k covers idx = 2p, 2p + 1 = 2t + 512 k (+1): swz(idx) = swz(2t) + 512 k
-    const u32 s0 = swz(2u * (u32)t);
+    const bool pair = c.multi_tile;
+    const u32 s0 = swz(2u * (u32)t, pair);
     const float2* src_a = src + s0;
     const float2* src_b = src + (s0 ^ 1u);
     float2* dst_t = dst + ((2u * (u32)t) & lowmask);
+    if (pair && !scaled) {
+#pragma unroll 4
+      for (u32 k = 0; k < tile; k += 512u)
+        *reinterpret_cast<float4*>(dst_t + ((k & lowmask) + c.s_scat[(2u * (u32)t + k) >> c.L])) =
+            *reinterpret_cast<const float4*>(src_a + k);
+      return;
+    }
     if (scaled) {
 #pragma unroll 4
       for (u32 k = 0; k < tile; k += 512u) {
@@ -196,13 +223,13 @@ TQB_FN void store_tile(const BlockCtx& c, int tid, float2* g, const float2* s) {
   }
   if (c.L >= 1) {
     for (u32 idx = 2u * t; idx < tile; idx += 2u * c.tps) {
-      float2 a = src[swz(idx)], bq = src[swz(idx + 1)];
+      float2 a = src[swz(idx, c.multi_tile)], bq = src[swz(idx + 1, c.multi_tile)];
       if (scaled) { a = cmul(f, a); bq = cmul(f, bq); }
       *reinterpret_cast<float4*>(dst + ((idx & lowmask) + c.s_scat[idx >> c.L])) = make_float4(a.x, a.y, bq.x, bq.y);
     }
   } else {
     for (u32 idx = t; idx < tile; idx += c.tps) {
-      float2 a = src[swz(idx)];
+      float2 a = src[swz(idx, c.multi_tile)];
       if (scaled) a = cmul(f, a);
       dst[c.s_scat[idx]] = a;
     }
@@ -849,8 +876,8 @@ TQB_FN void ladder_outer(const BlockCtx& c, int tid) {
 // forward kernel ran 35-40 % slower (profiles/r01_v3_notes.txt).
 // Separate function (not inlined): with this body inlined into the pass kernel, ptxas produced ~20 % slower code
 // for the whole kernel (every op type), although the group is never executed by those programs.
-TQB_COLD void ladder_group(const int32_t* s_prog, float2* s_psi, const float* s_msh, int T, int tps, u32 tile_ext, int tid,
-                           int g) {
+TQB_COLD void ladder_group(const int32_t* s_prog, float2* s_psi, const float* s_msh, int T, int tps, u32 tile_ext, bool pair,
+                           int tid, int g) {
   struct { const int32_t* s_prog; float2* s_psi; const float* s_msh; int T, tps; u32 tile_ext; } c = {s_prog, s_psi, s_msh, T, tps, tile_ext};
   const int ng = c.s_prog[TQB_S_NGROUPS];
   const int32_t* gh = c.s_prog + TQB_SEG_HDR_WORDS + g * TQB_GROUP_WORDS;
@@ -892,7 +919,7 @@ TQB_COLD void ladder_group(const int32_t* s_prog, float2* s_psi, const float* s_
 #pragma unroll
       for (u32 e = 0; e < 16u; ++e) {
         if (e < ne && (e & cm) == (cv & 15u)) {
-          const u32 a = swz(hi | e);
+          const u32 a = swz(hi | e, pair);
           sps[a] = cmul(cmul(ph, P[e]), sps[a]);
         }
       }
@@ -907,7 +934,7 @@ TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
   const int slot = tid / c.tps, t = tid % c.tps;
   u32 sp[R], zp[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) { sp[j] = (u32)gh[j]; zp[j] = swz(1u << sp[j]); }
+  for (int j = 0; j < R; ++j) { sp[j] = (u32)gh[j]; zp[j] = swz(1u << sp[j], c.multi_tile); }
   sort_positions<R>(sp);
   const int nops = gh[4];
   const int32_t* ops = c.s_prog + TQB_SEG_HDR_WORDS + ng * TQB_GROUP_WORDS + gh[5] * TQB_OP_WORDS;
@@ -920,7 +947,7 @@ TQB_FN void run_group(Exec& ex, const BlockCtx& c, int tid, int g) {
 
   for (int item = t; item < items; item += c.tps) {
     const u32 base = insert_zeros<R>((u32)item, sp);
-    const u32 sb = swz(base);
+    const u32 sb = swz(base, c.multi_tile);
     float2 x[1 << R];
     float2 y[1 << R];
 #pragma unroll
@@ -971,7 +998,7 @@ TQB_FN void run_tile(Exec& ex, const BlockCtx& c, bool shared_staged) {
     if (!BWD && c.s_prog[TQB_SEG_HDR_WORDS + 6] > 0) ex.par([&](int tid) { ladder_outer(c, tid); });
     for (int gi = 0; gi < ng; ++gi) {
       const int g = BWD ? ng - 1 - gi : gi;
-      if (!BWD && c.s_prog[TQB_SEG_HDR_WORDS + g * TQB_GROUP_WORDS + 7] == 1) ex.par([&](int tid) { ladder_group(c.s_prog, c.s_psi, c.s_msh, c.T, c.tps, c.tile_ext, tid, g); });
+      if (!BWD && c.s_prog[TQB_SEG_HDR_WORDS + g * TQB_GROUP_WORDS + 7] == 1) ex.par([&](int tid) { ladder_group(c.s_prog, c.s_psi, c.s_msh, c.T, c.tps, c.tile_ext, c.multi_tile, tid, g); });
       else ex.par([&](int tid) { run_group<R, BWD>(ex, c, tid, g); });
     }
     if (BWD && c.s_prog[TQB_S_G_LEN] > 0) {

@@ -40,6 +40,10 @@ struct CudaExec {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
   }
+  __device__ __forceinline__ void async_copy16(float2* dst, const float2* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+  }
   __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
   __device__ __forceinline__ void async_wait_prev() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
   __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -149,6 +153,8 @@ static int run_pass(bool bwd, const float* psi_src, const float* lam_src, float*
   if (sh_max > TQB_SEG_MAX_SH || ps_max > TQB_SEG_MAX_PS || g_max > TQB_SEG_MAX_G)
     return fail_msg("tqb pass: segment exceeds staging capacity");
   if (bsz <= 0) return 0;
+  if ((((uintptr_t)psi_src | (uintptr_t)psi | (uintptr_t)lam_src | (uintptr_t)lam) & 15) != 0)
+    return fail_msg("tqb pass: state pointers must be 16-byte aligned");
   PassGeom g;
   pass_geometry(n, bsz, T, R, L, bwd, sh_max, ps_max, g_max, 200 * 1024, g);
   if (g.lay.total > 227 * 1024) return fail_msg("tqb pass: tile does not fit shared memory");

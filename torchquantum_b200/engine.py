@@ -90,7 +90,7 @@ def run_fused_inplace(state, stage, n, rank, psh, pps, externs):
     buffer: a tile is fully staged on chip before it is written back).  Used by the sharded device,
     where a second copy of a 16-64 GiB shard is not affordable."""
     _native.check_device(state)
-    assert state.is_contiguous()
+    assert state.is_contiguous() and state.data_ptr() % 16 == 0
     bsz, dev = state.shape[0], state.device
     msh, mps = _build_mats(stage, bsz, psh, pps, externs, dev)
     stream = _native.stream_ptr(state)
@@ -109,6 +109,8 @@ class FusedFn(torch.autograd.Function):
     def forward(ctx, state, psh, pps, stage, n, rank, *externs):
         _native.check_device(state)
         state = state.contiguous()
+        if state.data_ptr() & 15:   # tiles are filled with 16-byte async copies
+            state = state.clone()
         bsz = state.shape[0]
         dev = state.device
         msh, mps = _build_mats(stage, bsz, psh, pps, externs, dev)

@@ -308,6 +308,28 @@ def _pack_groups(ops, R):
     return groups
 
 
+SCALED_MIN = 3   # fewer scaled ops than this in a pass: the deferred factor costs more than the forms save
+
+
+def _unscale(op):
+    """Scaled form -> the plain form of the same gate (a pass with only one or two of them pays more for applying
+    the deferred factor at write-back, 4 FP instructions per amplitude, than the forms save)."""
+    if op.type == C.T_RXS:
+        op.type = C.T_RX
+    elif op.type == C.T_RYS:
+        op.type = C.T_REAL
+    elif op.type == C.T_HS:
+        op.type, op.const = C.T_REAL, _pack_const(_H, C.T_REAL)
+    elif op.type == C.T_DIAGS:
+        op.type = C.T_DIAG
+        if op.kind == C.K_CONST:
+            rel, d0 = complex(op.const[0], op.const[1]), complex(op.const[2], op.const[3])
+            d1 = rel * d0
+            op.const = np.array([d0.real, d0.imag, d1.real, d1.imag], dtype=np.float32)
+    op.scale_const = None
+    op.nfloat = NFLOAT[op.type]
+
+
 def _fold_cnots(part, regs):
     """Fast programs: `G on t; cnot(c -> t)` with c and t both register bits of the group and G an uncontrolled
     one-qubit op on t becomes G with TQB_F_POSTX (the kernel exchanges the pair's outputs where c is set, which
@@ -334,12 +356,13 @@ def _fold_cnots(part, regs):
     return out
 
 
-def _swz(idx):
-    return idx ^ ((idx >> 4) & 15)
+def _swz(idx, pair):
+    # csrc/tqb_core.cuh swz(): pair layout for streamed states, 4-bit xor for single-tile states
+    return idx ^ (((idx >> 4) & 7) << 1) if pair else idx ^ ((idx >> 4) & 15)
 
 
 @functools.lru_cache(maxsize=4096)
-def _fill_registers(T, R, reg):
+def _fill_registers(T, R, reg, pair=False):
     """Complete `reg` (tuple of tile-local target bits) to R distinct bits, choosing the filler bits
     that minimise shared-memory bank conflicts of the group's 64-bit accesses."""
     reg = list(reg)
@@ -361,7 +384,7 @@ def _fill_registers(T, R, reg):
                     break
                 for p in sp:
                     w = ((w >> p) << (p + 1)) | (w & ((1 << p) - 1))
-                k = _swz(w) & 15
+                k = _swz(w, pair) & 15
                 banks[k] = banks.get(k, 0) + 1
             if banks:
                 worst = max(worst, max(banks.values()))
@@ -539,6 +562,10 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         loc = {g: i for i, g in enumerate(tile_bits)}
         outer = [p for p in range(n_total) if p not in loc]
         oloc = {g: i for i, g in enumerate(outer)}
+        if fast and sum(op.type in SCALED for op in ops) < SCALED_MIN:
+            for op in ops:
+                if op.type in SCALED:
+                    _unscale(op)
         for op in ops:
             op._lt = tuple(loc[t] for t in op.targets)
             op._lc, op._soft = None, ()
@@ -555,7 +582,7 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         # split oversize groups, then cut into segments
         flat = []
         for reg, part in groups:
-            regs = _fill_registers(T, R, tuple(reg))
+            regs = _fill_registers(T, R, tuple(reg), n_local > t_single)
             if fast:
                 part = _fold_cnots(part, regs)
             # a chunk of a group must fit one segment's staging capacity on its own
