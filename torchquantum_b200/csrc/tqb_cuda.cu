@@ -77,10 +77,10 @@ struct PassArgs {
 };
 
 // SMALL: CTAs of <= 128 threads (states of <= 11 qubits held whole in shared memory, several samples per CTA).
-// Backward: 2 CTAs/SM (255 registers, no spills) beat 3 (168 registers, 270 B of spills) and 4 (128 registers):
-// 3.17 / 3.51 / 4.19 ms on the config-2 adjoint pass (profiles/r01_v3_notes.txt)
+// Backward (config-2 adjoint pass, profiles/r01_v3_notes.txt): with the per-type dispatcher 3 CTAs/SM (168 registers,
+// 84 B of spills) = 2.28 ms beats 2 CTAs/SM (225 registers, no spills) = 2.47 ms; 4 CTAs/SM (128 registers) spills 200 B.
 #ifndef TQB_BWD_MINB_SMALL
-#define TQB_BWD_MINB_SMALL 2
+#define TQB_BWD_MINB_SMALL 3
 #endif
 template <int R, bool BWD, bool SMALL>
 __global__ void __launch_bounds__(SMALL ? 128 : 256, SMALL ? (BWD ? TQB_BWD_MINB_SMALL : 2 * TQB_FWD_MINB) : (BWD ? TQB_BWD_MINB : TQB_FWD_MINB))
