@@ -445,6 +445,15 @@ def run_ops(n_wires, bsz, ops, init_states=None):
 _PAULI = {"X": _X, "Y": _Y, "Z": _Z, "I": torch.eye(2, dtype=C64)}
 
 
+def pauli_string_matrix(observable):
+    """Kronecker product of the string's Pauli matrices (util/utils.py:990-1009, algorithm/hamiltonian.py:139-145)."""
+    observable = observable.upper()
+    ham = _PAULI[observable[0]]
+    for ch in observable[1:]:
+        ham = torch.kron(ham, _PAULI[ch])
+    return ham
+
+
 def expval_joint_analytical(states_1d, observable):
     """Dense-kron form, exactly measurements.py:232-279. O(4^n): small n only."""
     observable = observable.upper()

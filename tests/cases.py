@@ -382,3 +382,45 @@ def check_qft_phase_ladders(device, n=8, bsz=2):
                 base = off + C.SEG_HDR_WORDS + w[off + C.S_NGROUPS] * C.GROUP_WORDS
                 types += [(int(w[base + k * C.OP_WORDS]) >> 2) & 15 for k in range(w[off + C.S_NOPS])]
     assert types.count(C.T_LADDER) >= n - 3, types
+
+
+def check_vqe_hamiltonian(device, tmp_path):
+    """tq.Hamiltonian / tq.VQE: file format, dense matrix, fused energy and its gradients vs <psi|H|psi>
+    from the dense matrix on the oracle's state; a few optimiser steps lower the energy."""
+    path = str(tmp_path / "toy.txt")
+    with open(path, "w") as f:
+        f.write("toy jw 3\n-0.81 I0 I1\n0.25 Z0\n-0.4 Z1 Z2\n0.17 X0 X1\n0.3 Y1 Y2\n-0.22 X0 Z1 Y2\n")
+    hamil = tq.Hamiltonian.from_file(path)
+    assert hamil.paulis == ["III", "ZII", "IZZ", "XXI", "IYY", "XZY"] and len(hamil) == 6
+    H = sum(c * O.pauli_string_matrix(p) for c, p in zip(hamil.coeffs, hamil.paulis))
+    assert_close(hamil.matrix, H, what="Hamiltonian.matrix")
+    little = tq.Hamiltonian([1.0], ["XZI"], endianness="little")
+    assert little.paulis == ["IZX"]
+    torch.manual_seed(1)
+    ansatz = tq.EfficientSU2(n_wires=3, reps=2, entanglement_layer="linear")
+    vqe = tq.VQE(hamil, ansatz, {"device": device, "n_epochs": 2, "n_steps": 3, "lr": 0.1})
+    loss = vqe.get_loss()
+    params = list(ansatz.parameters())
+    grads = torch.autograd.grad(loss.sum(), params)
+    leaves = [p.detach().cpu().clone().requires_grad_(True) for p in params]
+    by_id = {id(p): l for p, l in zip(params, leaves)}
+    ops = []
+    for layer in ansatz.layers_all:
+        for k, o in enumerate(layer.ops_all):
+            if o.params is not None:
+                ops.append({"name": o.name.lower(), "wires": [k], "params": by_id[id(o.params)]})
+            else:
+                ops.append({"name": "cnot", "wires": [k, k + 1]})
+    st = O.run_ops(3, 1, ops)
+    want = torch.einsum("bi,ij,bj->b", st.conj(), H.to(st.dtype), st).real
+    assert_close(loss, want, rtol=1e-4, what="VQE energy")
+    gw = torch.autograd.grad(want.sum(), leaves)
+    assert_close(torch.cat([g.reshape(-1) for g in grads]), torch.cat([g.reshape(-1) for g in gw]), rtol=1e-4, what="VQE grads")
+    e0 = float(loss.detach())
+    e1 = vqe.train()
+    assert e1 < e0, (e0, e1)
+    # the reference's own per-term loop over hamil_info gives the same energy
+    q = tq.QuantumDevice(n_wires=3, bsz=1, device=device)
+    ansatz(q)
+    loop = sum(expval_joint_analytical(q, h["pauli_string"]) * h["coeff"] for h in hamil.hamil_info["hamil_list"])
+    assert_close(loop, vqe.get_expval(q), rtol=1e-4, what="per-term loop vs fused energy")

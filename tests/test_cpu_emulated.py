@@ -126,3 +126,7 @@ def test_qft_phase_ladders():
 def test_qft_phase_ladders_multi_tile():
     P.T_SINGLE, P.T_MULTI, P.L_MIN = 4, 5, 2
     cases.check_qft_phase_ladders("cpu", n=8, bsz=1)
+
+
+def test_vqe_hamiltonian(tmp_path):
+    cases.check_vqe_hamiltonian("cpu", tmp_path)

@@ -136,6 +136,10 @@ def test_qft_phase_ladders():
     cases.check_qft_phase_ladders(DEV, n=15, bsz=1)
 
 
+def test_vqe_hamiltonian(tmp_path):
+    cases.check_vqe_hamiltonian(DEV, tmp_path)
+
+
 def test_per_sample_params_large_batch():
     ops = cases.brickwork_ops(6, 6, seed=1, per_sample_bsz=300)
     cases.check_against_oracle(DEV, 6, 300, ops, grad=True)

@@ -18,5 +18,6 @@ from .measure_modules import MeasureAll, MeasureMultipleTimes, MeasureMultiPauli
 from .encoding import *  # noqa: F401,F403
 from .layer import *  # noqa: F401,F403
 from .graphs import GraphedStep  # noqa: F401
+from .algorithm import Hamiltonian, VQE  # noqa: F401
 
 __version__ = "0.1.0"
