@@ -424,3 +424,27 @@ def check_vqe_hamiltonian(device, tmp_path):
     ansatz(q)
     loop = sum(expval_joint_analytical(q, h["pauli_string"]) * h["coeff"] for h in hamil.hamil_info["hamil_list"])
     assert_close(loop, vqe.get_expval(q), rtol=1e-4, what="per-term loop vs fused energy")
+
+
+def check_speculative_readout(device, n=4, bsz=3):
+    """Single-string read-outs are served from one speculative multi-string launch when the previous state was
+    asked for the same strings; the values and gradients must not depend on what was predicted."""
+    from torchquantum_b200 import measurement as M
+
+    g = torch.Generator().manual_seed(2)
+    asks = [["ZIII", "IZII", "XXII"], ["ZIII", "IZII", "XXII"], ["ZIII", "YYZZ"], ["IZII"], ["XXII", "ZIII", "YYZZ"]]
+    for it, strings in enumerate(asks):
+        st = torch.randn(bsz, 2 ** n, 2, generator=g)
+        st = torch.view_as_complex(st / st.flatten(1).norm(dim=1).reshape(bsz, 1, 1)).contiguous()
+        sd = st.to(device).requires_grad_(True)
+        q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+        q.set_states(sd)
+        w = torch.randn(bsz, len(strings), generator=g)
+        got = torch.stack([expval_joint_analytical(q, s) for s in strings], dim=1)
+        sc = st.clone().requires_grad_(True)
+        want = torch.stack([O.expval_joint_analytical(sc, s) for s in strings], dim=1)
+        assert_close(got, want, what=f"speculative read-out, state {it}")
+        (gg,) = torch.autograd.grad((got * w.to(device)).sum(), sd)
+        (gw,) = torch.autograd.grad((want * w).sum(), sc)
+        assert_close(gg, gw, rtol=1e-4, what=f"speculative read-out grad, state {it}")
+    assert M._READOUT_HISTORY, "nothing was learned"

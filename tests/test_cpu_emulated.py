@@ -130,3 +130,7 @@ def test_qft_phase_ladders_multi_tile():
 
 def test_vqe_hamiltonian(tmp_path):
     cases.check_vqe_hamiltonian("cpu", tmp_path)
+
+
+def test_speculative_readout():
+    cases.check_speculative_readout("cpu")

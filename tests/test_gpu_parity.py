@@ -136,6 +136,10 @@ def test_qft_phase_ladders():
     cases.check_qft_phase_ladders(DEV, n=15, bsz=1)
 
 
+def test_speculative_readout():
+    cases.check_speculative_readout(DEV)
+
+
 def test_vqe_hamiltonian(tmp_path):
     cases.check_vqe_hamiltonian(DEV, tmp_path)
 

@@ -11,16 +11,12 @@
 #pragma once
 #include "tqb_program.h"
 
-#define TQB_UNREACHABLE() __builtin_unreachable()
+// compile-time op-type mask for experiments ("lean" builds holding only the op types one program family needs ran
+// 2-3 % faster: not worth extra binaries; profiles/r01_v3_notes.txt).  Default: every type.
 #ifndef TQB_TYPES
 #define TQB_TYPES 0xffffu
 #endif
 #define TQB_HAS(T) (((TQB_TYPES) >> (T)) & 1u)
-#ifndef TQB_FWD_MODE
-// forward op dispatch: 0 = if-chain (default), 1 = switch / jump table.  Measured on B200 (n=28, 64-gate pass):
-// if-chain 6.99 ms, switch 7.80 ms, switch + two ping-pong register arrays 8.83 ms (profiles/r01_kernel_variants.txt)
-#define TQB_FWD_MODE 0
-#endif
 #if defined(__CUDACC__)
 #define TQB_FN __device__ __forceinline__
 #define TQB_COLD __device__ __noinline__
@@ -649,13 +645,8 @@ TQB_FN void sort_positions(u32 (&sp)[R]) {
     }                                                                                                \
   } while (0))
 
-#define TQB_CASES_J(TYPE, CALL)                                                                   \
-  case TQB_OP_CODE(TYPE, 0): { constexpr int JJ = 0; CALL; } break;                                \
-  case TQB_OP_CODE(TYPE, 1): if constexpr (R > 1) { constexpr int JJ = 1; CALL; } break;           \
-  case TQB_OP_CODE(TYPE, 2): if constexpr (R > 2) { constexpr int JJ = 2; CALL; } break;           \
-  case TQB_OP_CODE(TYPE, 3): if constexpr (R > 3) { constexpr int JJ = 3; CALL; } break;
-
-// forward op, in place on the thread's register array (TQB_FWD_MODE 0: if-chain, 1: switch)
+// forward op, in place on the thread's register array.  Dispatch is an if-chain ordered by frequency: a switch /
+// jump table measured 10 % slower (profiles/r01_kernel_variants.txt)
 template <int R, class Exec>
 TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const int4 h, const Mat& m, const int32_t* op, u32 base) {
   const u32 w0 = (u32)h.x;
@@ -670,26 +661,6 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
     act = (u32)h.z & 0xffffu;
     if ((w0 & TQB_F_TCTRL) && (base & (u32)op[TQB_OP_CM_T]) != (u32)op[TQB_OP_CV_T]) act = 0u;
   }
-#if TQB_FWD_MODE == 1
-  switch (w0 & 63u) {
-    TQB_CASES_J(TQB_T_REAL, (u1q<R, JJ, TQB_T_REAL, false, false>(x, m, act)))
-    TQB_CASES_J(TQB_T_RX, (u1q<R, JJ, TQB_T_RX, false, false>(x, m, act)))
-    TQB_CASES_J(TQB_T_GEN, (masked ? u1q<R, JJ, TQB_T_GEN, true, false>(x, m, act) : u1q<R, JJ, TQB_T_GEN, false, false>(x, m, act)))
-    TQB_CASES_J(TQB_T_PERM, (perm<R, JJ>(x, act)))
-    case TQB_OP_CODE(TQB_T_DIAG, 0): case TQB_OP_CODE(TQB_T_DIAG, 1): case TQB_OP_CODE(TQB_T_DIAG, 2):
-    case TQB_OP_CODE(TQB_T_DIAG, 3): {
-      const float4 q = m.q0;
-      const u32 tp = (u32)(__popc(base & (u32)h.w) + __popc(c.tile_ext & (u32)op[TQB_OP_PM_O])) & 1u;
-      const float2 d0 = make_float2(q.x, q.y), d1 = make_float2(q.z, q.w);
-      if (masked) diag<R, true>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)h.z >> 16, act);
-      else diag<R, false>(x, tp ? d1 : d0, tp ? d0 : d1, (u32)h.z >> 16, act);
-    } break;
-    case TQB_OP_CODE(TQB_T_U2Q, 0):
-      if constexpr (R >= 2) u2q<R, false>(x, m, act);
-      break;
-    default: TQB_UNREACHABLE(); break;
-  }
-#else
   if (type >= TQB_T_RXS || (w0 & TQB_F_POSTX)) {
     // scaled forms and ops with a folded CNOT (programs without a backward)
     const bool postx = w0 & TQB_F_POSTX;
@@ -741,7 +712,6 @@ TQB_FN void apply_op_fwd_inplace(const BlockCtx& c, float2 (&x)[1 << R], const i
   } else if (TQB_HAS(TQB_T_U2Q)) {  // TQB_T_U2Q
     if constexpr (R >= 2) { if (act) u2q<R, false>(x, m, act); }
   }
-#endif
 }
 
 // backward of one op: x holds psi_out (psi_in when NOUNAPPLY), y holds lam_out; leaves psi_in / lam_in.

@@ -410,6 +410,52 @@ __global__ void tqb_expval_pauli_bwd_kernel(const float2* state, int n, long lon
   grad[i] = acc;
 }
 
+// Same for small states (n <= 13): one warp per sample, amplitude pairs as 128-bit loads / stores, the term table
+// (masks, phase, 2 g[b][t]) staged in shared memory 32 terms at a time.
+__global__ void __launch_bounds__(256) tqb_expval_pauli_bwd_warp_kernel(const float2* state, int n, long long bsz,
+                                                                         const u64* xm, const u64* zm, const int* ny,
+                                                                         int nterms, const float* gout, float2* grad) {
+  __shared__ u32 s_x[8][32], s_z[8][32], s_ph[8][32];
+  __shared__ float s_g[8][32];
+  const int wib = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  const long long b = (long long)blockIdx.x * 8 + wib;
+  const bool live = b < bsz;
+  const float4* psi4 = reinterpret_cast<const float4*>(state + ((live ? b : 0) << n));
+  float4* out4 = reinterpret_cast<float4*>(grad + ((live ? b : 0) << n));
+  const u32 npairs = 1u << (n - 1);
+  for (int t0 = 0; t0 < nterms; t0 += 32) {
+    const int nt = nterms - t0 < 32 ? nterms - t0 : 32;
+    __syncwarp();
+    if ((int)lane < nt) {
+      s_x[wib][lane] = (u32)xm[t0 + lane]; s_z[wib][lane] = (u32)zm[t0 + lane]; s_ph[wib][lane] = (u32)(ny[t0 + lane] & 3);
+      s_g[wib][lane] = live ? 2.f * gout[b * nterms + t0 + lane] : 0.f;
+    }
+    __syncwarp();
+    if (!live) continue;
+    for (u32 p = lane; p < npairs; p += 32u) {
+      float4 acc = t0 == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : out4[p];
+      for (int t = 0; t < nt; ++t) {
+        const u32 x = s_x[wib][t], z = s_z[wib][t], ph = s_ph[wib][t];
+        const float g = s_g[wib][t];
+        float4 v = psi4[p ^ (x >> 1)];                 // psi[j], j = k ^ x for k = 2p, 2p + 1
+        if (x & 1u) v = make_float4(v.z, v.w, v.x, v.y);
+        // i^ny psi[j]
+        if (ph == 1u) v = make_float4(-v.y, v.x, -v.w, v.z);
+        else if (ph == 2u) v = make_float4(-v.x, -v.y, -v.z, -v.w);
+        else if (ph == 3u) v = make_float4(v.y, -v.x, v.w, -v.z);
+        // sign (-1)^popc(j & z) for j = (2p ^ x) and (2p + 1) ^ x
+        const u32 j0 = (2u * p) ^ x;
+        const u32 par0 = (u32)__popc(j0 & z) & 1u, par1 = (u32)__popc((j0 ^ 1u) & z) & 1u;
+        const float g0 = par0 ? -g : g, g1 = par1 ? -g : g;
+        acc.x = fmaf(g0, v.x, acc.x); acc.y = fmaf(g0, v.y, acc.y);
+        acc.z = fmaf(g1, v.z, acc.z); acc.w = fmaf(g1, v.w, acc.w);
+      }
+      out4[p] = acc;
+    }
+  }
+}
+
 // out[b][j] (+)= sum_k |psi_k|^2 (1 - 2 bit_j(k)) for j < n ; out[b][n] (+)= sum_k |psi_k|^2
 __global__ void __launch_bounds__(256) tqb_expval_z_kernel(const float2* state, int n, float* out, int chunk_log2,
                                                             int use_atomic) {
@@ -609,6 +655,13 @@ int tqb_expval_pauli_bwd(const float* state, int n_qubits, long long bsz, const 
                          float* grad_state, void* stream) {
   const long long total = bsz << n_qubits;
   if (total <= 0) return 0;
+  if (n_qubits >= 1 && n_qubits <= 13 && bsz >= 64 && n_terms >= 1) {  // one warp per sample
+    tqb_expval_pauli_bwd_warp_kernel<<<(unsigned)((bsz + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(state), n_qubits, bsz, xmask_dev, zmask_dev, ny_dev, n_terms, grad_out,
+        reinterpret_cast<float2*>(grad_state));
+    TQB_CHECK_LAUNCH("tqb_expval_pauli_bwd_warp_kernel");
+    return 0;
+  }
   tqb_expval_pauli_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2*>(state), n_qubits, total, xmask_dev, zmask_dev, ny_dev, n_terms, grad_out,
       reinterpret_cast<float2*>(grad_state));

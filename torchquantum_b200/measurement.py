@@ -10,6 +10,7 @@
   with the reference's `random.choices` and the shared stream advances identically.
 """
 import random
+import weakref
 from collections import OrderedDict
 from typing import List, Union
 
@@ -103,17 +104,22 @@ class _StateHubFn(torch.autograd.Function):
         return grad, None, None
 
 
+def _launch_expval(state, n, xm, zm, ny):
+    bsz, nt = state.shape[0], xm.shape[0]
+    # blocks of one sample accumulate atomically only when the state spans several chunks (n > 12)
+    out = (torch.zeros if n > 12 else torch.empty)(bsz, nt, dtype=torch.float32, device=state.device)
+    _native.call("tqb_expval_pauli", _ptr(state), n, bsz, _ptr(xm), _ptr(zm), _ptr(ny), nt, _ptr(out),
+                 _native.stream_ptr(state))
+    STATS["launches"] += 1
+    return out
+
+
 class _ExpvalPauliFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, state, n, xm, zm, ny, observables, pending):
+    def forward(ctx, state, n, xm, zm, ny, observables, pending, precomputed=None):
         _native.check_device(state)
         state = state.contiguous()
-        bsz, nt = state.shape[0], xm.shape[0]
-        # blocks of one sample accumulate atomically only when the state spans several chunks (n > 12)
-        out = (torch.zeros if n > 12 else torch.empty)(bsz, nt, dtype=torch.float32, device=state.device)
-        _native.call("tqb_expval_pauli", _ptr(state), n, bsz, _ptr(xm), _ptr(zm), _ptr(ny), nt, _ptr(out),
-                     _native.stream_ptr(state))
-        STATS["launches"] += 1
+        out = precomputed if precomputed is not None else _launch_expval(state, n, xm, zm, ny)
         ctx.n, ctx.pending, ctx.observables = n, pending, observables
         if pending is None:
             ctx.save_for_backward(state, xm, zm, ny)
@@ -124,14 +130,14 @@ class _ExpvalPauliFn(torch.autograd.Function):
         if ctx.pending is not None:  # the state's hub node runs the kernel for all read-outs at once
             ctx.pending.obs.extend(ctx.observables)
             ctx.pending.gouts.append(gout)
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         state, xm, zm, ny = ctx.saved_tensors
         gout = gout.contiguous()
         grad = torch.empty_like(state)
         _native.call("tqb_expval_pauli_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(xm), _ptr(zm), _ptr(ny),
                      xm.shape[0], _ptr(gout), _ptr(grad), _native.stream_ptr(state))
         STATS["launches"] += 1
-        return grad, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None
 
 
 def _hub(qdev, states):
@@ -175,11 +181,43 @@ def expval_joint_analytical_multi(qdev, observables: List[str]):
     if getattr(qdev, "is_sharded", False):
         return qdev.expval_pauli(list(observables))
     states = qdev.get_states_1d()
+    obs = tuple(o.upper() for o in observables)
+    pre = _speculative_readout(qdev, states, obs[0]) if len(obs) == 1 else None
     xm, zm, ny = _mask_tensors(observables, states.device)
     pending = None
     if torch.is_grad_enabled() and states.requires_grad:
         states, pending = _hub(qdev, states)
-    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny, tuple(o.upper() for o in observables), pending)
+    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny, obs, pending, pre)
+
+
+# The reference API evaluates a Hamiltonian with ONE call per Pauli string (algorithm/vqe.py:88-95, examples/vqe), so a
+# training step asks for the same strings on every new state.  The strings read on the previous state of the same width
+# are remembered; the first single-string read-out on a new state evaluates all of them in one multi-term launch (the
+# terms share every load of the state) and the following calls are served from that result.  Values are identical to
+# per-string launches (same accumulation order per term); a string that was not predicted is simply launched on its own.
+_READOUT_HISTORY = {}   # (n_wires, device) -> tuple of strings read on the previous state of that width
+_READOUT_CURRENT = {}   # (n_wires, device) -> [weakref to the state being read, {string: [bsz, 1] values}, [strings so far]]
+SPECULATIVE_READOUT = True
+
+
+def _speculative_readout(qdev, states, ob):
+    if not SPECULATIVE_READOUT:
+        return None
+    key = (qdev.n_wires, states.device)
+    c = _READOUT_CURRENT.get(key)
+    if c is None or c[0]() is not states:
+        if c is not None and len(c[2]) > 1:
+            _READOUT_HISTORY[key] = tuple(dict.fromkeys(c[2]))   # what the previous state was asked for, in order
+        c = _READOUT_CURRENT[key] = [weakref.ref(states), {}, []]
+        predicted = _READOUT_HISTORY.get(key, ())
+        if len(predicted) > 1 and ob in predicted:
+            xm, zm, ny = _mask_tensors(list(predicted), states.device)
+            with torch.no_grad():
+                vals = _launch_expval(states.detach().contiguous(), qdev.n_wires, xm, zm, ny)
+            for t, name in enumerate(predicted):
+                c[1][name] = vals[:, t:t + 1]
+    c[2].append(ob)
+    return c[1].get(ob)
 
 
 def expval_joint_analytical(qdev, observable: str):
