@@ -19,7 +19,7 @@
  *                            (functional/gate_wrapper.py:96-140, :18-93), here many gates per pass
  *   tqb_pass_backward +   <- torch autograd through every bmm/permute/cos/sin node of the above
  *   tqb_build_mats_bwd       (exercised by examples/mnist/mnist.py:143-146); here an adjoint sweep
- *   tqb_apply_dense       <- the same bmm for arbitrary 2^k x 2^k matrices (qft, qubitunitary*)
+ *   tqb_apply_dense(_tc)  <- the same bmm for arbitrary 2^k x 2^k matrices (qft, qubitunitary*)
  *   tqb_expval_pauli      <- expval_joint_analytical (measurement/measurements.py:232-279)
  *   tqb_expval_z          <- the marginal/eigenvalue part of expval / MeasureAll (:297-312)
  *   tqb_probs, tqb_sample_counts <- measure (:37-74): |psi|^2 on the host + random.choices
@@ -77,6 +77,12 @@ int tqb_pass_backward(const float* psi_src, const float* lam_src, float* psi_dst
 int tqb_apply_dense(const float* in, float* out, int n_qubits, long long bsz, const float* mats,
                     long long mat_stride_complex, int k, const int* bitpos_dev, int conj_transpose,
                     void* stream);
+/* Tensor-core form of tqb_apply_dense for ONE matrix shared by the batch, 4 <= k <= 7 and n_qubits >= 12
+ * (mma.sync TF32 with a 3xTF32 error-compensated split).  bitpos_host: k bit positions on the
+ * HOST, matrix MSB first.  Replaces the same reference code as tqb_apply_dense (functional/qft.py:19-33,
+ * functional/qubit_unitary.py:19-93 through gate_wrapper.py:96-140). */
+int tqb_apply_dense_tc(const float* in, float* out, int n_qubits, long long bsz, const float* mat, int k,
+                       const int* bitpos_host, int conj_transpose, void* stream);
 /* G[b][r][c] = sum_rest lam_out[b][r,rest] conj(psi_in[b][c,rest]) (complex64 [bsz][2^k][2^k]) */
 int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long long bsz, int k,
                    const int* bitpos_dev, float* G, void* stream);

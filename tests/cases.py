@@ -448,3 +448,34 @@ def check_speculative_readout(device, n=4, bsz=3):
         (gw,) = torch.autograd.grad((want * w).sum(), sc)
         assert_close(gg, gw, rtol=1e-4, what=f"speculative read-out grad, state {it}")
     assert M._READOUT_HISTORY, "nothing was learned"
+
+
+def check_dense_blocks(device, n=13):
+    """Dense k-qubit unitaries (tqf.qft, qubitunitaryfast on 4..7 wires, forward / inverse / gradient w.r.t. the state)
+    vs the oracle; on the GPU with n >= 12 this is the tensor-core (3xTF32) kernel."""
+    g = torch.Generator().manual_seed(7)
+    init = torch.randn(2, 2 ** n, 2, generator=g)
+    init = torch.view_as_complex(init / init.flatten(1).norm(dim=1).reshape(2, 1, 1)).contiguous()
+    rng = np.random.default_rng(3)
+    for k in (4, 5, 6, 7):
+        wires = [int(w) for w in rng.choice(n, size=k, replace=False)]
+        a = torch.randn(2 ** k, 2 ** k, 2, generator=g)
+        u, _ = torch.linalg.qr(torch.view_as_complex(a).contiguous())
+        u = u.to(torch.complex64)
+        for inverse in (False, True):
+            sd = init.clone().to(device).requires_grad_(True)
+            q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+            q.set_states(sd)
+            tqf.qubitunitaryfast(q, wires=wires, params=u.to(device), inverse=inverse)
+            tqf.qft(q, wires=wires[:5] if k >= 5 else wires, inverse=not inverse)
+            got = q.get_states_1d()
+            sc = init.clone().requires_grad_(True)
+            ops = [{"name": "qubitunitaryfast", "wires": wires, "params": u, "inverse": inverse},
+                   {"name": "qft", "wires": wires[:5] if k >= 5 else wires, "inverse": not inverse}]
+            want = O.run_ops(n, 2, ops, init_states=sc)
+            assert_close(got, want, what=f"dense k={k} inverse={inverse}")
+            proj = torch.randn(2, 2 ** n, 2, generator=g)
+            proj = torch.view_as_complex(proj).contiguous()
+            (gg,) = torch.autograd.grad((got * proj.to(device).conj()).real.sum(), sd)
+            (gw,) = torch.autograd.grad((want * proj.conj()).real.sum(), sc)
+            assert_close(gg, gw, rtol=1e-4, what=f"dense k={k} grad wrt state")

@@ -148,6 +148,12 @@ int tqb_apply_dense(const float* in_, float* out_, int n, long long bsz, const f
   return 0;
 }
 
+int tqb_apply_dense_tc(const float* in_, float* out_, int n, long long bsz, const float* mat_, int k, const int* bitpos_host,
+                       int conj_t, void* st) {
+  if (k < 4 || k > 7 || n < 12) return fail_msg("tqb_apply_dense_tc: needs 4 <= k <= 7 and n_qubits >= 12");
+  return tqb_apply_dense(in_, out_, n, bsz, mat_, 0, k, bitpos_host, conj_t, st);
+}
+
 int tqb_dense_grad(const float* psi_, const float* lam_, int n, long long bsz, int k, const int* bitpos, float* G_, void*) {
   const cf* psi = reinterpret_cast<const cf*>(psi_);
   const cf* lam = reinterpret_cast<const cf*>(lam_);

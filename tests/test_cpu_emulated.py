@@ -134,3 +134,7 @@ def test_vqe_hamiltonian(tmp_path):
 
 def test_speculative_readout():
     cases.check_speculative_readout("cpu")
+
+
+def test_dense_blocks():
+    cases.check_dense_blocks("cpu", n=8)

@@ -136,6 +136,13 @@ def test_qft_phase_ladders():
     cases.check_qft_phase_ladders(DEV, n=15, bsz=1)
 
 
+def test_dense_blocks_tensor_core():
+    """K4: qubitunitaryfast / qft on 4-7 wires through the 3xTF32 tensor-core kernel (n >= 12) vs the oracle, and the
+    same circuit through the CUDA-core dense kernel (n = 11)."""
+    cases.check_dense_blocks(DEV, n=13)
+    cases.check_dense_blocks(DEV, n=11)
+
+
 def test_speculative_readout():
     cases.check_speculative_readout(DEV)
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     "tqb_pass_forward": [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _u, _vp],
     "tqb_pass_backward": [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _u, _vp],
     "tqb_apply_dense": [_vp, _vp, _i, _ll, _vp, _ll, _i, _vp, _i, _vp],
+    "tqb_apply_dense_tc": [_vp, _vp, _i, _ll, _vp, _i, _vp, _i, _vp],
     "tqb_dense_grad": [_vp, _vp, _i, _ll, _i, _vp, _vp, _vp],
     "tqb_expval_pauli": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp],
     "tqb_expval_pauli_bwd": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp],

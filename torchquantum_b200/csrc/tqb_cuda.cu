@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "tqb_core.cuh"
+#include "tqb_dense_tc.cuh"
 #include "../../include/tqb200.h"
 
 using namespace tqb;
@@ -604,6 +605,54 @@ int tqb_apply_dense(const float* in, float* out, int n_qubits, long long bsz, co
       reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n_qubits, total,
       reinterpret_cast<const float2*>(mats), mat_stride_complex, k, bitpos_dev, conj_transpose);
   TQB_CHECK_LAUNCH("tqb_dense_kernel");
+  return 0;
+}
+
+int tqb_apply_dense_tc(const float* in, float* out, int n_qubits, long long bsz, const float* mat, int k,
+                       const int* bitpos_host, int conj_transpose, void* stream) {
+  if (k < 4 || k > 7 || n_qubits < TQB_TC_T) return fail_msg("tqb_apply_dense_tc: needs 4 <= k <= 7 and n_qubits >= 12");
+  if (bsz <= 0) return 0;
+  DenseTcArgs a;
+  a.in = reinterpret_cast<const float2*>(in); a.out = reinterpret_cast<float2*>(out);
+  a.mat = reinterpret_cast<const float2*>(mat);
+  a.n = n_qubits; a.k = k; a.conj_t = conj_transpose;
+  a.n_tiles = bsz << (n_qubits - TQB_TC_T);
+  unsigned long long tmask = 0;
+  for (int q = 0; q < k; ++q) {
+    if (bitpos_host[q] < 0 || bitpos_host[q] >= n_qubits || ((tmask >> bitpos_host[q]) & 1ull))
+      return fail_msg("tqb_apply_dense_tc: bad bit positions");
+    tmask |= 1ull << bitpos_host[q];
+  }
+  unsigned long long tile_mask = tmask;
+  for (int p = 0, need = TQB_TC_T - k; need > 0; ++p)
+    if (!((tile_mask >> p) & 1ull)) { tile_mask |= 1ull << p; --need; }
+  int ti = 0, nshift = 0;
+  for (int p = 0; p < n_qubits; ++p) {
+    if (!((tile_mask >> p) & 1ull)) continue;
+    a.tbit[ti] = p;
+    if ((tmask >> p) & 1ull) {
+      for (int q = 0; q < k; ++q) if (bitpos_host[q] == p) a.role[ti] = k - 1 - q;
+    } else {
+      a.role[ti] = -(nshift++) - 1;
+    }
+    ++ti;
+  }
+  a.outer_mask = ((n_qubits >= 64 ? ~0ull : (1ull << n_qubits) - 1ull)) & ~tile_mask;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  switch (k) {
+    case 4: e = launch_dense_tc<4>(a, g_num_sms, st); break;
+    case 5: e = launch_dense_tc<5>(a, g_num_sms, st); break;
+    case 6: e = launch_dense_tc<6>(a, g_num_sms, st); break;
+    case 7: e = launch_dense_tc<7>(a, g_num_sms, st); break;
+  }
+  if (e != cudaSuccess) return fail("tqb_dense_tc_kernel", e);
   return 0;
 }
 

@@ -181,6 +181,21 @@ class FusedFn(torch.autograd.Function):
         return (gstate, gsh, gps, None, None, None, *gext)
 
 
+DENSE_TC = True   # tensor-core (3xTF32) dense kernel for one shared matrix on 4-7 wires of a state of >= 12 qubits
+
+
+def _dense_apply(src, dst, n, bsz, m, k, bitpos, bp_dev, conj_t):
+    """dst = U src (or U^H src) for the k-qubit matrix m on bit positions `bitpos` (matrix MSB first)."""
+    stream = _native.stream_ptr(src)
+    if DENSE_TC and m.dim() == 2 and 4 <= k <= 7 and n >= 12 and not _native.is_emulated():
+        host = (ctypes.c_int * k)(*[int(b) for b in bitpos])
+        _native.call("tqb_apply_dense_tc", _ptr(src), _ptr(dst), n, bsz, _ptr(m), k, host, 1 if conj_t else 0, stream)
+    else:
+        _native.call("tqb_apply_dense", _ptr(src), _ptr(dst), n, bsz, _ptr(m), (4 ** k) if m.dim() == 3 else 0,
+                     k, _ptr(bp_dev), 1 if conj_t else 0, stream)
+    STATS["launches"] += 1
+
+
 class DenseFn(torch.autograd.Function):
     """Generic k-qubit dense gate (qft, qubitunitary on >= 3 wires), out of place."""
 
@@ -193,11 +208,9 @@ class DenseFn(torch.autograd.Function):
         k = len(bitpos)
         out = torch.empty_like(state)
         bp = torch.tensor(bitpos, dtype=torch.int32, device=state.device)
-        _native.call("tqb_apply_dense", _ptr(state), _ptr(out), n, bsz, _ptr(m), (4 ** k) if m.dim() == 3 else 0,
-                     k, _ptr(bp), 1 if inverse else 0, _native.stream_ptr(state))
-        STATS["launches"] += 1
+        _dense_apply(state, out, n, bsz, m, k, bitpos, bp, inverse)
         ctx.save_for_backward(state, m, bp)
-        ctx.n, ctx.inverse, ctx.k = n, inverse, k
+        ctx.n, ctx.inverse, ctx.k, ctx.bitpos = n, inverse, k, tuple(bitpos)
         return out
 
     @staticmethod
@@ -210,9 +223,7 @@ class DenseFn(torch.autograd.Function):
         gstate = gmat = None
         if ctx.needs_input_grad[0]:
             gstate = torch.empty_like(state)
-            _native.call("tqb_apply_dense", _ptr(grad_out), _ptr(gstate), n, bsz, _ptr(m),
-                         (4 ** k) if m.dim() == 3 else 0, k, _ptr(bp), 0 if inverse else 1, stream)
-            STATS["launches"] += 1
+            _dense_apply(grad_out, gstate, n, bsz, m, k, ctx.bitpos, bp, not inverse)
         if ctx.needs_input_grad[1]:
             g = torch.empty(bsz, 2 ** k, 2 ** k, dtype=torch.complex64, device=state.device)
             _native.call("tqb_dense_grad", _ptr(state), _ptr(grad_out), n, bsz, k, _ptr(bp), _ptr(g), stream)

@@ -196,7 +196,7 @@ def expval_joint_analytical_multi(qdev, observables: List[str]):
 # terms share every load of the state) and the following calls are served from that result.  Values are identical to
 # per-string launches (same accumulation order per term); a string that was not predicted is simply launched on its own.
 _READOUT_HISTORY = {}   # (n_wires, device) -> tuple of strings read on the previous state of that width
-_READOUT_CURRENT = {}   # (n_wires, device) -> [weakref to the state being read, {string: [bsz, 1] values}, [strings so far]]
+_READOUT_CURRENT = {}   # (n_wires, device) -> [weakref to the state being read, {string: [bsz, 1] values}, [strings so far], version]
 SPECULATIVE_READOUT = True
 
 
@@ -205,10 +205,10 @@ def _speculative_readout(qdev, states, ob):
         return None
     key = (qdev.n_wires, states.device)
     c = _READOUT_CURRENT.get(key)
-    if c is None or c[0]() is not states:
+    if c is None or c[0]() is not states or c[3] != states._version:   # (a state edited in place is a new state)
         if c is not None and len(c[2]) > 1:
             _READOUT_HISTORY[key] = tuple(dict.fromkeys(c[2]))   # what the previous state was asked for, in order
-        c = _READOUT_CURRENT[key] = [weakref.ref(states), {}, []]
+        c = _READOUT_CURRENT[key] = [weakref.ref(states), {}, [], states._version]
         predicted = _READOUT_HISTORY.get(key, ())
         if len(predicted) > 1 and ob in predicted:
             xm, zm, ny = _mask_tensors(list(predicted), states.device)
