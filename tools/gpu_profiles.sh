@@ -10,4 +10,6 @@ python tools/configs.py --cfg 1 3 4 --out gpurun_out/configs.json > gpurun_out/c
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tqb_pass_kernel -s 7 -c 2 -f -o gpurun_out/n28_pass python tools/perf_probe.py --skip-cfg2 --big 28 > gpurun_out/ncu_n28.log 2>&1; echo "ncu n28 rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tqb_pass_kernel -s 4 -c 2 -f -o gpurun_out/cfg2_pass python tools/cfg2_kernels.py --iters 2 > gpurun_out/ncu_cfg2.log 2>&1; echo "ncu cfg2 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tqb_dense_tc_kernel -s 10 -c 1 -f -o gpurun_out/dense_tc python tools/dense_probe.py --n 26 > gpurun_out/ncu_dense.log 2>&1; echo "ncu dense rc=$?"
+python tools/dense_probe.py --n 28 > gpurun_out/dense_probe_n28.log 2>&1
 cat gpurun_out/bench.json | cut -c1-1500

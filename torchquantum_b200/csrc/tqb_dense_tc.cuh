@@ -62,14 +62,21 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
   constexpr int CGROUPS = 8 / STRIPS;       // column groups
   constexpr int NT = N / CGROUPS / 8;       // 8-column MMA tiles per warp
   static_assert(NT >= 1 && STRIPS * CGROUPS == 8, "warp layout");
+  // k <= 6: U is split into its TF32 hi / lo parts once per CTA (four planes); k = 7: two fp32 planes (135 KB), split
+  // again at every use
+  constexpr bool PRESPLIT = K <= 6;
+  constexpr int UPLANES = PRESPLIT ? 4 : 2;
   extern __shared__ __align__(16) float smem_tc[];
-  float* Ur = smem_tc;                      // [M][LD]
+  float* Ur = smem_tc;                      // [M][LD]   (PRESPLIT: hi part as tf32 bits)
   float* Ui = Ur + M * LD;
-  float* Br = Ui + M * LD;                  // [N][LD]  (column n, matrix index j contiguous)
+  float* Url = Ui + M * LD;                 // PRESPLIT only: lo parts
+  float* Uil = Url + M * LD;
+  float* Br = smem_tc + UPLANES * M * LD;   // [N][LD]  (column n, matrix index j contiguous)
   float* Bi = Br + N * LD;
   // tile-local index = lo6 | hi6 << 6: two 64-entry tables give its in-tile amplitude offset and (j, n) coordinates
   __shared__ unsigned long long s_off[128];
   __shared__ uint32_t s_jn[128];          // j | n << 16
+  __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 128) {
     const int half = tid >> 6;
@@ -88,8 +95,17 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
   for (int e = tid; e < M * M; e += TQB_TC_THREADS) {
     const int r = e / M, c = e % M;
     const float2 v = a.conj_t ? a.mat[c * M + r] : a.mat[e];
-    Ur[r * LD + c] = v.x;
-    Ui[r * LD + c] = a.conj_t ? -v.y : v.y;
+    const float im = a.conj_t ? -v.y : v.y;
+    if (PRESPLIT) {
+      uint32_t h, l;
+      tc_split(v.x, h, l);
+      Ur[r * LD + c] = __uint_as_float(h); Url[r * LD + c] = __uint_as_float(l);
+      tc_split(im, h, l);
+      Ui[r * LD + c] = __uint_as_float(h); Uil[r * LD + c] = __uint_as_float(l);
+    } else {
+      Ur[r * LD + c] = v.x;
+      Ui[r * LD + c] = im;
+    }
   }
   __syncthreads();
   // per-thread tile-local indices it moves: idx = tid + 256 i, i < 16; (j, n) and the in-tile global offset of each
@@ -97,28 +113,39 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
   const int g = lane >> 2, t = lane & 3;
   const int ntiles_log2 = a.n - TQB_TC_T;
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // amplitude offset of the tile: sample * 2^n + the tile index deposited on the non-tile bits
-    const unsigned long long sample = (unsigned long long)tile >> ntiles_log2;
-    unsigned long long rest = (unsigned long long)tile & ((1ull << ntiles_log2) - 1ull), base = sample << a.n;
-    {
+    // amplitude offset of the tile: sample * 2^n + the tile index deposited on the non-tile bits (one thread, then shared)
+    if (tid == 0) {
+      const unsigned long long sample = (unsigned long long)tile >> ntiles_log2;
+      unsigned long long rest = (unsigned long long)tile & ((1ull << ntiles_log2) - 1ull), bb = sample << a.n;
       unsigned long long m = a.outer_mask;
       while (m) {
         const int p = __ffsll((long long)m) - 1;
         m &= m - 1ull;
-        base |= (rest & 1ull) << p;
+        bb |= (rest & 1ull) << p;
         rest >>= 1;
       }
+      s_base = bb;
     }
-    // ---- load the tile into the B planes
-#pragma unroll 4
-    for (int i = 0; i < (1 << TQB_TC_T) / TQB_TC_THREADS; ++i) {
-      const uint32_t idx = (uint32_t)tid + TQB_TC_THREADS * i;
-      const unsigned long long off = s_off[idx & 63u] | s_off[64u + (idx >> 6)];
-      const uint32_t jn = s_jn[idx & 63u] | s_jn[64u + (idx >> 6)];
-      const int j = (int)(jn & 0xffffu), nn = (int)(jn >> 16);
-      const float2 v = a.in[base + off];
-      Br[nn * LD + j] = v.x;
-      Bi[nn * LD + j] = v.y;
+    __syncthreads();
+    const unsigned long long base = s_base;
+    // ---- load the tile into the B planes: all 16 loads of a thread in flight before the first shared store
+    {
+      constexpr int PER = (1 << TQB_TC_T) / TQB_TC_THREADS;
+      float2 v[PER];
+      uint32_t jn[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const uint32_t idx = (uint32_t)tid + TQB_TC_THREADS * i;
+        const unsigned long long off = s_off[idx & 63u] | s_off[64u + (idx >> 6)];
+        jn[i] = s_jn[idx & 63u] | s_jn[64u + (idx >> 6)];
+        v[i] = a.in[base + off];
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int j = (int)(jn[i] & 0xffffu), nn = (int)(jn[i] >> 16);
+        Br[nn * LD + j] = v[i].x;
+        Bi[nn * LD + j] = v[i].y;
+      }
     }
     __syncthreads();
     // ---- C strip = U strip x B (complex, 3xTF32)
@@ -131,15 +158,19 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
     for (int k0 = 0; k0 < M; k0 += 8) {
       uint32_t urh[4], url[4], uih[4], uil[4], nuih[4], nuil[4];
       {
-        const float* pr = Ur + (row0 + g) * LD + k0 + t;
-        const float* pi = Ui + (row0 + g) * LD + k0 + t;
-        const float ar[4] = {pr[0], pr[8 * LD], pr[4], pr[8 * LD + 4]};
-        const float ai[4] = {pi[0], pi[8 * LD], pi[4], pi[8 * LD + 4]};
+        const int o = (row0 + g) * LD + k0 + t;
+        const int fo[4] = {o, o + 8 * LD, o + 4, o + 8 * LD + 4};   // A fragment: (g, t) (g+8, t) (g, t+4) (g+8, t+4)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          tc_split(ar[e], urh[e], url[e]);
-          tc_split(ai[e], uih[e], uil[e]);
-          tc_split(-ai[e], nuih[e], nuil[e]);
+          if (PRESPLIT) {
+            urh[e] = __float_as_uint(Ur[fo[e]]); url[e] = __float_as_uint(Url[fo[e]]);
+            uih[e] = __float_as_uint(Ui[fo[e]]); uil[e] = __float_as_uint(Uil[fo[e]]);
+          } else {
+            tc_split(Ur[fo[e]], urh[e], url[e]);
+            tc_split(Ui[fo[e]], uih[e], uil[e]);
+          }
+          nuih[e] = uih[e] ^ 0x80000000u;    // tf32 rounding is symmetric: split(-x) = -split(x)
+          nuil[e] = uil[e] ^ 0x80000000u;
         }
       }
 #pragma unroll
@@ -182,7 +213,7 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
 template <int K>
 static cudaError_t launch_dense_tc(const DenseTcArgs& a, int num_sms, cudaStream_t st) {
   constexpr int M = 1 << K, N = 1 << (TQB_TC_T - K), LD = M + 4;
-  const size_t smem = (size_t)(2 * M * LD + 2 * N * LD) * sizeof(float);
+  const size_t smem = (size_t)((K <= 6 ? 4 : 2) * M * LD + 2 * N * LD) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tqb_dense_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
