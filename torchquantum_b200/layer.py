@@ -133,7 +133,7 @@ class Op2QDenseLayer(QuantumModule):
                 k += 1
 
 
-class RandomLayer(QuantumModule):
+class RandomLayer(QuantumModule, _RecordCache):
     """Random op soup (layer/layers/random_layers.py:80-229).  Determinism is the NumPy global RNG
     call order of the reference: per op one `np.random.choice(op_types, p=ratios)` then one
     `np.random.choice(wires, size=k, replace=False)`."""
@@ -200,8 +200,15 @@ class RandomLayer(QuantumModule):
                     param_cnt -= cls.num_params
                     del self.op_list[-1]
 
+    def _layer_ops_wires(self):
+        return [(operation, operation.wires) for operation in self.op_list]
+
     @static_support
     def forward(self, q_device):
+        recs = self.records(q_device)
+        if recs is not None:
+            q_device._queue.extend(recs)
+            return
         for operation in self.op_list:
             operation(q_device)
 
