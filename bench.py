@@ -247,6 +247,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep "NCCL version ..." off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import torchquantum_b200 as tq
     from torchquantum_b200 import engine
