@@ -479,3 +479,37 @@ def check_dense_blocks(device, n=13):
             (gg,) = torch.autograd.grad((got * proj.to(device).conj()).real.sum(), sd)
             (gw,) = torch.autograd.grad((want * proj.conj()).real.sum(), sc)
             assert_close(gg, gw, rtol=1e-4, what=f"dense k={k} grad wrt state")
+
+
+def check_op_hamil_exp(device):
+    """OpHamilExp / OpPauliExp against the literal values of the reference's own test
+    (test/operator/test_op_hamil_exp.py:32-108) and a gradient w.r.t. theta vs torch autograd through the dense form."""
+    hamil = tq.Hamiltonian(coeffs=[1.0, 0.5], paulis=["ZZ", "XX"])
+    op = tq.OpHamilExp(hamil=hamil, trainable=True, theta=0.45)
+    m = op.matrix.detach()
+    want00, want03 = 0.9686 - 0.2217j, -0.0250 - 0.1094j
+    assert abs(complex(m[0, 0]) - want00) < 2e-4 and abs(complex(m[0, 3]) - want03) < 2e-4
+    assert abs(complex(m[1, 1]) - (0.9686 + 0.2217j)) < 2e-4 and abs(complex(m[1, 2]) - (0.0250 - 0.1094j)) < 2e-4
+    e = op.exponent_matrix.detach()
+    assert abs(complex(e[0, 0]) - (-0.2250j)) < 1e-6 and abs(complex(e[0, 3]) - (-0.1125j)) < 1e-6
+    op = op.to(device)
+    qdev = tq.QuantumDevice(n_wires=2, device=device)
+    qdev.reset_states(bsz=2)
+    op(qdev, wires=[1, 0])
+    got = qdev.get_states_1d()
+    want = torch.tensor([[0.9686322 - 0.22169423j, 0, 0, -0.02504631 - 0.1094314j]] * 2, dtype=torch.complex64)
+    assert_close(got, want, what="OpHamilExp state (reference test literal)")
+    # gradient w.r.t. theta through the dense unitary
+    loss = got[:, 3].real.sum() + got[:, 0].imag.sum()
+    (g,) = torch.autograd.grad(loss, op.theta)
+    th = torch.tensor(0.45, requires_grad=True)
+    u = torch.matrix_exp(hamil.matrix * -1j * th / 2)
+    col = u[:, 0]                      # wires [1, 0] on |00>: the matrix is symmetric under the wire swap here
+    lw = 2 * (col[3].real + col[0].imag)
+    (gw,) = torch.autograd.grad(lw, th)
+    assert_close(g.reshape(()), gw, rtol=1e-4, what="OpHamilExp dL/dtheta")
+    pe = tq.OpPauliExp(coeffs=[1.0, 0.5], paulis=["ZZ", "XX"], trainable=False, theta=0.45)
+    q2 = tq.QuantumDevice(n_wires=2, device=device, record_op=True)
+    pe(q2, wires=[1, 0])
+    assert_close(q2.get_states_1d(), want[:1], what="OpPauliExp state")
+    assert q2.op_history[-2]["name"] == "OpPauliExp" and q2.op_history[-2]["paulis"] == ["ZZ", "XX"]

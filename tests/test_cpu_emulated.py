@@ -138,3 +138,7 @@ def test_speculative_readout():
 
 def test_dense_blocks():
     cases.check_dense_blocks("cpu", n=8)
+
+
+def test_op_hamil_exp():
+    cases.check_op_hamil_exp("cpu")

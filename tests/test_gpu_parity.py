@@ -147,6 +147,10 @@ def test_speculative_readout():
     cases.check_speculative_readout(DEV)
 
 
+def test_op_hamil_exp():
+    cases.check_op_hamil_exp(DEV)
+
+
 def test_vqe_hamiltonian(tmp_path):
     cases.check_vqe_hamiltonian(DEV, tmp_path)
 

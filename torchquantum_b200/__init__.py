@@ -19,5 +19,8 @@ from .encoding import *  # noqa: F401,F403
 from .layer import *  # noqa: F401,F403
 from .graphs import GraphedStep  # noqa: F401
 from .algorithm import Hamiltonian, VQE  # noqa: F401
+from .op_hamil_exp import OpHamilExp, OpPauliExp  # noqa: F401
+
+operator.OpHamilExp, operator.OpPauliExp = OpHamilExp, OpPauliExp   # reference location: torchquantum.operator
 
 __version__ = "0.1.0"
