@@ -83,8 +83,13 @@ struct PassArgs {
 #ifndef TQB_BWD_MINB_SMALL
 #define TQB_BWD_MINB_SMALL 3
 #endif
+// small-CTA forward: 6 CTAs/SM (80 registers, 56 B of spills) beat 4 (128 registers): config-2 forward 0.97 vs 1.03 ms,
+// forward-only program 0.82 vs 0.91 ms; the 256-thread forward kernel is the other way round (3 CTAs/SM: 3.31 vs 3.00 ms)
+#ifndef TQB_FWD_MINB_SMALL
+#define TQB_FWD_MINB_SMALL 6
+#endif
 template <int R, bool BWD, bool SMALL>
-__global__ void __launch_bounds__(SMALL ? 128 : 256, SMALL ? (BWD ? TQB_BWD_MINB_SMALL : 2 * TQB_FWD_MINB) : (BWD ? TQB_BWD_MINB : TQB_FWD_MINB))
+__global__ void __launch_bounds__(SMALL ? 128 : 256, SMALL ? (BWD ? TQB_BWD_MINB_SMALL : TQB_FWD_MINB_SMALL) : (BWD ? TQB_BWD_MINB : TQB_FWD_MINB))
 tqb_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockCtx c;
