@@ -2,8 +2,8 @@
 //
 //   out[b, i, rest] = sum_j U[i, j] in[b, j, rest]        i, j: patterns of the k target bits (matrix MSB first)
 //
-// Every CTA loops over tiles of 2^12 amplitudes = the k target bits + the 12-k lowest other bits, stages a tile as
-// real / imaginary planes B[n][j] (n: pattern of the non-target tile bits), and computes the complex product
+// Every CTA loops over tiles of 2^12 amplitudes = the k target bits + the 12-k lowest other bits, stages a tile with
+// cp.async one tile ahead as B[n][j] (n: pattern of the non-target tile bits), and computes the complex product
 //   Cr = Ur Br - Ui Bi,   Ci = Ur Bi + Ui Br
 // with mma.sync m16n8k8 TF32 MMAs.  Each fp32 operand x is split as hi = tf32(x), lo = tf32(x - hi) and a product uses
 // hi*hi + hi*lo + lo*hi (the lo*lo term is below fp32 rounding), which keeps the result within ~1e-6 of an fp32
@@ -53,6 +53,11 @@ __device__ __forceinline__ void tc_mma3(float (&c)[4], const uint32_t (&ah)[4], 
   tc_mma(c, ah, bh);
 }
 
+__device__ __forceinline__ void tc_cp_async8(float2* dst, const float2* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
+}
+
 template <int K>
 __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc_kernel(const DenseTcArgs a) {
   constexpr int M = 1 << K;                 // matrix dimension
@@ -61,22 +66,24 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
   constexpr int STRIPS = M / 16;            // 16-row strips of C
   constexpr int CGROUPS = 8 / STRIPS;       // column groups
   constexpr int NT = N / CGROUPS / 8;       // 8-column MMA tiles per warp
+  constexpr int PER = (1 << TQB_TC_T) / TQB_TC_THREADS;   // amplitudes a thread moves per tile
   static_assert(NT >= 1 && STRIPS * CGROUPS == 8, "warp layout");
-  // k <= 6: U is split into its TF32 hi / lo parts once per CTA (four planes); k = 7: two fp32 planes (135 KB), split
-  // again at every use
-  constexpr bool PRESPLIT = K <= 6;
+  // k <= 5: U is split into its TF32 hi / lo parts once per CTA (four planes); k >= 6: two fp32 planes, split at every use
+  // (four planes would cost the second resident CTA at k = 6 and do not fit at k = 7)
+  constexpr bool PRESPLIT = K <= 5;
   constexpr int UPLANES = PRESPLIT ? 4 : 2;
   extern __shared__ __align__(16) float smem_tc[];
   float* Ur = smem_tc;                      // [M][LD]   (PRESPLIT: hi part as tf32 bits)
   float* Ui = Ur + M * LD;
   float* Url = Ui + M * LD;                 // PRESPLIT only: lo parts
   float* Uil = Url + M * LD;
-  float* Br = smem_tc + UPLANES * M * LD;   // [N][LD]  (column n, matrix index j contiguous)
-  float* Bi = Br + N * LD;
+  // two tile buffers B[n][j] of complex amplitudes (column n, matrix index j contiguous), filled by cp.async one tile
+  // ahead; the product C overwrites the buffer it was computed from and is written back from there
+  float2* Bbuf = reinterpret_cast<float2*>(smem_tc + UPLANES * M * LD);
   // tile-local index = lo6 | hi6 << 6: two 64-entry tables give its in-tile amplitude offset and (j, n) coordinates
   __shared__ unsigned long long s_off[128];
   __shared__ uint32_t s_jn[128];          // j | n << 16
-  __shared__ unsigned long long s_base;
+  __shared__ unsigned long long s_base[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 128) {
     const int half = tid >> 6;
@@ -107,47 +114,50 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
       Ui[r * LD + c] = im;
     }
   }
-  __syncthreads();
-  // per-thread tile-local indices it moves: idx = tid + 256 i, i < 16; (j, n) and the in-tile global offset of each
   const int strip = warp % STRIPS, cgroup = warp / STRIPS;
   const int g = lane >> 2, t = lane & 3;
   const int ntiles_log2 = a.n - TQB_TC_T;
+  // amplitude offset of a tile: sample * 2^n + the tile index deposited on the non-tile bits
+  auto tile_base = [&](long long tile) {
+    const unsigned long long sample = (unsigned long long)tile >> ntiles_log2;
+    unsigned long long rest = (unsigned long long)tile & ((1ull << ntiles_log2) - 1ull), bb = sample << a.n;
+    unsigned long long m = a.outer_mask;
+    while (m) {
+      const int p = __ffsll((long long)m) - 1;
+      m &= m - 1ull;
+      bb |= (rest & 1ull) << p;
+      rest >>= 1;
+    }
+    return bb;
+  };
+  // this thread's 16 (offset, smem slot) pairs are the same for every tile
+  auto issue = [&](unsigned long long base, float2* B) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const uint32_t idx = (uint32_t)tid + TQB_TC_THREADS * i;
+      const unsigned long long off = s_off[idx & 63u] | s_off[64u + (idx >> 6)];
+      const uint32_t jn = s_jn[idx & 63u] | s_jn[64u + (idx >> 6)];
+      tc_cp_async8(B + (jn >> 16) * LD + (jn & 0xffffu), a.in + base + off);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  if (tid == 0 && (long long)blockIdx.x < a.n_tiles) s_base[0] = tile_base(blockIdx.x);
+  __syncthreads();
+  if ((long long)blockIdx.x < a.n_tiles) issue(s_base[0], Bbuf);
+  int buf = 0;
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // amplitude offset of the tile: sample * 2^n + the tile index deposited on the non-tile bits (one thread, then shared)
-    if (tid == 0) {
-      const unsigned long long sample = (unsigned long long)tile >> ntiles_log2;
-      unsigned long long rest = (unsigned long long)tile & ((1ull << ntiles_log2) - 1ull), bb = sample << a.n;
-      unsigned long long m = a.outer_mask;
-      while (m) {
-        const int p = __ffsll((long long)m) - 1;
-        m &= m - 1ull;
-        bb |= (rest & 1ull) << p;
-        rest >>= 1;
-      }
-      s_base = bb;
+    float2* B = Bbuf + (size_t)buf * N * LD;
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < a.n_tiles) s_base[buf ^ 1] = tile_base(next);
+    __syncthreads();   // s_base[buf ^ 1] visible; the other buffer was drained by the previous iteration's store
+    const unsigned long long base = s_base[buf];
+    if (next < a.n_tiles) {
+      issue(s_base[buf ^ 1], Bbuf + (size_t)(buf ^ 1) * N * LD);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    // ---- load the tile into the B planes: all 16 loads of a thread in flight before the first shared store
-    {
-      constexpr int PER = (1 << TQB_TC_T) / TQB_TC_THREADS;
-      float2 v[PER];
-      uint32_t jn[PER];
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const uint32_t idx = (uint32_t)tid + TQB_TC_THREADS * i;
-        const unsigned long long off = s_off[idx & 63u] | s_off[64u + (idx >> 6)];
-        jn[i] = s_jn[idx & 63u] | s_jn[64u + (idx >> 6)];
-        v[i] = a.in[base + off];
-      }
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const int j = (int)(jn[i] & 0xffffu), nn = (int)(jn[i] >> 16);
-        Br[nn * LD + j] = v[i].x;
-        Bi[nn * LD + j] = v[i].y;
-      }
-    }
-    __syncthreads();
+    __syncthreads();   // this tile's amplitudes have landed for every thread
     // ---- C strip = U strip x B (complex, 3xTF32)
     float cr[NT][4], ci[NT][4];
 #pragma unroll
@@ -175,52 +185,50 @@ __global__ void __launch_bounds__(TQB_TC_THREADS, (K <= 6 ? 2 : 1)) tqb_dense_tc
       }
 #pragma unroll
       for (int q = 0; q < NT; ++q) {
-        const int col = (cgroup * NT + q) * 8 + g;     // B fragment: (k = t / t + 4, n = g)
-        const float* qr = Br + col * LD + k0 + t;
-        const float* qi = Bi + col * LD + k0 + t;
+        const int col = (cgroup * NT + q) * 8 + g;     // B fragment: (k = t / t + 4, n = g), re and im in one 64-bit read
+        const float2 b0 = B[col * LD + k0 + t], b1 = B[col * LD + k0 + t + 4];
         uint32_t brh[2], brl[2], bih[2], bil[2];
-        tc_split(qr[0], brh[0], brl[0]); tc_split(qr[4], brh[1], brl[1]);
-        tc_split(qi[0], bih[0], bil[0]); tc_split(qi[4], bih[1], bil[1]);
+        tc_split(b0.x, brh[0], brl[0]); tc_split(b1.x, brh[1], brl[1]);
+        tc_split(b0.y, bih[0], bil[0]); tc_split(b1.y, bih[1], bil[1]);
         tc_mma3(cr[q], urh, url, brh, brl);      // Cr += Ur Br
         tc_mma3(cr[q], nuih, nuil, bih, bil);    // Cr -= Ui Bi
         tc_mma3(ci[q], urh, url, bih, bil);      // Ci += Ur Bi
         tc_mma3(ci[q], uih, uil, brh, brl);      // Ci += Ui Br
       }
     }
-    __syncthreads();   // every warp is done reading B: reuse the planes for C
+    __syncthreads();   // every warp is done reading B: reuse the buffer for C
 #pragma unroll
     for (int q = 0; q < NT; ++q) {
       const int col = (cgroup * NT + q) * 8 + 2 * t;    // C fragment: rows g / g + 8, columns 2t / 2t + 1
-      Br[col * LD + row0 + g] = cr[q][0];       Bi[col * LD + row0 + g] = ci[q][0];
-      Br[(col + 1) * LD + row0 + g] = cr[q][1]; Bi[(col + 1) * LD + row0 + g] = ci[q][1];
-      Br[col * LD + row0 + g + 8] = cr[q][2];   Bi[col * LD + row0 + g + 8] = ci[q][2];
-      Br[(col + 1) * LD + row0 + g + 8] = cr[q][3]; Bi[(col + 1) * LD + row0 + g + 8] = ci[q][3];
+      B[col * LD + row0 + g] = make_float2(cr[q][0], ci[q][0]);
+      B[(col + 1) * LD + row0 + g] = make_float2(cr[q][1], ci[q][1]);
+      B[col * LD + row0 + g + 8] = make_float2(cr[q][2], ci[q][2]);
+      B[(col + 1) * LD + row0 + g + 8] = make_float2(cr[q][3], ci[q][3]);
     }
     __syncthreads();
     // ---- store
 #pragma unroll 4
-    for (int i = 0; i < (1 << TQB_TC_T) / TQB_TC_THREADS; ++i) {
+    for (int i = 0; i < PER; ++i) {
       const uint32_t idx = (uint32_t)tid + TQB_TC_THREADS * i;
       const unsigned long long off = s_off[idx & 63u] | s_off[64u + (idx >> 6)];
       const uint32_t jn = s_jn[idx & 63u] | s_jn[64u + (idx >> 6)];
-      const int j = (int)(jn & 0xffffu), nn = (int)(jn >> 16);
-      a.out[base + off] = make_float2(Br[nn * LD + j], Bi[nn * LD + j]);
+      a.out[base + off] = B[(jn >> 16) * LD + (jn & 0xffffu)];
     }
-    __syncthreads();
+    buf ^= 1;
   }
 }
 
 template <int K>
 static cudaError_t launch_dense_tc(const DenseTcArgs& a, int num_sms, cudaStream_t st) {
   constexpr int M = 1 << K, N = 1 << (TQB_TC_T - K), LD = M + 4;
-  const size_t smem = (size_t)((K <= 6 ? 4 : 2) * M * LD + 2 * N * LD) * sizeof(float);
+  const size_t smem = (size_t)((K <= 5 ? 4 : 2) * M * LD) * sizeof(float) + (size_t)2 * N * LD * sizeof(float2);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tqb_dense_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  // k <= 6: two CTAs per SM (70 KB of planes at k = 6) so that one CTA's tile traffic overlaps the other's MMAs
+  // k <= 6: two CTAs per SM (<= 103 KB each); k = 7: one (201 KB)
   const long long resident = (long long)num_sms * (K <= 6 ? 2 : 1);
   long long grid = a.n_tiles < resident ? a.n_tiles : resident;
   tqb_dense_tc_kernel<K><<<(unsigned)grid, TQB_TC_THREADS, smem, st>>>(a);
