@@ -1,0 +1,96 @@
+"""Host planner unit tests (no kernels): lowering choices, folds and program structure of torchquantum_b200/plan.py."""
+import numpy as np
+
+from torchquantum_b200 import _codes as C
+from torchquantum_b200 import plan as P
+
+
+def _types(plan):
+    out = []
+    for st in plan.stages:
+        for pp in st.passes:
+            w = pp.prog
+            for si in range(w[C.H_NSEG]):
+                off = w[C.H_SEGOFF + si]
+                base = off + C.SEG_HDR_WORDS + w[off + C.S_NGROUPS] * C.GROUP_WORDS
+                for k in range(w[off + C.S_NOPS]):
+                    w0 = int(w[base + k * C.OP_WORDS]) & 0xFFFFFFFF
+                    out.append(((w0 >> 2) & 15, bool(w0 & C.F_POSTX)))
+    return out
+
+
+def _key(ops):
+    return tuple((name, tuple(wires), False, pm, grad, 0) for name, wires, pm, grad in ops)
+
+
+def test_grad_programs_use_plain_forms_and_forward_only_programs_scaled_ones():
+    ops = [("rx", [0], "sh", True), ("ry", [1], "sh", True), ("rz", [2], "sh", True), ("hadamard", [3], None, False),
+           ("rx", [1], "sh", True), ("ry", [2], "sh", True)]
+    grad = {t for t, _ in _types(P.build_plan(4, _key(ops), True))}
+    assert grad == {C.T_RX, C.T_REAL, C.T_DIAG}
+    fwd_ops = [(n, w, pm, False) for n, w, pm, _ in ops]
+    fwd = {t for t, _ in _types(P.build_plan(4, _key(fwd_ops), False))}
+    assert fwd == {C.T_RXS, C.T_RYS, C.T_DIAGS, C.T_HS}
+    # fewer than SCALED_MIN scaled ops in the pass: plain forms again (the deferred factor would cost more)
+    short = {t for t, _ in _types(P.build_plan(4, _key(fwd_ops[:2]), False))}
+    assert short == {C.T_RX, C.T_REAL}
+
+
+def test_cnot_sandwich_folds_into_one_parity_diagonal():
+    ops = [("cnot", [0, 1], None, False), ("rz", [1], "sh", True), ("cnot", [0, 1], None, False)]
+    plan = P.build_plan(3, _key(ops), True)
+    assert [t for t, _ in _types(plan)] == [C.T_DIAG]
+
+
+def test_cnot_folds_into_the_preceding_gate_in_forward_only_programs():
+    ops = [("ry", [0], "sh", False), ("rx", [1], "sh", False), ("rz", [2], "sh", False), ("cnot", [0, 1], None, False),
+           ("ry", [2], "sh", False)]
+    types = _types(P.build_plan(3, _key(ops), False))
+    assert (C.T_RXS, True) in types and all(t != C.T_PERM for t, _ in types), types
+    # with autograd the CNOT stays a register swap of its own
+    gtypes = _types(P.build_plan(3, _key([(n, w, pm, pm is not None) for n, w, pm, _ in ops]), True))
+    assert (C.T_PERM, False) in gtypes
+
+
+def test_qft_rungs_fold_into_ladders():
+    n = 9
+    ops = []
+    for top in range(n):
+        ops.append(("hadamard", [top], None, False))
+        for w in range(top + 1, n):
+            ops.append(("cu1", [w, top], "sh", False))
+    plan = P.build_plan(n, _key(ops), False)
+    types = [t for t, _ in _types(plan)]
+    assert types.count(C.T_LADDER) == n - 1 - (P.LADDER_MIN - 1)   # the last LADDER_MIN - 1 rung sets are too short
+    assert plan.stages[0].P_sh == n * (n - 1) // 2                  # every rung keeps its parameter slot
+    # programs that run backward keep one masked diagonal per rung
+    gplan = P.build_plan(n, _key([(nm, w, pm, pm is not None) for nm, w, pm, _ in ops]), True)
+    assert all(t != C.T_LADDER for t, _ in _types(gplan))
+
+
+def test_streamed_states_are_cut_into_passes_of_at_most_seven_free_bits():
+    n = 20
+    ops = [("rx", [w], "sh", False) for w in range(n)]
+    plan = P.build_plan(n, _key(ops), False)
+    st = plan.stages[0]
+    assert len(st.passes) == 3 and all(pp.T == P.T_MULTI for pp in st.passes)   # 15 high bits / 7 per pass
+    for pp in st.passes:
+        assert pp.tile_bits[:P.L_MIN] == list(range(P.L_MIN))                    # 256-byte runs
+        assert int(pp.prog[C.H_WORDS]) == len(pp.prog)
+    covered = set()
+    for pp in st.passes:
+        covered |= set(pp.tile_bits)
+    assert covered == set(range(n))
+
+
+def test_segments_respect_staging_capacity():
+    n = 6
+    rng = np.random.default_rng(0)
+    ops = [("u3", [int(rng.integers(n))], "sh", True) for _ in range(200)]
+    plan = P.build_plan(n, _key(ops), True)
+    for pp in plan.stages[0].passes:
+        w = pp.prog
+        assert w[C.H_G_MAX] <= C.SEG_MAX_G and w[C.H_SH_MAX] <= C.SEG_MAX_SH
+        for si in range(w[C.H_NSEG]):
+            off = w[C.H_SEGOFF + si]
+            assert w[off + C.S_NOPS] <= C.SEG_MAX_OPS and w[off + C.S_G_LEN] <= C.SEG_MAX_G
