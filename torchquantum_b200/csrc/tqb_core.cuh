@@ -9,6 +9,8 @@
 // Per-thread state therefore never lives across two `par` phases: amplitudes go back to the
 // staged tile at the end of every group.
 #pragma once
+#include <type_traits>
+
 #include "tqb_program.h"
 
 // compile-time op-type mask for experiments ("lean" builds holding only the op types one program family needs ran
@@ -876,9 +878,8 @@ TQB_COLD void ladder_group(const int32_t* s_prog, float2* s_psi, const float* s_
 #pragma unroll
       for (int e = (1 << jj); e < (2 << jj); ++e) P[e] = cmul(P[e ^ (1 << jj)], tj);
     }
-    for (u32 item = (u32)t; item < items; item += (u32)c.tps) {
-      const u32 hi = item << 4;
-      if ((hi & cm & ~15u) != (cv & ~15u)) continue;
+    // phase of the ladder bits >= 4 that are set in `hi`, times the tile's outer phase
+    auto hi_phase = [&](u32 hi) {
       float2 ph = lph;
       u32 mt = hi & pm;
       while (mt) {
@@ -886,6 +887,55 @@ TQB_COLD void ladder_group(const int32_t* s_prog, float2* s_psi, const float* s_
         mt &= mt - 1u;
         ph = cmul(ph, *reinterpret_cast<const float2*>(tab + 2 * b));
       }
+      return ph;
+    };
+    if (w0 & TQB_F_PREH) {
+      // H on the control bit c, then the ladder: (a, b) -> (a + b, (a - b) * phase(b's index)) on every pair of bit c
+      const u32 pc = TQB_OP_PC(w0), cb = 1u << pc;
+      if (pc < 4u) {
+        // (compile-time bit position: a run-time index into P[] would push the array into local memory)
+        auto low_case = [&](auto pcc) {
+          constexpr u32 CB = 1u << decltype(pcc)::value;
+          for (u32 item = (u32)t; item < items; item += (u32)c.tps) {
+            const u32 hi = item << 4;
+            const float2 ph = hi_phase(hi);
+#pragma unroll
+            for (u32 e = 0; e < 16u; ++e) {
+              if (!(e & CB) && (e | CB) < ne) {
+                const u32 a0 = swz(hi | e, pair), a1 = swz(hi | e | CB, pair);
+                const float2 A = sps[a0], B = sps[a1];
+                sps[a0] = make_float2(A.x + B.x, A.y + B.y);
+                sps[a1] = cmul(cmul(ph, P[e | CB]), make_float2(A.x - B.x, A.y - B.y));
+              }
+            }
+          }
+        };
+        if (pc == 0u) low_case(std::integral_constant<int, 0>{});
+        else if (pc == 1u) low_case(std::integral_constant<int, 1>{});
+        else if (pc == 2u) low_case(std::integral_constant<int, 2>{});
+        else low_case(std::integral_constant<int, 3>{});
+      } else {
+        const u32 lowm = (1u << (pc - 4u)) - 1u;
+        for (u32 it = (u32)t; it < (items >> 1); it += (u32)c.tps) {
+          const u32 hi0 = (((it & ~lowm) << 1) | (it & lowm)) << 4, hi1 = hi0 | cb;
+          const float2 ph = hi_phase(hi1);
+#pragma unroll
+          for (u32 e = 0; e < 16u; ++e) {
+            if (e < ne) {
+              const u32 a0 = swz(hi0 | e, pair), a1 = swz(hi1 | e, pair);
+              const float2 A = sps[a0], B = sps[a1];
+              sps[a0] = make_float2(A.x + B.x, A.y + B.y);
+              sps[a1] = cmul(cmul(ph, P[e]), make_float2(A.x - B.x, A.y - B.y));
+            }
+          }
+        }
+      }
+      continue;
+    }
+    for (u32 item = (u32)t; item < items; item += (u32)c.tps) {
+      const u32 hi = item << 4;
+      if ((hi & cm & ~15u) != (cv & ~15u)) continue;
+      const float2 ph = hi_phase(hi);
 #pragma unroll
       for (u32 e = 0; e < 16u; ++e) {
         if (e < ne && (e & cm) == (cv & 15u)) {

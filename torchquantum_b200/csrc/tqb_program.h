@@ -73,7 +73,7 @@
 #define TQB_OP_GSLOT 9  // float offset of this op's gradient accumulators in the segment's gradient floats
 #define TQB_OP_LPH 10   // TQB_T_LADDER: words 10-11 are SCRATCH in the staged copy: the kernel writes the tile's outer-bit phase
                         // (re, im as float bits) here once per tile, every thread reads it back
-#define TQB_OP_LREG(w0) (((w0) >> 22) & 15)
+#define TQB_OP_PC(w0) (((w0) >> 22) & 15)   // TQB_F_PREH: tile-local position of the control bit
 
 // op types.  Matrix slots are padded to a multiple of 4 floats (16-byte staged loads).
 #define TQB_T_GEN 0    // 2x2 complex on register bit j; 8 floats row-major (re,im)
@@ -101,6 +101,9 @@
 #define TQB_F_NOUNAPPLY 0x800  // backward: psi already holds the op's INPUT (non-unitary single-op node)
 #define TQB_F_OCTRL 0x1000     // has controls on outer (non-tile) bits (CM_O/CV_O valid)
 #define TQB_F_DJ 0x2000        // DIAG whose only register-resident parity bit is register bit j (element parity = bit j of e)
+#define TQB_F_PREH 0x8000      // TQB_T_LADDER: an (unnormalised) Hadamard on the ladder's control bit is applied first, i.e. one rung set
+                               // H_c; cu1(c+1, c); cu1(c+2, c) ... of a QFT in a single sweep over the tile; w0 bits 22-25: tile-local
+                               // position of c; the 1/sqrt(2) joins the pass's deferred scale factor
 #define TQB_F_POSTX 0x4000     // a CNOT (control = register bit JC, target = this op's bit j) is folded in: the two outputs
                                // of every pair whose control bit is set are exchanged (costs nothing: register renaming)
 

@@ -40,7 +40,7 @@ class LOp:
     """A lowered micro-op on global bit positions."""
     __slots__ = ("type", "targets", "pmask", "cmask", "cval", "nfloat", "kind", "inverse", "pmode",
                  "poff", "nparam", "const", "rec", "grad", "gkind", "ngrad", "nounapply", "qmask", "ext_dim", "_lt",
-                 "_lc", "_soft", "postx", "scale_const", "rungs")
+                 "_lc", "_soft", "postx", "scale_const", "rungs", "preh")
 
     def __init__(self):
         self.pmask = self.cmask = self.cval = 0
@@ -50,6 +50,7 @@ class LOp:
         self.gkind, self.ngrad = C.G_NONE, 0
         self._lc, self._soft, self.postx, self.scale_const = None, (), None, None
         self.rungs = None   # T_LADDER: [(global bit, source LOp)]
+        self.preh = False   # T_LADDER: a Hadamard on the control bit is folded in (TQB_F_PREH)
 
     @property
     def per_sample(self):
@@ -247,6 +248,24 @@ def fold_phase_ladders(lops):
     return out
 
 
+def fold_h_into_ladders(lops):
+    """`H on c; ladder controlled by c` (one rung set of a QFT) -> the ladder with TQB_F_PREH: one sweep over the staged tile
+    does (a, b) -> (a + b, (a - b) * phase) on the pairs of bit c instead of a register group for H plus a ladder group."""
+    out, i = [], 0
+    while i < len(lops):
+        a = lops[i]
+        if (a.type == C.T_HS and i + 1 < len(lops) and lops[i + 1].type == C.T_LADDER and not lops[i + 1].preh
+                and lops[i + 1].cmask == 1 << a.targets[0] and not (lops[i + 1].pmask >> a.targets[0]) & 1):
+            lad = lops[i + 1]
+            lad.preh, lad.targets, lad.scale_const = True, a.targets, a.scale_const
+            out.append(lad)
+            i += 2
+            continue
+        out.append(a)
+        i += 1
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 # greedy, dependency-respecting packing
 # ---------------------------------------------------------------------------------------
@@ -273,11 +292,13 @@ def _pack_groups(ops, R):
     U2Q ops need their targets at register indices (1, 0)."""
     remaining, groups = list(ops), []
     while remaining:
-        reg, blocked, part, rest, soft, ladder_group = [], 0, [], [], [], False
+        reg, blocked, part, rest, soft, ladder_group, closed = [], 0, [], [], [], False, False
         for op in remaining:
             ok = not (op.qmask & blocked)
             if ok and (op.type == C.T_LADDER) != ladder_group and part:
                 ok = False   # ladders run in groups of their own (applied on the staged tile, no register bits)
+            if ok and part and (closed or op.preh):
+                ok = False   # a ladder with a folded Hadamard pairs amplitudes of different threads: one per group (barrier)
             if ok and not part:
                 ladder_group = op.type == C.T_LADDER
             if ok:
@@ -297,6 +318,7 @@ def _pack_groups(ops, R):
             if ok:
                 soft.extend(op._soft)
                 part.append(op)
+                closed = closed or op.preh
             else:
                 blocked |= op.qmask
                 rest.append(op)
@@ -497,11 +519,13 @@ def _encode_op(op, regs, R, loc, oloc):
         j = reg_par[0]
     if op.type == C.T_U2Q:
         assert regs[0] == op._lt[1] and regs[1] == op._lt[0]
-    elif op._lt:
+    elif op._lt and op.type != C.T_LADDER:
         j = regidx[op._lt[0]]
     if op.type in (C.T_REAL, C.T_RX):
         assert not (flags & (C.F_TCTRL | C.F_RCTRL)), "REAL / RX micro-ops cannot be controlled"
     w0 = (op.type << 2) | j | flags | (op.gkind << 16)
+    if op.type == C.T_LADDER and op.preh:
+        w0 |= C.F_PREH | (op._lt[0] << 22)
     if op.postx is not None:
         assert op.postx in regidx and regidx[op.postx] != j and (op.type != C.T_DIAGS or flags & C.F_DJ)
         w0 |= C.F_POSTX | (regidx[op.postx] << 20)
@@ -692,7 +716,7 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
             g_off += g_len
         # deferred scale factor of the pass (scaled op forms): constant part folded here, parametric part by the
         # matrix builder (K_SCALE records scan this pass's records)
-        scaled = [op for op in ops if op.type in SCALED]
+        scaled = [op for op in ops if op.type in SCALED or op.scale_const is not None]
         if scaled:
             pre = complex(1.0)
             for op in scaled:
@@ -762,7 +786,7 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
         if cur:
             ops = fold_cnot_sandwiches(cur)
             if fast:
-                ops = fold_phase_ladders(ops)
+                ops = fold_h_into_ladders(fold_phase_ladders(ops))
             plan.stages.append(build_fused_stage(ops, n, n_total, **tile_kw))
             cur.clear()
 
