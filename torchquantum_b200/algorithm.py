@@ -60,33 +60,34 @@ class Hamiltonian(object):
     """Weighted sum of Pauli strings (algorithm/hamiltonian.py:93-198)."""
 
     def __init__(self, coeffs: List[float], paulis: List[str], endianness: str = "big") -> None:
-        if endianness not in ["big", "little"]:
+        # same checks and messages as the reference constructor (algorithm/hamiltonian.py:116-137)
+        self._validate(coeffs, paulis, endianness)
+        self.endianness = endianness
+        self.coeffs = coeffs
+        self.paulis = list(paulis) if endianness == "big" else [p[::-1] for p in paulis]
+        self.n_wires = len(paulis[0])
+        self._coeff_cache = {}
+
+    @staticmethod
+    def _validate(coeffs, paulis, endianness):
+        if endianness not in ("big", "little"):
             raise ValueError("Endianness must be either big or little.")
         if len(coeffs) != len(paulis):
             raise ValueError("The number of coefficients and operators must be the same.")
-        for op in paulis:
-            if len(op) != len(paulis[0]):
-                raise ValueError("The length of each operator must be the same.")
-            for char in op:
-                if char not in ["X", "Y", "Z", "I"]:
-                    raise ValueError("The operator must be a string of X, Y, Z, and I.")
-        self.n_wires = len(paulis[0])
-        self.coeffs = coeffs
-        self.paulis = paulis
-        self.endianness = endianness
-        if self.endianness == "little":
-            self.paulis = [pauli[::-1] for pauli in self.paulis]
-        self._coeff_cache = {}
+        width = len(paulis[0])
+        if any(len(p) != width for p in paulis):
+            raise ValueError("The length of each operator must be the same.")
+        if any(ch not in "XYZI" for p in paulis for ch in p):
+            raise ValueError("The operator must be a string of X, Y, Z, and I.")
 
     @property
     def matrix(self) -> torch.Tensor:
         return self.get_matrix()
 
     def get_matrix(self) -> torch.Tensor:
-        matrix = self.coeffs[0] * pauli_string_to_matrix(self.paulis[0])
-        for coeff, pauli in zip(self.coeffs[1:], self.paulis[1:]):
-            matrix = matrix + coeff * pauli_string_to_matrix(pauli)
-        return matrix
+        """Dense 2^n x 2^n matrix sum_t c_t P_t (small n only; the engine never builds it)."""
+        terms = [c * pauli_string_to_matrix(p) for c, p in zip(self.coeffs, self.paulis)]
+        return torch.stack(terms).sum(0)
 
     @property
     def hamil_info(self) -> dict:
@@ -142,15 +143,16 @@ class VQE(object):
         return self.get_expval(qdev)
 
     def train(self):
-        optimizer = getattr(torch.optim, self.optimizer_name)(self.ansatz.parameters(), lr=self.lr)
-        lr_scheduler = getattr(torch.optim.lr_scheduler, self.scheduler_name)(optimizer, T_max=self.n_epochs)
-        loss = None
+        """Adam / cosine schedule by default (train_configs), `n_epochs` x `n_steps` steps; returns the last energy."""
+        opt = getattr(torch.optim, self.optimizer_name)(self.ansatz.parameters(), lr=self.lr)
+        sched = getattr(torch.optim.lr_scheduler, self.scheduler_name)(opt, T_max=self.n_epochs)
+        energy = None
         for epoch in range(self.n_epochs):
             for step in range(self.n_steps):
-                loss = self.get_loss()
-                optimizer.zero_grad()
-                loss.backward()
-                optimizer.step()
-                print(f"Epoch: {epoch}, Step: {step}, Loss: {loss}")
-            lr_scheduler.step()
-        return loss.detach().cpu().item()
+                opt.zero_grad()
+                energy = self.get_loss()
+                energy.backward()
+                opt.step()
+                print(f"Epoch: {epoch}, Step: {step}, Loss: {energy}")
+            sched.step()
+        return energy.detach().cpu().item()

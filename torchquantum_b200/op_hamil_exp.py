@@ -44,24 +44,16 @@ class OpHamilExp(QuantumModule):
 
 
 class OpPauliExp(OpHamilExp):
+    """OpHamilExp built from coefficients and Pauli strings; records itself in `op_history` (op_hamil_exp.py:96-150)."""
+
     def __init__(self, coeffs: List[float], paulis: List[str], endianness: str = "big", trainable: bool = True,
                  theta: float = 0.0):
-        self.hamil = Hamiltonian(coeffs, paulis, endianness)
-        super().__init__(hamil=self.hamil, trainable=trainable, theta=theta)
-        self.coeffs = coeffs
-        self.paulis = paulis
-        self.trainable = trainable
+        super().__init__(hamil=Hamiltonian(coeffs, paulis, endianness), trainable=trainable, theta=theta)
+        self.coeffs, self.paulis, self.trainable = coeffs, paulis, trainable
 
     def forward(self, qdev, wires):
-        matrix = self.matrix.to(qdev.compute_device)
         if qdev.record_op:
-            qdev.op_history.append({
-                "name": self.__class__.__name__,
-                "wires": np.array(wires).squeeze().tolist(),
-                "coeffs": self.coeffs,
-                "paulis": self.paulis,
-                "inverse": False,
-                "trainable": self.trainable,
-                "params": self.theta.item(),
-            })
-        tqf.qubitunitaryfast(q_device=qdev, wires=wires, params=matrix)
+            entry = dict(name=type(self).__name__, wires=np.array(wires).squeeze().tolist(), coeffs=self.coeffs,
+                         paulis=self.paulis, inverse=False, trainable=self.trainable, params=self.theta.item())
+            qdev.op_history.append(entry)
+        super().forward(qdev, wires)
