@@ -365,7 +365,7 @@ def run_ours(args):
         cstep = cpu_reference_step(sample_bsz, threads)
         cstep()
         t0 = time.perf_counter()
-        reps = 3
+        reps = 8   # ~3-4 s of CPU work on 16 cores: enough to average out scheduling noise, short enough for the default run
         for _ in range(reps):
             cstep()
         dt = (time.perf_counter() - t0) / reps
