@@ -118,9 +118,13 @@ tqb_pass_kernel(const PassArgs a) {
 
 template <int R, bool BWD, bool SMALL>
 static int launch_pass_t(const PassArgs& a, size_t smem, cudaStream_t st) {
-  static int configured_smem = -1;  // per instantiation
+  // per instantiation AND per device (kernel attributes are per device; one process normally drives one GPU)
+  static int cached_dev = -1, configured_smem = -1;
   static int occ_threads = 0, occ_smem = -1, occ_blocks = 0;
   const int threads = a.S * a.tps;
+  int dev_now = 0;
+  cudaGetDevice(&dev_now);
+  if (dev_now != cached_dev) { cached_dev = dev_now; configured_smem = -1; occ_threads = 0; occ_smem = -1; }
   if ((int)smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(tqb_pass_kernel<R, BWD, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(pass)", e);

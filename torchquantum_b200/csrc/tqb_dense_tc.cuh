@@ -222,11 +222,13 @@ template <int K>
 static cudaError_t launch_dense_tc(const DenseTcArgs& a, int num_sms, cudaStream_t st) {
   constexpr int M = 1 << K, N = 1 << (TQB_TC_T - K), LD = M + 4;
   const size_t smem = (size_t)((K <= 5 ? 4 : 2) * M * LD) * sizeof(float) + (size_t)2 * N * LD * sizeof(float2);
-  static bool configured = false;
-  if (!configured) {
+  static int configured_dev = -1;   // kernel attributes are per device
+  int dev_now = 0;
+  cudaGetDevice(&dev_now);
+  if (dev_now != configured_dev) {
     cudaError_t e = cudaFuncSetAttribute(tqb_dense_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured_dev = dev_now;
   }
   // k <= 6: two CTAs per SM (<= 103 KB each); k = 7: one (201 KB)
   const long long resident = (long long)num_sms * (K <= 6 ? 2 : 1);
