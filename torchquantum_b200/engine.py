@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _codes as C
+from . import _codes as C  # noqa: F401  (re-exported for tools)
 from . import _native
 from . import gates as G
 from . import plan as P
