@@ -199,11 +199,37 @@ def run_cfg1(dev, bsz=256):
             "circuits_per_s_graphed": bsz / (graphed * 1e-3), "ok": True}
 
 
+def run_cfg3_batch_sharded(out_path):
+    """cfg 3 batch-sharded over the ranks of a torchrun launch (no data-path collective, per-sample angles and
+    gradients stay on their rank): 64 circuits in total, 64 / world per GPU; time = max over ranks."""
+    import torch.distributed as dist
+
+    local, world = int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    res = run_cfg3(dev, bsz=64 // world)
+    t = torch.tensor([res["fwd_ms"], res["fwd_bwd_ms"], 0.0 if res["ok"] else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if dist.get_rank() == 0:
+        out = {"workload": res["workload"] + f" per rank, batch-sharded over {world} B200 (64 circuits in total)",
+               "world": world, "fwd_ms": t[0].item(), "fwd_bwd_ms": t[1].item(),
+               "circuits_per_s_fwd_bwd": 64 / (t[1].item() * 1e-3), "scaling": "strong", "ok": t[2].item() == 0.0,
+               "grad_vs_finite_difference_rel": res["grad_vs_finite_difference_rel"]}
+        print(json.dumps({"cfg3_batch_sharded": out}))
+        if out_path:
+            json.dump(out, open(out_path, "w"), indent=1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", type=int, nargs="*", default=[1, 3, 4])
     ap.add_argument("--out", default="")
     a = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_cfg3_batch_sharded(a.out)
     dev = torch.device("cuda", 0)
     out = {"gpu": torch.cuda.get_device_name(0)}
     for c in a.cfg:
