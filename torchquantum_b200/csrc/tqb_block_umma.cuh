@@ -1,0 +1,477 @@
+// K4 on Blackwell tensor cores: one dense 6-qubit block unitary per pass over the state.
+//
+// Replaces (for forward-only programs) what the reference's static mode does on the host, torchquantum/graph/graphs.py:
+// 713-861 (block-unitary product + one bmm per block), and the per-gate apply_unitary_bmm of
+// torchquantum/functional/gate_wrapper.py:96-140 for every gate the planner folded into the block.
+//
+// Maths.  The block acts on 6 physical index bits kpos[0..5] (ascending, all >= 6); j / i = 6-bit input / output
+// pattern of those bits, n = the 6 lowest index bits, c = re/im.  A tile is the 4096 amplitudes that share all the
+// other bits.  With A[2i+w][j] = (w ? Im : Re) U[i][j]  (128 x 64, real) and S[j][(n,c)] the tile as a real
+// 64 x 128 matrix,  D = A * S  is ONE tensor-core GEMM  M=128 (TMEM lanes), N=128, K=64;  lanes 2i / 2i+1 hold
+// P = Re(U) S and Q = Im(U) S of output pattern i, and  out[i][n] = (P_re - Q_im) + i (P_im + Q_re)  is formed by the
+// epilogue from a lane-pair shuffle.  fp32 accuracy comes from the 3xTF32 split: A = Ah + Al, S = Sh + Sl (each part
+// rounded to TF32 with cvt.rna), D = Ah Sh + Ah Sl + Al Sh, accumulated in fp32 in TMEM.
+//
+// Data path per tile (persistent CTA, one per SM, 12 warps):
+//   TMA (cp.async.bulk.tensor.5d, SWIZZLE_128B_ATOM_32B) loads the raw tile straight into the MN-major UMMA operand
+//   layout [n/16][j][16 amplitudes] (the tensor map's dims: 32 floats, 128-byte rows of the whole state, then the
+//   <= 3 runs of contiguous block bits)  ->  4 splitter warps turn it in place into Sh and write Sl beside it  ->
+//   one thread issues 24 tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory) into one of two TMEM
+//   accumulators  ->  4 epilogue warps tcgen05.ld it, combine lane pairs and write the finished tile to a staging
+//   buffer in the same layout  ->  TMA store.  `transpose` writes the tile with the roles of the block bits and
+//   the low bits exchanged (pattern i goes to index bits 0-5, n to kpos), which is how the planner rotates
+//   qubits out of the low index bits without a pass of its own.
+// 3 operand stages (64 KiB each) + 32 KiB staging = 224 KiB of shared memory; TMEM: A 128 + D 2 x 128 columns.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tqb_umma {
+
+constexpr int kStages = 3;
+constexpr int kThreads = 384;
+constexpr uint32_t kPlane = 32768;              // bytes of one operand plane (hi or lo) of a tile
+constexpr uint32_t kStageBytes = 2 * kPlane;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kPlane + 1024 /* alignment slack */ + 512 /* barriers, norms */;
+constexpr uint32_t kTmemCols = 512;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A K-major (TMEM), B MN-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Params {
+  const float* a_planes;   // [2][128][64]: TF32-rounded hi plane, lo plane of A
+  uint32_t n_tiles;
+  int transpose;
+  int renorm;              // block is unitary: rescale every tile to the norm it came in with (see the epilogue)
+  int nseg;                // outer (non-tile) index bits as <= 4 runs: bits [lo, lo+len) of the tile id go to bit pos
+  int seg_lo[4], seg_len[4], seg_pos[4];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// a wait that cannot hang the GPU: a mis-programmed pipeline traps after ~2 s instead of spinning for ever
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin == 64) t0 = clock64();
+    if (spin > 64 && (spin & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
+// shared-memory matrix descriptor of one K=8 slice of a tile plane: MN-major, SWIZZLE_128B_BASE32B (the only layout
+// for MN-major 32-bit operands), LBO = 8192 B between the 32-element N atoms, SBO = 512 B between 4-row K atoms
+__device__ __forceinline__ uint64_t b_desc(uint32_t addr) {
+  const uint32_t lo = ((addr >> 4) & 0x3fffu) | (((8192u >> 4) & 0x3fffu) << 16);
+  const uint32_t hi = ((512u >> 4) & 0x3fffu) | (1u << 14) | (1u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+#define TQB_R32(v) \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),     \
+  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),     \
+  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define TQB_I32(v) \
+  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), \
+  "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),   \
+  "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),   \
+  "r"(v[31])
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+      "%26, %27, %28, %29, %30, %31}, [%32];"
+      : TQB_R32(v)
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
+      "%27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), TQB_I32(v)
+      : "memory");
+}
+
+// 128-byte row index of the tile's first amplitude
+__device__ __forceinline__ uint32_t tile_row(const Params& p, uint32_t tile) {
+  unsigned long long off = 0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+    if (s < p.nseg) {
+      const unsigned long long part = (tile >> p.seg_lo[s]) & ((p.seg_len[s] >= 32 ? 0ull : (1ull << p.seg_len[s])) - 1ull);
+      off |= part << p.seg_pos[s];
+    }
+  return (uint32_t)(off >> 4);
+}
+
+// byte offset of 16-byte chunk c16 of row `row` inside an 8 KiB group: 32-byte units are XOR-ed with row % 4
+__device__ __forceinline__ uint32_t swz32(uint32_t row, uint32_t c16) {
+  return row * 128u + ((((c16 >> 1) ^ (row & 3u)) << 5) | ((c16 & 1u) << 4));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg = base + kStages * kStageBytes;          // epilogue staging tile
+  const uint32_t bars = stg + kPlane;
+  // barrier slots (8 bytes each): full[3] ready[3] empty[3] dfull[2] dempty[2]; then the TMEM base address
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto ready = [&](int s) { return bars + 8u * (3 + s); };
+  auto empty = [&](int s) { return bars + 8u * (6 + s); };
+  auto dfull = [&](int d) { return bars + 8u * (9 + d); };
+  auto dempty = [&](int d) { return bars + 8u * (11 + d); };
+  const uint32_t tmem_slot = bars + 8u * 13;
+  const uint32_t nin_slot = bars + 128u;    // [8 tiles in flight][4 splitter warps] squared norms of the raw tile
+  const uint32_t nout_slot = bars + 256u;   // [4 epilogue warps] squared norms of the computed tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), 128); mbar_init(empty(s), 1); }
+    for (int d = 0; d < 2; ++d) { mbar_init(dfull(d), 1); mbar_init(dempty(d), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_src) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dst) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+  const uint32_t t_ahi = tmem, t_alo = tmem + 64u, t_d0 = tmem + 128u;
+
+  // A -> TMEM: lane m of TMEM = row m of A, column k = A[m][k]
+  if (warp >= 4 && warp < 8) {
+    const int q = warp & 3, m = 32 * q + lane;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4* src = reinterpret_cast<const float4*>(p.a_planes + ((size_t)pl * 128 + m) * 64 + h * 32);
+        uint32_t v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 f = __ldg(src + k);
+          v[4 * k] = __float_as_uint(f.x); v[4 * k + 1] = __float_as_uint(f.y);
+          v[4 * k + 2] = __float_as_uint(f.z); v[4 * k + 3] = __float_as_uint(f.w);
+        }
+        tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(pl * 64 + h * 32), v);
+      }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
+        mbar_wait(empty(s), ph ^ 1u);
+        mbar_expect_tx(full(s), kPlane);
+        const uint32_t row = tile_row(p, t);
+        const uint32_t dst = base + s * kStageBytes;
+#pragma unroll
+        for (int ng = 0; ng < 4; ++ng) tma_load_5d(dst + ng * 8192u, &tm_src, full(s), 0, (int)(row + ng), 0, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages, d = it & 1;
+        const uint32_t ph = (it / kStages) & 1u, dph = (it >> 1) & 1u;
+        mbar_wait(ready(s), ph);
+        mbar_wait(dempty(d), dph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t bh = base + s * kStageBytes, bl = bh + kPlane;
+        const uint32_t dt = t_d0 + 128u * d;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dh = b_desc(bh + ks * 1024u), dl = b_desc(bl + ks * 1024u);
+          umma_tf32_ts(dt, t_alo + 8u * ks, dh, ks > 0);
+          umma_tf32_ts(dt, t_ahi + 8u * ks, dl, 1u);
+          umma_tf32_ts(dt, t_ahi + 8u * ks, dh, 1u);
+        }
+        umma_commit(empty(s));
+        umma_commit(dfull(d));
+      }
+    }
+  } else if (warp >= 8) {
+    // ---------------- splitters: raw fp32 -> TF32 hi (in place) + TF32 lo ----------------
+    const int tid = threadIdx.x - 256;
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1u;
+      mbar_wait(full(s), ph);
+      const uint32_t bh = base + s * kStageBytes + 16u * tid;
+      float ss = 0.f;
+#pragma unroll 4
+      for (int v = 0; v < 16; ++v) {
+        const uint32_t a = bh + 2048u * v;
+        float x0, x1, x2, x3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(a) : "memory");
+        ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+        const uint32_t h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+        const uint32_t l0 = tf32_rna(x0 - __uint_as_float(h0)), l1 = tf32_rna(x1 - __uint_as_float(h1));
+        const uint32_t l2 = tf32_rna(x2 - __uint_as_float(h2)), l3 = tf32_rna(x3 - __uint_as_float(h3));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + kPlane), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+      }
+      if (p.renorm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(nin_slot + 4u * (4u * (it & 7u) + (uint32_t)(warp - 8))), "f"(ss) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(ready(s));
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int q = warp & 3, et = threadIdx.x - 128;
+    const uint32_t i = 16u * q + (lane >> 1), w = lane & 1u;
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int d = it & 1;
+      const uint32_t dph = (it >> 1) & 1u;
+      mbar_wait(dfull(d), dph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t trow = t_d0 + 128u * d + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+      for (uint32_t ng = 0; ng < 4; ++ng) {
+        uint32_t v[32];
+        tmem_ld32(trow + 32u * ng, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // lane pair exchange: the even lane (P) finishes n = 0..7 of the group, the odd lane (Q) n = 8..15
+        float o[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t send = w ? v[k] : v[16 + k];
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          o[k] = __uint_as_float(recv);
+        }
+        float r[16];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) {
+          // P = (pr, pi), Q = (qr, qi) of amplitude nn (even lane) / 8 + nn (odd lane)
+          const float pr = w ? o[2 * nn] : __uint_as_float(v[2 * nn]);
+          const float pi = w ? o[2 * nn + 1] : __uint_as_float(v[2 * nn + 1]);
+          const float qr = w ? __uint_as_float(v[16 + 2 * nn]) : o[2 * nn];
+          const float qi = w ? __uint_as_float(v[16 + 2 * nn + 1]) : o[2 * nn + 1];
+          r[2 * nn] = pr - qi;
+          r[2 * nn + 1] = pi + qr;
+        }
+        if (!p.transpose) {
+          const uint32_t g = stg + ng * 8192u;
+#pragma unroll
+          for (uint32_t qq = 0; qq < 4; ++qq) {
+            const uint32_t a = g + swz32(i, 4u * w + qq);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r[4 * qq]), "f"(r[4 * qq + 1]), "f"(r[4 * qq + 2]),
+                         "f"(r[4 * qq + 3])
+                         : "memory");
+          }
+        } else {
+          const uint32_t g = stg + (i >> 4) * 8192u;
+          const uint32_t c16 = (i & 15u) >> 1, sub = (i & 1u) * 8u;
+#pragma unroll
+          for (uint32_t nn = 0; nn < 8; ++nn) {
+            const uint32_t n = 16u * ng + 8u * w + nn;
+            const uint32_t a = g + swz32(n, c16) + sub;
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(r[2 * nn]), "f"(r[2 * nn + 1]) : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(dempty(d));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const uint32_t row = tile_row(p, t);
+#pragma unroll
+        for (int ng = 0; ng < 4; ++ng) tma_store_5d(&tm_dst, stg + ng * 8192u, 0, (int)(row + ng), 0, 0, 0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// tensor map over the whole state for tiles of {index bits 0-5} x {kpos[0..5]}: dims (fastest first)
+//   32 floats | 128-byte rows of the state | up to three runs of contiguous block bits
+// box = 32 x 1 x run sizes = 64 rows of 128 bytes (one n/16 group of a tile)
+inline const char* make_tensor_map(CUtensorMap* tm, const float* state, int n_qubits, long long bsz, const int* kpos) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled not available";
+  int run_start[3], run_len[3], nruns = 0;
+  for (int b = 0; b < 6;) {
+    int e = b;
+    while (e + 1 < 6 && kpos[e + 1] == kpos[e] + 1) ++e;
+    if (nruns == 3) return "block bits form more than three runs";
+    run_start[nruns] = kpos[b];
+    run_len[nruns] = e - b + 1;
+    ++nruns;
+    b = e + 1;
+  }
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = 32; box[0] = 32;
+  dims[1] = ((cuuint64_t)bsz << n_qubits) >> 4; box[1] = 1;
+  strides[0] = 128;
+  cuuint64_t prev = 128ull * 4;  // filler stride for absent runs: any multiple of 16
+  for (int r = 0; r < 3; ++r) {
+    if (r < nruns) {
+      dims[2 + r] = 1ull << run_len[r];
+      box[2 + r] = 1u << run_len[r];
+      strides[1 + r] = 8ull << run_start[r];
+      prev = strides[1 + r] * dims[2 + r];
+    } else {
+      dims[2 + r] = 1; box[2 + r] = 1;
+      strides[1 + r] = prev;
+    }
+  }
+  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(state), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
+  return nullptr;
+}
+
+// kpos: 6 ascending physical bit positions, all >= 6 and < n_qubits
+inline const char* launch_block6(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
+                                 const int* kpos, int transpose, int num_sms, cudaStream_t st) {
+  if (n_qubits < 12) return "block6 needs n_qubits >= 12";
+  for (int b = 0; b < 6; ++b) {
+    if (kpos[b] < 6 || kpos[b] >= n_qubits) return "block bit out of range (must be >= 6)";
+    if (b && kpos[b] <= kpos[b - 1]) return "block bits must ascend";
+  }
+  static int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != configured_dev) {
+    if (cudaFuncSetAttribute(tqb_block6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return "cudaFuncSetAttribute(block6) failed";
+    configured_dev = dev;
+  }
+  CUtensorMap tm_src, tm_dst;
+  const char* err = make_tensor_map(&tm_src, src, n_qubits, bsz, kpos);
+  if (err) return err;
+  err = make_tensor_map(&tm_dst, dst, n_qubits, bsz, kpos);
+  if (err) return err;
+  Params p;
+  p.a_planes = a_planes;
+  p.transpose = transpose;
+  const unsigned long long tiles = ((unsigned long long)bsz << n_qubits) >> 12;
+  if (tiles > 0xffffffffull) return "too many tiles";
+  p.n_tiles = (uint32_t)tiles;
+  // outer bits = everything except bits 0-5 and kpos, as runs (the batch index continues the top run)
+  p.nseg = 0;
+  int consumed = 0;
+  int pos = 6;
+  for (int b = 0; b <= 6; ++b) {
+    const int upto = b < 6 ? kpos[b] : 64;
+    if (upto > pos) {
+      if (p.nseg == 4) return "too many outer runs";
+      p.seg_lo[p.nseg] = consumed;
+      p.seg_len[p.nseg] = b < 6 ? upto - pos : 32;
+      p.seg_pos[p.nseg] = pos;
+      consumed += upto - pos;
+      ++p.nseg;
+    }
+    pos = upto + 1;
+  }
+  for (int s = p.nseg; s < 4; ++s) { p.seg_lo[s] = 0; p.seg_len[s] = 0; p.seg_pos[s] = 0; }
+  const unsigned grid = (unsigned)(tiles < (unsigned long long)num_sms ? tiles : num_sms);
+  tqb_block6_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_src, tm_dst, p);
+  if (cudaGetLastError() != cudaSuccess) return "block6 launch failed";
+  return nullptr;
+}
+
+}  // namespace tqb_umma

@@ -6,6 +6,7 @@
 
 #include "tqb_core.cuh"
 #include "tqb_dense_tc.cuh"
+#include "tqb_block_umma.cuh"
 #include "../../include/tqb200.h"
 
 using namespace tqb;
@@ -662,6 +663,21 @@ int tqb_apply_dense_tc(const float* in, float* out, int n_qubits, long long bsz,
     case 7: e = launch_dense_tc<7>(a, g_num_sms, st); break;
   }
   if (e != cudaSuccess) return fail("tqb_dense_tc_kernel", e);
+  return 0;
+}
+
+int tqb_apply_block6(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
+                     const int* kpos_host, int transpose_out, void* stream) {
+  if (bsz <= 0) return 0;
+  if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)a_planes) & 15) != 0) return fail_msg("tqb_apply_block6: pointers must be 16-byte aligned");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const char* err = tqb_umma::launch_block6(src, dst, n_qubits, bsz, a_planes, kpos_host, transpose_out, g_num_sms, (cudaStream_t)stream);
+  if (err) return fail_msg(err);
   return 0;
 }
 
