@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 3
+#define TQB_ABI_VERSION 4
 
 int tqb_abi_version(void);
 const char* tqb_last_error(void);
@@ -83,6 +83,21 @@ int tqb_apply_dense(const float* in, float* out, int n_qubits, long long bsz, co
  * functional/qubit_unitary.py:19-93 through gate_wrapper.py:96-140). */
 int tqb_apply_dense_tc(const float* in, float* out, int n_qubits, long long bsz, const float* mat, int k,
                        const int* bitpos_host, int conj_transpose, void* stream);
+/* Forward-only block programs (csrc/tqb_program.h "Block programs"): runs of gates on <= 6 qubits are multiplied on the
+ * device into dense 6-qubit block unitaries, each applied in ONE tensor-core pass over the state (tcgen05.mma kind::tf32
+ * with the 3xTF32 split, TMEM accumulators, TMA tile loads / stores).  Replaces what the reference's static mode does on
+ * the host (graph/graphs.py:384-509 block scheduling, :713-861 block unitaries, one bmm per block through
+ * functional/gate_wrapper.py:96-140).
+ * tqb_block_build: blocks_dev [n_blocks][TQB_KB_WORDS], ops_dev [*][TQB_KO_WORDS], constant pool, shared parameters
+ *   -> a_planes [n_blocks][2][128][64] float (TF32 hi / lo planes of A[2i+w][j] = (Re, Im)[w] U[i][j]).  `rank` resolves
+ *   controls / parity bits that live in the rank index of a sharded state.
+ * tqb_apply_blocks: applies the blocks in order; the first reads src, the others work in place on dst (dst may equal
+ *   src).  blocks_host: the same block headers on the HOST (bit positions for the tensor maps).  n_qubits >= 12.
+ *   renorm != 0: every block is unitary, tiles are rescaled to the norm they came in with. */
+int tqb_block_build(const int32_t* blocks_dev, int n_blocks, const int32_t* ops_dev, const float* consts,
+                    const float* params_sh, unsigned rank, float* a_planes, void* stream);
+int tqb_apply_blocks(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
+                     const int32_t* blocks_host, int n_blocks, int renorm, void* stream);
 /* G[b][r][c] = sum_rest lam_out[b][r,rest] conj(psi_in[b][c,rest]) (complex64 [bsz][2^k][2^k]) */
 int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long long bsz, int k,
                    const int* bitpos_dev, float* G, void* stream);

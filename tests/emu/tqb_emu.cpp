@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../torchquantum_b200/csrc/tqb_core.cuh"
+#include "../../torchquantum_b200/csrc/tqb_block_build.cuh"
 #include "../../include/tqb200.h"
 
 using namespace tqb;
@@ -152,6 +153,59 @@ int tqb_apply_dense_tc(const float* in_, float* out_, int n, long long bsz, cons
                        int conj_t, void* st) {
   if (k < 4 || k > 7 || n < 12) return fail_msg("tqb_apply_dense_tc: needs 4 <= k <= 7 and n_qubits >= 12");
   return tqb_apply_dense(in_, out_, n, bsz, mat_, 0, k, bitpos_host, conj_t, st);
+}
+
+int tqb_block_build(const int32_t* blocks, int n_blocks, const int32_t* ops, const float* consts, const float* psh, unsigned rank,
+                    float* planes, void*) {
+  for (int b = 0; b < n_blocks; ++b)
+    for (int j = 0; j < 64; ++j) block_build_one(blocks, ops, consts, psh, rank, b, j, planes);
+  return 0;
+}
+
+// host restatement of tqb_block6_kernel's arithmetic contract: out tile = (A_hi + A_lo) * tile, the block's bits and the
+// index bits 0-5 exchanged on the way out when the block is transposing (fp32 data, double accumulation)
+int tqb_apply_blocks(const float* src_, float* dst_, int n, long long bsz, const float* planes_all, const int32_t* blocks_host,
+                     int n_blocks, int, void*) {
+  if (n < 12) return fail_msg("block6 needs n_qubits >= 12");
+  const u64 N = 1ull << n;
+  std::vector<cf> tmp(N);
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const int32_t* bh = blocks_host + (size_t)blk * TQB_KB_WORDS;
+    const float* pl = planes_all + (size_t)blk * 2 * 128 * 64;
+    int kpos[6];
+    u64 kmask = 0;
+    for (int k = 0; k < 6; ++k) {
+      kpos[k] = bh[TQB_KB_KPOS + k];
+      if (kpos[k] < 6 || kpos[k] >= n || (k && kpos[k] <= kpos[k - 1])) return fail_msg("block bit out of range (must be >= 6)");
+      kmask |= 1ull << kpos[k];
+    }
+    const bool tr = bh[TQB_KB_FLAGS] & TQB_KBF_TRANSPOSE;
+    std::vector<cd> U(64 * 64);
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < 64; ++j)
+        U[i * 64 + j] = cd((double)pl[(2 * i) * 64 + j] + (double)pl[(128 + 2 * i) * 64 + j],
+                           (double)pl[(2 * i + 1) * 64 + j] + (double)pl[(128 + 2 * i + 1) * 64 + j]);
+    auto spread = [&](int pat) { u64 o = 0; for (int k = 0; k < 6; ++k) if ((pat >> k) & 1) o |= 1ull << kpos[k]; return o; };
+    for (long long b = 0; b < bsz; ++b) {
+      const cf* in = reinterpret_cast<const cf*>(blk == 0 ? src_ : dst_) + (u64)b * N;
+      cf* out = reinterpret_cast<cf*>(dst_) + (u64)b * N;
+      for (u64 base = 0; base < N; ++base) {
+        if (base & (kmask | 63ull)) continue;
+        for (int nn = 0; nn < 64; ++nn) {
+          cd v[64];
+          for (int j = 0; j < 64; ++j) v[j] = cd(in[base | spread(j) | (u64)nn]);
+          for (int i = 0; i < 64; ++i) {
+            cd acc = 0;
+            for (int j = 0; j < 64; ++j) acc += U[i * 64 + j] * v[j];
+            const u64 at = tr ? (base | spread(nn) | (u64)i) : (base | spread(i) | (u64)nn);
+            tmp[at] = cf((float)acc.real(), (float)acc.imag());
+          }
+        }
+      }
+      for (u64 a = 0; a < N; ++a) out[a] = tmp[a];
+    }
+  }
+  return 0;
 }
 
 int tqb_dense_grad(const float* psi_, const float* lam_, int n, long long bsz, int k, const int* bitpos, float* G_, void*) {

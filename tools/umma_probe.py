@@ -1,4 +1,4 @@
-"""GPU probe of tqb_apply_block6 (tcgen05 dense 6-qubit block): numerics vs a float64 torch contraction for
+"""GPU probe of tqb_apply_blocks (tcgen05 dense 6-qubit block): numerics vs a float64 torch contraction for
 several block placements (normal and transposed write-back) and timing at n = 28.
 Run on the GPU box: python tools/umma_probe.py [--n 20] [--time-n 28]"""
 import argparse
@@ -55,10 +55,11 @@ def main():
     args = ap.parse_args()
     lib = ctypes.CDLL(os.path.join(ROOT, "torchquantum_b200", "lib", "libtqb200.so"))
     lib.tqb_last_error.restype = ctypes.c_char_p
-    fn = lib.tqb_apply_block6
+    fn = lib.tqb_apply_blocks
     fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
-                   ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_void_p]
+                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     fn.restype = ctypes.c_int
+    renorm = [1]
     dev = "cuda:0"
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(1)
@@ -72,8 +73,10 @@ def main():
                   list(range(n - 6, n))]
 
     def run(src, dst, nq, bsz, kpos, tr):
-        arr = (ctypes.c_int * 6)(*kpos)
-        rc = fn(src.data_ptr(), dst.data_ptr(), nq, bsz, planes.data_ptr(), arr, tr, torch.cuda.current_stream().cuda_stream)
+        hdr = [0, 0, tr, 0] + list(kpos) + [0, 0]   # csrc/tqb_program.h: TQB_KB_*
+        arr = (ctypes.c_int32 * 12)(*hdr)
+        rc = fn(src.data_ptr(), dst.data_ptr(), nq, bsz, planes.data_ptr(), ctypes.addressof(arr), 1, renorm[0],
+                torch.cuda.current_stream().cuda_stream)
         if rc != 0:
             raise RuntimeError(lib.tqb_last_error().decode())
 
@@ -108,6 +111,18 @@ def main():
                     print("  in-place differs from out-of-place!", (st2 - out).abs().max().item(), flush=True)
                 results["cases"][-1]["inplace_equal"] = bool(same)
 
+    # norm drift over 64 applications of the same block, with and without the per-tile renormalisation
+    for rn in (0, 1):
+        renorm[0] = rn
+        st = torch.randn(1, 2 ** n, 2, device=dev, dtype=torch.float32)
+        st /= st.double().norm().float()
+        n0 = st.double().norm().item()
+        for _ in range(64):
+            run(st, st, n, 1, list(range(8, 14)), 0)
+        torch.cuda.synchronize()
+        results["norm_drift_64_renorm%d" % rn] = st.double().norm().item() / n0 - 1.0
+        print("norm drift after 64 blocks, renorm", rn, results["norm_drift_64_renorm%d" % rn], flush=True)
+    renorm[0] = 1
     # timing
     nt = args.time_n
     st = torch.randn(1, 2 ** nt, 2, device=dev, dtype=torch.float32)

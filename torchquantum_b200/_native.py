@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TQB200_LIB") or os.path.join(_HERE, "lib", "libtqb200.so")  # env: kernel A/B experiments
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 _emulated = False
@@ -24,6 +24,8 @@ SIGNATURES = {
     "tqb_pass_backward": [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _u, _vp],
     "tqb_apply_dense": [_vp, _vp, _i, _ll, _vp, _ll, _i, _vp, _i, _vp],
     "tqb_apply_dense_tc": [_vp, _vp, _i, _ll, _vp, _i, _vp, _i, _vp],
+    "tqb_block_build": [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp],
+    "tqb_apply_blocks": [_vp, _vp, _i, _ll, _vp, _vp, _i, _i, _vp],
     "tqb_dense_grad": [_vp, _vp, _i, _ll, _i, _vp, _vp, _vp],
     "tqb_expval_pauli": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp],
     "tqb_expval_pauli_bwd": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp],

@@ -245,13 +245,14 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t bh = base + s * kStageBytes, bl = bh + kPlane;
         const uint32_t dt = t_d0 + 128u * d;
+        // the two correction products first: the accumulator is still 2^-11 of its final size while they are added, so
+        // the tensor core's truncating fp32 accumulation costs 8 full-size roundings per tile instead of 24
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dh = b_desc(bh + ks * 1024u), dl = b_desc(bl + ks * 1024u);
-          umma_tf32_ts(dt, t_alo + 8u * ks, dh, ks > 0);
-          umma_tf32_ts(dt, t_ahi + 8u * ks, dl, 1u);
-          umma_tf32_ts(dt, t_ahi + 8u * ks, dh, 1u);
-        }
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_alo + 8u * ks, b_desc(bh + ks * 1024u), ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bl + ks * 1024u), 1u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bh + ks * 1024u), 1u);
         umma_commit(empty(s));
         umma_commit(dfull(d));
       }
@@ -291,9 +292,15 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
     const int q = warp & 3, et = threadIdx.x - 128;
     const uint32_t i = 16u * q + (lane >> 1), w = lane & 1u;
     uint32_t it = 0;
+    // Unitary blocks preserve the norm of every tile; the accumulation above truncates, which shrinks it by a few 1e-7
+    // per pass, systematically.  The epilogue therefore rescales by g = sqrt(|tile in|^2 / |tile out|^2), measured on the
+    // PREVIOUS tile of this CTA (the shrink is a property of the arithmetic, the same from tile to tile; using the
+    // previous tile's value keeps the epilogue single-pass).
+    float g = 1.f;
     for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
       const int d = it & 1;
       const uint32_t dph = (it >> 1) & 1u;
+      float ss_out = 0.f;
       mbar_wait(dfull(d), dph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -320,8 +327,11 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
           const float pi = w ? o[2 * nn + 1] : __uint_as_float(v[2 * nn + 1]);
           const float qr = w ? __uint_as_float(v[16 + 2 * nn]) : o[2 * nn];
           const float qi = w ? __uint_as_float(v[16 + 2 * nn + 1]) : o[2 * nn + 1];
-          r[2 * nn] = pr - qi;
-          r[2 * nn + 1] = pi + qr;
+          const float re = pr - qi, im = pi + qr;
+          ss_out = fmaf(re, re, ss_out);
+          ss_out = fmaf(im, im, ss_out);
+          r[2 * nn] = re * g;
+          r[2 * nn + 1] = im * g;
         }
         if (!p.transpose) {
           const uint32_t g = stg + ng * 8192u;
@@ -345,8 +355,22 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(dempty(d));
+      if (p.renorm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss_out += __shfl_xor_sync(0xffffffffu, ss_out, o);
+        if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(nout_slot + 4u * (uint32_t)q), "f"(ss_out) : "memory");
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.renorm) {
+        float4 a, b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(nin_slot + 16u * (it & 7u)) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(nout_slot) : "memory");
+        const float sin2 = (a.x + a.y) + (a.z + a.w), sout2 = (b.x + b.y) + (b.z + b.w);
+        float gn = 1.f;
+        if (sout2 > 0.f && sin2 > 0.f) gn = sqrtf(sin2 / sout2);
+        g = fabsf(gn - 1.f) < 1e-4f ? gn : 1.f;
+      }
       if (et == 0) {
         const uint32_t row = tile_row(p, t);
 #pragma unroll
@@ -426,7 +450,7 @@ inline const char* make_tensor_map(CUtensorMap* tm, const float* state, int n_qu
 
 // kpos: 6 ascending physical bit positions, all >= 6 and < n_qubits
 inline const char* launch_block6(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
-                                 const int* kpos, int transpose, int num_sms, cudaStream_t st) {
+                                 const int* kpos, int transpose, int renorm, int num_sms, cudaStream_t st) {
   if (n_qubits < 12) return "block6 needs n_qubits >= 12";
   for (int b = 0; b < 6; ++b) {
     if (kpos[b] < 6 || kpos[b] >= n_qubits) return "block bit out of range (must be >= 6)";
@@ -448,6 +472,7 @@ inline const char* launch_block6(const float* src, float* dst, int n_qubits, lon
   Params p;
   p.a_planes = a_planes;
   p.transpose = transpose;
+  p.renorm = renorm;
   const unsigned long long tiles = ((unsigned long long)bsz << n_qubits) >> 12;
   if (tiles > 0xffffffffull) return "too many tiles";
   p.n_tiles = (uint32_t)tiles;

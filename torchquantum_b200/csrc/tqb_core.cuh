@@ -1153,6 +1153,15 @@ TQB_FN void s_sincos(float a, float& s, float& c) {
   s = sinf(a); c = cosf(a);
 #endif
 }
+// double: the block-unitary builder (tqb_block_build.cuh) instantiates build_gate<double>
+TQB_FN double s_const(double, float c) { return (double)c; }
+TQB_FN void s_sincos(double a, double& s, double& c) {
+#if defined(__CUDA_ARCH__)
+  sincos(a, &s, &c);
+#else
+  s = sin(a); c = cos(a);
+#endif
+}
 TQB_FN void s_sincos(Dual a, Dual& s, Dual& c) {
   float sv, cv;
   s_sincos(a.v, sv, cv);

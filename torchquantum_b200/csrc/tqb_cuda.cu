@@ -7,6 +7,7 @@
 #include "tqb_core.cuh"
 #include "tqb_dense_tc.cuh"
 #include "tqb_block_umma.cuh"
+#include "tqb_block_build.cuh"
 #include "../../include/tqb200.h"
 
 using namespace tqb;
@@ -227,6 +228,12 @@ __global__ void tqb_build_bwd_kernel(const int32_t* table, int nrec, long long b
 // ---------------------------------------------------------------------------------------
 // generic dense k-qubit gate, out of place (rare: qft / qubitunitary on >= 3 wires)
 // ---------------------------------------------------------------------------------------
+// one CTA per block, one thread per column of the block unitary (tqb_block_build.cuh)
+__global__ void __launch_bounds__(64) tqb_block_build_kernel(const int32_t* blocks, const int32_t* ops, const float* consts,
+                                                             const float* params_sh, unsigned rank, float* planes) {
+  block_build_one(blocks, ops, consts, params_sh, rank, (int)blockIdx.x, (int)threadIdx.x, planes);
+}
+
 __global__ void tqb_dense_kernel(const float2* in, float2* out, int n, long long total, const float2* mats,
                                  long long mat_stride, int k, const int* bitpos /* msb first */, int conj_t) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -666,18 +673,33 @@ int tqb_apply_dense_tc(const float* in, float* out, int n_qubits, long long bsz,
   return 0;
 }
 
-int tqb_apply_block6(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
-                     const int* kpos_host, int transpose_out, void* stream) {
-  if (bsz <= 0) return 0;
-  if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)a_planes) & 15) != 0) return fail_msg("tqb_apply_block6: pointers must be 16-byte aligned");
+int tqb_block_build(const int32_t* blocks_dev, int n_blocks, const int32_t* ops_dev, const float* consts, const float* params_sh,
+                    unsigned rank, float* a_planes, void* stream) {
+  if (n_blocks <= 0) return 0;
+  tqb_block_build_kernel<<<n_blocks, 64, 0, (cudaStream_t)stream>>>(blocks_dev, ops_dev, consts, params_sh, rank, a_planes);
+  TQB_CHECK_LAUNCH("tqb_block_build");
+  return 0;
+}
+
+int tqb_apply_blocks(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
+                     const int32_t* blocks_host, int n_blocks, int renorm, void* stream) {
+  if (bsz <= 0 || n_blocks <= 0) return 0;
+  if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)a_planes) & 15) != 0) return fail_msg("tqb_apply_blocks: pointers must be 16-byte aligned");
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  const char* err = tqb_umma::launch_block6(src, dst, n_qubits, bsz, a_planes, kpos_host, transpose_out, g_num_sms, (cudaStream_t)stream);
-  if (err) return fail_msg(err);
+  for (int b = 0; b < n_blocks; ++b) {
+    const int32_t* bh = blocks_host + (size_t)b * TQB_KB_WORDS;
+    int kpos[6];
+    for (int k = 0; k < 6; ++k) kpos[k] = bh[TQB_KB_KPOS + k];
+    // the first block reads the caller's state, every later one works in place on dst
+    const char* err = tqb_umma::launch_block6(b == 0 ? src : dst, dst, n_qubits, bsz, a_planes + (size_t)b * 2 * 128 * 64, kpos,
+                                              bh[TQB_KB_FLAGS] & TQB_KBF_TRANSPOSE, renorm, g_num_sms, (cudaStream_t)stream);
+    if (err) return fail_msg(err);
+  }
   return 0;
 }
 

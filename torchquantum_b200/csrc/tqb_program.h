@@ -147,3 +147,29 @@ enum {
   TQB_K_SCALE = 19,  // deferred scale factor of one pass (see TQB_BF_* above)
   TQB_K_COUNT = 20
 };
+
+// ---------------------------------------------------------------------------------------
+// Block programs (forward-only, streamed states): runs of 1-2(-6)-qubit gates multiplied on the device into dense
+// 6-qubit block unitaries (tqb_block_build), each applied in one tensor-core pass (tqb_apply_blocks).
+// Block header: 12 words per block.
+#define TQB_KB_WORDS 12
+#define TQB_KB_OPFIRST 0   // first op record of the block
+#define TQB_KB_NOPS 1
+#define TQB_KB_FLAGS 2     // bit 0: transposed write-back (block bits <-> index bits 0-5 exchanged afterwards)
+#define TQB_KB_KPOS 4      // 6 words: ascending physical bit positions (all >= 6) of block-local bits 0..5
+#define TQB_KBF_TRANSPOSE 1
+// Block op record: 8 words.  Bits are block-local (0..5) unless stated.
+#define TQB_KO_WORDS 8
+#define TQB_KO_W0 0        // bits 0-3 form, 4-7 number of parameters, bit 8 inverse
+#define TQB_KO_BITS 1      // bits 0-7 target t0 (matrix lsb), 8-15 target t1 (matrix msb, 2-qubit forms)
+#define TQB_KO_MASKS 2     // bits 0-7 control mask, 8-15 control value, 16-23 parity mask (diagonal forms)
+#define TQB_KO_RCM 3       // sharded states: control mask over the rank index ...
+#define TQB_KO_RCV 4       // ... its required value ...
+#define TQB_KO_RPM 5       // ... and the parity mask over the rank index (diagonal forms)
+#define TQB_KO_KIND 6      // TQB_K_CONST or a parametric builder kind (TQB_K_RX ...)
+#define TQB_KO_OFF 7       // K_CONST: float offset in the constant pool (full complex form, inverse folded in);
+                           // parametric: first parameter (float offset in params_sh)
+#define TQB_KF_U1 0        // 2x2 complex on t0 where the controls hold            (consts: 8 floats)
+#define TQB_KF_DIAG 1      // amp *= d[parity] where the controls hold               (consts: 4 floats)
+#define TQB_KF_U2 2        // 4x4 complex on (t1, t0) where the controls hold      (consts: 32 floats)
+#define TQB_KF_X 3         // exchange the pair of t0 where the controls hold        (no floats)

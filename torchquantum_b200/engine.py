@@ -102,6 +102,26 @@ def run_fused_inplace(state, stage, n, rank, psh, pps, externs):
     return state
 
 
+def run_blocks(state, stage, n, rank, psh, inplace):
+    """Forward-only block stage (plan.BlockStage): the block unitaries are built on the device from the live parameters,
+    then every block is one tensor-core pass; the first reads `state`, the rest work in place on the result."""
+    _native.check_device(state)
+    state = state.contiguous()
+    if state.data_ptr() & 15:
+        state, inplace = state.clone(), True
+    bsz, dev = state.shape[0], state.device
+    stream = _native.stream_ptr(state)
+    blocks_dev, ops_dev, consts = _dev(stage, "blocks", dev), _dev(stage, "ops", dev), _dev(stage, "consts", dev)
+    planes = torch.empty(stage.n_blocks, 2, 128, 64, dtype=torch.float32, device=dev)
+    _native.call("tqb_block_build", _ptr(blocks_dev), stage.n_blocks, _ptr(ops_dev), _ptr(consts), _ptr(psh), rank,
+                 _ptr(planes), stream)
+    out = state if inplace else torch.empty_like(state)
+    _native.call("tqb_apply_blocks", _ptr(state), _ptr(out), n, bsz, _ptr(planes), stage.blocks.ctypes.data, stage.n_blocks, 1,
+                 stream)
+    STATS["launches"] += 1 + stage.n_blocks
+    return out
+
+
 class FusedFn(torch.autograd.Function):
     """state [bsz, 2^n] complex64 -> state, through all passes of one fused stage."""
 
@@ -337,6 +357,14 @@ def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False):
                 state = run_fused_inplace(state, stage, n, rank, psh, pps, externs)
             else:
                 state = FusedFn.apply(state, psh, pps, stage, n, rank, *externs)
+        elif stage.kind == "blocks":
+            dev = state.device
+            if stage.sh_recs:
+                psh = torch.cat([records[r][2].reshape(1, -1) for r in stage.sh_recs], dim=1).reshape(-1)
+                psh = psh.detach().to(device=dev, dtype=torch.float32)
+            else:
+                psh = torch.zeros(1, dtype=torch.float32, device=dev)
+            state = run_blocks(state, stage, n, rank, psh, inplace)
         elif stage.kind == "dense":
             name, wires, params, inverse = records[stage.rec]
             if stage.const is not None:

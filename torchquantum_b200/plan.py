@@ -19,6 +19,7 @@ import os
 import numpy as np
 
 from . import _codes as C
+from . import blockplan as B
 from . import gates as G
 
 T_SINGLE = 13   # largest state handled as one tile per sample (2^13 amplitudes = 64 KiB)
@@ -26,7 +27,22 @@ T_MULTI = 12    # tile bits when the state is streamed through HBM
 L_MIN = 5       # contiguous low bits always in the tile (2^5 amplitudes = 256 B runs)
 R_MAX = int(os.environ.get("TQB200_R", C.MAX_R))   # register bits per thread (env: kernel experiments)
 R_GRAD = int(os.environ.get("TQB200_RGRAD", C.MAX_R))
-FAST_FWD = os.environ.get("TQB200_FAST_FWD", "1") != "0"   # scaled op forms + CNOT folding in forward-only programs  # register bits of programs that also run backward (two arrays live per thread)
+FAST_FWD = os.environ.get("TQB200_FAST_FWD", "1") != "0"   # forward-only programs: CNOT folding, scaled H, phase ladders
+# Scaled rx / ry / one-bit-diagonal forms (TQB_T_RXS / RYS / DIAGS: the gate's cos / sin / d0 factor deferred to the end of
+# the pass) are NOT emitted: the un-normalised intermediates grow by up to sqrt(2) per gate, so a deep on-chip pass
+# (hundreds of rotations on a <= 13-qubit state) overflowed fp32 while the deferred product underflowed (NaN state), and
+# at moderate depth the rounding of the ratio forms drifted the norm (1 + 2.9e-6 after a depth-100 brickwork at n = 14,
+# 1 + 5.9e-5 at n = 28) where the plain forms stay at 1 - 4e-7.  The kernel keeps the op types; the planner does not use them.
+# Dense 6-qubit tensor-core blocks (blockplan.py) for forward-only programs on streamed states of >= BLOCK_MIN_N local
+# qubits: a run of >= BLOCK_MIN_RUN fusable gates becomes a block stage when the schedule averages >= BLOCK_MIN_AVG gates
+# per block (one block pass costs about as much as a register-tile pass holding 3 gates: 0.86 ms vs 0.62 + 0.093 k ms at
+# n = 28; below ~8 gates per block the deep register-tile passes are cheaper per gate).
+BLOCKS = os.environ.get("TQB200_BLOCKS", "1") != "0"
+BLOCK_MIN_N = 16
+BLOCK_MIN_RUN = 24
+BLOCK_MIN_AVG = 8.0
+SCALED_ROT = False
+SCALED_MAX = 24   # most scaled ops (H with its 1/sqrt(2) deferred) in one pass: intermediates grow by <= 2^12
 
 NFLOAT = {C.T_GEN: 8, C.T_REAL: 4, C.T_RX: 4, C.T_DIAG: 4, C.T_PERM: 0, C.T_U2Q: 32,
           C.T_RXS: 4, C.T_RYS: 4, C.T_HS: 0, C.T_DIAGS: 4}
@@ -40,7 +56,7 @@ class LOp:
     """A lowered micro-op on global bit positions."""
     __slots__ = ("type", "targets", "pmask", "cmask", "cval", "nfloat", "kind", "inverse", "pmode",
                  "poff", "nparam", "const", "rec", "grad", "gkind", "ngrad", "nounapply", "qmask", "ext_dim", "_lt",
-                 "_lc", "_soft", "postx", "scale_const", "rungs", "preh")
+                 "_lc", "_soft", "postx", "scale_const", "rungs", "preh", "unitary")
 
     def __init__(self):
         self.pmask = self.cmask = self.cval = 0
@@ -51,6 +67,7 @@ class LOp:
         self._lc, self._soft, self.postx, self.scale_const = None, (), None, None
         self.rungs = None   # T_LADDER: [(global bit, source LOp)]
         self.preh = False   # T_LADDER: a Hadamard on the control bit is folded in (TQB_F_PREH)
+        self.unitary = True
 
     @property
     def per_sample(self):
@@ -83,6 +100,7 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0, fast=False):
     spec = G.SPECS[name]
     op = LOp()
     op.rec, op.grad, op.inverse, op.pmode = rec, grad, inverse, pmode
+    op.unitary = spec.unitary
     bits = _bits(n, wires)
     kind = spec.kind
     const = spec.const
@@ -114,9 +132,9 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0, fast=False):
         op.targets = (rest[0],)
         if parametric:
             if spec.builder == C.K_RX:
-                op.type, op.gkind = (C.T_GEN if op.cmask else (C.T_RXS if fast else C.T_RX)), C.G_X
+                op.type, op.gkind = (C.T_GEN if op.cmask else (C.T_RXS if fast and SCALED_ROT else C.T_RX)), C.G_X
             elif spec.builder == C.K_RY:
-                op.type, op.gkind = (C.T_GEN if op.cmask else (C.T_RYS if fast else C.T_REAL)), C.G_Y
+                op.type, op.gkind = (C.T_GEN if op.cmask else (C.T_RYS if fast and SCALED_ROT else C.T_REAL)), C.G_Y
             else:
                 op.type, op.gkind = C.T_GEN, C.G_FULL
         elif ext:
@@ -139,7 +157,7 @@ def lower(n, name, wires, inverse, pmode, grad, rec, ext_dim=0, fast=False):
         for b in rest:
             op.pmask |= 1 << b
         phase_like = (spec.builder == C.K_PHASE) if parametric else (applied is not None and applied[0] == 1)
-        if fast and len(rest) == 1 and not op.cmask and (parametric or (applied is not None and abs(applied[0]) > 0.5)):
+        if fast and SCALED_ROT and len(rest) == 1 and not op.cmask and (parametric or (applied is not None and abs(applied[0]) > 0.5)):
             op.type = C.T_DIAGS   # d0 diag(1, d1/d0): half the amplitudes are touched, d0 joins the pass's scale factor
             if not parametric:
                 op.scale_const = complex(applied[0])
@@ -586,10 +604,19 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
         loc = {g: i for i, g in enumerate(tile_bits)}
         outer = [p for p in range(n_total) if p not in loc]
         oloc = {g: i for i, g in enumerate(outer)}
-        if fast and sum(op.type in SCALED for op in ops) < SCALED_MIN:
+        n_scaled = sum(op.type in SCALED or op.preh for op in ops)
+        if fast and (n_scaled < SCALED_MIN or n_scaled > SCALED_MAX):
+            plain = []
             for op in ops:
                 if op.type in SCALED:
                     _unscale(op)
+                elif op.preh and n_scaled > SCALED_MAX:
+                    # un-fold the Hadamard of a ladder: a plain H in front, the ladder without TQB_F_PREH
+                    h = lower(n_total, "hadamard", [n_total - 1 - op.targets[0]], False, None, False, op.rec)
+                    op.preh, op.targets, op.scale_const = False, (), None
+                    plain.append(h)
+                plain.append(op)
+            ops = plain
         for op in ops:
             op._lt = tuple(loc[t] for t in op.targets)
             op._lc, op._soft = None, ()
@@ -755,6 +782,37 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
     return st
 
 
+def _split_block_runs(ops, n_local):
+    """Forward-only program -> [("blocks", BlockStage) | ("fused", [LOp])]: maximal runs of block-fusable ops that the
+    block scheduler packs densely enough go to the tensor-core block kernel, everything else (ladders, per-sample
+    parameters, explicit matrices, sparse runs) stays with the register-tile pass kernel."""
+    out, i = [], 0
+
+    def fused(part):
+        if out and out[-1][0] == "fused":
+            out[-1][1].extend(part)
+        else:
+            out.append(("fused", list(part)))
+
+    while i < len(ops):
+        k = i
+        if B.fusable(ops[i], n_local):
+            while k < len(ops) and B.fusable(ops[k], n_local):
+                k += 1
+            run = ops[i:k]
+            stage = B.build_block_stage(run, n_local, BLOCK_MIN_AVG) if len(run) >= BLOCK_MIN_RUN else None
+            if stage is not None:
+                out.append(("blocks", stage))
+            else:
+                fused(run)
+        else:
+            while k < len(ops) and not B.fusable(ops[k], n_local):
+                k += 1
+            fused(ops[i:k])
+        i = k
+    return out
+
+
 class CircuitPlan:
     def __init__(self, n):
         self.n = n
@@ -763,7 +821,7 @@ class CircuitPlan:
 
     @property
     def n_passes(self):
-        return sum(len(s.passes) for s in self.stages if s.kind == "fused")
+        return sum(len(s.passes) if s.kind == "fused" else s.n_blocks for s in self.stages if s.kind in ("fused", "blocks"))
 
 
 def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
@@ -787,7 +845,11 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
             ops = fold_cnot_sandwiches(cur)
             if fast:
                 ops = fold_h_into_ladders(fold_phase_ladders(ops))
-            plan.stages.append(build_fused_stage(ops, n, n_total, **tile_kw))
+            for kind, part in _split_block_runs(ops, n) if (fast and BLOCKS and n >= BLOCK_MIN_N) else [("fused", ops)]:
+                if kind == "blocks":
+                    plan.stages.append(part)
+                else:
+                    plan.stages.append(build_fused_stage(part, n, n_total, **tile_kw))
             cur.clear()
 
     for rec, (name, wires, inverse, pmode, grad, ext_dim) in enumerate(key):
