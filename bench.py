@@ -8,8 +8,9 @@ parameters) behind a per-sample `10_ry` encoder, bsz=4096 per GPU, 19-term energ
 (sum Z_i Z_{i+1} + sum X_i), forward + adjoint backward through the public drop-in API.
   value    : circuits/s with inputs resident in HBM (device-timed, max over ranks)
   e2e      : the same step fed from pinned HOST memory, loss read back every step
-  roofline : the fused gate-pass kernel timed live on the config-4 family (n=28 state, 2 GiB,
-             larger than L2) against the measured HBM peak (MEASURED_PEAKS.json)
+  roofline : every gate-pass launch of a config-4 style circuit as the planner schedules it (tensor-core block
+             passes + register-tile passes), timed live on an n=28 state (2 GiB, larger than L2) against the
+             measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference : the CPU oracle port of the reference path (torch on the
              host cores) on a bounded sample of the same workload.
 N > 1 (torchrun): the batch is sharded, 4096 circuits per rank (weak scaling); the only exchange is
@@ -106,40 +107,9 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _time_passes(n, key, thetas, dev, reps=3):
-    """Per-launch CUDA-event times (ms) of tqb_pass_forward for every pass of the circuit `key`."""
-    from torchquantum_b200 import _native, engine
-    from torchquantum_b200.engine import _build_mats, _desc, _dev, _ptr
-
-    plan = engine.get_plan(n, tuple(key), False)
-    stage = plan.stages[0]
-    psh = torch.tensor(thetas or [0.0], dtype=torch.float32, device=dev)
-    pps = torch.zeros(1, 1, dtype=torch.float32, device=dev)
-    state = torch.zeros(1, 2 ** n, dtype=torch.complex64, device=dev)
-    state[0, 0] = 1
-    msh, mps = _build_mats(stage, 1, psh, pps, [], dev)
-    stream = _native.stream_ptr(state)
-    times = []
-    for rep in range(reps + 1):
-        for pp in stage.passes:
-            prog = _dev(pp, "prog", dev)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, 1, _ptr(prog), _desc(pp), _ptr(msh),
-                         _ptr(mps), stage.M_ps, 0, stream)
-            e.record()
-            if rep > 0:
-                times.append((s, e))
-    torch.cuda.synchronize()
-    norm = float(state.abs().pow(2).sum().item())
-    return [s.elapsed_time(e) for s, e in times], len(stage.passes), norm
-
-
-def gate_pass_roofline(dev, n=28, layers=4):
-    """Time every launch of the fused gate-pass kernel on a config-4 style circuit (rx/ry/rz on every
-    wire + brickwork CNOTs) over a 2^n state (2 GiB at n=28: far larger than the 126 MB L2), plus a
-    sweep of single passes holding k gates (k = 1: one HBM round trip per gate)."""
-    rng = np.random.default_rng(0)
+def _cfg4_family(n, layers, seed=0):
+    """plan key + angles of a config-4 style circuit: rx/ry/rz on every wire + brickwork CNOTs per layer"""
+    rng = np.random.default_rng(seed)
     key, thetas = [], []
     for layer in range(layers):
         for w in range(n):
@@ -147,13 +117,73 @@ def gate_pass_roofline(dev, n=28, layers=4):
             thetas.append(rng.uniform(-np.pi, np.pi))
         for w in range(layer % 2, n - 1, 2):
             key.append(("cnot", (w, w + 1), False, None, False, 0))
-    ms, n_pass, norm = _time_passes(n, key, thetas, dev)
-    avg_ms = float(np.mean(ms))
+            thetas.append(None)
+    return key, thetas
+
+
+def _time_planned_circuit(n, key, thetas, dev, reps=3):
+    """Runs the forward-only plan of `key` on a 2^n state, one ABI call per kernel launch, CUDA events around each.
+    -> {"block": [ms...], "pass": [ms...]}, launches per repetition, gates per kind, norm of the final state."""
+    from torchquantum_b200 import _native, engine
+    from torchquantum_b200.engine import _build_mats, _desc, _dev, _ptr
+
+    plan = engine.get_plan(n, tuple(key), False)
+    state = torch.zeros(1, 2 ** n, dtype=torch.complex64, device=dev)
+    state[0, 0] = 1
+    stream = _native.stream_ptr(state)
+    evs = {"block": [], "pass": []}
+    per_rep = {"block": 0, "pass": 0}
+    pps = torch.zeros(1, 1, dtype=torch.float32, device=dev)
+    for rep in range(reps + 1):
+        for stage in plan.stages:
+            psh = torch.tensor([thetas[r] for r in stage.sh_recs] or [0.0], dtype=torch.float32, device=dev)
+            if stage.kind == "blocks":
+                t = []
+                engine.run_blocks(state, stage, n, 0, psh, True, timing=t)
+                if rep > 0:
+                    evs["block"] += t
+                elif rep == 0:
+                    per_rep["block"] += len(t)
+            elif stage.kind == "fused":
+                msh, mps = _build_mats(stage, 1, psh, pps, [], dev)
+                for pp in stage.passes:
+                    prog = _dev(pp, "prog", dev)
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, 1, _ptr(prog), _desc(pp), _ptr(msh),
+                                 _ptr(mps), stage.M_ps, 0, stream)
+                    e.record()
+                    if rep > 0:
+                        evs["pass"].append((s, e))
+                    else:
+                        per_rep["pass"] += 1
+            else:
+                raise RuntimeError(f"unexpected stage kind {stage.kind} in the roofline circuit")
+    torch.cuda.synchronize()
+    norm = float(torch.linalg.vector_norm(torch.view_as_real(state).reshape(-1), dtype=torch.float64).item())
+    return {k: [s.elapsed_time(e) for s, e in v] for k, v in evs.items()}, per_rep, norm
+
+
+def gate_pass_roofline(dev, n=28, layers=16):
+    """Time every launch of the gate-pass kernels on a config-4 style circuit (rx/ry/rz on every wire + brickwork
+    CNOTs) over a 2^n state (2 GiB at n=28: far larger than the 126 MB L2), exactly as the planner schedules it:
+    tensor-core block passes (tqb_block6_kernel: one dense 6-qubit block unitary per pass, whatever number of gates it
+    absorbed) and register-tile passes (tqb_pass_kernel) for what is left.  The roofline object describes the kernel
+    with the larger share of the time; a sweep of single register-tile passes holding k gates is kept beside it."""
+    key, thetas = _cfg4_family(n, layers)
+    n_gates = len(key)
+    ms, per_rep, norm = _time_planned_circuit(n, key, thetas, dev)
     alg_bytes = 16.0 * 2 ** n
     peak, peak_src = measured_peak()
+    tot = {k: float(np.sum(v)) for k, v in ms.items()}
+    dom = "block" if tot["block"] >= tot["pass"] else "pass"
+    avg_ms = float(np.mean(ms[dom]))
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    reps = max(len(ms[dom]) // max(per_rep[dom], 1), 1)
+    circuit_ms = (tot["block"] + tot["pass"]) / reps
+    launches = per_rep["block"] + per_rep["pass"]
     sweep = []
-    for k in (1, 4, 8, 16):  # k gates on the qubits of one tile -> exactly one pass
+    for k in (1, 4, 8, 16):  # k gates on the qubits of one register tile -> exactly one tqb_pass_kernel launch
         r2 = np.random.default_rng(k)
         bits = list(range(5)) + list(range(n - 7, n))
         key_k, th_k = [], []
@@ -161,25 +191,36 @@ def gate_pass_roofline(dev, n=28, layers=4):
             b = bits[r2.integers(len(bits))]
             key_k.append((["rx", "ry", "rz"][r2.integers(3)], (n - 1 - b,), False, "sh", False, 0))
             th_k.append(r2.uniform(-np.pi, np.pi))
-        ms_k, np_k, _ = _time_passes(n, key_k, th_k, dev)
-        if np_k == 1:
-            t = float(np.mean(ms_k))
+        ms_k, rep_k, _ = _time_planned_circuit(n, key_k, th_k, dev)
+        if rep_k["pass"] == 1 and rep_k["block"] == 0:
+            t = float(np.mean(ms_k["pass"]))
             sweep.append({"gates_in_pass": k, "ms": round(t, 4), "GBps": round(alg_bytes / t / 1e6, 1),
                           "frac": round(alg_bytes / t / 1e6 / peak, 4)})
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        ent = tj.get("tqb_block6_kernel" if dom == "block" else "tqb_pass_kernel", {})
+        traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
+    kernel = "tqb_block6_kernel (tcgen05 3xTF32, TMA tile IO)" if dom == "block" else "tqb_pass_kernel<R=4,fwd>"
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-            "kernel": "tqb_pass_kernel<R=4,fwd>", "algorithmic_bytes_per_launch": alg_bytes,
-            "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(ms),
-            "workload": f"cfg4 family: n={n} single statevector, {len(key)} gates in {n_pass} fused passes "
-                        f"({len(key) / n_pass:.1f} gates/pass)", "state_norm_after": round(norm, 6),
-            "gate_amp_updates_per_s": round(len(key) * 2.0 ** n / (sum(ms) / (len(ms) / n_pass) * 1e-3), 1),
-            "single_pass_sweep": sweep,
-            "note": "a pass is HBM-bound up to ~2 gates and FP32-issue-bound beyond; the planner still fuses "
-                    "as deep as the tile allows because that minimises total time"}
+            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "kernel": kernel, "algorithmic_bytes_per_launch": alg_bytes,
+            "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(ms[dom]),
+            "share_of_circuit_time": round(tot[dom] / max(tot["block"] + tot["pass"], 1e-9), 4),
+            "workload": f"cfg4 family: n={n} single statevector, {layers} layers = {n_gates} gates in "
+                        f"{per_rep['block']} tensor-core block passes + {per_rep['pass']} register-tile passes "
+                        f"({n_gates / max(launches, 1):.1f} gates/pass)",
+            "state_norm_after": round(norm, 7),
+            "circuit": {"ms": round(circuit_ms, 3), "launches": launches,
+                        "algorithmic_GBps": round(launches * alg_bytes / (circuit_ms * 1e-3) / 1e9, 1),
+                        "frac_of_peak": round(launches * alg_bytes / (circuit_ms * 1e-3) / 1e9 / peak, 4),
+                        "gate_amp_updates_per_s": round(n_gates * 2.0 ** n / (circuit_ms * 1e-3), 1)},
+            "per_kind_avg_ms": {k: (round(float(np.mean(v)), 4) if v else None) for k, v in ms.items()},
+            "register_tile_single_pass_sweep": sweep,
+            "note": "a block pass costs the same whatever it holds (one 64x64 complex unitary per 2^12-amplitude tile, "
+                    "24 tcgen05.mma per tile); the register-tile kernel is HBM-bound up to ~4 gates per pass and "
+                    "issue-bound beyond (sweep)"}
 
 
 def cpu_reference_step(bsz, threads):

@@ -34,9 +34,10 @@ def _load():
 O64 = _load()
 
 
-def run_ops64(n_wires, bsz, ops, device="cpu", init_states=None):
+def run_ops64(n_wires, bsz, ops, device="cpu", init_states=None, keep_graph=False):
     """ops as for tq_oracle.run_ops (parameters are read as the float32 values the engine sees, then promoted).
-    Returns [bsz, 2**n] complex128 on `device`."""
+    Returns [bsz, 2**n] complex128 on `device`.  keep_graph: parameters stay attached to autograd (the tiny gate
+    matrices are built on the CPU and moved, differentiably, to `device`), so gradients come out in float64 too."""
     dev = torch.device(device)
     if init_states is None:
         s = torch.zeros(bsz, 2 ** n_wires, dtype=torch.complex128, device=dev)
@@ -48,7 +49,10 @@ def run_ops64(n_wires, bsz, ops, device="cpu", init_states=None):
         wires = [op["wires"]] if isinstance(op["wires"], int) else [int(w) for w in op["wires"]]
         p = op.get("params")
         if p is not None:
-            p = torch.as_tensor(p).detach().to("cpu")
+            p = torch.as_tensor(p)
+            if not keep_graph:
+                p = p.detach()
+            p = p.to("cpu")
             p = p.to(torch.complex128 if p.is_complex() else torch.float64)
         m = O64.gate_matrix(op["name"], p, n_wires=op.get("n_wires") if op.get("n_wires") is not None else len(wires),
                             inverse=op.get("inverse", False))

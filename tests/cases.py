@@ -11,7 +11,7 @@ import torchquantum_b200.functional as tqf
 from oracle import tq_oracle as O
 from torchquantum_b200.measurement import (expval, expval_joint_analytical, expval_joint_analytical_multi,
                                            measure)
-from tests.helpers import assert_close, load, op_params  # noqa: F401
+from tests.helpers import GRAD_RTOL, RTOL, assert_close, load, op_params  # noqa: F401
 
 
 def apply_ops(qdev, ops, device, requires_grad=False):
@@ -67,8 +67,8 @@ def check_random_circuits(device, min_n=0):
         assert_close(loss, z[pre + "loss"], what=pre + "loss")
         grads = torch.autograd.grad(loss, leaves + [init])
         for gi, g in enumerate(grads[:-1]):
-            assert_close(g, z[pre + f"g{gi}"], rtol=1e-4, what=pre + f"grad{gi}")  # reference tests: grads 1e-4
-        assert_close(grads[-1], z[pre + "ginit"], rtol=1e-4, what=pre + "grad_init")
+            assert_close(g, z[pre + f"g{gi}"], rtol=GRAD_RTOL, what=pre + f"grad{gi}")  # reference tests: grads 1e-4
+        assert_close(grads[-1], z[pre + "ginit"], rtol=GRAD_RTOL, what=pre + "grad_init")
 
 
 class _Obs:
@@ -133,9 +133,9 @@ def check_mnist_cfg1(device):
     loss = F.nll_loss(F.log_softmax(out.reshape(bsz, 2, 2).sum(-1), dim=1), torch.tensor(z["target"]).to(device))
     assert_close(loss, z["loss"], what="cfg1 loss")
     grads = torch.autograd.grad(loss, [x] + leaves)
-    assert_close(grads[0], z["grad_x"], rtol=1e-4, what="cfg1 grad_x")
+    assert_close(grads[0], z["grad_x"], rtol=GRAD_RTOL, what="cfg1 grad_x")
     for g, w in zip(grads[1:], man["param_grads"]):
-        assert_close(g.reshape(-1), torch.tensor(w["grad"]), rtol=1e-4, what="cfg1 param grad")
+        assert_close(g.reshape(-1), torch.tensor(w["grad"]), rtol=GRAD_RTOL, what="cfg1 param grad")
 
 
 def brickwork_ops(n, depth, seed, per_sample_bsz=None):
@@ -179,12 +179,12 @@ def check_against_oracle(device, n, bsz, ops, grad=False, rtol=1e-5):
         obs = "".join("ZXYI"[i % 4] for i in range(n))
         ev = expval_joint_analytical(q, obs).sum()
         ev_cpu = O.expval_joint_rotated(want, obs).sum()
-        assert_close(ev, ev_cpu, rtol=1e-4, what="expval")
+        assert_close(ev, ev_cpu, rtol=GRAD_RTOL, what="expval")
         leaves = [o["params"] for o in ops_dev if o.get("params") is not None]
         leaves_cpu = [o["params"] for o in ops_cpu if o.get("params") is not None]
         g = torch.autograd.grad(ev, leaves)
         g_cpu = torch.autograd.grad(ev_cpu, leaves_cpu)
-        assert_close(torch.cat([a.reshape(-1) for a in g]), torch.cat([a.reshape(-1) for a in g_cpu]), rtol=1e-4,
+        assert_close(torch.cat([a.reshape(-1) for a in g]), torch.cat([a.reshape(-1) for a in g_cpu]), rtol=GRAD_RTOL,
                      what=f"grads n={n}")
     return states
 
@@ -244,9 +244,9 @@ def check_cfg2_vqe(device, n=5, reps=3, bsz=6, graphed=False):
         e, g = oracle(x.detach().cpu().clone().requires_grad_(True))
         assert_close(loss, e, what=f"cfg2 energy step {it}")
         assert_close(torch.cat([p.grad.reshape(-1) for p in params]), torch.cat([a.reshape(-1) for a in g[:-1]]),
-                     rtol=1e-4, what=f"cfg2 param grads step {it}")
+                     rtol=GRAD_RTOL, what=f"cfg2 param grads step {it}")
         if gx is not None:
-            assert_close(gx, g[-1], rtol=1e-4, what=f"cfg2 grad x step {it}")
+            assert_close(gx, g[-1], rtol=GRAD_RTOL, what=f"cfg2 grad x step {it}")
 
 
 QAOA_EDGES_8 = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 0), (0, 4), (1, 5), (2, 6), (3, 7)]
@@ -281,11 +281,11 @@ def check_cfg3_qaoa(device, n=8, p=3, bsz=4, edges=QAOA_EDGES_8):
     st = O.run_ops(n, bsz, circuit(bc, gc))
     assert_close(q.get_states_1d(), st, what="cfg3 states")
     cost_cpu = sum(0.5 * O.expval_joint_analytical(st, zz(i, j)) for (i, j) in edges)
-    assert_close(cost, cost_cpu, rtol=1e-4, what="cfg3 cost")
+    assert_close(cost, cost_cpu, rtol=GRAD_RTOL, what="cfg3 cost")
     gb, gg = torch.autograd.grad(cost.sum(), [bd, gd])
     gbc, ggc = torch.autograd.grad(cost_cpu.sum(), [bc, gc])
-    assert_close(gb, gbc, rtol=1e-4, what="cfg3 grad beta")
-    assert_close(gg, ggc, rtol=1e-4, what="cfg3 grad gamma")
+    assert_close(gb, gbc, rtol=GRAD_RTOL, what="cfg3 grad beta")
+    assert_close(gg, ggc, rtol=GRAD_RTOL, what="cfg3 grad gamma")
 
 
 def special_angle_ops(n, bsz):
@@ -413,9 +413,9 @@ def check_vqe_hamiltonian(device, tmp_path):
                 ops.append({"name": "cnot", "wires": [k, k + 1]})
     st = O.run_ops(3, 1, ops)
     want = torch.einsum("bi,ij,bj->b", st.conj(), H.to(st.dtype), st).real
-    assert_close(loss, want, rtol=1e-4, what="VQE energy")
+    assert_close(loss, want, rtol=GRAD_RTOL, what="VQE energy")
     gw = torch.autograd.grad(want.sum(), leaves)
-    assert_close(torch.cat([g.reshape(-1) for g in grads]), torch.cat([g.reshape(-1) for g in gw]), rtol=1e-4, what="VQE grads")
+    assert_close(torch.cat([g.reshape(-1) for g in grads]), torch.cat([g.reshape(-1) for g in gw]), rtol=GRAD_RTOL, what="VQE grads")
     e0 = float(loss.detach())
     e1 = vqe.train()
     assert e1 < e0, (e0, e1)
@@ -423,7 +423,7 @@ def check_vqe_hamiltonian(device, tmp_path):
     q = tq.QuantumDevice(n_wires=3, bsz=1, device=device)
     ansatz(q)
     loop = sum(expval_joint_analytical(q, h["pauli_string"]) * h["coeff"] for h in hamil.hamil_info["hamil_list"])
-    assert_close(loop, vqe.get_expval(q), rtol=1e-4, what="per-term loop vs fused energy")
+    assert_close(loop, vqe.get_expval(q), rtol=GRAD_RTOL, what="per-term loop vs fused energy")
 
 
 def check_speculative_readout(device, n=4, bsz=3):
@@ -446,7 +446,7 @@ def check_speculative_readout(device, n=4, bsz=3):
         assert_close(got, want, what=f"speculative read-out, state {it}")
         (gg,) = torch.autograd.grad((got * w.to(device)).sum(), sd)
         (gw,) = torch.autograd.grad((want * w).sum(), sc)
-        assert_close(gg, gw, rtol=1e-4, what=f"speculative read-out grad, state {it}")
+        assert_close(gg, gw, rtol=GRAD_RTOL, what=f"speculative read-out grad, state {it}")
     assert M._READOUT_HISTORY, "nothing was learned"
 
 
@@ -478,7 +478,7 @@ def check_dense_blocks(device, n=13):
             proj = torch.view_as_complex(proj).contiguous()
             (gg,) = torch.autograd.grad((got * proj.to(device).conj()).real.sum(), sd)
             (gw,) = torch.autograd.grad((want * proj.conj()).real.sum(), sc)
-            assert_close(gg, gw, rtol=1e-4, what=f"dense k={k} grad wrt state")
+            assert_close(gg, gw, rtol=GRAD_RTOL, what=f"dense k={k} grad wrt state")
 
 
 def check_op_hamil_exp(device):
@@ -507,7 +507,7 @@ def check_op_hamil_exp(device):
     col = u[:, 0]                      # wires [1, 0] on |00>: the matrix is symmetric under the wire swap here
     lw = 2 * (col[3].real + col[0].imag)
     (gw,) = torch.autograd.grad(lw, th)
-    assert_close(g.reshape(()), gw, rtol=1e-4, what="OpHamilExp dL/dtheta")
+    assert_close(g.reshape(()), gw, rtol=GRAD_RTOL, what="OpHamilExp dL/dtheta")
     pe = tq.OpPauliExp(coeffs=[1.0, 0.5], paulis=["ZZ", "XX"], trainable=False, theta=0.45)
     q2 = tq.QuantumDevice(n_wires=2, device=device, record_op=True)
     pe(q2, wires=[1, 0])

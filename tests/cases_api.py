@@ -1,0 +1,270 @@
+"""Device-agnostic checks of the host mirror's semantics (lazy queue vs the reference's eager calls, record caches,
+checkpoints, static mode, op_history).  Run on the CPU emulation by tests/test_api_layer.py and on the B200 by
+tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import torchquantum_b200 as tq
+import torchquantum_b200.functional as tqf
+from oracle import tq_oracle as O
+from tests.helpers import GRAD_RTOL, assert_close
+
+
+def _oracle_state(n, bsz, ops):
+    return O.run_ops(n, bsz, ops)
+
+
+def check_record_cache_follows_the_op_list(device):
+    """a layer's cached queue records must follow the live op list."""
+    np.random.seed(11)
+    torch.manual_seed(11)
+    n = 4
+    L = tq.RandomLayer(n_ops=12, wires=list(range(n))).to(device)
+    other = tq.RandomLayer(n_ops=9, wires=list(range(n)), seed=5).to(device)
+
+    def run(layer):
+        q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+        q.h(wires=0)
+        layer(q)
+        return q.get_states_1d().clone()
+
+    before = run(L)
+    L.rebuild_random_layer_from_op_list(other.n_ops, other.wires, other.op_list)
+    L.to(device)
+    with torch.no_grad():
+        for a, b in zip(L.op_list, other.op_list):
+            if a.params is not None:
+                a.params.copy_(b.params)
+    after = run(L)
+    assert_close(after, run(other), what="rebuilt RandomLayer runs the new op list")
+    assert (after - before).abs().max().item() > 1e-3
+
+    layer = tq.Op1QAllLayer(op=tq.RX, n_wires=n, has_params=True, trainable=True).to(device)
+    s0 = run(layer)
+    layer.ops_all[1] = tq.RY(has_params=True, trainable=True).to(device)
+    s1 = run(layer)
+    q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+    q.h(wires=0)
+    for k, o in enumerate(layer.ops_all):
+        o(q, wires=k)
+    assert_close(s1, q.get_states_1d(), what="replaced entry of ops_all is used")
+    assert (s1 - s0).abs().max().item() > 1e-3
+
+    # the template-level chunk cache (LayerTemplate0) inherits the fix
+    es = tq.EfficientSU2(n_wires=n, reps=2, entanglement_layer="linear").to(device)
+    run(es)
+    es.layers_all[0].ops_all[0] = tq.RX(has_params=True, trainable=True).to(device)
+    q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+    q.h(wires=0)
+    for layer_k in es.layers_all:
+        for o, w in layer_k._layer_ops_wires():
+            o(q, wires=w)
+    assert_close(run(es), q.get_states_1d(), what="EfficientSU2 after replacing an operator")
+
+
+def check_grad_mode_is_sampled_when_gates_are_issued(device):
+    """reading the state under no_grad mid-circuit must not drop the graph of the gates before it, and
+    gates issued under no_grad must not be tracked when flushed outside it."""
+    th = torch.tensor([[0.7]], device=device, requires_grad=True)
+    ph = torch.tensor([[0.4]], device=device, requires_grad=True)
+
+    def circuit(peek):
+        q = tq.QuantumDevice(n_wires=2, bsz=1, device=device)
+        tqf.rx(q, wires=0, params=th)
+        if peek:
+            with torch.no_grad():
+                q.get_states_1d()
+        tqf.ry(q, wires=0, params=ph)
+        return tq.expval_joint_analytical(q, "ZI").sum()
+
+    g_plain = torch.autograd.grad(circuit(False), [th, ph])
+    g_peek = torch.autograd.grad(circuit(True), [th, ph])
+    assert_close(torch.cat(g_peek).reshape(-1), torch.cat(g_plain).reshape(-1), rtol=GRAD_RTOL, what="grad after a no_grad peek")
+    thc, phc = th.detach().cpu().requires_grad_(True), ph.detach().cpu().requires_grad_(True)
+    s = O.run_ops(2, 1, [{"name": "rx", "wires": [0], "params": thc}, {"name": "ry", "wires": [0], "params": phc}])
+    want = torch.autograd.grad(O.expval_joint_analytical(s, "ZI").sum(), [thc, phc])
+    assert_close(torch.cat(g_peek).reshape(-1), torch.cat(want).reshape(-1), rtol=GRAD_RTOL, what="grad vs oracle")
+    # the reverse: queued under no_grad, flushed outside -> constant w.r.t. th
+    q = tq.QuantumDevice(n_wires=2, bsz=1, device=device)
+    with torch.no_grad():
+        tqf.rx(q, wires=0, params=th)
+    tqf.ry(q, wires=0, params=ph)
+    e = tq.expval_joint_analytical(q, "ZI").sum()
+    g = torch.autograd.grad(e, [th, ph], allow_unused=True)
+    assert g[0] is None and g[1] is not None
+
+
+def check_parameter_values_are_read_at_the_gate_call(device):
+    """the reference consumes parameter values when the gate is called."""
+    q = tq.QuantumDevice(n_wires=2, bsz=1, device=device)
+    p = torch.tensor([[0.3]], device=device)
+    tqf.rx(q, wires=0, params=p)
+    p.fill_(1.1)
+    tqf.rx(q, wires=1, params=p)
+    q.ry(wires=0, params=p)
+    p.fill_(-2.0)
+    want = _oracle_state(2, 1, [{"name": "rx", "wires": [0], "params": torch.tensor([[0.3]])},
+                                {"name": "rx", "wires": [1], "params": torch.tensor([[1.1]])},
+                                {"name": "ry", "wires": [0], "params": torch.tensor([[1.1]])}])
+    assert_close(q.get_states_1d(), want, what="values at call time")
+    # operators with non-trainable parameters go through the same snapshot
+    op = tq.RX(has_params=True, trainable=False, init_params=0.5).to(device)
+    q = tq.QuantumDevice(n_wires=1, bsz=1, device=device)
+    op(q, wires=0)
+    with torch.no_grad():
+        op.params.fill_(0.9)
+    op(q, wires=0)
+    want = _oracle_state(1, 1, [{"name": "rx", "wires": [0], "params": torch.tensor([[0.5]])},
+                                {"name": "rx", "wires": [0], "params": torch.tensor([[0.9]])}])
+    assert_close(q.get_states_1d(), want, what="operator buffer values at call time")
+    # a tensor that is part of the autograd graph is kept by reference; editing it in place is an error, not a
+    # silently different circuit
+    w = torch.tensor([[0.2]], device=device, requires_grad=True)
+    v = w * 2
+    q = tq.QuantumDevice(n_wires=1, bsz=1, device=device)
+    tqf.rx(q, wires=0, params=v)
+    with torch.no_grad():
+        v.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        q.get_states_1d()
+
+
+def check_checkpoint_round_trip(device):
+    """`<prefix>q_device.states` is always a key, and a reference-format checkpoint loads strictly."""
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_device = tq.QuantumDevice(n_wires=3, bsz=2)
+            self.rx = tq.RX(has_params=True, trainable=True)
+
+        def forward(self):
+            self.q_device.reset_states(2)
+            self.rx(self.q_device, wires=1)
+            return tq.expval_joint_analytical(self.q_device, "IZI")
+
+    m = Model().to(device)
+    sd0 = m.state_dict()
+    assert "q_device.states" in sd0 and "q_device.state" in sd0
+    assert tuple(sd0["q_device.states"].shape) == (2, 2, 2, 2)
+    m()
+    sd1 = m.state_dict()
+    assert set(sd1) == set(sd0)
+    # a checkpoint written by the reference: same keys, states [bsz, 2, 2, 2] complex64
+    ref_sd = {"q_device.state": torch.zeros(2, 2, 2, dtype=torch.complex64),
+              "q_device.states": torch.zeros(2, 2, 2, 2, dtype=torch.complex64),
+              "rx.params": torch.tensor([[0.25]])}
+    ref_sd["q_device.state"][0, 0, 0] = 1
+    ref_sd["q_device.states"][:, 1, 0, 1] = 1
+    fresh = Model().to(device)
+    fresh.load_state_dict(ref_sd, strict=True)
+    assert_close(fresh.q_device.states, ref_sd["q_device.states"], what="states restored")
+    assert_close(fresh.rx.params.detach(), ref_sd["rx.params"], what="params restored")
+    fresh2 = Model().to(device)
+    fresh2.load_state_dict(sd1, strict=True)
+    assert_close(fresh2.q_device.get_states_1d(), m.q_device.get_states_1d(), what="own checkpoint")
+    with pytest.raises(RuntimeError, match="states"):
+        bad = dict(ref_sd)
+        del bad["q_device.states"]
+        Model().to(device).load_state_dict(bad, strict=True)
+
+
+def check_from_op_history_and_get_unitary(device):
+    """op_history wire format -> module -> same state; get_unitary column check."""
+    qdev = tq.QuantumDevice(n_wires=3, bsz=2, record_op=True, device=device)
+    qdev.h(wires=0)
+    qdev.crx(wires=[0, 2], params=torch.tensor([0.4]))
+    qdev.u3(wires=1, params=torch.tensor([[0.1, 0.2, 0.3]]))
+    qdev.cnot(wires=[2, 1], inverse=True)
+    want = qdev.get_states_1d().clone()
+    mod = tq.QuantumModule.from_op_history(qdev.op_history).to(device)
+    q2 = tq.QuantumDevice(n_wires=3, bsz=2, device=device)
+    mod(q2)
+    assert_close(q2.get_states_1d(), want, what="from_op_history")
+    mod.n_wires = 3
+    u = mod.get_unitary(device=device)
+    assert_close(u[:, 0], want[0], what="get_unitary column 0")
+    assert_close((u.conj().T @ u).cpu(), torch.eye(8, dtype=torch.complex64), what="unitarity")
+    ref = _oracle_state(3, 2, [{"name": "hadamard", "wires": [0]},
+                               {"name": "crx", "wires": [0, 2], "params": torch.tensor([[0.4]])},
+                               {"name": "u3", "wires": [1], "params": torch.tensor([[0.1, 0.2, 0.3]])},
+                               {"name": "cnot", "wires": [2, 1], "inverse": True}])
+    assert_close(want, ref, what="recorded circuit vs oracle")
+
+
+def check_static_mode_equals_dynamic(device):
+    """SURVEY §8 a9 / f2 (test/static_mode_test.py: static == dynamic, states 1e-5, gradients)."""
+    np.random.seed(3)
+    torch.manual_seed(3)
+    layer = tq.RandomLayerAllTypes(n_ops=60, wires=list(range(5))).to(device)
+    params = [p for p in layer.parameters()]
+
+    def run():
+        q = tq.QuantumDevice(n_wires=5, bsz=3, device=device)
+        layer(q)
+        s = q.get_states_1d()
+        loss = tq.expval_joint_analytical(q, "ZXIYZ").sum()
+        return s.detach().clone(), torch.autograd.grad(loss, params, allow_unused=True)
+
+    dyn, gdyn = run()
+    for wpb in (2, 3, 4):
+        layer.static_on(wires_per_block=wpb)
+        st, gst = run()
+        assert_close(st, dyn, what=f"static({wpb}) == dynamic")
+        for a, b in zip(gst, gdyn):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert_close(a, b, rtol=GRAD_RTOL, what=f"static({wpb}) gradients")
+        layer.static_off()
+    assert not layer.static_mode
+
+
+def check_layer_classes(device):
+    """a15: RandomLayer / QFTLayer / MeasureAll classes (and Op2QAllLayer circular) against the oracle."""
+    n = 6
+    q = tq.QuantumDevice(n_wires=n, bsz=1, device=device)
+    q.x(wires=2)
+    tq.QFTLayer(n_wires=n)(q)
+    assert_close(q.get_states_1d().abs().cpu(), torch.full((1, 64), 1 / 8.0), what="QFT|x> is flat")
+    from tests import cases
+    want = _oracle_state(n, 1, [{"name": "paulix", "wires": [2]}] + cases.qft_ops(n))
+    assert_close(q.get_states_1d(), want, what="QFTLayer vs oracle QFT ops")
+    z = tq.MeasureAll(tq.PauliZ)(q)
+    zw, _ = O.expval(want.reshape([1] + [2] * n), list(range(n)), ["Z"] * n)
+    assert_close(z, zw, what="MeasureAll(PauliZ) after QFT")
+    np.random.seed(7)
+    rl = tq.RandomLayer(n_ops=30, wires=list(range(n)), seed=7).to(device)
+    q = tq.QuantumDevice(n_wires=n, bsz=2, device=device, record_op=True)
+    rl(q)
+    got = q.get_states_1d()
+    ops = []
+    for h in q.op_history:
+        p = h["params"]
+        ops.append({"name": h["name"], "wires": h["wires"] if isinstance(h["wires"], list) else [h["wires"]],
+                    "params": None if p is None else torch.tensor(p, dtype=torch.float32).reshape(1, -1),
+                    "inverse": h["inverse"]})
+    assert_close(got, _oracle_state(n, 2, ops), what="RandomLayer vs oracle replay of its op_history")
+
+
+def check_einsum_broadcast(device):
+    """a3/a4: the pure functions; apply_unitary_einsum broadcasts a bsz-1 state over a batched matrix
+    (functional/gate_wrapper.py:18-93), apply_unitary_bmm refuses a batch mismatch."""
+    torch.manual_seed(1)
+    n = 4
+    st = torch.randn(1, 2 ** n, dtype=torch.complex64)
+    st = (st / st.norm()).reshape([1] + [2] * n)
+    mats = torch.linalg.qr(torch.randn(3, 4, 4, dtype=torch.complex64))[0]
+    got = tqf.apply_unitary_einsum(st.to(device), mats.to(device), [2, 0])
+    assert tuple(got.shape) == (3, 2, 2, 2, 2)
+    for b in range(3):
+        want = O.apply_unitary_bmm(st, mats[b], [2, 0])
+        assert_close(got[b:b + 1], want, what=f"einsum broadcast sample {b}")
+    st3 = torch.randn(3, 2 ** n, dtype=torch.complex64).reshape([3] + [2] * n)
+    got = tqf.apply_unitary_bmm(st3.to(device), mats.to(device), [1, 3])
+    want = O.apply_unitary_bmm(st3, mats, [1, 3])
+    assert_close(got, want, what="bmm, batched matrix")
+    got = tqf.apply_unitary_bmm(st3.to(device), mats[0].to(device), [0, 1])
+    assert_close(got, O.apply_unitary_bmm(st3, mats[0], [0, 1]), what="bmm, shared matrix")
+    with pytest.raises(RuntimeError):
+        tqf.apply_unitary_bmm(st.to(device), mats.to(device), [2, 0])

@@ -10,6 +10,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # north_star tolerance: 1e-5 relative on states / expectation values / gradients (complex64).
 # "relative" = rel-L2 plus max-abs scaled by the largest reference magnitude.
 RTOL = 1e-5
+# gradients: the same bar (north_star); the reference's own tests use 1e-4 (test/static_mode_test.py)
+GRAD_RTOL = 1e-5
 
 
 def load(name):
@@ -27,8 +29,9 @@ def assert_close(got, want, rtol=RTOL, what=""):
     ref_norm = max(torch.linalg.vector_norm(want).item(), 1e-30)
     rel_l2 = torch.linalg.vector_norm(got - want).item() / ref_norm
     max_abs = diff.max().item() if diff.numel() else 0.0
-    # absolute floor for quantities that are analytically ~0 (rounding noise of O(eps))
-    ok = (rel_l2 <= rtol and max_abs <= rtol * scale) or max_abs <= 2e-6
+    # absolute floor ONLY for small tensors of scalars that are analytically ~0 (cancelling expectation values /
+    # gradients: rounding noise of O(eps) has no reference magnitude to be relative to); states never use it
+    ok = (rel_l2 <= rtol and max_abs <= rtol * scale) or (got.numel() <= 64 and max_abs <= 2e-6)
     assert ok, f"{what}: rel_l2={rel_l2:.3e} max_abs={max_abs:.3e} scale={scale:.3e}"
 
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import tq_oracle as O
-from tests.helpers import assert_close, load, op_params
+from tests.helpers import GRAD_RTOL, assert_close, load, op_params
 
 
 def test_every_gate_matches_reference():
@@ -51,8 +51,8 @@ def test_random_circuits_states_expvals_grads():
         assert_close(loss, z[pre + "loss"], what=pre + "loss")
         grads = torch.autograd.grad(loss, leaves + [init])
         for gi, g in enumerate(grads[:-1]):
-            assert_close(g, z[pre + f"g{gi}"], rtol=1e-4, what=pre + f"g{gi}")
-        assert_close(grads[-1], z[pre + "ginit"], rtol=1e-4, what=pre + "ginit")
+            assert_close(g, z[pre + f"g{gi}"], rtol=GRAD_RTOL, what=pre + f"g{gi}")
+        assert_close(grads[-1], z[pre + "ginit"], rtol=GRAD_RTOL, what=pre + "ginit")
 
 
 def test_expval_per_wire_and_state_mutation():
@@ -102,11 +102,11 @@ def test_mnist_cfg1_forward_backward():
     loss = F.nll_loss(F.log_softmax(out.reshape(bsz, 2, 2).sum(-1), dim=1), torch.tensor(z["target"]))
     assert_close(loss, z["loss"], what="cfg1 loss")
     grads = torch.autograd.grad(loss, [x] + leaves)
-    assert_close(grads[0], z["grad_x"], rtol=1e-4, what="cfg1 grad_x")
+    assert_close(grads[0], z["grad_x"], rtol=GRAD_RTOL, what="cfg1 grad_x")
     want = [g["grad"] for g in man["param_grads"]]
     assert len(want) == len(leaves) == 45
     for g, w in zip(grads[1:], want):
-        assert_close(g.reshape(-1), torch.tensor(w), rtol=1e-4, what="cfg1 param grad")
+        assert_close(g.reshape(-1), torch.tensor(w), rtol=GRAD_RTOL, what="cfg1 param grad")
 
 
 def test_known_answers_from_reference_tests():

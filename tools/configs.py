@@ -57,27 +57,63 @@ def qaoa_cost(betas, gammas, n, edges, dev):
     return 0.5 * ev.sum(1), q
 
 
-def run_cfg3(dev, n=20, p=8, bsz=64, edges=QAOA_EDGES_20, timing=True):
-    """fwd + adjoint bwd at full size; check: directional derivative of the batch cost along a random direction
-    vs a central finite difference of two forward runs (a property that needs no reference at n=20)."""
+def qaoa_ops(betas, gammas, n, edges):
+    """the same circuit as an op list for the oracle (tests/cases.apply_ops format)"""
+    p = betas.shape[1]
+    ops = [{"name": "hadamard", "wires": [w]} for w in range(n)]
+    for layer in range(p):
+        for w in range(n):
+            ops.append({"name": "rx", "wires": [w], "params": betas[:, layer:layer + 1]})
+        for (i, j) in edges:
+            ops.append({"name": "cnot", "wires": [i, j]})
+            ops.append({"name": "rz", "wires": [j], "params": gammas[:, layer:layer + 1]})
+            ops.append({"name": "cnot", "wires": [i, j]})
+    return ops
+
+
+def cfg3_oracle_parity(dev, betas, gammas, states, cost, gb, gg, n, edges, samples):
+    """Full-size parity of chosen samples against the float64 twin of the oracle run with torch's CUDA ops
+    (oracle/tq_oracle64.py; test infrastructure): states, cost and adjoint gradients, rel-L2 each."""
+    from oracle.tq_oracle64 import run_ops64
+
+    idx = torch.tensor(samples, device=dev)
+    b64 = betas.detach()[idx].double().cpu().requires_grad_(True)
+    g64 = gammas.detach()[idx].double().cpu().requires_grad_(True)
+    st = run_ops64(n, len(samples), qaoa_ops(b64, g64, n, edges), device=dev, keep_graph=True)
+    probs = st.real ** 2 + st.imag ** 2
+    k = torch.arange(2 ** n, device=dev)
+    c64 = 0
+    for (i, j) in edges:   # <Z_i Z_j> = sum_k p_k (-1)^(k_i + k_j), wire w = index bit n-1-w (device/devices.py:57-71)
+        sign = 1.0 - 2.0 * (((k >> (n - 1 - i)) ^ (k >> (n - 1 - j))) & 1).double()
+        c64 = c64 + 0.5 * (probs * sign).sum(1)
+    gb64, gg64 = torch.autograd.grad(c64.sum(), [b64, g64])
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+        return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+
+    got_states = states.detach()[idx].to(torch.complex128)
+    return {"samples": list(samples),
+            "states_rel_l2": float(torch.linalg.vector_norm(got_states - st.detach()) / torch.linalg.vector_norm(st.detach())),
+            "cost_rel": rel(cost[idx], c64), "grad_beta_rel_l2": rel(gb[idx], gb64), "grad_gamma_rel_l2": rel(gg[idx], gg64)}
+
+
+def run_cfg3(dev, n=20, p=8, bsz=64, edges=QAOA_EDGES_20, timing=True, parity_samples=(0, -1)):
+    """fwd + adjoint bwd at full size.  Checks at the FULL size (n=20, p=8): unit norm (float64 accumulation) and, for
+    `parity_samples` of the batch, states / cost / gradients against the float64 oracle twin (bars 1e-5)."""
     g = torch.Generator().manual_seed(0)
     betas = (0.4 * torch.rand(bsz, p, generator=g)).to(dev).requires_grad_(True)
     gammas = (0.4 * torch.rand(bsz, p, generator=g)).to(dev).requires_grad_(True)
     cost, q = qaoa_cost(betas, gammas, n, edges, dev)
-    norm = float(q.get_states_1d().detach().abs().pow(2).sum(1).mean())
+    states = q.get_states_1d()
+    norms = torch.linalg.vector_norm(torch.view_as_real(states.detach()).reshape(bsz, -1), dim=1, dtype=torch.float64)
+    norm_err = float((norms - 1).abs().max())
     gb, gg = torch.autograd.grad(cost.sum(), [betas, gammas])
-    db, dg = torch.randn(bsz, p, generator=g).to(dev), torch.randn(bsz, p, generator=g).to(dev)
-    analytic = (gb * db).sum(1) + (gg * dg).sum(1)
-    h = 2e-2
-    with torch.no_grad():
-        cp, _ = qaoa_cost(betas + h * db, gammas + h * dg, n, edges, dev)
-        cm, _ = qaoa_cost(betas - h * db, gammas - h * dg, n, edges, dev)
-        cp2, _ = qaoa_cost(betas + 2 * h * db, gammas + 2 * h * dg, n, edges, dev)
-        cm2, _ = qaoa_cost(betas - 2 * h * db, gammas - 2 * h * dg, n, edges, dev)
-    fd = (8 * (cp - cm) - (cp2 - cm2)) / (12 * h)   # 4th-order central difference
-    rel = float((analytic - fd).norm() / fd.norm())
+    samples = sorted({s % bsz for s in parity_samples})
+    par = cfg3_oracle_parity(dev, betas, gammas, states, cost, gb, gg, n, edges, samples)
+    worst = max(par["states_rel_l2"], par["cost_rel"], par["grad_beta_rel_l2"], par["grad_gamma_rel_l2"])
     res = {"workload": f"cfg3: {n}-qubit QAOA MaxCut p={p}, bsz={bsz}, {len(edges)} edges, {n + p * (n + 3 * len(edges))} gates",
-           "state_norm": norm, "grad_vs_finite_difference_rel": rel, "ok": bool(abs(norm - 1) < 1e-4 and rel < 2e-3)}
+           "max_norm_err": norm_err, "oracle64_parity": par, "ok": bool(norm_err < 1e-5 and worst < 1e-5)}
     if timing:
         def step():
             betas.grad = gammas.grad = None
@@ -110,42 +146,77 @@ def brickwork(n, layers, seed=0):
     return ops
 
 
-def apply_ops(q, ops, dev, inverse=False):
-    seq = reversed(ops) if inverse else ops
-    for name, wires, p in seq:
+def apply_ops(q, ops, dev, inverse=False, thetas=None):
+    """thetas: the circuit's angles as [1, 1] views of ONE device tensor made by `device_angles` (no per-gate upload);
+    without it every gate uploads its own angle, as a user script written against the reference would."""
+    seq = list(enumerate(ops))
+    for i, (name, wires, p) in (reversed(seq) if inverse else seq):
         if p is None:
             getattr(tqf, name)(q, wires=wires, inverse=inverse)
+        elif thetas is not None:
+            getattr(tqf, name)(q, wires=wires, params=thetas[i], inverse=inverse)
         else:
             getattr(tqf, name)(q, wires=wires, params=torch.tensor([[p]], dtype=torch.float32, device=dev), inverse=inverse)
 
 
+def device_angles(ops, dev):
+    """All angles of the circuit in one device tensor; [1, 1] views of it that take part in autograd (the circuit's
+    trainable parameters) are handed to the gate calls by reference."""
+    flat = torch.tensor([0.0 if p is None else p for _, _, p in ops], dtype=torch.float32, device=dev).requires_grad_(True)
+    return [None if p is None else flat[i:i + 1].view(1, 1) for i, (_, _, p) in enumerate(ops)]
+
+
+def norm64(s):
+    return float(torch.linalg.vector_norm(torch.view_as_real(s).reshape(-1), dtype=torch.float64))
+
+
 def run_cfg4(dev, n=28, layers=100, timing=True):
-    """Forward only.  Checks: norm, all <Z_w> in [-1, 1], and circuit followed by its inverse returns |0...0>."""
+    """Forward only.  Checks (bars 1e-5, norms accumulated in float64): norm, all <Z_w> in [-1, 1], and circuit followed
+    by its inverse returns |0...0>.  Full-depth parity against the fp64 oracle: tools/depth_parity.py."""
     ops = brickwork(n, layers)
+    thetas = device_angles(ops, dev)
     q = tq.QuantumDevice(n_wires=n, bsz=1, device=dev)
     with torch.no_grad():
-        apply_ops(q, ops, dev)
+        apply_ops(q, ops, dev, thetas=thetas)
         s = q.get_states_1d()
-        norm = float(s.abs().pow(2).sum())
+        norm = norm64(s)
         z = tq.expval_joint_analytical_multi(q, ["I" * w + "Z" + "I" * (n - 1 - w) for w in range(0, n, 5)])
-        apply_ops(q, ops, dev, inverse=True)
+        apply_ops(q, ops, dev, inverse=True, thetas=thetas)
         s0 = q.get_states_1d()
         back = float(s0[0, 0].abs())
-        leak = float(s0[0, 1:].abs().max())
+        s0[0, 0] = 0
+        leak = norm64(s0)
     res = {"workload": f"cfg4: {n}-qubit brickwork rx/ry/rz + cnot, depth {layers}, {len(ops)} gates, single statevector",
-           "state_norm": norm, "z_max_abs": float(z.abs().max()), "amp0_after_inverse": back, "max_leak_after_inverse": leak,
-           "ok": bool(abs(norm - 1) < 2e-3 and abs(back - 1) < 2e-3 and leak < 1e-3 and float(z.abs().max()) <= 1.001)}
+           "state_norm": norm, "z_max_abs": float(z.abs().max()), "amp0_after_inverse": back,
+           "leak_norm_after_inverse": leak,
+           "ok": bool(abs(norm - 1) < 1e-5 and abs(back - 1) < 2e-5 and leak < 2e-5 and float(z.abs().max()) <= 1.00001)}
     if timing:
+        def queue():
+            q.reset_states(1)
+            apply_ops(q, ops, dev, thetas=thetas)
+
         def run():
             with torch.no_grad():
-                q.reset_states(1)
-                apply_ops(q, ops, dev)
+                queue()
                 q.get_states_1d()
 
         l0 = engine.STATS["launches"]
         run()
         res["passes"] = engine.STATS["launches"] - l0 - 1
-        res["fwd_ms"] = ev_ms(run, warm=1, iters=3)
+        res["fwd_ms_incl_python_queueing"] = ev_ms(run, warm=1, iters=3)
+        # the gates are queued by Python first (host only); the timed region is the flush = every kernel of the circuit
+        times = []
+        for _ in range(4):
+            with torch.no_grad():
+                queue()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                q.get_states_1d()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+        res["fwd_ms"] = float(np.median(times[1:]))
         res["gate_amp_updates_per_s"] = len(ops) * 2.0 ** n / (res["fwd_ms"] * 1e-3)
         res["algorithmic_GBps"] = res["passes"] * 16 * 2.0 ** n / (res["fwd_ms"] * 1e-3) / 1e9
         res["gates_per_pass"] = len(ops) / max(res["passes"], 1)
@@ -215,7 +286,7 @@ def run_cfg3_batch_sharded(out_path):
         out = {"workload": res["workload"] + f" per rank, batch-sharded over {world} B200 (64 circuits in total)",
                "world": world, "fwd_ms": t[0].item(), "fwd_bwd_ms": t[1].item(),
                "circuits_per_s_fwd_bwd": 64 / (t[1].item() * 1e-3), "scaling": "strong", "ok": t[2].item() == 0.0,
-               "grad_vs_finite_difference_rel": res["grad_vs_finite_difference_rel"]}
+               "oracle64_parity": res["oracle64_parity"]}
         print(json.dumps({"cfg3_batch_sharded": out}))
         if out_path:
             json.dump(out, open(out_path, "w"), indent=1)

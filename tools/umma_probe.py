@@ -80,7 +80,7 @@ def main():
         if rc != 0:
             raise RuntimeError(lib.tqb_last_error().decode())
 
-    for bsz in (1, 2):
+    for bsz in ((1, 2) if n >= 12 else ()):
         for kpos in placements:
             for tr in (0, 1):
                 st = torch.randn(bsz, 2 ** n, 2, device=dev, dtype=torch.float32)
@@ -112,7 +112,7 @@ def main():
                 results["cases"][-1]["inplace_equal"] = bool(same)
 
     # norm drift over 64 applications of the same block, with and without the per-tile renormalisation
-    for rn in (0, 1):
+    for rn in ((0, 1) if n >= 12 else ()):
         renorm[0] = rn
         st = torch.randn(1, 2 ** n, 2, device=dev, dtype=torch.float32)
         st /= st.double().norm().float()

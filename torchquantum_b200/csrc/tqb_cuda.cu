@@ -717,12 +717,14 @@ int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long
 
 static int expval_chunk_log2(int n) { return n < 12 ? n : 12; }
 
+static int tqb_expval_pauli_slice(const float2* st2, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
+                                  const unsigned long long* zmask_dev, const int* ny_dev, int n_terms, float* out, int cl,
+                                  cudaStream_t st);
+
 int tqb_expval_pauli(const float* state, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
                      const unsigned long long* zmask_dev, const int* ny_dev, int n_terms, float* out, void* stream) {
   if (bsz <= 0 || n_terms <= 0) return 0;
   const int cl = expval_chunk_log2(n_qubits);
-  dim3 grid(1u << (n_qubits - cl), (unsigned)bsz);
-  if (bsz > 65535) return fail_msg("tqb_expval_pauli: bsz > 65535");
   const float2* st2 = reinterpret_cast<const float2*>(state);
   cudaStream_t st = (cudaStream_t)stream;
   if (n_qubits >= 1 && n_qubits <= 13 && bsz >= 64) {  // one warp per sample
@@ -736,6 +738,20 @@ int tqb_expval_pauli(const float* state, int n_qubits, long long bsz, const unsi
     TQB_CHECK_LAUNCH("tqb_expval_pauli_warp_kernel");
     return 0;
   }
+  // block-per-chunk kernel: the sample index is gridDim.y (<= 65535); larger batches go in slices
+  for (long long b0 = 0; b0 < bsz; b0 += 65535) {
+    const long long nb = bsz - b0 < 65535 ? bsz - b0 : 65535;
+    const int rc = tqb_expval_pauli_slice(st2 + (b0 << n_qubits), n_qubits, nb, xmask_dev, zmask_dev, ny_dev, n_terms,
+                                          out + b0 * n_terms, cl, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int tqb_expval_pauli_slice(const float2* st2, int n_qubits, long long bsz, const unsigned long long* xmask_dev,
+                                  const unsigned long long* zmask_dev, const int* ny_dev, int n_terms, float* out, int cl,
+                                  cudaStream_t st) {
+  dim3 grid(1u << (n_qubits - cl), (unsigned)bsz);
   if (n_terms == 1)
     tqb_expval_pauli_kernel<1><<<grid, 256, 0, st>>>(st2, n_qubits, xmask_dev, zmask_dev, ny_dev, n_terms, out, cl, grid.x > 1);
   else if (n_terms <= 4)

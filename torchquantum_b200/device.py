@@ -17,6 +17,49 @@ from .macro import C_DTYPE
 __all__ = ["QuantumDevice"]
 
 
+class GateQueue(list):
+    """The lazy gate queue of a device.  Two pieces of bookkeeping keep lazy execution equal to the reference's
+    eager one (functional/gate_wrapper.py:324-446 consumes parameter values and the autograd mode at call time):
+
+    * `grad`: the autograd mode the queued gates were *issued* under.  A gate issued under another mode first
+      runs what is queued (under the mode it was issued with), so `with torch.no_grad(): qdev.get_states_1d()` in
+      the middle of a circuit neither drops the graph of the gates before it nor tracks gates issued inside it;
+    * `guard`: (tensor, version) of every parameter tensor queued through the public gate calls; `check()` raises
+      when one was modified in place between the gate call and the flush (leaf tensors without grad are snapshotted
+      at the call instead, see functional._snapshot)."""
+    __slots__ = ("owner", "grad", "guard")
+
+    def __init__(self, owner):
+        super().__init__()
+        self.owner, self.grad, self.guard = owner, torch.is_grad_enabled(), []
+
+    def _mode(self):
+        g = torch.is_grad_enabled()
+        if g != self.grad:
+            if len(self):
+                self.owner.flush()
+                self.owner._queue._mode()
+                return self.owner._queue
+            self.grad = g
+        return self
+
+    def append(self, rec):
+        q = self._mode()
+        list.append(q, rec)
+        if type(rec) is tuple and rec[2] is not None:
+            q.guard.append((rec[2], rec[2]._version))
+
+    def extend(self, recs):
+        list.extend(self._mode(), recs)
+
+    def check(self):
+        for t, v in self.guard:
+            if t._version != v:
+                raise RuntimeError(
+                    "a gate parameter tensor was modified in place after the gate was queued and before the state "
+                    "was read (gates run lazily): read the state (`qdev.states`) before modifying it, or pass a clone")
+
+
 class QuantumDevice(nn.Module):
     accepts_record_chunks = True  # the queue may hold engine.RecordChunk items (layer templates)
 
@@ -31,7 +74,7 @@ class QuantumDevice(nn.Module):
         _state[:1].fill_(1)
         _state = torch.reshape(_state, [2] * n_wires)
         self.register_buffer("state", _state)
-        self._queue = []
+        self._queue = GateQueue(self)
         self._flat = None
         self._buffers["states"] = None
         self.reset_states(bsz)
@@ -41,7 +84,7 @@ class QuantumDevice(nn.Module):
 
     # --- state container --------------------------------------------------------------
     def _set_flat(self, flat):
-        self._queue = []
+        self._queue = GateQueue(self)
         self._flat = flat
         self._buffers["states"] = None  # materialised lazily as a view
 
@@ -80,8 +123,36 @@ class QuantumDevice(nn.Module):
     def flush(self):
         """Run every queued gate (fused) and materialise the state."""
         if self._queue:
-            q, self._queue = self._queue, []
-            self._flat = engine.run_circuit(self._flat, self.n_wires, q)
+            q, self._queue = self._queue, GateQueue(self)
+            q.check()
+            if q.grad == torch.is_grad_enabled():
+                self._flat = engine.run_circuit(self._flat, self.n_wires, q)
+            else:
+                with torch.set_grad_enabled(q.grad):
+                    self._flat = engine.run_circuit(self._flat, self.n_wires, q)
+
+    # --- checkpoints: `states` is always a key of the state dict, as in the reference (device/devices.py:57-71) ----
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        self.states  # flush + materialise the [bsz, 2, ..., 2] view as the `states` buffer
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        key = prefix + "states"
+        if key in state_dict:
+            v = state_dict[key]
+            if v.numel() % (2 ** self.n_wires) != 0:
+                error_msgs.append(f"size mismatch for {key}: {tuple(v.shape)} is not [bsz] + [2] * {self.n_wires}")
+            else:
+                self.states = v.detach().to(device=self._flat.device, dtype=C_DTYPE).reshape(-1, 2 ** self.n_wires).clone()
+                self.bsz = self._flat.shape[0]
+            state_dict = {k: t for k, t in state_dict.items() if k != key}
+        elif strict:
+            missing_keys.append(key)
+        self.flush()
+        self._buffers["states"] = None
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
 
     def enqueue(self, name, wires, params, inverse):
         self._queue.append((name, wires, params, inverse))

@@ -4,7 +4,7 @@ MultiPhaseEncoder, StateEncoder).  Encoders only build gate lists with per-sampl
 import torch
 
 from . import functional as tqf
-from .functional import func_name_dict
+from .functional import borrowed_params, func_name_dict
 from .module import QuantumModule, static_support
 from .operator import op_name_dict
 
@@ -41,13 +41,14 @@ class GeneralEncoder(Encoder):
 
     @static_support
     def forward(self, qdev, x):
-        for info in self.func_list:
-            if op_name_dict[info["func"]].num_params > 0:
-                params = self._columns(x, info["input_idx"])
-            else:
-                params = None
-            func_name_dict[info["func"]](qdev, wires=info["wires"], params=params, static=self.static_mode,
-                                         parent_graph=self.graph)
+        with borrowed_params():
+            for info in self.func_list:
+                if op_name_dict[info["func"]].num_params > 0:
+                    params = self._columns(x, info["input_idx"])
+                else:
+                    params = None
+                func_name_dict[info["func"]](qdev, wires=info["wires"], params=params, static=self.static_mode,
+                                             parent_graph=self.graph)
 
 
 class PhaseEncoder(Encoder):
@@ -59,7 +60,7 @@ class PhaseEncoder(Encoder):
 
     @static_support
     def forward(self, qdev, x):
-        for k in range(x.shape[1]):
+        for k in range(x.shape[1]):  # x[:, [k]] is a fresh tensor already
             self.func(qdev, wires=k, params=x[:, [k]], static=self.static_mode, parent_graph=self.graph)
 
 
@@ -75,11 +76,12 @@ class MultiPhaseEncoder(Encoder):
     def forward(self, qdev, x):
         wires = self.wires if self.wires is not None else list(range(qdev.n_wires)) * (len(self.funcs) // qdev.n_wires)
         x_id = 0
-        for k, func in enumerate(self.funcs):
-            stride = 3 if func in ("u3", "cu3") else (2 if func in ("u2",) else 1)
-            func_name_dict[func](qdev, wires=wires[k], params=x[:, x_id:x_id + stride], static=self.static_mode,
-                                 parent_graph=self.graph)
-            x_id += stride
+        with borrowed_params():
+            for k, func in enumerate(self.funcs):
+                stride = 3 if func in ("u3", "cu3") else (2 if func in ("u2",) else 1)
+                func_name_dict[func](qdev, wires=wires[k], params=x[:, x_id:x_id + stride], static=self.static_mode,
+                                     parent_graph=self.graph)
+                x_id += stride
 
 
 class StateEncoder(Encoder):

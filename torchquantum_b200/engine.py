@@ -102,9 +102,11 @@ def run_fused_inplace(state, stage, n, rank, psh, pps, externs):
     return state
 
 
-def run_blocks(state, stage, n, rank, psh, inplace):
+def run_blocks(state, stage, n, rank, psh, inplace, timing=None):
     """Forward-only block stage (plan.BlockStage): the block unitaries are built on the device from the live parameters,
-    then every block is one tensor-core pass; the first reads `state`, the rest work in place on the result."""
+    then every block is one tensor-core pass; the first reads `state`, the rest work in place on the result.
+    timing: a list -> the blocks are launched one ABI call each and (start, end) CUDA events of every launch are
+    appended (bench.py's per-launch roofline)."""
     _native.check_device(state)
     state = state.contiguous()
     if state.data_ptr() & 15:
@@ -116,8 +118,17 @@ def run_blocks(state, stage, n, rank, psh, inplace):
     _native.call("tqb_block_build", _ptr(blocks_dev), stage.n_blocks, _ptr(ops_dev), _ptr(consts), _ptr(psh), rank,
                  _ptr(planes), stream)
     out = state if inplace else torch.empty_like(state)
-    _native.call("tqb_apply_blocks", _ptr(state), _ptr(out), n, bsz, _ptr(planes), stage.blocks.ctypes.data, stage.n_blocks, 1,
-                 stream)
+    if timing is not None:
+        for b in range(stage.n_blocks):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _native.call("tqb_apply_blocks", _ptr(state if b == 0 else out), _ptr(out), n, bsz, _ptr(planes[b]),
+                         stage.blocks[b:].ctypes.data, 1, 1, stream)
+            e1.record()
+            timing.append((e0, e1))
+    else:
+        _native.call("tqb_apply_blocks", _ptr(state), _ptr(out), n, bsz, _ptr(planes), stage.blocks.ctypes.data,
+                     stage.n_blocks, 1, stream)
     STATS["launches"] += 1 + stage.n_blocks
     return out
 

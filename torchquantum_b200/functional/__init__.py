@@ -19,6 +19,31 @@ from .matrices import (mat_dict, multirz_eigvals, multirz_matrix, multicnot_matr
 __all__ = ["func_name_dict", "mat_dict", "gate_wrapper", "apply_unitary_bmm", "apply_unitary_einsum"]
 
 
+_BORROW = [0]
+
+
+class borrowed_params:
+    """Inside this context gate calls keep the caller's parameter tensors by reference instead of snapshotting them
+    (encoders slicing one input batch into many gates: the batch outlives the flush; the version guard of the queue
+    still catches an in-place edit)."""
+
+    def __enter__(self):
+        _BORROW[0] += 1
+
+    def __exit__(self, *exc):
+        _BORROW[0] -= 1
+
+
+def _snapshot(params):
+    """The reference consumes parameter VALUES when the gate is called (functional/gate_wrapper.py:361-377 builds the
+    matrix immediately); a lazily executed gate must not see later in-place edits of the caller's tensor.  Tensors
+    that take part in autograd are kept by reference (their in-place edits are caught by the queue's version guard);
+    plain value tensors are tiny and copied."""
+    if params.requires_grad or _BORROW[0]:
+        return params
+    return params.clone()
+
+
 def _normalize_params(name, params):
     """Shape rules of the reference (functional/gate_wrapper.py:361-377)."""
     if params is None:
@@ -71,7 +96,7 @@ def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, 
         assert np.log2(params.shape[-1]) == len(wires_t)  # functional/gate_wrapper.py:433
         if params.device != q_device.compute_device:
             params = params.to(q_device.compute_device)
-        q_device.enqueue(cname, wires_t, params.to(C_DTYPE), bool(inverse))
+        q_device.enqueue(cname, wires_t, _snapshot(params.to(C_DTYPE)), bool(inverse))
         return
     expected = spec.n_wires if spec.n_wires is not None else len(wires_t)
     assert expected == len(wires_t), f"{name}: expected {expected} wires, got {len(wires_t)}"
@@ -81,6 +106,8 @@ def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, 
         params = None
     elif params.device != q_device.compute_device:
         params = params.to(q_device.compute_device)
+    else:
+        params = _snapshot(params)
     q_device.enqueue(cname, wires_t, params, bool(inverse))
 
 
@@ -111,6 +138,8 @@ def _make(name):
                 dev = q_device._flat.device
                 if params.device != dev:
                     params = params.to(dev)
+                elif not params.requires_grad and not _BORROW[0]:
+                    params = params.clone()  # _snapshot
             q_device._queue.append((cname, wires_t, params, bool(inverse)))
             return
         gate_wrapper(name=cname, mat=mat_dict.get(cname), method=comp_method, q_device=q_device, wires=wires,

@@ -15,6 +15,10 @@ __all__ = ["RandomLayer", "RandomLayerAllTypes", "Op1QAllLayer", "Op2QAllLayer",
            "LayerTemplate0", "NLocal", "TwoLocal", "EfficientSU2", "RealAmplitudes", "QFTLayer"]
 
 
+def _wires_tuple(wires):
+    return (int(wires),) if isinstance(wires, (int, np.integer)) else tuple(int(w) for w in wires)
+
+
 class _RecordCache:
     """Template layers queue the same records (same Parameter objects, wires, inverse flags) every step.
     `records(q_device)` returns them from a cache that is re-validated by the operators' version
@@ -29,14 +33,20 @@ class _RecordCache:
             return None
         dev = q_device._flat.device
         c = self.__dict__.get("_rec_cache")
-        if c is not None and c[0] == dev:
-            ver = 0
-            for o in c[2]:
+        live = self._layer_ops_wires()
+        if c is not None and c[0] == dev and len(live) == len(c[2]):
+            # the cache is good only for the SAME operator objects on the same wires (a rebuilt op list, a replaced
+            # entry of ops_all or a changed jump / wire order invalidates it) whose version counters did not move
+            ver, same = 0, True
+            for (o, wires), oc, rc in zip(live, c[2], c[3]):
+                if o is not oc or _wires_tuple(wires) != rc[1]:
+                    same = False
+                    break
                 ver += o.__dict__["_ver"]
-            if ver == c[1] and all(p.device == dev for p in c[4]):
+            if same and ver == c[1] and all(p.device == dev for p in c[4]):
                 return c[3]
         ops, recs, ver = [], [], 0
-        for o, wires in self._layer_ops_wires():
+        for o, wires in live:
             r = o.fast_record(q_device, wires)
             if r is None:
                 self.__dict__["_rec_cache"] = None

@@ -64,8 +64,10 @@ class ShardedQuantumDevice:
             raise ValueError("the number of ranks must be a power of two")
         self.n_wires, self.device_name, self.bsz = n_wires, device_name, bsz
         self.nl = n_wires - self.g
-        if self.nl < max(self.g, 1):
-            raise ValueError("too few qubits for this many ranks")
+        if self.nl < 1 or (self.g and self.nl < max(2 * self.g - 1, self.g + 2)):
+            # an exchange parks g local qubits in the rank index while a 2-qubit gate keeps 2 on chip, and
+            # canonicalize() parks g more beside the g - 1 it is sorting
+            raise ValueError(f"too few qubits ({n_wires}) for {self.world} ranks: need n - g >= max(2g - 1, g + 2)")
         self.device = torch.device(device)
         self.record_op = record_op
         self._op_history, self._history_pending = [], []
@@ -174,12 +176,21 @@ class ShardedQuantumDevice:
         to the top local bits (fused local pass), all-to-all."""
         n, nl, g = self.n_wires, self.nl, self.g
         nxt = self._next_need(rest)
+        name0, wires0, params0, _ = rest[0]
+        need0 = {n - 1 - w for w in _local_bits_needed(name0, wires0, params0)}
+        if len(need0) > nl - g:
+            raise NotImplementedError(
+                f"{name0} on wires {list(wires0)} needs {len(need0)} qubits on one GPU at once, but with {self.world} "
+                f"ranks only {nl - g} of the {nl} local qubits can stay while the {g} rank qubits are exchanged: "
+                "decompose the gate (e.g. tq.QFT / QFTLayer instead of the dense tqf.qft) or use fewer ranks")
         inv = {p: l for l, p in enumerate(self.pos)}
-        local_logical = [inv[p] for p in range(nl)]
+        local_logical = [inv[p] for p in range(nl) if inv[p] not in need0]
         order = sorted(local_logical, key=lambda l: (-nxt.get(l, 1 << 60), -self.pos[l]))
         victims = order[:g]
         self._move_to_top(victims)
         self._all_to_all()
+        if any(self.pos[l] >= nl for l in need0):   # progress guarantee of flush()
+            raise AssertionError(f"exchange left {name0} on wires {list(wires0)} blocked (layout {self.pos})")
 
     def _move_to_top(self, victims):
         """Local bit permutation so that `victims` (logical bits) occupy physical bits [nl-g, nl)."""
