@@ -125,12 +125,11 @@ def _time_planned_circuit(n, key, thetas, dev, reps=3):
     """Runs the forward-only plan of `key` on a 2^n state, one ABI call per kernel launch, CUDA events around each.
     -> {"block": [ms...], "pass": [ms...]}, launches per repetition, gates per kind, norm of the final state."""
     from torchquantum_b200 import _native, engine
-    from torchquantum_b200.engine import _build_mats, _desc, _dev, _ptr
+    from torchquantum_b200.engine import _build_mats, _desc, _dev
 
     plan = engine.get_plan(n, tuple(key), False)
     state = torch.zeros(1, 2 ** n, dtype=torch.complex64, device=dev)
     state[0, 0] = 1
-    stream = _native.stream_ptr(state)
     evs = {"block": [], "pass": []}
     per_rep = {"block": 0, "pass": 0}
     pps = torch.zeros(1, 1, dtype=torch.float32, device=dev)
@@ -150,8 +149,8 @@ def _time_planned_circuit(n, key, thetas, dev, reps=3):
                     prog = _dev(pp, "prog", dev)
                     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     s.record()
-                    _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, 1, _ptr(prog), _desc(pp), _ptr(msh),
-                                 _ptr(mps), stage.M_ps, 0, stream)
+                    _native.call("tqb_pass_forward", state, state, n, 1, prog, _desc(pp), msh,
+                                 mps, stage.M_ps, 0)
                     e.record()
                     if rep > 0:
                         evs["pass"].append((s, e))

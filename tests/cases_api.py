@@ -268,3 +268,23 @@ def check_einsum_broadcast(device):
     assert_close(got, O.apply_unitary_bmm(st3, mats[0], [0, 1]), what="bmm, shared matrix")
     with pytest.raises(RuntimeError):
         tqf.apply_unitary_bmm(st.to(device), mats.to(device), [2, 0])
+
+
+def check_dropped_device_is_freed_by_refcount(device):
+    """A device that goes out of scope must be freed at once (no reference cycle): its state can be GiBs, and a stale
+    autograd graph kept alive behind it breaks CUDA-graph capture of the next step (AccumulateGrad stream mismatch)."""
+    import gc
+    import weakref
+
+    gc.disable()
+    try:
+        q = tq.QuantumDevice(n_wires=3, bsz=2, device=device)
+        p = torch.tensor([[0.3]], device=device, requires_grad=True)
+        tqf.rx(q, wires=0, params=p)
+        q.get_states_1d()
+        q.ry(wires=1, params=p)
+        ref = weakref.ref(q)
+        del q
+        assert ref() is None, "QuantumDevice is kept alive by a reference cycle"
+    finally:
+        gc.enable()

@@ -27,9 +27,24 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 14
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/tqb200.h but not exported"
-    assert set(_native.SIGNATURES) | {"tqb_abi_version", "tqb_last_error"} == set(syms)
+    assert set(_native.OP_NAMES) | {"tqb_abi_version", "tqb_last_error"} == set(syms)
     lib.tqb_abi_version.restype = ctypes.c_int
     assert lib.tqb_abi_version() == _native.ABI_VERSION
+
+
+def test_every_abi_entry_is_a_registered_torch_op():
+    """north_star / SURVEY §8b: the front end reaches the kernels through torch.library custom ops registered by the
+    thin C++ extension (csrc/tqb_torch_ops.cpp); schema check only, no compute."""
+    from torchquantum_b200 import _native
+
+    ops = _native._load_ops()
+    assert set(ops) == set(_native.OP_NAMES)
+    for name in _native.OP_NAMES:
+        schema = getattr(torch.ops.tqb200, name).default._schema
+        assert schema.name == f"tqb200::{name}"
+        assert any(a.alias_info is not None and a.alias_info.is_write for a in schema.arguments), f"{name}: no output argument"
+        keys = torch._C._dispatch_dump(f"tqb200::{name}")
+        assert "CUDA" in keys, f"{name}: no CUDA kernel registered"
 
 
 def test_python_constants_mirror_header():

@@ -83,7 +83,8 @@ def test_cfg1_model_from_classes_matches_reference_golden():
 @pytest.mark.parametrize("check", ["check_record_cache_follows_the_op_list", "check_grad_mode_is_sampled_when_gates_are_issued",
                                    "check_parameter_values_are_read_at_the_gate_call", "check_checkpoint_round_trip",
                                    "check_from_op_history_and_get_unitary", "check_static_mode_equals_dynamic",
-                                   "check_layer_classes", "check_einsum_broadcast"])
+                                   "check_layer_classes", "check_einsum_broadcast",
+                                   "check_dropped_device_is_freed_by_refcount"])
 def test_host_mirror_semantics(check):
     from tests import cases_api
 

@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torchquantum_b200 import _native, engine  # noqa: E402
-from torchquantum_b200.engine import _build_mats, _desc, _dev, _ptr  # noqa: E402
+from torchquantum_b200.engine import _build_mats, _desc, _dev  # noqa: E402
 
 
 def cfg2_key(n, reps, grad):
@@ -47,18 +47,17 @@ def main():
         psi2, lam2 = torch.empty_like(state), torch.empty_like(state)
         gr = torch.zeros(bsz, stage.G, dtype=torch.float32, device=dev)
         msh, mps = _build_mats(stage, bsz, psh, pps, [], dev)
-        stream = _native.stream_ptr(state)
         assert len(stage.passes) == 1
         pp = stage.passes[0]
         prog = _dev(pp, "prog", dev)
 
         def fwd():
-            _native.call("tqb_pass_forward", _ptr(state), _ptr(dst), n, bsz, _ptr(prog), _desc(pp), _ptr(msh), _ptr(mps),
-                         stage.M_ps, 0, stream)
+            _native.call("tqb_pass_forward", state, dst, n, bsz, prog, _desc(pp), msh, mps,
+                         stage.M_ps, 0)
 
         def bwd():
-            _native.call("tqb_pass_backward", _ptr(dst), _ptr(lam), _ptr(psi2), _ptr(lam2), n, bsz, _ptr(prog), _desc(pp),
-                         _ptr(msh), _ptr(mps), stage.M_ps, _ptr(gr), stage.G, 0, stream)
+            _native.call("tqb_pass_backward", dst, lam, psi2, lam2, n, bsz, prog, _desc(pp),
+                         msh, mps, stage.M_ps, gr, stage.G, 0)
 
         for name, fn in (("fwd", fwd),) + ((("bwd", bwd),) if grad else ()):
             for _ in range(3):

@@ -2,7 +2,6 @@
 (b) the CUDA-core dense kernel, and (c) the same unitary's worth of brickwork gates through the fused interpreter.
 Usage: python tools/dense_probe.py [--n 26]"""
 import argparse
-import ctypes
 import os
 import sys
 
@@ -10,7 +9,6 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torchquantum_b200 import _native  # noqa: E402
-from torchquantum_b200.engine import _ptr  # noqa: E402
 
 
 def ev(fn, iters=5):
@@ -31,16 +29,15 @@ def main():
     st = torch.randn(1, 2 ** n, dtype=torch.complex64, device=dev)
     st /= st.norm()
     out = torch.empty_like(st)
-    stream = _native.stream_ptr(st)
     for k in (4, 5, 6, 7):
         u, _ = torch.linalg.qr(torch.randn(2 ** k, 2 ** k, dtype=torch.complex64))
         u = u.to(dev).contiguous()
         for label, bits in (("low bits", list(range(k))[::-1]), ("high bits", list(range(n - k, n))[::-1])):
-            host = (ctypes.c_int * k)(*bits)
+            host = [int(b) for b in bits]
             bp = torch.tensor(bits, dtype=torch.int32, device=dev)
-            t_tc = ev(lambda: _native.call("tqb_apply_dense_tc", _ptr(st), _ptr(out), n, 1, _ptr(u), k, host, 0, stream))
+            t_tc = ev(lambda: _native.call("tqb_apply_dense_tc", st, out, n, 1, u, k, host, 0))
             ref = torch.empty_like(st)
-            t_cc = ev(lambda: _native.call("tqb_apply_dense", _ptr(st), _ptr(ref), n, 1, _ptr(u), 0, k, _ptr(bp), 0, stream), iters=2)
+            t_cc = ev(lambda: _native.call("tqb_apply_dense", st, ref, n, 1, u, 0, k, bp, 0), iters=2)
             err = float((out - ref).abs().max() / ref.abs().max())
             flops = 8.0 * 2 ** k * 3 * 2 ** n
             print(f"n={n} k={k} {label:9s}: tensor-core {t_tc:7.3f} ms ({16 * 2 ** n / t_tc / 1e6:6.0f} GB/s alg, "

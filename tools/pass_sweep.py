@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torchquantum_b200 import _native, engine  # noqa: E402
-from torchquantum_b200.engine import _build_mats, _desc, _dev, _ptr  # noqa: E402
+from torchquantum_b200.engine import _build_mats, _desc, _dev  # noqa: E402
 
 
 def one_pass_key(n, k, rng, kinds=("rx", "ry", "rz"), cnot_every=3, hi_bits=7):
@@ -41,7 +41,6 @@ def time_passes(n, key, thetas, dev, bwd=False, reps=5):
     lam = torch.zeros_like(state) if bwd else None
     gr = torch.zeros(1, stage.G, dtype=torch.float32, device=dev)
     msh, mps = _build_mats(stage, 1, psh, pps, [], dev)
-    stream = _native.stream_ptr(state)
     evs = []
     for rep in range(reps + 1):
         for pp in stage.passes:
@@ -49,11 +48,11 @@ def time_passes(n, key, thetas, dev, bwd=False, reps=5):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             if bwd:
-                _native.call("tqb_pass_backward", _ptr(state), _ptr(lam), _ptr(state), _ptr(lam), n, 1, _ptr(prog),
-                             _desc(pp), _ptr(msh), _ptr(mps), stage.M_ps, _ptr(gr), stage.G, 0, stream)
+                _native.call("tqb_pass_backward", state, lam, state, lam, n, 1, prog,
+                             _desc(pp), msh, mps, stage.M_ps, gr, stage.G, 0)
             else:
-                _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, 1, _ptr(prog), _desc(pp), _ptr(msh),
-                             _ptr(mps), stage.M_ps, 0, stream)
+                _native.call("tqb_pass_forward", state, state, n, 1, prog, _desc(pp), msh,
+                             mps, stage.M_ps, 0)
             e.record()
             if rep > 0:
                 evs.append((s, e))

@@ -1,71 +1,78 @@
-"""ctypes binding of libtqb200.so (the C ABI in include/tqb200.h).
+"""Binding of libtqb200.so (the C ABI in include/tqb200.h) as torch.library custom ops.
 
-There is no CPU fallback: if the CUDA library is missing or does not load, every entry point
-raises.  (The CPU test-suite injects a host *emulation* build of the same kernel source through
-``use_library_for_testing``; the package itself never looks for it.)
+`lib/libtqb200_torch.so` (csrc/tqb_torch_ops.cpp, a thin C++ extension) registers one op per ABI entry point in
+the `tqb200` namespace — `torch.ops.tqb200.tqb_pass_forward(src, dst, n, bsz, prog, desc, msh, mps, stride, ext_hi)` —
+and forwards to the C ABI with raw pointers and the current CUDA stream.  `call(name, *args)` below is how the
+package reaches them: the argument order of include/tqb200.h, Tensors for device pointers, int lists / CPU tensors
+for host arrays, no stream argument.
+
+There is no CPU fallback: if either library is missing or does not load, every entry point raises, and a CPU
+tensor raises inside the op.  (The CPU test-suite injects a host *emulation* build of the same kernel source
+through ``use_library_for_testing``; the package itself never looks for it.)
 """
-import ctypes
 import os
+
+import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TQB200_LIB") or os.path.join(_HERE, "lib", "libtqb200.so")  # env: kernel A/B experiments
+OPS_LIB_PATH = os.path.join(_HERE, "lib", "libtqb200_torch.so")
 ABI_VERSION = 4
 
-_lib = None
+# every ABI entry point registered as torch.ops.tqb200.<name> (mirrors include/tqb200.h)
+OP_NAMES = (
+    "tqb_build_mats", "tqb_build_mats_bwd", "tqb_pass_forward", "tqb_pass_backward", "tqb_apply_dense",
+    "tqb_apply_dense_tc", "tqb_block_build", "tqb_apply_blocks", "tqb_dense_grad", "tqb_expval_pauli",
+    "tqb_expval_pauli_bwd", "tqb_expval_z", "tqb_expval_z_bwd", "tqb_probs", "tqb_sample_counts",
+)
+
+_ops = None          # name -> OpOverload
+_cuda_bound = False
 _emulated = False
 
-_vp, _i, _ll, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_uint
 
-# name -> argtypes (all return int); mirrors include/tqb200.h
-SIGNATURES = {
-    "tqb_build_mats": [_vp, _i, _i, _ll, _vp, _vp, _i, _vp, _vp, _vp, _ll, _vp],
-    "tqb_build_mats_bwd": [_vp, _i, _ll, _vp, _vp, _i, _vp, _ll, _vp, _i, _vp, _vp],
-    "tqb_pass_forward": [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _u, _vp],
-    "tqb_pass_backward": [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _u, _vp],
-    "tqb_apply_dense": [_vp, _vp, _i, _ll, _vp, _ll, _i, _vp, _i, _vp],
-    "tqb_apply_dense_tc": [_vp, _vp, _i, _ll, _vp, _i, _vp, _i, _vp],
-    "tqb_block_build": [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp],
-    "tqb_apply_blocks": [_vp, _vp, _i, _ll, _vp, _vp, _i, _i, _vp],
-    "tqb_dense_grad": [_vp, _vp, _i, _ll, _i, _vp, _vp, _vp],
-    "tqb_expval_pauli": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp],
-    "tqb_expval_pauli_bwd": [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "tqb_expval_z": [_vp, _i, _ll, _vp, _vp],
-    "tqb_expval_z_bwd": [_vp, _i, _ll, _vp, _vp, _vp],
-    "tqb_probs": [_vp, _i, _ll, _vp, _vp],
-    "tqb_sample_counts": [_vp, _i, _ll, _vp, _i, _vp, _vp, _vp],
-}
-
-
-def _bind(handle):
-    handle.tqb_abi_version.restype = ctypes.c_int
-    handle.tqb_last_error.restype = ctypes.c_char_p
-    for name, argtypes in SIGNATURES.items():
-        fn = getattr(handle, name)
-        fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
-    if handle.tqb_abi_version() != ABI_VERSION:
-        raise RuntimeError("libtqb200: ABI version mismatch")
-    return handle
+def _load_ops():
+    global _ops
+    if _ops is None:
+        if not os.path.exists(OPS_LIB_PATH):
+            raise RuntimeError(
+                f"torchquantum_b200: op library {OPS_LIB_PATH} not built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        torch.ops.load_library(OPS_LIB_PATH)
+        _ops = {name: getattr(torch.ops.tqb200, name).default for name in OP_NAMES}
+    return _ops
 
 
 def lib():
-    global _lib
-    if _lib is None:
+    """Loads both libraries (once) and binds the CUDA one; -> the op table."""
+    global _cuda_bound
+    ops = _load_ops()
+    if not _cuda_bound and not _emulated:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"torchquantum_b200: CUDA library {LIB_PATH} not built "
                 "(run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
-        _lib = _bind(ctypes.CDLL(LIB_PATH))
-    return _lib
+        version = torch.ops.tqb200._bind(LIB_PATH, False)
+        if version != ABI_VERSION:
+            raise RuntimeError("libtqb200: ABI version mismatch")
+        _cuda_bound = True
+    return ops
+
+
+def abi_version():
+    lib()
+    return ABI_VERSION
 
 
 def use_library_for_testing(path):
-    """Tests only: route the ABI to another build (the host emulation of the kernel source)."""
-    global _lib, _emulated
+    """Tests only: route CPU tensors to another build of the ABI (the host emulation of the kernel source)."""
+    global _emulated
+    _load_ops()
     if path is None:
-        _lib, _emulated = None, False
+        torch.ops.tqb200._bind("", True)
+        _emulated = False
         return
-    _lib = _bind(ctypes.CDLL(path))
+    torch.ops.tqb200._bind(path, True)
     _emulated = True
 
 
@@ -74,9 +81,8 @@ def is_emulated():
 
 
 def call(name, *args):
-    rc = getattr(lib(), name)(*args)
-    if rc != 0:
-        raise RuntimeError(f"{name} failed: {lib().tqb_last_error().decode()}")
+    ops = _ops if (_cuda_bound or _emulated) else lib()
+    ops[name](*args)
 
 
 def check_device(t):
@@ -87,11 +93,3 @@ def check_device(t):
     if not _emulated:
         raise RuntimeError(
             "torchquantum_b200 runs on CUDA (sm_100a) only: got a CPU tensor and there is no CPU fallback")
-
-
-def stream_ptr(t):
-    if t.is_cuda:
-        import torch
-
-        return torch.cuda.current_stream(t.device).cuda_stream
-    return 0

@@ -71,8 +71,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
-    if (spin == 64) t0 = clock64();
-    if (spin > 64 && (spin & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    if ((spin & 1023u) == 1023u) {   // (try_wait itself blocks for a hardware-defined time slice per attempt)
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
   }
 }
 
@@ -108,11 +110,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest (ties away from zero) to the 10-bit TF32 mantissa on the bit pattern: what cvt.rna.tf32.f32 computes for
+// finite values, in 2 integer instructions (ptxas expands the cvt into ~10 with its NaN / Inf handling, and the splitter
+// runs it 16 384 times per tile; amplitudes are finite and <= 1)
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
 #define TQB_R32(v) \
   "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
@@ -128,6 +129,16 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+      "%26, %27, %28, %29, %30, %31}, [%32];"
+      : TQB_R32(v)
+      : "r"(taddr));
+}
+// 16 lanes x 64 columns: register 4k + 2j + c = lane (t / 4) + 8 j, column 8 k + 2 (t % 4) + c  (the mma m16n8 accumulator
+// fragment repeated 8 times along the columns)
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
       "%26, %27, %28, %29, %30, %31}, [%32];"
       : TQB_R32(v)
@@ -195,9 +206,12 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
   const uint32_t t_ahi = tmem, t_alo = tmem + 64u, t_d0 = tmem + 128u;
 
-  // A -> TMEM: lane m of TMEM = row m of A, column k = A[m][k]
+  // A -> TMEM, column k of lane l = A[m(l)][k].  The planes hold row 2i + w = (Re, Im)[w] of U[i]; TMEM lane 16 G + r holds
+  // Re U[8 G + r] for r < 8 and Im U[8 G + r - 8] for r >= 8, so that the epilogue's 16-lane accumulator loads (rows r and
+  // r + 8 in one thread) deliver P = Re(U) S and Q = Im(U) S of the SAME output pattern to the same thread
   if (warp >= 4 && warp < 8) {
-    const int q = warp & 3, m = 32 * q + lane;
+    const int q = warp & 3, l = 32 * q + lane;
+    const int m = 2 * (8 * (l >> 4) + (l & 7)) + ((l >> 3) & 1);
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
@@ -290,7 +304,6 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const int q = warp & 3, et = threadIdx.x - 128;
-    const uint32_t i = 16u * q + (lane >> 1), w = lane & 1u;
     uint32_t it = 0;
     // Unitary blocks preserve the norm of every tile; the accumulation above truncates, which shrinks it by a few 1e-7
     // per pass, systematically.  The epilogue therefore rescales by g = sqrt(|tile in|^2 / |tile out|^2), measured on the
@@ -305,52 +318,27 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t trow = t_d0 + 128u * d + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
-      for (uint32_t ng = 0; ng < 4; ++ng) {
+      for (uint32_t ld = 0; ld < 4; ++ld) {
+        // 16 accumulator lanes (8 output patterns, P and Q) x 64 columns (32 amplitudes) per load
+        const uint32_t h = ld >> 1, half = ld & 1u;
+        const uint32_t i = 16u * q + 8u * h + (lane >> 2);   // output pattern of this thread
         uint32_t v[32];
-        tmem_ld32(trow + 32u * ng, v);
+        tmem_ld_16x256b_x8(t_d0 + 128u * d + ((uint32_t)(32 * q + 16 * h) << 16) + 64u * half, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // lane pair exchange: the even lane (P) finishes n = 0..7 of the group, the odd lane (Q) n = 8..15
-        float o[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const uint32_t send = w ? v[k] : v[16 + k];
-          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-          o[k] = __uint_as_float(recv);
-        }
-        float r[16];
-#pragma unroll
-        for (int nn = 0; nn < 8; ++nn) {
-          // P = (pr, pi), Q = (qr, qi) of amplitude nn (even lane) / 8 + nn (odd lane)
-          const float pr = w ? o[2 * nn] : __uint_as_float(v[2 * nn]);
-          const float pi = w ? o[2 * nn + 1] : __uint_as_float(v[2 * nn + 1]);
-          const float qr = w ? __uint_as_float(v[16 + 2 * nn]) : o[2 * nn];
-          const float qi = w ? __uint_as_float(v[16 + 2 * nn + 1]) : o[2 * nn + 1];
+        for (uint32_t c = 0; c < 8; ++c) {
+          // amplitude n of pattern i:  P = (pr, pi) = Re(U) S,  Q = (qr, qi) = Im(U) S,  out = P + i Q
+          const float pr = __uint_as_float(v[4 * c]), pi = __uint_as_float(v[4 * c + 1]);
+          const float qr = __uint_as_float(v[4 * c + 2]), qi = __uint_as_float(v[4 * c + 3]);
           const float re = pr - qi, im = pi + qr;
           ss_out = fmaf(re, re, ss_out);
           ss_out = fmaf(im, im, ss_out);
-          r[2 * nn] = re * g;
-          r[2 * nn + 1] = im * g;
-        }
-        if (!p.transpose) {
-          const uint32_t g = stg + ng * 8192u;
-#pragma unroll
-          for (uint32_t qq = 0; qq < 4; ++qq) {
-            const uint32_t a = g + swz32(i, 4u * w + qq);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r[4 * qq]), "f"(r[4 * qq + 1]), "f"(r[4 * qq + 2]),
-                         "f"(r[4 * qq + 3])
-                         : "memory");
-          }
-        } else {
-          const uint32_t g = stg + (i >> 4) * 8192u;
-          const uint32_t c16 = (i & 15u) >> 1, sub = (i & 1u) * 8u;
-#pragma unroll
-          for (uint32_t nn = 0; nn < 8; ++nn) {
-            const uint32_t n = 16u * ng + 8u * w + nn;
-            const uint32_t a = g + swz32(n, c16) + sub;
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(r[2 * nn]), "f"(r[2 * nn + 1]) : "memory");
-          }
+          const uint32_t n = 32u * half + 4u * c + (lane & 3u);
+          uint32_t a;
+          if (!p.transpose) a = stg + (n >> 4) * 8192u + swz32(i, (n & 15u) >> 1) + (n & 1u) * 8u;
+          else a = stg + (i >> 4) * 8192u + swz32(n, (i & 15u) >> 1) + (i & 1u) * 8u;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(re * g), "f"(im * g) : "memory");
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

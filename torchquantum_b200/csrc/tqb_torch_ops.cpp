@@ -1,0 +1,282 @@
+// torch.library registration of the libtqb200 C ABI (include/tqb200.h): namespace `tqb200`, one custom op per ABI entry
+// point, same argument order; device pointers become Tensors, host arrays become int[] / CPU tensors, the stream is
+// the current CUDA stream of the first tensor's device.  This file is the whole "thin C++ extension" north_star asks
+// for: it holds no arithmetic and no torch types cross into libtqb200.so, which stays a plain C ABI resolved with
+// dlopen/dlsym (so the reference-side stub in INTEGRATION.md can bind the same library without torch).
+//
+// What sits behind these ops in the reference: torchquantum/functional/gate_wrapper.py:324-446 (gate_wrapper ->
+// apply_unitary_bmm :96-140), the matrix builders of functional/*.py, torchquantum/measurement/measurements.py:37-343.
+//
+// Dispatch keys: CUDA -> the sm_100a library.  CPU -> ONLY the host emulation build that the test-suite injects with
+// tqb200::_bind(path, emulated=True); without it a CPU tensor raises (there is no CPU fallback).
+#include <ATen/ATen.h>
+#include <c10/cuda/CUDAStream.h>
+#include <dlfcn.h>
+#include <torch/library.h>
+
+#include <string>
+
+#include "../../include/tqb200.h"
+
+namespace {
+
+struct Abi {
+  void* handle = nullptr;
+  decltype(&tqb_abi_version) abi_version = nullptr;
+  decltype(&tqb_last_error) last_error = nullptr;
+  decltype(&tqb_build_mats) build_mats = nullptr;
+  decltype(&tqb_build_mats_bwd) build_mats_bwd = nullptr;
+  decltype(&tqb_pass_forward) pass_forward = nullptr;
+  decltype(&tqb_pass_backward) pass_backward = nullptr;
+  decltype(&tqb_apply_dense) apply_dense = nullptr;
+  decltype(&tqb_apply_dense_tc) apply_dense_tc = nullptr;
+  decltype(&tqb_block_build) block_build = nullptr;
+  decltype(&tqb_apply_blocks) apply_blocks = nullptr;
+  decltype(&tqb_dense_grad) dense_grad = nullptr;
+  decltype(&tqb_expval_pauli) expval_pauli = nullptr;
+  decltype(&tqb_expval_pauli_bwd) expval_pauli_bwd = nullptr;
+  decltype(&tqb_expval_z) expval_z = nullptr;
+  decltype(&tqb_expval_z_bwd) expval_z_bwd = nullptr;
+  decltype(&tqb_probs) probs = nullptr;
+  decltype(&tqb_sample_counts) sample_counts = nullptr;
+};
+
+Abi g_cuda, g_emu;
+
+template <class F>
+void resolve(void* h, const char* name, F& fn, bool required) {
+  fn = reinterpret_cast<F>(dlsym(h, name));
+  TORCH_CHECK(fn != nullptr || !required, "libtqb200: symbol ", name, " not found");
+}
+
+int64_t bind(const std::string& path, bool emulated) {
+  Abi& a = emulated ? g_emu : g_cuda;
+  if (path.empty()) {  // unbind (tests switch back to the CUDA library)
+    a = Abi();
+    return 0;
+  }
+  void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  TORCH_CHECK(h != nullptr, "libtqb200: cannot load ", path, ": ", dlerror());
+  Abi n;
+  n.handle = h;
+  resolve(h, "tqb_abi_version", n.abi_version, true);
+  resolve(h, "tqb_last_error", n.last_error, true);
+  resolve(h, "tqb_build_mats", n.build_mats, true);
+  resolve(h, "tqb_build_mats_bwd", n.build_mats_bwd, true);
+  resolve(h, "tqb_pass_forward", n.pass_forward, true);
+  resolve(h, "tqb_pass_backward", n.pass_backward, true);
+  resolve(h, "tqb_apply_dense", n.apply_dense, true);
+  resolve(h, "tqb_apply_dense_tc", n.apply_dense_tc, !emulated);
+  resolve(h, "tqb_block_build", n.block_build, true);
+  resolve(h, "tqb_apply_blocks", n.apply_blocks, true);
+  resolve(h, "tqb_dense_grad", n.dense_grad, true);
+  resolve(h, "tqb_expval_pauli", n.expval_pauli, true);
+  resolve(h, "tqb_expval_pauli_bwd", n.expval_pauli_bwd, true);
+  resolve(h, "tqb_expval_z", n.expval_z, true);
+  resolve(h, "tqb_expval_z_bwd", n.expval_z_bwd, true);
+  resolve(h, "tqb_probs", n.probs, true);
+  resolve(h, "tqb_sample_counts", n.sample_counts, true);
+  TORCH_CHECK(n.abi_version() == TQB_ABI_VERSION, "libtqb200: ABI version ", n.abi_version(), " != ", TQB_ABI_VERSION);
+  a = n;
+  return n.abi_version();
+}
+
+const Abi& abi_for(const at::Tensor& t) {
+  if (t.is_cuda()) {
+    TORCH_CHECK(g_cuda.handle != nullptr, "torchquantum_b200: the CUDA library libtqb200.so is not loaded (run "
+                                          "__graft_entry__.build()); there is no CPU fallback");
+    return g_cuda;
+  }
+  TORCH_CHECK(g_emu.handle != nullptr,
+              "torchquantum_b200 runs on CUDA (sm_100a) only: got a CPU tensor and there is no CPU fallback");
+  return g_emu;
+}
+
+void* stream_of(const at::Tensor& t) {
+  return t.is_cuda() ? static_cast<void*>(c10::cuda::getCurrentCUDAStream(t.device().index()).stream()) : nullptr;
+}
+
+void check(const Abi& a, int rc, const char* what) { TORCH_CHECK(rc == 0, what, " failed: ", a.last_error()); }
+
+const float* fp(const at::Tensor& t) {
+  TORCH_CHECK(t.is_contiguous(), "libtqb200 ops take contiguous tensors");
+  return static_cast<const float*>(t.data_ptr());
+}
+const float* fp(const c10::optional<at::Tensor>& t) { return t.has_value() && t->defined() ? fp(*t) : nullptr; }
+float* fpm(at::Tensor& t) {
+  TORCH_CHECK(t.is_contiguous(), "libtqb200 ops take contiguous tensors");
+  return static_cast<float*>(t.data_ptr());
+}
+const int32_t* ip(const at::Tensor& t) {
+  TORCH_CHECK(t.is_contiguous() && t.scalar_type() == at::kInt, "libtqb200: expected a contiguous int32 tensor");
+  return static_cast<const int32_t*>(t.data_ptr());
+}
+const unsigned long long* up(const at::Tensor& t) {
+  TORCH_CHECK(t.is_contiguous() && t.element_size() == 8, "libtqb200: expected a contiguous 64-bit mask tensor");
+  return static_cast<const unsigned long long*>(t.data_ptr());
+}
+
+void build_mats(const at::Tensor& table, int64_t n_records, int64_t n_shared, int64_t bsz,
+                const c10::optional<at::Tensor>& params_sh, const c10::optional<at::Tensor>& params_ps, int64_t ps_stride,
+                const c10::optional<at::Tensor>& consts, at::Tensor& msh, at::Tensor& mps, int64_t mps_stride) {
+  const Abi& a = abi_for(msh);
+  check(a, a.build_mats(ip(table), (int)n_records, (int)n_shared, bsz, fp(params_sh), fp(params_ps), (int)ps_stride, fp(consts),
+                        fpm(msh), fpm(mps), mps_stride, stream_of(msh)), "tqb_build_mats");
+}
+
+void build_mats_bwd(const at::Tensor& table, int64_t n_records, int64_t bsz, const c10::optional<at::Tensor>& params_sh,
+                    const c10::optional<at::Tensor>& params_ps, int64_t ps_stride, const at::Tensor& gr, int64_t gr_stride,
+                    at::Tensor& gsh_partial, int64_t sh_stride, at::Tensor& gps) {
+  const Abi& a = abi_for(gr);
+  check(a, a.build_mats_bwd(ip(table), (int)n_records, bsz, fp(params_sh), fp(params_ps), (int)ps_stride, fp(gr), gr_stride,
+                            fpm(gsh_partial), (int)sh_stride, fpm(gps), stream_of(gr)), "tqb_build_mats_bwd");
+}
+
+void pass_forward(const at::Tensor& src, at::Tensor& dst, int64_t n, int64_t bsz, const at::Tensor& prog, at::IntArrayRef desc,
+                  const at::Tensor& msh, const at::Tensor& mps, int64_t mps_stride, int64_t ext_hi) {
+  const Abi& a = abi_for(src);
+  TORCH_CHECK(desc.size() == 8, "tqb_pass_forward: desc holds 8 ints");
+  int d[8];
+  for (int i = 0; i < 8; ++i) d[i] = (int)desc[i];
+  check(a, a.pass_forward(fp(src), fpm(dst), (int)n, bsz, ip(prog), d, fp(msh), fp(mps), mps_stride, (unsigned)ext_hi,
+                          stream_of(src)), "tqb_pass_forward");
+}
+
+void pass_backward(const at::Tensor& psi_src, const at::Tensor& lam_src, at::Tensor& psi_dst, at::Tensor& lam_dst, int64_t n,
+                   int64_t bsz, const at::Tensor& prog, at::IntArrayRef desc, const at::Tensor& msh, const at::Tensor& mps,
+                   int64_t mps_stride, at::Tensor& gr, int64_t gr_stride, int64_t ext_hi) {
+  const Abi& a = abi_for(psi_src);
+  TORCH_CHECK(desc.size() == 8, "tqb_pass_backward: desc holds 8 ints");
+  int d[8];
+  for (int i = 0; i < 8; ++i) d[i] = (int)desc[i];
+  check(a, a.pass_backward(fp(psi_src), fp(lam_src), fpm(psi_dst), fpm(lam_dst), (int)n, bsz, ip(prog), d, fp(msh), fp(mps),
+                           mps_stride, fpm(gr), gr_stride, (unsigned)ext_hi, stream_of(psi_src)), "tqb_pass_backward");
+}
+
+void apply_dense(const at::Tensor& in, at::Tensor& out, int64_t n, int64_t bsz, const at::Tensor& mats, int64_t mat_stride,
+                 int64_t k, const at::Tensor& bitpos, int64_t conj_t) {
+  const Abi& a = abi_for(in);
+  check(a, a.apply_dense(fp(in), fpm(out), (int)n, bsz, fp(mats), mat_stride, (int)k, ip(bitpos), (int)conj_t, stream_of(in)),
+        "tqb_apply_dense");
+}
+
+void apply_dense_tc(const at::Tensor& in, at::Tensor& out, int64_t n, int64_t bsz, const at::Tensor& mat, int64_t k,
+                    at::IntArrayRef bitpos_host, int64_t conj_t) {
+  const Abi& a = abi_for(in);
+  TORCH_CHECK(a.apply_dense_tc != nullptr, "tqb_apply_dense_tc: not available in this build");
+  TORCH_CHECK((int64_t)bitpos_host.size() == k && k <= 16, "tqb_apply_dense_tc: bitpos holds k ints");
+  int b[16];
+  for (int64_t i = 0; i < k; ++i) b[i] = (int)bitpos_host[i];
+  check(a, a.apply_dense_tc(fp(in), fpm(out), (int)n, bsz, fp(mat), (int)k, b, (int)conj_t, stream_of(in)), "tqb_apply_dense_tc");
+}
+
+void block_build(const at::Tensor& blocks, int64_t n_blocks, const at::Tensor& ops, const at::Tensor& consts,
+                 const at::Tensor& params_sh, int64_t rank, at::Tensor& a_planes) {
+  const Abi& a = abi_for(a_planes);
+  check(a, a.block_build(ip(blocks), (int)n_blocks, ip(ops), fp(consts), fp(params_sh), (unsigned)rank, fpm(a_planes),
+                         stream_of(a_planes)), "tqb_block_build");
+}
+
+void apply_blocks(const at::Tensor& src, at::Tensor& dst, int64_t n, int64_t bsz, const at::Tensor& a_planes,
+                  const at::Tensor& blocks_host, int64_t n_blocks, int64_t renorm) {
+  const Abi& a = abi_for(src);
+  TORCH_CHECK(!blocks_host.is_cuda(), "tqb_apply_blocks: the block headers are read on the host");
+  check(a, a.apply_blocks(fp(src), fpm(dst), (int)n, bsz, fp(a_planes), ip(blocks_host), (int)n_blocks, (int)renorm,
+                          stream_of(src)), "tqb_apply_blocks");
+}
+
+void dense_grad(const at::Tensor& psi_in, const at::Tensor& lam_out, int64_t n, int64_t bsz, int64_t k, const at::Tensor& bitpos,
+                at::Tensor& G) {
+  const Abi& a = abi_for(psi_in);
+  check(a, a.dense_grad(fp(psi_in), fp(lam_out), (int)n, bsz, (int)k, ip(bitpos), fpm(G), stream_of(psi_in)), "tqb_dense_grad");
+}
+
+void expval_pauli(const at::Tensor& state, int64_t n, int64_t bsz, const at::Tensor& xm, const at::Tensor& zm, const at::Tensor& ny,
+                  int64_t n_terms, at::Tensor& out) {
+  const Abi& a = abi_for(state);
+  check(a, a.expval_pauli(fp(state), (int)n, bsz, up(xm), up(zm), ip(ny), (int)n_terms, fpm(out), stream_of(state)),
+        "tqb_expval_pauli");
+}
+
+void expval_pauli_bwd(const at::Tensor& state, int64_t n, int64_t bsz, const at::Tensor& xm, const at::Tensor& zm,
+                      const at::Tensor& ny, int64_t n_terms, const at::Tensor& grad_out, at::Tensor& grad_state) {
+  const Abi& a = abi_for(state);
+  check(a, a.expval_pauli_bwd(fp(state), (int)n, bsz, up(xm), up(zm), ip(ny), (int)n_terms, fp(grad_out), fpm(grad_state),
+                              stream_of(state)), "tqb_expval_pauli_bwd");
+}
+
+void expval_z(const at::Tensor& state, int64_t n, int64_t bsz, at::Tensor& out) {
+  const Abi& a = abi_for(state);
+  check(a, a.expval_z(fp(state), (int)n, bsz, fpm(out), stream_of(state)), "tqb_expval_z");
+}
+
+void expval_z_bwd(const at::Tensor& state, int64_t n, int64_t bsz, const at::Tensor& grad_out, at::Tensor& grad_state) {
+  const Abi& a = abi_for(state);
+  check(a, a.expval_z_bwd(fp(state), (int)n, bsz, fp(grad_out), fpm(grad_state), stream_of(state)), "tqb_expval_z_bwd");
+}
+
+void probs(const at::Tensor& state, int64_t n, int64_t bsz, at::Tensor& out) {
+  const Abi& a = abi_for(state);
+  check(a, a.probs(fp(state), (int)n, bsz, fpm(out), stream_of(state)), "tqb_probs");
+}
+
+void sample_counts(const at::Tensor& probs_t, int64_t n, int64_t bsz, const at::Tensor& uniforms, int64_t n_shots,
+                   at::Tensor& cdf_scratch, at::Tensor& counts) {
+  const Abi& a = abi_for(probs_t);
+  TORCH_CHECK(counts.is_contiguous() && counts.scalar_type() == at::kInt, "tqb_sample_counts: counts is int32");
+  check(a, a.sample_counts(fp(probs_t), (int)n, bsz, fp(uniforms), (int)n_shots, fpm(cdf_scratch),
+                           static_cast<int*>(counts.data_ptr()), stream_of(probs_t)), "tqb_sample_counts");
+}
+
+}  // namespace
+
+TORCH_LIBRARY(tqb200, m) {
+  m.def("_bind(str path, bool emulated) -> int", &bind);
+  m.def("tqb_build_mats(Tensor table, int n_records, int n_shared_records, int bsz, Tensor? params_sh, Tensor? params_ps, "
+        "int ps_stride, Tensor? consts, Tensor(a!) msh, Tensor(b!) mps, int mps_stride) -> ()");
+  m.def("tqb_build_mats_bwd(Tensor table, int n_records, int bsz, Tensor? params_sh, Tensor? params_ps, int ps_stride, "
+        "Tensor gr, int gr_stride, Tensor(a!) gparams_sh_partial, int sh_stride, Tensor(b!) gparams_ps) -> ()");
+  m.def("tqb_pass_forward(Tensor src, Tensor(a!) dst, int n_qubits, int bsz, Tensor prog, int[] desc, Tensor msh, Tensor mps, "
+        "int mps_stride, int ext_hi) -> ()");
+  m.def("tqb_pass_backward(Tensor psi_src, Tensor lam_src, Tensor(a!) psi_dst, Tensor(b!) lam_dst, int n_qubits, int bsz, "
+        "Tensor prog, int[] desc, Tensor msh, Tensor mps, int mps_stride, Tensor(c!) gr, int gr_stride, int ext_hi) -> ()");
+  m.def("tqb_apply_dense(Tensor src, Tensor(a!) dst, int n_qubits, int bsz, Tensor mats, int mat_stride_complex, int k, "
+        "Tensor bitpos, int conj_transpose) -> ()");
+  m.def("tqb_apply_dense_tc(Tensor src, Tensor(a!) dst, int n_qubits, int bsz, Tensor mat, int k, int[] bitpos_host, "
+        "int conj_transpose) -> ()");
+  m.def("tqb_block_build(Tensor blocks, int n_blocks, Tensor ops, Tensor consts, Tensor params_sh, int rank, "
+        "Tensor(a!) a_planes) -> ()");
+  m.def("tqb_apply_blocks(Tensor src, Tensor(a!) dst, int n_qubits, int bsz, Tensor a_planes, Tensor blocks_host, "
+        "int n_blocks, int renorm) -> ()");
+  m.def("tqb_dense_grad(Tensor psi_in, Tensor lam_out, int n_qubits, int bsz, int k, Tensor bitpos, Tensor(a!) G) -> ()");
+  m.def("tqb_expval_pauli(Tensor state, int n_qubits, int bsz, Tensor xmask, Tensor zmask, Tensor ny, int n_terms, "
+        "Tensor(a!) out) -> ()");
+  m.def("tqb_expval_pauli_bwd(Tensor state, int n_qubits, int bsz, Tensor xmask, Tensor zmask, Tensor ny, int n_terms, "
+        "Tensor grad_out, Tensor(a!) grad_state) -> ()");
+  m.def("tqb_expval_z(Tensor state, int n_qubits, int bsz, Tensor(a!) out) -> ()");
+  m.def("tqb_expval_z_bwd(Tensor state, int n_qubits, int bsz, Tensor grad_out, Tensor(a!) grad_state) -> ()");
+  m.def("tqb_probs(Tensor state, int n_qubits, int bsz, Tensor(a!) probs) -> ()");
+  m.def("tqb_sample_counts(Tensor probs, int n_qubits, int bsz, Tensor uniforms, int n_shots, Tensor(a!) cdf_scratch, "
+        "Tensor(b!) counts) -> ()");
+}
+
+#define TQB_IMPL_ALL(m)                                  \
+  m.impl("tqb_build_mats", &build_mats);                 \
+  m.impl("tqb_build_mats_bwd", &build_mats_bwd);         \
+  m.impl("tqb_pass_forward", &pass_forward);             \
+  m.impl("tqb_pass_backward", &pass_backward);           \
+  m.impl("tqb_apply_dense", &apply_dense);               \
+  m.impl("tqb_apply_dense_tc", &apply_dense_tc);         \
+  m.impl("tqb_block_build", &block_build);               \
+  m.impl("tqb_apply_blocks", &apply_blocks);             \
+  m.impl("tqb_dense_grad", &dense_grad);                 \
+  m.impl("tqb_expval_pauli", &expval_pauli);             \
+  m.impl("tqb_expval_pauli_bwd", &expval_pauli_bwd);     \
+  m.impl("tqb_expval_z", &expval_z);                     \
+  m.impl("tqb_expval_z_bwd", &expval_z_bwd);             \
+  m.impl("tqb_probs", &probs);                           \
+  m.impl("tqb_sample_counts", &sample_counts);
+
+TORCH_LIBRARY_IMPL(tqb200, CUDA, m) { TQB_IMPL_ALL(m) }
+// CPU key: reaches only the injected host-emulation build (tests); abi_for() raises otherwise
+TORCH_LIBRARY_IMPL(tqb200, CPU, m) { TQB_IMPL_ALL(m) }

@@ -5,6 +5,7 @@ are *queued* and run as fused passes when the state is read (`.states`, `get_sta
 measurement): the lazy queue is what lets many gates share one trip through HBM.
 The exposed `states` tensor is always contiguous `[bsz] + [2] * n_wires` complex64.
 """
+import weakref
 from typing import Union
 
 import numpy as np
@@ -31,15 +32,18 @@ class GateQueue(list):
 
     def __init__(self, owner):
         super().__init__()
-        self.owner, self.grad, self.guard = owner, torch.is_grad_enabled(), []
+        # weak: a device <-> queue cycle would keep a dropped device (its state, and the autograd graph behind it)
+        # alive until the cycle collector runs
+        self.owner, self.grad, self.guard = weakref.ref(owner), torch.is_grad_enabled(), []
 
     def _mode(self):
         g = torch.is_grad_enabled()
         if g != self.grad:
             if len(self):
-                self.owner.flush()
-                self.owner._queue._mode()
-                return self.owner._queue
+                owner = self.owner()
+                owner.flush()
+                owner._queue._mode()
+                return owner._queue
             self.grad = g
         return self
 

@@ -7,8 +7,6 @@ the backward, which un-applies the gates in reverse (tqb_pass_backward) while ac
 dL/dU, then maps dL/dU to dL/dtheta (tqb_build_mats_bwd): training memory is O(2^n) per sample
 instead of the reference's O(depth * 2^n) autograd tape.
 """
-import ctypes
-
 import numpy as np
 import torch
 
@@ -20,10 +18,6 @@ from . import plan as P
 _PLAN_CACHE = {}
 _DEV_CACHE = {}
 STATS = {"launches": 0, "plans_built": 0}
-
-
-def _ptr(t):
-    return 0 if t is None else t.data_ptr()
 
 
 def get_plan(n, key, grad_mode, n_total=None):
@@ -53,7 +47,7 @@ def _dev(obj, attr, device):
 
 def _desc(pp):
     if pp._desc_c is None:
-        pp._desc_c = (ctypes.c_int * 8)(*pp.desc)
+        pp._desc_c = [int(v) for v in pp.desc]
     return pp._desc_c
 
 
@@ -63,9 +57,8 @@ def _build_mats(stage, bsz, psh, pps, externs, device):
     if stage.table.shape[0]:
         table = _dev(stage, "table", device)
         consts = _dev(stage, "consts", device)
-        _native.call("tqb_build_mats", _ptr(table), table.shape[0], stage.n_sh_rec, bsz, _ptr(psh), _ptr(pps),
-                     pps.shape[1] if pps is not None else 0, _ptr(consts), _ptr(msh), _ptr(mps), stage.M_ps,
-                     _native.stream_ptr(msh))
+        _native.call("tqb_build_mats", table, table.shape[0], stage.n_sh_rec, bsz, psh, pps,
+                     pps.shape[1] if pps is not None else 0, consts, msh, mps, stage.M_ps)
         STATS["launches"] += 1
     for (rec, moff, dim, inverse, per_sample, goff), u in zip(stage.externs, externs):
         m = u.detach().to(torch.complex64)
@@ -93,11 +86,10 @@ def run_fused_inplace(state, stage, n, rank, psh, pps, externs):
     assert state.is_contiguous() and state.data_ptr() % 16 == 0
     bsz, dev = state.shape[0], state.device
     msh, mps = _build_mats(stage, bsz, psh, pps, externs, dev)
-    stream = _native.stream_ptr(state)
     for pp in stage.passes:
         prog = _dev(pp, "prog", dev)
-        _native.call("tqb_pass_forward", _ptr(state), _ptr(state), n, bsz, _ptr(prog), _desc(pp), _ptr(msh),
-                     _ptr(mps), stage.M_ps, _ext_hi(rank, n, pp), stream)
+        _native.call("tqb_pass_forward", state, state, n, bsz, prog, _desc(pp), msh,
+                     mps, stage.M_ps, _ext_hi(rank, n, pp))
         STATS["launches"] += 1
     return state
 
@@ -112,23 +104,22 @@ def run_blocks(state, stage, n, rank, psh, inplace, timing=None):
     if state.data_ptr() & 15:
         state, inplace = state.clone(), True
     bsz, dev = state.shape[0], state.device
-    stream = _native.stream_ptr(state)
     blocks_dev, ops_dev, consts = _dev(stage, "blocks", dev), _dev(stage, "ops", dev), _dev(stage, "consts", dev)
     planes = torch.empty(stage.n_blocks, 2, 128, 64, dtype=torch.float32, device=dev)
-    _native.call("tqb_block_build", _ptr(blocks_dev), stage.n_blocks, _ptr(ops_dev), _ptr(consts), _ptr(psh), rank,
-                 _ptr(planes), stream)
+    _native.call("tqb_block_build", blocks_dev, stage.n_blocks, ops_dev, consts, psh, rank,
+                 planes)
     out = state if inplace else torch.empty_like(state)
     if timing is not None:
         for b in range(stage.n_blocks):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _native.call("tqb_apply_blocks", _ptr(state if b == 0 else out), _ptr(out), n, bsz, _ptr(planes[b]),
-                         stage.blocks[b:].ctypes.data, 1, 1, stream)
+            _native.call("tqb_apply_blocks", state if b == 0 else out, out, n, bsz, planes[b],
+                         torch.from_numpy(stage.blocks[b:b + 1]), 1, 1)
             e1.record()
             timing.append((e0, e1))
     else:
-        _native.call("tqb_apply_blocks", _ptr(state), _ptr(out), n, bsz, _ptr(planes), stage.blocks.ctypes.data,
-                     stage.n_blocks, 1, stream)
+        _native.call("tqb_apply_blocks", state, out, n, bsz, planes, torch.from_numpy(stage.blocks),
+                     stage.n_blocks, 1)
     STATS["launches"] += 1 + stage.n_blocks
     return out
 
@@ -147,11 +138,10 @@ class FusedFn(torch.autograd.Function):
         msh, mps = _build_mats(stage, bsz, psh, pps, externs, dev)
         out = torch.empty_like(state)
         src = state
-        stream = _native.stream_ptr(state)
         for pp in stage.passes:
             prog = _dev(pp, "prog", dev)
-            _native.call("tqb_pass_forward", _ptr(src), _ptr(out), n, bsz, _ptr(prog), _desc(pp), _ptr(msh),
-                         _ptr(mps), stage.M_ps, _ext_hi(rank, n, pp), stream)
+            _native.call("tqb_pass_forward", src, out, n, bsz, prog, _desc(pp), msh,
+                         mps, stage.M_ps, _ext_hi(rank, n, pp))
             STATS["launches"] += 1
             src = out
         if not stage.passes:
@@ -175,11 +165,10 @@ class FusedFn(torch.autograd.Function):
         psi = torch.empty_like(psi0)
         lam = torch.empty_like(psi0)
         psrc, lsrc = psi0, grad_out
-        stream = _native.stream_ptr(psi0)
         for pp in reversed(stage.passes):
             prog = _dev(pp, "prog", dev)
-            _native.call("tqb_pass_backward", _ptr(psrc), _ptr(lsrc), _ptr(psi), _ptr(lam), n, bsz, _ptr(prog),
-                         _desc(pp), _ptr(msh), _ptr(mps), stage.M_ps, _ptr(gr), stage.G, _ext_hi(rank, n, pp), stream)
+            _native.call("tqb_pass_backward", psrc, lsrc, psi, lam, n, bsz, prog,
+                         _desc(pp), msh, mps, stage.M_ps, gr, stage.G, _ext_hi(rank, n, pp))
             STATS["launches"] += 1
             psrc, lsrc = psi, lam
         if not stage.passes:
@@ -189,9 +178,9 @@ class FusedFn(torch.autograd.Function):
             table = _dev(stage, "table", dev)
             gsh_part = torch.zeros(bsz, max(stage.P_sh, 1), dtype=torch.float32, device=dev)
             gps_full = torch.zeros(bsz, max(stage.P_ps, 1), dtype=torch.float32, device=dev)
-            _native.call("tqb_build_mats_bwd", _ptr(table), table.shape[0], bsz, _ptr(psh), _ptr(pps),
-                         pps.shape[1], _ptr(gr), stage.G, _ptr(gsh_part), gsh_part.shape[1],
-                         _ptr(gps_full), stream)
+            _native.call("tqb_build_mats_bwd", table, table.shape[0], bsz, psh, pps,
+                         pps.shape[1], gr, stage.G, gsh_part, gsh_part.shape[1],
+                         gps_full)
             STATS["launches"] += 1
             if stage.P_sh and ctx.needs_input_grad[1]:
                 gsh = gsh_part.sum(0)
@@ -217,13 +206,12 @@ DENSE_TC = True   # tensor-core (3xTF32) dense kernel for one shared matrix on 4
 
 def _dense_apply(src, dst, n, bsz, m, k, bitpos, bp_dev, conj_t):
     """dst = U src (or U^H src) for the k-qubit matrix m on bit positions `bitpos` (matrix MSB first)."""
-    stream = _native.stream_ptr(src)
     if DENSE_TC and m.dim() == 2 and 4 <= k <= 7 and n >= 12 and not _native.is_emulated():
-        host = (ctypes.c_int * k)(*[int(b) for b in bitpos])
-        _native.call("tqb_apply_dense_tc", _ptr(src), _ptr(dst), n, bsz, _ptr(m), k, host, 1 if conj_t else 0, stream)
+        host = [int(b) for b in bitpos]
+        _native.call("tqb_apply_dense_tc", src, dst, n, bsz, m, k, host, 1 if conj_t else 0)
     else:
-        _native.call("tqb_apply_dense", _ptr(src), _ptr(dst), n, bsz, _ptr(m), (4 ** k) if m.dim() == 3 else 0,
-                     k, _ptr(bp_dev), 1 if conj_t else 0, stream)
+        _native.call("tqb_apply_dense", src, dst, n, bsz, m, (4 ** k) if m.dim() == 3 else 0,
+                     k, bp_dev, 1 if conj_t else 0)
     STATS["launches"] += 1
 
 
@@ -250,14 +238,13 @@ class DenseFn(torch.autograd.Function):
         n, inverse, k = ctx.n, ctx.inverse, ctx.k
         bsz = state.shape[0]
         grad_out = grad_out.contiguous()
-        stream = _native.stream_ptr(state)
         gstate = gmat = None
         if ctx.needs_input_grad[0]:
             gstate = torch.empty_like(state)
             _dense_apply(grad_out, gstate, n, bsz, m, k, ctx.bitpos, bp, not inverse)
         if ctx.needs_input_grad[1]:
             g = torch.empty(bsz, 2 ** k, 2 ** k, dtype=torch.complex64, device=state.device)
-            _native.call("tqb_dense_grad", _ptr(state), _ptr(grad_out), n, bsz, k, _ptr(bp), _ptr(g), stream)
+            _native.call("tqb_dense_grad", state, grad_out, n, bsz, k, bp, g)
             STATS["launches"] += 1
             if inverse:
                 g = g.conj().transpose(-1, -2)

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .engine import STATS, _ptr
+from .engine import STATS
 
 __all__ = ["expval_joint_analytical", "expval_joint_analytical_multi", "expval", "measure", "gen_bitstrings",
            "expval_joint_sampling", "expval_joint_sampling_grouping", "find_observable_groups"]
@@ -96,8 +96,8 @@ class _StateHubFn(torch.autograd.Function):
         xm, zm, ny = _mask_tensors(obs, state.device)
         gout = (gouts[0] if len(gouts) == 1 else torch.cat(gouts, dim=1)).contiguous()
         grad = torch.empty_like(state)
-        _native.call("tqb_expval_pauli_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(xm), _ptr(zm), _ptr(ny),
-                     xm.shape[0], _ptr(gout), _ptr(grad), _native.stream_ptr(state))
+        _native.call("tqb_expval_pauli_bwd", state, ctx.n, state.shape[0], xm, zm, ny,
+                     xm.shape[0], gout, grad)
         STATS["launches"] += 1
         if g is not None:
             grad += g
@@ -108,8 +108,7 @@ def _launch_expval(state, n, xm, zm, ny):
     bsz, nt = state.shape[0], xm.shape[0]
     # blocks of one sample accumulate atomically only when the state spans several chunks (n > 12)
     out = (torch.zeros if n > 12 else torch.empty)(bsz, nt, dtype=torch.float32, device=state.device)
-    _native.call("tqb_expval_pauli", _ptr(state), n, bsz, _ptr(xm), _ptr(zm), _ptr(ny), nt, _ptr(out),
-                 _native.stream_ptr(state))
+    _native.call("tqb_expval_pauli", state, n, bsz, xm, zm, ny, nt, out)
     STATS["launches"] += 1
     return out
 
@@ -134,8 +133,8 @@ class _ExpvalPauliFn(torch.autograd.Function):
         state, xm, zm, ny = ctx.saved_tensors
         gout = gout.contiguous()
         grad = torch.empty_like(state)
-        _native.call("tqb_expval_pauli_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(xm), _ptr(zm), _ptr(ny),
-                     xm.shape[0], _ptr(gout), _ptr(grad), _native.stream_ptr(state))
+        _native.call("tqb_expval_pauli_bwd", state, ctx.n, state.shape[0], xm, zm, ny,
+                     xm.shape[0], gout, grad)
         STATS["launches"] += 1
         return grad, None, None, None, None, None, None, None
 
@@ -157,7 +156,7 @@ class _ExpvalZFn(torch.autograd.Function):
         state = state.contiguous()
         bsz = state.shape[0]
         out = (torch.zeros if n > 12 else torch.empty)(bsz, n + 1, dtype=torch.float32, device=state.device)
-        _native.call("tqb_expval_z", _ptr(state), n, bsz, _ptr(out), _native.stream_ptr(state))
+        _native.call("tqb_expval_z", state, n, bsz, out)
         STATS["launches"] += 1
         ctx.save_for_backward(state)
         ctx.n = n
@@ -168,8 +167,7 @@ class _ExpvalZFn(torch.autograd.Function):
         (state,) = ctx.saved_tensors
         gout = gout.contiguous()
         grad = torch.empty_like(state)
-        _native.call("tqb_expval_z_bwd", _ptr(state), ctx.n, state.shape[0], _ptr(gout), _ptr(grad),
-                     _native.stream_ptr(state))
+        _native.call("tqb_expval_z_bwd", state, ctx.n, state.shape[0], gout, grad)
         STATS["launches"] += 1
         return grad, None
 
@@ -282,16 +280,15 @@ def measure(qdev, n_shots=1024, draw_id=None):
     _native.check_device(states)
     bsz, N = states.shape
     dev = states.device
-    stream = _native.stream_ptr(states)
     probs = torch.empty(bsz, N, dtype=torch.float32, device=dev)
-    _native.call("tqb_probs", _ptr(states), n, bsz, _ptr(probs), stream)
+    _native.call("tqb_probs", states, n, bsz, probs)
     # one random.random() per (sample, shot), in the reference's order; float32(u) is what NumPy 2
     # promotes to when multiplying by the float32 total
     u = np.array([random.random() for _ in range(bsz * n_shots)], dtype=np.float64).astype(np.float32)
     u_dev = torch.from_numpy(u).to(dev)
     cdf = torch.empty(bsz, N, dtype=torch.float32, device=dev)
     counts = torch.zeros(bsz, N, dtype=torch.int32, device=dev)
-    _native.call("tqb_sample_counts", _ptr(probs), n, bsz, _ptr(u_dev), n_shots, _ptr(cdf), _ptr(counts), stream)
+    _native.call("tqb_sample_counts", probs, n, bsz, u_dev, n_shots, cdf, counts)
     STATS["launches"] += 3
     counts = counts.cpu().numpy()
     keys = gen_bitstrings(n)

@@ -29,7 +29,7 @@ import torch.distributed as dist
 
 from . import _native, engine
 from . import gates as G
-from .engine import STATS, _ptr
+from .engine import STATS
 from .macro import C_DTYPE
 
 __all__ = ["ShardedQuantumDevice"]
@@ -405,8 +405,8 @@ class ShardedQuantumDevice:
         state = self._flat
         _native.check_device(state)
         out = torch.zeros(self.bsz, len(observables), dtype=torch.float32, device=dev)
-        _native.call("tqb_expval_pauli", _ptr(state), nl, self.bsz, _ptr(xm), _ptr(zm), _ptr(ny), len(observables),
-                     _ptr(out), _native.stream_ptr(state))
+        _native.call("tqb_expval_pauli", state, nl, self.bsz, xm, zm, ny, len(observables),
+                     out)
         STATS["launches"] += 1
         return out * torch.tensor(signs, dtype=torch.float32, device=dev)
 
@@ -417,7 +417,7 @@ class ShardedQuantumDevice:
         state = self._flat
         dev = state.device
         loc = torch.zeros(self.bsz, nl + 1, dtype=torch.float32, device=dev)
-        _native.call("tqb_expval_z", _ptr(state), nl, self.bsz, _ptr(loc), _native.stream_ptr(state))
+        _native.call("tqb_expval_z", state, nl, self.bsz, loc)
         STATS["launches"] += 1
         out = torch.empty(self.bsz, n + 1, dtype=torch.float32, device=dev)
         norm = loc[:, nl]
