@@ -278,14 +278,18 @@ def check_cfg3_qaoa(device, n=8, p=3, bsz=4, edges=QAOA_EDGES_8):
     apply_ops(q, circuit(bd, gd), device)
     cost = sum(0.5 * expval_joint_analytical(q, zz(i, j)) for (i, j) in edges)
     bc, gc = betas.clone().requires_grad_(True), gammas.clone().requires_grad_(True)
-    st = O.run_ops(n, bsz, circuit(bc, gc))
-    assert_close(q.get_states_1d(), st, what="cfg3 states")
     if n <= 12:
+        st = O.run_ops(n, bsz, circuit(bc, gc))
         cost_cpu = sum(0.5 * O.expval_joint_analytical(st, zz(i, j)) for (i, j) in edges)
     else:
-        # the oracle's dense Kronecker observable is O(4^n) memory (34 GB at n=16): use its rotated-basis form
-        # (measurements.py:123-229 restated, all-Z strings need no rotation)
-        cost_cpu = sum(0.5 * O.expval_joint_rotated(st, zz(i, j)) for (i, j) in edges)
+        # Beyond n = 12 the oracle's dense Kronecker observable is O(4^n) memory, and at several hundred gates two
+        # float32 computations (the reference's and ours) each carry ~5e-6 of their own rounding, so they cannot be
+        # compared to 1e-5 with each other: both are held against the float64 twin of the oracle instead
+        # (oracle/tq_oracle64.py; rotated-basis read-out, measurements.py:123-229 restated)
+        from oracle.tq_oracle64 import O64, run_ops64
+        st = run_ops64(n, bsz, circuit(bc, gc), keep_graph=True)
+        cost_cpu = sum(0.5 * O64.expval_joint_rotated(st, zz(i, j)) for (i, j) in edges)
+    assert_close(q.get_states_1d(), st, what="cfg3 states")
     assert_close(cost, cost_cpu, rtol=GRAD_RTOL, what="cfg3 cost")
     gb, gg = torch.autograd.grad(cost.sum(), [bd, gd])
     gbc, ggc = torch.autograd.grad(cost_cpu.sum(), [bc, gc])
@@ -517,7 +521,10 @@ def check_op_hamil_exp(device):
     q2 = tq.QuantumDevice(n_wires=2, device=device, record_op=True)
     pe(q2, wires=[1, 0])
     assert_close(q2.get_states_1d(), want[:1], what="OpPauliExp state")
-    assert q2.op_history[-2]["name"] == "OpPauliExp" and q2.op_history[-2]["paulis"] == ["ZZ", "XX"]
+    # ONE history entry per gate (the reference also records the qubitunitaryfast it queues, which replays the gate
+    # twice through from_op_history; see torchquantum_b200/op_hamil_exp.py)
+    assert len(q2.op_history) == 1
+    assert q2.op_history[-1]["name"] == "OpPauliExp" and q2.op_history[-1]["paulis"] == ["ZZ", "XX"]
 
 
 def depth_parity(device, n, depth, mode, seed=5, oracle_device=None, blocks=None):

@@ -20,6 +20,7 @@ from .layer import *  # noqa: F401,F403
 from .graphs import GraphedStep  # noqa: F401
 from .algorithm import Hamiltonian, VQE  # noqa: F401
 from .op_hamil_exp import OpHamilExp, OpPauliExp  # noqa: F401
+from .gradients import parameter_shift_gradient, hadamard_grad  # noqa: F401
 
 operator.OpHamilExp, operator.OpPauliExp = OpHamilExp, OpPauliExp   # reference location: torchquantum.operator
 

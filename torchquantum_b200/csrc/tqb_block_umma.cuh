@@ -9,31 +9,39 @@
 // other bits.  With A[2i+w][j] = (w ? Im : Re) U[i][j]  (128 x 64, real) and S[j][(n,c)] the tile as a real
 // 64 x 128 matrix,  D = A * S  is ONE tensor-core GEMM  M=128 (TMEM lanes), N=128, K=64;  lanes 2i / 2i+1 hold
 // P = Re(U) S and Q = Im(U) S of output pattern i, and  out[i][n] = (P_re - Q_im) + i (P_im + Q_re)  is formed by the
-// epilogue from a lane-pair shuffle.  fp32 accuracy comes from the 3xTF32 split: A = Ah + Al, S = Sh + Sl (each part
+// epilogue (the TMEM lanes are permuted so that both land in one thread).  fp32 accuracy comes from the 3xTF32 split: A = Ah + Al, S = Sh + Sl (each part
 // rounded to TF32 with cvt.rna), D = Ah Sh + Ah Sl + Al Sh, accumulated in fp32 in TMEM.
 //
-// Data path per tile (persistent CTA, one per SM, 12 warps):
-//   TMA (cp.async.bulk.tensor.5d, SWIZZLE_128B_ATOM_32B) loads the raw tile straight into the MN-major UMMA operand
-//   layout [n/16][j][16 amplitudes] (the tensor map's dims: 32 floats, 128-byte rows of the whole state, then the
-//   <= 3 runs of contiguous block bits)  ->  4 splitter warps turn it in place into Sh and write Sl beside it  ->
-//   one thread issues 24 tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory) into one of two TMEM
-//   accumulators  ->  4 epilogue warps tcgen05.ld it, combine lane pairs and write the finished tile to a staging
-//   buffer in the same layout  ->  TMA store.  `transpose` writes the tile with the roles of the block bits and
-//   the low bits exchanged (pattern i goes to index bits 0-5, n to kpos), which is how the planner rotates
-//   qubits out of the low index bits without a pass of its own.
-// 3 operand stages (64 KiB each) + 32 KiB staging = 224 KiB of shared memory; TMEM: A 128 + D 2 x 128 columns.
+// Data path per tile (persistent CTA, one per SM, 12 warps; every hand-off is an mbarrier):
+//   warp 0  TMA (cp.async.bulk.tensor.5d, SWIZZLE_128B_ATOM_32B) loads the raw tile straight into the MN-major UMMA
+//           operand layout [n/16][j][16 amplitudes] (the tensor map's dims: 32 floats, 128-byte rows of the whole state,
+//           then the <= 3 runs of contiguous block bits) into one of 4 "hi" planes: up to 4 tiles in flight;
+//   warps 8-11  split it: TF32 hi part in place, TF32 lo part into one of 3 "lo" planes (integer rounding, 2 instructions);
+//   warp 1  one thread issues 24 tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory) into one of 3 TMEM
+//           accumulators; the commit frees the hi plane for the next load;
+//   warps 4-7  epilogue: tcgen05.ld.16x256b (P and Q of one output pattern arrive in the same thread, no shuffles),
+//           out = P + iQ, rescale, written in the tensor map's layout INTO THE TILE'S OWN LO PLANE (its MMAs are done);
+//   warp 3  issues the TMA store of that plane and frees it as soon as the store engine has read it.
+//   `transpose` writes the tile with the roles of the block bits and the low bits exchanged (pattern i goes to index
+//   bits 0-5, n to kpos), which is how the planner rotates qubits out of the low index bits without a pass of its own.
+// 7 planes of 32 KiB = 224 KiB of shared memory; TMEM: A 128 + D 3 x 128 columns.
+// What the ablation runs showed (profiles/r02_block6_ablation.txt): with one staging buffer the epilogue's arithmetic and
+// the store's read-out of that buffer serialised (0.92 ms per pass at n = 28, 0.72 ms with either removed); the tile's own
+// lo plane as staging plus the dedicated store warp take the store off the epilogue's path.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace tqb_umma {
 
-constexpr int kStages = 3;
+constexpr uint32_t kHi = 4;                     // raw / hi planes: tiles in flight between TMA load and the end of their MMAs
+constexpr uint32_t kLo = 3;                     // lo planes, reused as the tile's output staging until the TMA store has read it
+constexpr uint32_t kAcc = 3;                    // TMEM accumulators (128 columns each)
 constexpr int kThreads = 384;
 constexpr uint32_t kPlane = 32768;              // bytes of one operand plane (hi or lo) of a tile
-constexpr uint32_t kStageBytes = 2 * kPlane;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + kPlane + 1024 /* alignment slack */ + 512 /* barriers, norms */;
+constexpr uint32_t kSmemBytes = (kHi + kLo) * kPlane + 1024 /* alignment slack */ + 512 /* barriers, norms */;
 constexpr uint32_t kTmemCols = 512;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A K-major (TMEM), B MN-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -42,6 +50,7 @@ struct Params {
   const float* a_planes;   // [2][128][64]: TF32-rounded hi plane, lo plane of A
   uint32_t n_tiles;
   int transpose;
+  int debug;               // TQB200_BLOCK_DEBUG bit mask (timing experiments only): 1 no split, 2 8 MMAs, 4 no epilogue math, 8 no store
   int renorm;              // block is unitary: rescale every tile to the norm it came in with (see the epilogue)
   int nseg;                // outer (non-tile) index bits as <= 4 runs: bits [lo, lo+len) of the tile id go to bit pos
   int seg_lo[4], seg_len[4], seg_pos[4];
@@ -174,23 +183,29 @@ __global__ void __launch_bounds__(kThreads, 1)
 tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stg = base + kStages * kStageBytes;          // epilogue staging tile
-  const uint32_t bars = stg + kPlane;
-  // barrier slots (8 bytes each): full[3] ready[3] empty[3] dfull[2] dempty[2]; then the TMEM base address
-  auto full = [&](int s) { return bars + 8u * s; };
-  auto ready = [&](int s) { return bars + 8u * (3 + s); };
-  auto empty = [&](int s) { return bars + 8u * (6 + s); };
-  auto dfull = [&](int d) { return bars + 8u * (9 + d); };
-  auto dempty = [&](int d) { return bars + 8u * (11 + d); };
-  const uint32_t tmem_slot = bars + 8u * 13;
-  const uint32_t nin_slot = bars + 128u;    // [8 tiles in flight][4 splitter warps] squared norms of the raw tile
-  const uint32_t nout_slot = bars + 256u;   // [4 epilogue warps] squared norms of the computed tile
+  // buffer rings (32 KiB planes): kHi planes that receive the raw tile and become its TF32 hi part in place, kLo planes
+  // that hold the TF32 lo part and, once the MMAs of the tile are done, the finished tile on its way to the TMA store
+  auto hi_plane = [&](uint32_t k) { return base + k * kPlane; };
+  auto lo_plane = [&](uint32_t k) { return base + (kHi + k) * kPlane; };
+  const uint32_t bars = base + (kHi + kLo) * kPlane;
+  // barrier slots (8 bytes each); then the TMEM base address
+  auto full = [&](uint32_t k) { return bars + 8u * k; };                            // [kHi] raw tile landed (TMA tx)
+  auto ready = [&](uint32_t k) { return bars + 8u * (kHi + k); };                   // [kHi] hi / lo parts written (128 splitters)
+  auto empty = [&](uint32_t k) { return bars + 8u * (2 * kHi + k); };               // [kHi] MMAs of the tile done: hi plane free
+  auto dfull = [&](uint32_t d) { return bars + 8u * (3 * kHi + d); };               // [kAcc] accumulator complete
+  auto dempty = [&](uint32_t d) { return bars + 8u * (3 * kHi + kAcc + d); };       // [kAcc] accumulator read out (128 threads)
+  auto outready = [&](uint32_t k) { return bars + 8u * (3 * kHi + 2 * kAcc + k); }; // [kLo] finished tile staged in the lo plane
+  auto stored = [&](uint32_t k) { return bars + 8u * (3 * kHi + 2 * kAcc + kLo + k); };  // [kLo] TMA store has read it: lo plane free
+  const uint32_t tmem_slot = bars + 8u * (3 * kHi + 2 * kAcc + 2 * kLo);
+  const uint32_t nin_slot = bars + 256u;    // [8 tiles in flight][4 splitter warps] squared norms of the raw tile
+  const uint32_t nout_slot = bars + 384u;   // [2][4 epilogue warps] squared norms of the computed tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), 128); mbar_init(empty(s), 1); }
-    for (int d = 0; d < 2; ++d) { mbar_init(dfull(d), 1); mbar_init(dempty(d), 128); }
+    for (uint32_t k = 0; k < kHi; ++k) { mbar_init(full(k), 1); mbar_init(ready(k), 128); mbar_init(empty(k), 1); }
+    for (uint32_t d = 0; d < kAcc; ++d) { mbar_init(dfull(d), 1); mbar_init(dempty(d), 128); }
+    for (uint32_t k = 0; k < kLo; ++k) { mbar_init(outready(k), 1); mbar_init(stored(k), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_src) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dst) : "memory");
@@ -233,18 +248,16 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   if (warp == 0) {
-    // ---------------- TMA producer ----------------
+    // ---------------- TMA producer: up to kHi raw tiles in flight ----------------
     if (lane == 0) {
       uint32_t it = 0;
       for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
-        mbar_wait(empty(s), ph ^ 1u);
-        mbar_expect_tx(full(s), kPlane);
+        const uint32_t k = it % kHi, ph = (it / kHi) & 1u;
+        mbar_wait(empty(k), ph ^ 1u);
+        mbar_expect_tx(full(k), kPlane);
         const uint32_t row = tile_row(p, t);
-        const uint32_t dst = base + s * kStageBytes;
 #pragma unroll
-        for (int ng = 0; ng < 4; ++ng) tma_load_5d(dst + ng * 8192u, &tm_src, full(s), 0, (int)(row + ng), 0, 0, 0);
+        for (int ng = 0; ng < 4; ++ng) tma_load_5d(hi_plane(k) + ng * 8192u, &tm_src, full(k), 0, (int)(row + ng), 0, 0, 0);
       }
     }
   } else if (warp == 1) {
@@ -252,37 +265,56 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
     if (lane == 0) {
       uint32_t it = 0;
       for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-        const int s = it % kStages, d = it & 1;
-        const uint32_t ph = (it / kStages) & 1u, dph = (it >> 1) & 1u;
-        mbar_wait(ready(s), ph);
-        mbar_wait(dempty(d), dph ^ 1u);
+        const uint32_t k = it % kHi, l = it % kLo, d = it % kAcc;
+        mbar_wait(ready(k), (it / kHi) & 1u);
+        mbar_wait(dempty(d), ((it / kAcc) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t bh = base + s * kStageBytes, bl = bh + kPlane;
+        const uint32_t bh = hi_plane(k), bl = lo_plane(l);
         const uint32_t dt = t_d0 + 128u * d;
         // the two correction products first: the accumulator is still 2^-11 of its final size while they are added, so
         // the tensor core's truncating fp32 accumulation costs 8 full-size roundings per tile instead of 24
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_alo + 8u * ks, b_desc(bh + ks * 1024u), ks > 0);
+        if (!(p.debug & 2)) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bl + ks * 1024u), 1u);
+          for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bl + ks * 1024u), 1u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bh + ks * 1024u), 1u);
-        umma_commit(empty(s));
+          for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bh + ks * 1024u), 1u);
+        }
+        umma_commit(empty(k));
         umma_commit(dfull(d));
       }
+    }
+  } else if (warp == 3) {
+    // ---------------- TMA store issuer: frees a lo plane as soon as the store engine has read it ----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const uint32_t l = it % kLo;
+        mbar_wait(outready(l), (it / kLo) & 1u);
+        if (!(p.debug & 8)) {
+          const uint32_t row = tile_row(p, t);
+#pragma unroll
+          for (int ng = 0; ng < 4; ++ng) tma_store_5d(&tm_dst, lo_plane(l) + ng * 8192u, 0, (int)(row + ng), 0, 0, 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        mbar_arrive(stored(l));
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= 8) {
     // ---------------- splitters: raw fp32 -> TF32 hi (in place) + TF32 lo ----------------
     const int tid = threadIdx.x - 256;
     uint32_t it = 0;
     for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-      const int s = it % kStages;
-      const uint32_t ph = (it / kStages) & 1u;
-      mbar_wait(full(s), ph);
-      const uint32_t bh = base + s * kStageBytes + 16u * tid;
+      const uint32_t k = it % kHi, l = it % kLo;
+      mbar_wait(full(k), (it / kHi) & 1u);
+      mbar_wait(stored(l), ((it / kLo) & 1u) ^ 1u);   // the tile that used this lo plane last has left it
+      const uint32_t bh = hi_plane(k) + 16u * tid, bl = lo_plane(l) + 16u * tid;
       float ss = 0.f;
 #pragma unroll 4
-      for (int v = 0; v < 16; ++v) {
+      for (int v = 0; v < ((p.debug & 1) ? 0 : 16); ++v) {
         const uint32_t a = bh + 2048u * v;
         float x0, x1, x2, x3;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(a) : "memory");
@@ -291,7 +323,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         const uint32_t l0 = tf32_rna(x0 - __uint_as_float(h0)), l1 = tf32_rna(x1 - __uint_as_float(h1));
         const uint32_t l2 = tf32_rna(x2 - __uint_as_float(h2)), l3 = tf32_rna(x3 - __uint_as_float(h3));
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + kPlane), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bl + 2048u * v), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
       }
       if (p.renorm) {
 #pragma unroll
@@ -299,7 +331,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(nin_slot + 4u * (4u * (it & 7u) + (uint32_t)(warp - 8))), "f"(ss) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(ready(s));
+      mbar_arrive(ready(k));
     }
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
@@ -311,15 +343,13 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
     // previous tile's value keeps the epilogue single-pass).
     float g = 1.f;
     for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
-      const int d = it & 1;
-      const uint32_t dph = (it >> 1) & 1u;
+      const uint32_t d = it % kAcc, l = it % kLo;
+      const uint32_t stg = lo_plane(l);   // the tile's own lo plane: its MMAs are done (dfull), nobody else touches it
       float ss_out = 0.f;
-      mbar_wait(dfull(d), dph);
+      mbar_wait(dfull(d), (it / kAcc) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-      for (uint32_t ld = 0; ld < 4; ++ld) {
+      for (uint32_t ld = 0; ld < ((p.debug & 4) ? 0u : 4u); ++ld) {
         // 16 accumulator lanes (8 output patterns, P and Q) x 64 columns (32 amplitudes) per load
         const uint32_t h = ld >> 1, half = ld & 1u;
         const uint32_t i = 16u * q + 8u * h + (lane >> 2);   // output pattern of this thread
@@ -346,27 +376,21 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       if (p.renorm) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss_out += __shfl_xor_sync(0xffffffffu, ss_out, o);
-        if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(nout_slot + 4u * (uint32_t)q), "f"(ss_out) : "memory");
+        if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(nout_slot + 16u * (it & 1u) + 4u * (uint32_t)q), "f"(ss_out) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) mbar_arrive(outready(l));
       if (p.renorm) {
         float4 a, b;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(nin_slot + 16u * (it & 7u)) : "memory");
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(nout_slot) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(nout_slot + 16u * (it & 1u)) : "memory");   // (two slots: a warp may write tile t + 1 while another still reads t)
         const float sin2 = (a.x + a.y) + (a.z + a.w), sout2 = (b.x + b.y) + (b.z + b.w);
         float gn = 1.f;
         if (sout2 > 0.f && sin2 > 0.f) gn = sqrtf(sin2 / sout2);
         g = fabsf(gn - 1.f) < 1e-4f ? gn : 1.f;
       }
-      if (et == 0) {
-        const uint32_t row = tile_row(p, t);
-#pragma unroll
-        for (int ng = 0; ng < 4; ++ng) tma_store_5d(&tm_dst, stg + ng * 8192u, 0, (int)(row + ng), 0, 0, 0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
     }
-    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -461,6 +485,9 @@ inline const char* launch_block6(const float* src, float* dst, int n_qubits, lon
   p.a_planes = a_planes;
   p.transpose = transpose;
   p.renorm = renorm;
+  static int debug = -1;
+  if (debug < 0) { const char* e = getenv("TQB200_BLOCK_DEBUG"); debug = e ? atoi(e) : 0; }
+  p.debug = debug;
   const unsigned long long tiles = ((unsigned long long)bsz << n_qubits) >> 12;
   if (tiles > 0xffffffffull) return "too many tiles";
   p.n_tiles = (uint32_t)tiles;

@@ -431,7 +431,8 @@ class QubitUnitaryFast(Operation, metaclass=ABCMeta):
         n_c = len(wires)
         t_flat = [t_wires.item()] if t_wires.ndim == 0 else [int(w) for w in t_wires.flatten()]
         wires += t_flat
-        n_sets = max(len(t_flat) // op.n_wires, 1)
+        # (the operator's own n_wires may be None for fixed gates such as tq.PauliX(): its matrix tells the arity)
+        n_sets = max(len(t_flat) // int(np.log2(orig_u.shape[-1])), 1)
         block = orig_u
         for _ in range(n_sets - 1):
             block = torch.kron(block, orig_u)
