@@ -222,6 +222,38 @@ def gate_pass_roofline(dev, n=28, layers=16):
                     "issue-bound beyond (sweep)"}
 
 
+def sharded_configs(dev, world, rank):
+    """N > 1 only, after the headline measurement: the two multi-GPU configs BASELINE.json names, each with its own
+    correctness check, so that the driver's scaling run carries them (tools/configs.py holds the workloads).
+      cfg 3: 20-qubit QAOA p=8, 64 circuits in total, batch-sharded (strong scaling, no data-path collective);
+      cfg 5: QFT + 4 brickwork layers on a statevector of 31 + log2(N) qubits sharded over the N GPUs (32 qubits on 2,
+             33 on 4, 34 on 8: 16 GiB per GPU), global <-> local qubit exchanges timed against the NVLink peak."""
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import configs
+
+    out = {}
+    try:
+        r3 = configs.run_cfg3(dev, bsz=max(64 // world, 1))
+        t = torch.tensor([r3["fwd_ms"], r3["fwd_bwd_ms"], 0.0 if r3["ok"] else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["cfg3"] = {"workload": r3["workload"] + f" per rank: 64 circuits in total, batch-sharded over {world} B200",
+                       "scaling": "strong", "fwd_ms": round(t[0].item(), 3), "fwd_bwd_ms": round(t[1].item(), 3),
+                       "circuits_per_s_fwd_bwd": round(64 / (t[1].item() * 1e-3), 1), "ok": t[2].item() == 0.0,
+                       "oracle64_parity_rank0": r3["oracle64_parity"], "max_norm_err_rank0": r3["max_norm_err"]}
+    except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+        out["cfg3"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    try:
+        g = int(np.log2(world))
+        out["cfg5"] = configs.run_cfg5(dev, 31 + g)
+    except Exception as e:  # noqa: BLE001
+        out["cfg5"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference_step(bsz, threads):
     """One fwd+bwd of the config-2 workload on the CPU oracle port (torch on the host cores)."""
     from oracle import tq_oracle as O
@@ -378,6 +410,7 @@ def run_ours(args):
     e2e_step_ms, e2e_wall_ms = timed(graphed_step, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     launches = launches_per_step * args.steps
+    sharded = sharded_configs(dev, world, rank) if world > 1 and not args.no_sharded_configs else None
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -409,6 +442,8 @@ def run_ours(args):
         "device_ms_per_step": round(step_ms, 4), "wall_ms_per_step": round(wall_ms, 4),
         "clocks": clocks, "roofline": roof,
     }
+    if sharded is not None:
+        line["sharded_configs"] = sharded
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample_bsz = 256
@@ -435,6 +470,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-configs", action="store_true", help="N > 1: skip the cfg 3 / cfg 5 runs after the headline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

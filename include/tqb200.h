@@ -124,6 +124,21 @@ int tqb_probs(const float* state, int n_qubits, long long bsz, float* probs, voi
 int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const float* uniforms, int n_shots,
                       float* cdf_scratch, int* counts, void* stream);
 
+/* Sharded statevector (no counterpart in the reference, which is single-device: device/devices.py:36-136; README.md:52 only
+ * claims multi-GPU): swap the g rank-index qubits with the g local index bits victim_bits_host[0..g) (ascending) by
+ * writing every amplitude of `src` (this rank's slab [bsz][2^n_local]) straight into its place in the destination slab of
+ * the rank that owns it afterwards.  peer_dst_host: 2^g device pointers (HOST array), entry r = destination slab of rank r
+ * mapped into this process (CUDA IPC / symmetric memory), entry `rank` = the local destination (must differ from src).
+ * The caller synchronises the ranks after the launch (all slabs complete) before anybody reads a destination. */
+int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local, long long bsz, int g,
+                     const int* victim_bits_host, int rank, void* stream);
+
+/* HOST function (no device work): out_host[i] = float32(random.random()) for the next n draws of CPython's Mersenne
+ * Twister, whose state (`random.getstate()[1]`: 624 words + position) is advanced in place.  Replaces the interpreter loop
+ * behind `random.choices(..., k=n_shots)` in measure (measurement/measurements.py:37-74); the stream itself must stay the
+ * host's for histograms to be bit-exact with the reference. */
+int tqb_host_uniforms(uint32_t* mt_state625_host, long long n, float* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@
 
 #include "../../torchquantum_b200/csrc/tqb_core.cuh"
 #include "../../torchquantum_b200/csrc/tqb_block_build.cuh"
+#include "../../torchquantum_b200/csrc/tqb_host_rng.h"
 #include "../../include/tqb200.h"
 
 using namespace tqb;
@@ -303,6 +304,14 @@ int tqb_sample_counts(const float* probs, int n, long long bsz, const float* u, 
       counts[b * N + lo] += 1;
     }
   }
+  return 0;
+}
+int tqb_exchange_p2p(const float*, float* const*, int, long long, int, const int*, int, void*) {
+  return fail_msg("tqb_exchange_p2p: peer memory exists only on the GPU build (the gloo tests exchange through all_to_all)");
+}
+int tqb_host_uniforms(uint32_t* mt_state625_host, long long n, float* out_host) {
+  if (n < 0 || !mt_state625_host || mt_state625_host[624] > 624u) return fail_msg("tqb_host_uniforms: bad arguments");
+  tqb_mt19937_uniforms(mt_state625_host, n, out_host);
   return 0;
 }
 }  // extern "C"

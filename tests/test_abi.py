@@ -44,7 +44,8 @@ def test_every_abi_entry_is_a_registered_torch_op():
         assert schema.name == f"tqb200::{name}"
         assert any(a.alias_info is not None and a.alias_info.is_write for a in schema.arguments), f"{name}: no output argument"
         keys = torch._C._dispatch_dump(f"tqb200::{name}")
-        assert "CUDA" in keys, f"{name}: no CUDA kernel registered"
+        if name != "tqb_host_uniforms":   # the one HOST helper of the ABI (Python's Mersenne Twister stream)
+            assert "CUDA" in keys, f"{name}: no CUDA kernel registered"
 
 
 def test_python_constants_mirror_header():

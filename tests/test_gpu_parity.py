@@ -246,18 +246,34 @@ def test_cfg4_full_size_properties():
     assert r["ok"], r
 
 
-def test_sharded_statevector_two_gpus():
-    """Amplitude-sharded device over NCCL vs the same circuit on one GPU (needs >= 2 visible GPUs;
-    the world_size-2/4 gloo suite in tests/test_sharded_gloo.py covers the logic on CPU)."""
+def _torchrun(nproc, args, port, timeout=900):
     import os
     import subprocess
     import sys
 
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "dist_sharded.py")] + args, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("world,n,bsz", [(2, 20, 1), (4, 18, 2)])
+def test_sharded_statevector_ranks_sharing_one_gpu(world, n, bsz):
+    """SURVEY §8e, amplitude axis, on a ONE-GPU box: `world` processes share cuda:0 (gloo process group, exchanges staged
+    through the host), every rank runs the real sm_100a kernels on its slab with its rank bits, and the slabs are compared
+    with the same circuit (QFT + brickwork, config-5 family) on one device.  Covers the rank-index controls / diagonals
+    (K11), the pack pass and the layout bookkeeping on the GPU; the NVLink paths need >= 2 GPUs (next test)."""
+    out = _torchrun(world, ["--check", str(n), "--check-bsz", str(bsz), "--backend", "gloo", "--exchange", "collective"],
+                    29541 + world)
+    assert '"ok": true' in out, out[-1500:]
+
+
+def test_sharded_statevector_two_gpus():
+    """Amplitude-sharded device over NCCL / NVLink peer stores vs the same circuit on one GPU (needs >= 2 visible GPUs)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533",
-                        os.path.join(root, "tools", "dist_sharded.py"), "--check", "20"],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for backend in ("p2p", "collective"):
+        out = _torchrun(2, ["--check", "22", "--exchange", backend], 29533)
+        assert '"ok": true' in out and f'"exchange_backend": "{backend}"' in out, out[-1500:]

@@ -270,6 +270,83 @@ def run_cfg1(dev, bsz=256):
             "circuits_per_s_graphed": bsz / (graphed * 1e-3), "ok": True}
 
 
+# ---------------------------------------------------------------------------------------
+# cfg 5: QFT + brickwork layers on a statevector sharded over the ranks of an initialised process group
+def qft_gate_list(n):
+    ops = []
+    for top in range(n):
+        ops.append(("hadamard", [top], None))
+        for w in range(top + 1, n):
+            ops.append(("cu1", [w, top], float(np.pi / 2 ** (w - top))))
+    ops += [("swap", [w, n - 1 - w], None) for w in range(n // 2)]
+    return ops
+
+
+def run_cfg5(dev, n, layers=4, exchange="auto", reps=2):
+    """QFT on a random basis state |x>, then `layers` brickwork layers, on a ShardedQuantumDevice over the default group.
+    Checks: the QFT amplitudes at sampled indices against the analytic value exp(2 pi i x k / 2^n) / 2^(n/2)
+    and the norm after the brickwork layers accumulated in float64 (bars 1e-5).  Exchange time is reported against the
+    NVLink peak (900 GB/s per direction per GPU)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    rng = np.random.default_rng(7)
+    x = int(rng.integers(1 << 62)) & ((1 << n) - 1)
+    prep = [("paulix", [w], None) for w in range(n) if (x >> (n - 1 - w)) & 1]
+    circuit = prep + qft_gate_list(n)
+    bricks = brickwork(n, layers, seed=2)
+    th_c, th_b = device_angles(circuit, dev), device_angles(bricks, dev)
+    q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device=dev, exchange=exchange)
+    q.time_exchanges = True
+    with torch.no_grad():
+        for rep in range(reps):   # rep 0 warms up (plan build, NCCL channels / symmetric-memory rendezvous)
+            q.reset_states(1)
+            q.stats.update(exchanges=0, exchange_bytes_sent=0, exchange_ms=[], local_permute_passes=0, local_runs=[])
+            dist.barrier()
+            torch.cuda.synchronize()
+            l0 = engine.STATS["launches"]
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            apply_ops(q, circuit, dev, thetas=th_c)
+            q.flush()
+            e1.record()
+            ks = [0, 1, (1 << n) - 1] + [int(v) & ((1 << n) - 1) for v in rng.integers(1 << 62, size=13)]
+            amps = q.read_amplitudes(ks)[0].cpu().numpy() if rep == reps - 1 else None
+            apply_ops(q, bricks, dev, thetas=th_b)
+            q.flush()
+            e2.record()
+            torch.cuda.synchronize()
+        norm2 = torch.linalg.vector_norm(torch.view_as_real(q._flat).reshape(-1), dtype=torch.float64) ** 2
+        dist.all_reduce(norm2)
+    qft_ms, brick_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    ex_ms = q.exchange_times_ms()
+    t = torch.tensor([qft_ms, brick_ms, sum(ex_ms)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    want = np.array([np.exp(2j * np.pi * ((x * k) % (1 << n)) / (1 << n)) / 2 ** (n / 2) for k in ks])
+    amp_err = float(np.abs(amps - want).max() * 2 ** (n / 2))   # relative to the amplitude magnitude
+    norm = float(norm2.sqrt())
+    sent = q.stats["exchange_bytes_sent"]
+    n_gates = len(circuit) + len(bricks)
+    total_ms = t[0].item() + t[1].item()
+    return {
+        "workload": f"cfg5: {n}-qubit QFT on |x> + {layers} brickwork layers ({n_gates} gates), statevector sharded over "
+                    f"{world} B200",
+        "n": n, "world": world, "gates": n_gates, "exchange_backend": q.exchange_backend,
+        "total_ms": round(total_ms, 3), "qft_ms": round(t[0].item(), 3), "brickwork_ms": round(t[1].item(), 3),
+        "exchanges": q.stats["exchanges"], "local_permute_passes": q.stats["local_permute_passes"],
+        "exchange_ms_total": round(t[2].item(), 3), "exchange_ms_each": [round(v, 3) for v in ex_ms],
+        "exchange_bytes_sent_per_rank": sent,
+        "exchange_GBps_per_rank_per_direction": round(sent / max(t[2].item(), 1e-9) / 1e6, 1),
+        "nvlink_peak_GBps_per_direction": 900.0,
+        "exchange_frac_of_nvlink": round(sent / max(t[2].item(), 1e-9) / 1e6 / 900.0, 4),
+        "kernel_launches_per_rank": engine.STATS["launches"] - l0,
+        "local_runs_gates_launches_ms": q.local_run_times(),
+        "gate_amp_updates_per_s": round(n_gates * 2.0 ** n / (total_ms * 1e-3), 1),
+        "qft_amp_rel_err_max": amp_err, "norm_after": norm,
+        "ok": bool(amp_err < 1e-5 and abs(norm - 1) < 1e-5),
+    }
+
+
 def run_cfg3_batch_sharded(out_path):
     """cfg 3 batch-sharded over the ranks of a torchrun launch (no data-path collective, per-sample angles and
     gradients stay on their rank): 64 circuits in total, 64 / world per GPU; time = max over ranks."""

@@ -53,14 +53,20 @@ def apply(q, ops, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", type=int, default=0)
+    ap.add_argument("--check-bsz", type=int, default=1)
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="gloo: several ranks may share one GPU")
     ap.add_argument("--bench", type=int, default=0)
     ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "collective", "both"])
     ap.add_argument("--out", default="")
     a = ap.parse_args()
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if a.backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     results = {}
 
@@ -69,73 +75,39 @@ def main():
         rng = np.random.default_rng(5)
         xbits = [w for w in range(n) if rng.integers(2)]
         ops = [("paulix", [w], None) for w in xbits] + qft_ops(n) + brick_ops(n, 3, seed=1)
-        q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device=dev)
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=a.check_bsz, device=dev,
+                                    exchange="auto" if a.exchange == "both" else a.exchange)
         apply(q, ops, dev)
         obs = ["".join("ZXYI"[(i + s) % 4] for i in range(n)) for s in range(2)] + ["Z" * n]
         ev = tq.expval_joint_analytical_multi(q, obs)
         slab = q.get_states_1d()
-        ref = tq.QuantumDevice(n_wires=n, bsz=1, device=dev)   # every rank: the same circuit on one GPU
+        ref = tq.QuantumDevice(n_wires=n, bsz=a.check_bsz, device=dev)   # every rank: the same circuit on one GPU
         apply(ref, ops, dev)
         want = ref.get_states_1d()
         ev_want = tq.expval_joint_analytical_multi(ref, obs)
         nl = q.nl
-        err = (slab - want[:, rank << nl:(rank + 1) << nl]).abs().max().item()
+        mine = want[:, rank << nl:(rank + 1) << nl]
+        d2 = (slab - mine).abs().double().pow(2).sum().item()
+        w2 = mine.abs().double().pow(2).sum().item()
         ev_err = (ev - ev_want).abs().max().item()
-        t = torch.tensor([err, ev_err], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        results["check"] = {"n": n, "world": world, "max_abs_state_err": t[0].item(), "max_abs_expval_err": t[1].item(),
-                            "exchanges": q.stats["exchanges"], "ok": bool(t[0].item() < 2e-6 and t[1].item() < 2e-5)}
+        cpu = a.backend == "gloo"
+        t = torch.tensor([d2, w2], dtype=torch.float64, device="cpu" if cpu else dev)
+        dist.all_reduce(t)
+        m = torch.tensor([ev_err], dtype=torch.float64, device="cpu" if cpu else dev)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        rel = float((t[0] / t[1]).sqrt())
+        results["check"] = {"n": n, "world": world, "exchange_backend": q.exchange_backend, "bsz": a.check_bsz,
+                            "state_rel_l2_vs_one_gpu": rel, "max_abs_expval_err": m[0].item(),
+                            "exchanges": q.stats["exchanges"], "ok": bool(rel < 1e-5 and m[0].item() < 1e-5)}
         assert results["check"]["ok"], results["check"]
 
     if a.bench:
-        n = a.bench
-        rng = np.random.default_rng(7)
-        x = int(rng.integers(1 << 62)) & ((1 << n) - 1)
-        prep = [("paulix", [w], None) for w in range(n) if (x >> (n - 1 - w)) & 1]
-        circuit = prep + qft_ops(n)
-        q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device=dev)
-        q.time_exchanges = True
-        for rep in range(2):   # rep 0 warms up (plan build, NCCL channels)
-            q.reset_states(1)
-            q.stats.update(exchanges=0, exchange_bytes_sent=0, exchange_ms=[], local_permute_passes=0, local_runs=[])
-            dist.barrier(); torch.cuda.synchronize()
-            l0 = engine.STATS["launches"]
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            apply(q, circuit, dev)
-            q.flush()
-            e1.record()
-            ks = [0, 1, (1 << n) - 1] + [int(v) & ((1 << n) - 1) for v in rng.integers(1 << 62, size=13)]
-            amps = q.read_amplitudes(ks)[0].cpu().numpy() if rep == 1 else None
-            apply(q, brick_ops(n, a.layers, seed=2), dev)
-            q.flush()
-            e2.record()
-            torch.cuda.synchronize()
-            z = q.expval_z_all()
-        qft_ms, brick_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
-        ex_ms = q.exchange_times_ms()
-        t = torch.tensor([qft_ms, brick_ms, sum(ex_ms)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        want = np.array([np.exp(2j * np.pi * ((x * k) % (1 << n)) / (1 << n)) / 2 ** (n / 2) for k in ks])
-        amp_err = float(np.abs(amps - want).max() * 2 ** (n / 2))   # relative to the amplitude magnitude
-        norm = z[0, n].item()
-        sent = q.stats["exchange_bytes_sent"]
-        n_gates = len(circuit) + len(brick_ops(n, a.layers, seed=2))
-        results["bench"] = {
-            "workload": f"cfg5: {n}-qubit QFT on |x> + {a.layers} brickwork layers, statevector sharded over {world} B200",
-            "n": n, "world": world, "gates": n_gates, "qft_ms": round(t[0].item(), 3), "brickwork_ms": round(t[1].item(), 3),
-            "exchanges": q.stats["exchanges"], "local_permute_passes": q.stats["local_permute_passes"],
-            "exchange_ms_total": round(t[2].item(), 3), "exchange_ms_each": [round(v, 3) for v in ex_ms],
-            "exchange_bytes_sent_per_rank": sent,
-            "exchange_GBps_per_rank_per_direction": round(sent / max(t[2].item(), 1e-9) / 1e6, 1),
-            "nvlink_peak_GBps_per_direction": 900.0,
-            "exchange_frac_of_nvlink": round(sent / max(t[2].item(), 1e-9) / 1e6 / 900.0, 4),
-            "kernel_launches": engine.STATS["launches"] - l0,
-            "local_runs_gates_launches_ms": q.local_run_times(),
-            "gate_amp_updates_per_s": round(n_gates * 2.0 ** n / ((t[0].item() + t[1].item()) * 1e-3), 1),
-            "qft_amp_rel_err_max": amp_err, "norm_after": norm,
-            "ok": bool(amp_err < 1e-4 and abs(norm - 1) < 1e-3),
-        }
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import configs
+
+        for backend in ([a.exchange] if a.exchange != "both" else ["p2p", "collective"]):
+            results["bench_" + backend] = configs.run_cfg5(dev, a.bench, layers=a.layers, exchange=backend)
+            torch.cuda.empty_cache()
     if rank == 0:
         print(json.dumps(results))
         if a.out:

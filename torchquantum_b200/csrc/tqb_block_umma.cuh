@@ -49,7 +49,9 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((
 struct Params {
   const float* a_planes;   // [2][128][64]: TF32-rounded hi plane, lo plane of A
   uint32_t n_tiles;
+  uint32_t tile_mult;      // odd: tile index -> (index * tile_mult) mod n_tiles (n_tiles is a power of two) spreads concurrent tiles
   int transpose;
+  unsigned long long* trace;  // debug: [64 tiles][10] clock64 stamps of CTA 0 (tools/block_trace.py), or null
   int debug;               // TQB200_BLOCK_DEBUG bit mask (timing experiments only): 1 no split, 2 8 MMAs, 4 no epilogue math, 8 no store
   int renorm;              // block is unitary: rescale every tile to the norm it came in with (see the epilogue)
   int nseg;                // outer (non-tile) index bits as <= 4 runs: bits [lo, lo+len) of the tile id go to bit pos
@@ -164,6 +166,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 
 // 128-byte row index of the tile's first amplitude
 __device__ __forceinline__ uint32_t tile_row(const Params& p, uint32_t tile) {
+  tile = (tile * p.tile_mult) & (p.n_tiles - 1u);
   unsigned long long off = 0;
 #pragma unroll
   for (int s = 0; s < 4; ++s)
@@ -178,6 +181,8 @@ __device__ __forceinline__ uint32_t tile_row(const Params& p, uint32_t tile) {
 __device__ __forceinline__ uint32_t swz32(uint32_t row, uint32_t c16) {
   return row * 128u + ((((c16 >> 1) ^ (row & 3u)) << 5) | ((c16 & 1u) << 4));
 }
+
+#define TQB_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 10 + (slot)] = (unsigned long long)clock64(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, const Params p) {
@@ -254,6 +259,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const uint32_t k = it % kHi, ph = (it / kHi) & 1u;
         mbar_wait(empty(k), ph ^ 1u);
+        TQB_TRACE(0);
         mbar_expect_tx(full(k), kPlane);
         const uint32_t row = tile_row(p, t);
 #pragma unroll
@@ -267,7 +273,9 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const uint32_t k = it % kHi, l = it % kLo, d = it % kAcc;
         mbar_wait(ready(k), (it / kHi) & 1u);
+        TQB_TRACE(4);
         mbar_wait(dempty(d), ((it / kAcc) & 1u) ^ 1u);
+        TQB_TRACE(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t bh = hi_plane(k), bl = lo_plane(l);
         const uint32_t dt = t_d0 + 128u * d;
@@ -292,6 +300,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const uint32_t l = it % kLo;
         mbar_wait(outready(l), (it / kLo) & 1u);
+        TQB_TRACE(8);
         if (!(p.debug & 8)) {
           const uint32_t row = tile_row(p, t);
 #pragma unroll
@@ -299,6 +308,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+        TQB_TRACE(9);
         mbar_arrive(stored(l));
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -310,7 +320,9 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
     for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
       const uint32_t k = it % kHi, l = it % kLo;
       mbar_wait(full(k), (it / kHi) & 1u);
+      if (tid == 0) TQB_TRACE(1);
       mbar_wait(stored(l), ((it / kLo) & 1u) ^ 1u);   // the tile that used this lo plane last has left it
+      if (tid == 0) TQB_TRACE(2);
       const uint32_t bh = hi_plane(k) + 16u * tid, bl = lo_plane(l) + 16u * tid;
       float ss = 0.f;
 #pragma unroll 4
@@ -331,6 +343,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(nin_slot + 4u * (4u * (it & 7u) + (uint32_t)(warp - 8))), "f"(ss) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid == 0) TQB_TRACE(3);
       mbar_arrive(ready(k));
     }
   } else if (warp >= 4) {
@@ -347,6 +360,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       const uint32_t stg = lo_plane(l);   // the tile's own lo plane: its MMAs are done (dfull), nobody else touches it
       float ss_out = 0.f;
       mbar_wait(dfull(d), (it / kAcc) & 1u);
+      if (et == 0) TQB_TRACE(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (uint32_t ld = 0; ld < ((p.debug & 4) ? 0u : 4u); ++ld) {
@@ -372,6 +386,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (et == 0) TQB_TRACE(7);
       mbar_arrive(dempty(d));
       if (p.renorm) {
 #pragma unroll
@@ -460,6 +475,8 @@ inline const char* make_tensor_map(CUtensorMap* tm, const float* state, int n_qu
   return nullptr;
 }
 
+static unsigned long long* g_block_trace = nullptr;   // set by tqb_debug_block_trace (tools/block_trace.py)
+
 // kpos: 6 ascending physical bit positions, all >= 6 and < n_qubits
 inline const char* launch_block6(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
                                  const int* kpos, int transpose, int renorm, int num_sms, cudaStream_t st) {
@@ -488,6 +505,10 @@ inline const char* launch_block6(const float* src, float* dst, int n_qubits, lon
   static int debug = -1;
   if (debug < 0) { const char* e = getenv("TQB200_BLOCK_DEBUG"); debug = e ? atoi(e) : 0; }
   p.debug = debug;
+  static long long mult = -1;
+  if (mult < 0) { const char* e = getenv("TQB200_TILE_MULT"); mult = e ? atoll(e) : 1; }
+  p.tile_mult = (uint32_t)mult | 1u;
+  p.trace = g_block_trace;
   const unsigned long long tiles = ((unsigned long long)bsz << n_qubits) >> 12;
   if (tiles > 0xffffffffull) return "too many tiles";
   p.n_tiles = (uint32_t)tiles;

@@ -8,6 +8,7 @@
 #include "tqb_dense_tc.cuh"
 #include "tqb_block_umma.cuh"
 #include "tqb_block_build.cuh"
+#include "tqb_host_rng.h"
 #include "../../include/tqb200.h"
 
 using namespace tqb;
@@ -570,6 +571,45 @@ __global__ void tqb_sample_kernel(const float* cdf, const float* u, long long bs
 }
 
 // ---------------------------------------------------------------------------------------
+// K10: global <-> local qubit exchange over peer memory (NVLink P2P stores), pack and transfer in ONE kernel.
+// Rank r swaps its g rank-index bits with the g local index bits `vpos` (any positions, ascending): amplitude i of the
+// local slab goes to rank v = (bits of i at vpos) at local index i with those bits replaced by the bits of r.  Every
+// thread moves one 16-byte vector (VEC = 2 amplitudes; VEC = 1 when bit 0 is a victim) straight into the destination
+// slab of the peer; a warp writes 512 contiguous bytes to one peer whenever the lowest victim bit is >= 6, which is what
+// the victim choice in sharded.py prefers.  No staging buffer, no separate pack pass, no NCCL.
+// ---------------------------------------------------------------------------------------
+struct ExchangeArgs {
+  float* dst[16];        // destination slab of every rank (peer-mapped device pointers), dst[rank] is local
+  int vpos[4];
+  int g, rank, nl;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) tqb_exchange_kernel(const float* __restrict__ src, const ExchangeArgs a, long long total_vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned long long slab_mask = (1ull << a.nl) - 1ull;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += stride) {
+    const unsigned long long flat = (unsigned long long)v * VEC;   // amplitude index within [bsz][2^nl]
+    unsigned long long i = flat & slab_mask;
+    int to = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < a.g) {
+        to |= (int)((i >> a.vpos[k]) & 1ull) << k;
+        i = (i & ~(1ull << a.vpos[k])) | ((unsigned long long)((a.rank >> k) & 1) << a.vpos[k]);
+      }
+    const unsigned long long out = (flat & ~slab_mask) | i;
+    if (VEC == 2) {
+      const float4 val = __ldcs(reinterpret_cast<const float4*>(src) + v);
+      reinterpret_cast<float4*>(a.dst[to])[out >> 1] = val;
+    } else {
+      const float2 val = __ldcs(reinterpret_cast<const float2*>(src) + v);
+      reinterpret_cast<float2*>(a.dst[to])[out] = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
 extern "C" {
@@ -825,5 +865,47 @@ int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const flo
   }
   return 0;
 }
+
+int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local, long long bsz, int g,
+                     const int* victim_bits_host, int rank, void* stream) {
+  if (g <= 0 || g > 4 || bsz <= 0) return fail_msg("tqb_exchange_p2p: 1 <= g <= 4 rank-index qubits");
+  if (n_local < g + 1 || n_local > 40) return fail_msg("tqb_exchange_p2p: bad n_local");
+  ExchangeArgs a;
+  a.g = g; a.rank = rank; a.nl = n_local;
+  for (int k = 0; k < 4; ++k) a.vpos[k] = k < g ? victim_bits_host[k] : 0;
+  for (int k = 0; k < g; ++k) {
+    if (a.vpos[k] < 0 || a.vpos[k] >= n_local || (k && a.vpos[k] <= a.vpos[k - 1])) return fail_msg("tqb_exchange_p2p: victim bits must ascend within the slab");
+  }
+  for (int r = 0; r < 16; ++r) a.dst[r] = r < (1 << g) ? peer_dst_host[r] : nullptr;
+  for (int r = 0; r < (1 << g); ++r)
+    if (!a.dst[r] || ((uintptr_t)a.dst[r] & 15)) return fail_msg("tqb_exchange_p2p: destination slabs must be 16-byte aligned");
+  if ((uintptr_t)src & 15) return fail_msg("tqb_exchange_p2p: source slab must be 16-byte aligned");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const long long total = bsz << n_local;
+  const unsigned grid = (unsigned)g_num_sms * 8u;
+  if (a.vpos[0] >= 1) {
+    tqb_exchange_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(src, a, total / 2);
+  } else {
+    tqb_exchange_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(src, a, total);
+  }
+  TQB_CHECK_LAUNCH("tqb_exchange_kernel");
+  return 0;
+}
+
+int tqb_host_uniforms(uint32_t* mt_state625_host, long long n, float* out_host) {
+  if (n < 0 || !mt_state625_host || (n > 0 && !out_host)) return fail_msg("tqb_host_uniforms: bad arguments");
+  if (mt_state625_host[624] > 624u) return fail_msg("tqb_host_uniforms: corrupt generator position");
+  tqb_mt19937_uniforms(mt_state625_host, n, out_host);
+  return 0;
+}
+
+// debug hook (not part of the ABI header): device buffer of 64 x 10 clock64 stamps written by CTA 0 of every following
+// tqb_block6_kernel launch; null switches the trace off
+void tqb_debug_block_trace(unsigned long long* dev_ptr) { tqb_umma::g_block_trace = dev_ptr; }
 
 }  // extern "C"

@@ -39,6 +39,8 @@ struct Abi {
   decltype(&tqb_expval_z_bwd) expval_z_bwd = nullptr;
   decltype(&tqb_probs) probs = nullptr;
   decltype(&tqb_sample_counts) sample_counts = nullptr;
+  decltype(&tqb_host_uniforms) host_uniforms = nullptr;
+  decltype(&tqb_exchange_p2p) exchange_p2p = nullptr;
 };
 
 Abi g_cuda, g_emu;
@@ -76,6 +78,8 @@ int64_t bind(const std::string& path, bool emulated) {
   resolve(h, "tqb_expval_z_bwd", n.expval_z_bwd, true);
   resolve(h, "tqb_probs", n.probs, true);
   resolve(h, "tqb_sample_counts", n.sample_counts, true);
+  resolve(h, "tqb_host_uniforms", n.host_uniforms, true);
+  resolve(h, "tqb_exchange_p2p", n.exchange_p2p, true);
   TORCH_CHECK(n.abi_version() == TQB_ABI_VERSION, "libtqb200: ABI version ", n.abi_version(), " != ", TQB_ABI_VERSION);
   a = n;
   return n.abi_version();
@@ -228,9 +232,40 @@ void sample_counts(const at::Tensor& probs_t, int64_t n, int64_t bsz, const at::
                            static_cast<int*>(counts.data_ptr()), stream_of(probs_t)), "tqb_sample_counts");
 }
 
+// peer_ptrs: the destination slab of every rank as raw device addresses (symmetric memory: _SymmetricMemory.buffer_ptrs)
+void exchange_p2p(const at::Tensor& src, at::Tensor& local_dst, at::IntArrayRef peer_ptrs, int64_t n_local, int64_t bsz,
+                  at::IntArrayRef victim_bits, int64_t rank) {
+  const Abi& a = abi_for(src);
+  const int g = (int)victim_bits.size();
+  TORCH_CHECK(g >= 1 && g <= 4 && (int64_t)peer_ptrs.size() == (1ll << g), "tqb_exchange_p2p: 2^g peer pointers for g victim bits");
+  TORCH_CHECK(rank >= 0 && rank < (int64_t)peer_ptrs.size() &&
+                  reinterpret_cast<void*>((uintptr_t)peer_ptrs[rank]) == local_dst.data_ptr(),
+              "tqb_exchange_p2p: peer_ptrs[rank] must be the local destination slab");
+  float* ptrs[16];
+  int vb[4];
+  for (size_t r = 0; r < peer_ptrs.size(); ++r) ptrs[r] = reinterpret_cast<float*>((uintptr_t)peer_ptrs[r]);
+  for (int k = 0; k < g; ++k) vb[k] = (int)victim_bits[k];
+  check(a, a.exchange_p2p(fp(src), ptrs, (int)n_local, bsz, g, vb, (int)rank, stream_of(src)), "tqb_exchange_p2p");
+}
+
+// HOST helper of the ABI (CPython's Mersenne Twister stream, csrc/tqb_host_rng.h): CPU tensors by design; served by
+// whichever build of the ABI is bound (the stream is the host's in both)
+void host_uniforms(at::Tensor& mt_state, int64_t n, at::Tensor& out) {
+  const Abi& a = g_cuda.handle != nullptr ? g_cuda : g_emu;
+  TORCH_CHECK(a.handle != nullptr, "torchquantum_b200: libtqb200.so is not loaded");
+  TORCH_CHECK(!mt_state.is_cuda() && !out.is_cuda() && mt_state.is_contiguous() && out.is_contiguous() &&
+                  mt_state.numel() == 625 && mt_state.element_size() == 4 && out.scalar_type() == at::kFloat && out.numel() >= n,
+              "tqb_host_uniforms: expects a 625-word host state and a float32 host buffer of n elements");
+  check(a, a.host_uniforms(static_cast<uint32_t*>(mt_state.data_ptr()), n, static_cast<float*>(out.data_ptr())),
+        "tqb_host_uniforms");
+}
+
 }  // namespace
 
 TORCH_LIBRARY(tqb200, m) {
+  m.def("tqb_host_uniforms(Tensor(a!) mt_state, int n, Tensor(b!) out) -> ()");
+  m.def("tqb_exchange_p2p(Tensor src, Tensor(a!) local_dst, int[] peer_ptrs, int n_local, int bsz, int[] victim_bits, "
+        "int rank) -> ()");
   m.def("_bind(str path, bool emulated) -> int", &bind);
   m.def("tqb_build_mats(Tensor table, int n_records, int n_shared_records, int bsz, Tensor? params_sh, Tensor? params_ps, "
         "int ps_stride, Tensor? consts, Tensor(a!) msh, Tensor(b!) mps, int mps_stride) -> ()");
@@ -275,8 +310,12 @@ TORCH_LIBRARY(tqb200, m) {
   m.impl("tqb_expval_z", &expval_z);                     \
   m.impl("tqb_expval_z_bwd", &expval_z_bwd);             \
   m.impl("tqb_probs", &probs);                           \
-  m.impl("tqb_sample_counts", &sample_counts);
+  m.impl("tqb_sample_counts", &sample_counts);    \
+  m.impl("tqb_exchange_p2p", &exchange_p2p);
 
 TORCH_LIBRARY_IMPL(tqb200, CUDA, m) { TQB_IMPL_ALL(m) }
 // CPU key: reaches only the injected host-emulation build (tests); abi_for() raises otherwise
-TORCH_LIBRARY_IMPL(tqb200, CPU, m) { TQB_IMPL_ALL(m) }
+TORCH_LIBRARY_IMPL(tqb200, CPU, m) {
+  TQB_IMPL_ALL(m)
+  m.impl("tqb_host_uniforms", &host_uniforms);
+}

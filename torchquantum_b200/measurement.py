@@ -267,6 +267,19 @@ def expval(qdev, wires: Union[int, List[int]], observables):
     return torch.stack(cols, dim=-1)
 
 
+def _host_uniforms(count):
+    """float32(random.random()) x count from Python's GLOBAL Mersenne Twister stream, generated by the C ABI's host helper
+    (csrc/tqb_host_rng.h) and the interpreter's state advanced by exactly the numbers consumed: the same stream the
+    reference's random.choices draws from, without one interpreter call per shot."""
+    version, internal, gauss = random.getstate()
+    state = np.array(internal, dtype=np.uint32)
+    out = torch.empty(count, dtype=torch.float32, pin_memory=torch.cuda.is_available() and not _native.is_emulated())
+    if count:
+        _native.call("tqb_host_uniforms", torch.from_numpy(state.view(np.int32)), count, out)
+        random.setstate((version, tuple(state.tolist()), gauss))
+    return out
+
+
 def measure(qdev, n_shots=1024, draw_id=None):
     """Sample bitstrings (measurements.py:37-74) -> list[OrderedDict[bitstring -> count]] with all
     2^n keys.  Bit-exact with the reference under the shared global `random` stream."""
@@ -284,8 +297,7 @@ def measure(qdev, n_shots=1024, draw_id=None):
     _native.call("tqb_probs", states, n, bsz, probs)
     # one random.random() per (sample, shot), in the reference's order; float32(u) is what NumPy 2
     # promotes to when multiplying by the float32 total
-    u = np.array([random.random() for _ in range(bsz * n_shots)], dtype=np.float64).astype(np.float32)
-    u_dev = torch.from_numpy(u).to(dev)
+    u_dev = _host_uniforms(bsz * n_shots).to(dev, non_blocking=True)
     cdf = torch.empty(bsz, N, dtype=torch.float32, device=dev)
     counts = torch.zeros(bsz, N, dtype=torch.int32, device=dev)
     _native.call("tqb_sample_counts", probs, n, bsz, u_dev, n_shots, cdf, counts)

@@ -53,7 +53,11 @@ class ShardedQuantumDevice:
 
     is_sharded = True
 
-    def __init__(self, n_wires, device_name="default", bsz=1, device="cuda", record_op=False, process_group=None):
+    def __init__(self, n_wires, device_name="default", bsz=1, device="cuda", record_op=False, process_group=None,
+                 exchange="auto"):
+        """exchange: "p2p" = pack + transfer in one kernel that stores straight into the peers' slabs over NVLink
+        (symmetric memory; CUDA only), "collective" = local permute pass + torch.distributed all_to_all_single (NCCL on
+        GPUs, gloo in the CPU tests), "auto" = p2p when the symmetric-memory rendezvous succeeds."""
         if not dist.is_initialized():
             raise RuntimeError("ShardedQuantumDevice needs torch.distributed to be initialised")
         self.group = process_group
@@ -74,12 +78,47 @@ class ShardedQuantumDevice:
         self._queue = []
         self.stats = {"exchanges": 0, "exchange_bytes_sent": 0, "exchange_ms": [], "local_permute_passes": 0}
         self.time_exchanges = False
+        if exchange not in ("auto", "p2p", "collective"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'collective'")
+        self._exchange_pref = exchange
+        self._symm = None   # (two symmetric slabs, their rendezvous handles, index of the slab holding the state)
         self.reset_states(bsz)
 
     # --- state container ------------------------------------------------------------------
+    def _new_slab(self, bsz):
+        """The slab this rank's state lives in.  With the p2p exchange it is one of two symmetric-memory buffers (every
+        rank can store into every other rank's copy); otherwise a plain device tensor."""
+        want = self._exchange_pref != "collective" and self.device.type == "cuda" and self.g > 0
+        if want and (self._symm is None or self._symm[0][0].numel() != 2 * (bsz << self.nl)):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                group = self.group if self.group is not None else dist.group.WORLD
+                bufs = [symm_mem.empty(2 * (bsz << self.nl), dtype=torch.float32, device=self.device) for _ in range(2)]
+                handles = [symm_mem.rendezvous(b, group) for b in bufs]
+                self._symm = [bufs, handles, 0]
+            except Exception as e:  # noqa: BLE001  (no peer access, old driver, unsupported backend ...)
+                if self._exchange_pref == "p2p":
+                    raise RuntimeError(f"ShardedQuantumDevice(exchange='p2p'): symmetric memory is not available: {e}") from e
+                self._symm = None
+                self._exchange_pref = "collective"
+        if not want or self._symm is None:
+            self._symm = None
+            return torch.empty(bsz, 1 << self.nl, dtype=C_DTYPE, device=self.device)
+        self._symm[2] = 0
+        return self._symm_view(0, bsz)
+
+    def _symm_view(self, which, bsz):
+        return torch.view_as_complex(self._symm[0][which].view(bsz, 1 << self.nl, 2))
+
+    @property
+    def exchange_backend(self):
+        return "p2p" if self._symm is not None else "collective"
+
     def reset_states(self, bsz):
         self.bsz = bsz
-        flat = torch.zeros(bsz, 1 << self.nl, dtype=C_DTYPE, device=self.device)
+        flat = self._new_slab(bsz)
+        flat.zero_()
         if self.rank == 0:
             flat[:, 0] = 1
         self._flat = flat
@@ -88,8 +127,11 @@ class ShardedQuantumDevice:
 
     def set_local_states(self, flat):
         """Install this rank's slab (canonical layout: global index = rank * 2^nl + local index)."""
-        self._flat = flat.reshape(flat.shape[0], 1 << self.nl).to(C_DTYPE).contiguous()
-        self.bsz = self._flat.shape[0]
+        flat = flat.reshape(flat.shape[0], 1 << self.nl)
+        self.bsz = flat.shape[0]
+        slab = self._new_slab(self.bsz)
+        slab.copy_(flat)
+        self._flat = slab
         self._queue = []
         self.pos = list(range(self.n_wires))
 
@@ -127,8 +169,11 @@ class ShardedQuantumDevice:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 l0 = engine.STATS["launches"]
                 e0.record()
-            self._flat = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank,
-                                            inplace=True)
+            out = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank, inplace=True)
+            if self._symm is not None and out.data_ptr() != self._flat.data_ptr():
+                self._flat.copy_(out)   # an out-of-place stage (dense block, reset): back into the symmetric slab
+            else:
+                self._flat = out
             if timed:
                 e1.record()
                 self.stats.setdefault("local_runs", []).append((len(records), engine.STATS["launches"] - l0, e0, e1))
@@ -187,8 +232,11 @@ class ShardedQuantumDevice:
         local_logical = [inv[p] for p in range(nl) if inv[p] not in need0]
         order = sorted(local_logical, key=lambda l: (-nxt.get(l, 1 << 60), -self.pos[l]))
         victims = order[:g]
-        self._move_to_top(victims)
-        self._all_to_all()
+        if self._symm is not None:
+            self._exchange_p2p(sorted(self.pos[v] for v in victims))   # no pack pass: any local positions
+        else:
+            self._move_to_top(victims)
+            self._all_to_all()
         if any(self.pos[l] >= nl for l in need0):   # progress guarantee of flush()
             raise AssertionError(f"exchange left {name0} on wires {list(wires0)} blocked (layout {self.pos})")
 
@@ -212,10 +260,41 @@ class ShardedQuantumDevice:
             self.stats["local_permute_passes"] += 1
             self._run_local(recs)
 
+    def _exchange_p2p(self, vpos):
+        """Swap rank-index bit k <-> local physical bit vpos[k] (ascending) with ONE kernel per rank that stores every
+        amplitude straight into the slab of the rank that owns it afterwards (NVLink peer stores into symmetric memory),
+        then a device-side barrier over the symmetric-memory signal pads.  K10, fused pack + exchange."""
+        nl, g = self.nl, self.g
+        bufs, handles, cur = self._symm
+        dst = 1 - cur
+        timed = self.time_exchanges
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _native.call("tqb_exchange_p2p", self._flat, bufs[dst], [int(p) for p in handles[dst].buffer_ptrs], nl, self.bsz,
+                     [int(p) for p in vpos], self.rank)
+        STATS["launches"] += 1
+        handles[dst].barrier(channel=0)   # every rank's stores have landed before anybody reads its new slab
+        if timed:
+            e1.record()
+            self.stats["exchange_ms"].append((e0, e1))
+        self.stats["exchanges"] += 1
+        self.stats["exchange_bytes_sent"] += (self.world - 1) * (1 << (nl - g)) * self.bsz * 8
+        self._symm[2] = dst
+        self._flat = self._symm_view(dst, self.bsz)
+        where = {p: k for k, p in enumerate(vpos)}
+        for l, p in enumerate(self.pos):
+            if p in where:
+                self.pos[l] = nl + where[p]
+            elif p >= nl:
+                self.pos[l] = vpos[p - nl]
+
     def _all_to_all(self):
         """Swap physical bits [nl-g, nl) <-> [nl, n): chunk j of the slab goes to rank j and the chunk
         received from rank i lands at chunk position i (K10)."""
         nl, g, W = self.nl, self.g, self.world
+        if self._symm is not None:
+            return self._exchange_p2p(list(range(nl - g, nl)))
         flat = self._flat
         bsz = flat.shape[0]
         chunk = 1 << (nl - g)
@@ -228,7 +307,15 @@ class ShardedQuantumDevice:
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+        if flat.is_cuda and dist.get_backend(self.group) == "gloo":
+            # a process group that cannot move device memory (several ranks sharing one GPU in the test-suite): the
+            # chunks go through pinned host buffers; the kernels on either side are the same
+            h_send = torch.view_as_real(send).cpu()
+            h_recv = torch.empty_like(h_send)
+            dist.all_to_all_single(h_recv, h_send, group=self.group)
+            torch.view_as_real(recv).copy_(h_recv)
+        else:
+            dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
         if timed:
             e1.record()
             self.stats["exchange_ms"].append((e0, e1))
@@ -308,6 +395,11 @@ class ShardedQuantumDevice:
     def gather_states_1d(self):
         """Full [bsz, 2^n] state on every rank (tests / small n only)."""
         local = self.get_states_1d().contiguous()
+        if local.is_cuda and dist.get_backend(self.group) == "gloo":
+            h = torch.view_as_real(local).cpu()
+            hp = [torch.empty_like(h) for _ in range(self.world)]
+            dist.all_gather(hp, h, group=self.group)
+            return torch.cat([torch.view_as_complex(x) for x in hp], dim=1).to(local.device)
         parts = [torch.empty_like(local) for _ in range(self.world)]
         dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(local), group=self.group)
         return torch.cat(parts, dim=1)
@@ -333,6 +425,11 @@ class ShardedQuantumDevice:
 
     # --- measurement (dispatched from torchquantum_b200.measurement) -----------------------
     def _all_reduce(self, t):
+        if t.is_cuda and dist.get_backend(self.group) == "gloo":
+            h = t.cpu()
+            dist.all_reduce(h, group=self.group)
+            t.copy_(h)
+            return t
         dist.all_reduce(t, group=self.group)
         return t
 
