@@ -301,7 +301,8 @@ def run_cfg5(dev, n, layers=4, exchange="auto", reps=2):
     with torch.no_grad():
         for rep in range(reps):   # rep 0 warms up (plan build, NCCL channels / symmetric-memory rendezvous)
             q.reset_states(1)
-            q.stats.update(exchanges=0, exchange_bytes_sent=0, exchange_ms=[], local_permute_passes=0, local_runs=[])
+            q.stats.update(exchanges=0, exchange_bytes_sent=0, exchange_ms=[], local_permute_passes=0, local_runs=[],
+                           exchange_victim_bits=[])
             dist.barrier()
             torch.cuda.synchronize()
             l0 = engine.STATS["launches"]
@@ -335,7 +336,7 @@ def run_cfg5(dev, n, layers=4, exchange="auto", reps=2):
         "total_ms": round(total_ms, 3), "qft_ms": round(t[0].item(), 3), "brickwork_ms": round(t[1].item(), 3),
         "exchanges": q.stats["exchanges"], "local_permute_passes": q.stats["local_permute_passes"],
         "exchange_ms_total": round(t[2].item(), 3), "exchange_ms_each": [round(v, 3) for v in ex_ms],
-        "exchange_bytes_sent_per_rank": sent,
+        "exchange_bytes_sent_per_rank": sent, "exchange_victim_bits": q.stats.get("exchange_victim_bits"),
         "exchange_GBps_per_rank_per_direction": round(sent / max(t[2].item(), 1e-9) / 1e6, 1),
         "nvlink_peak_GBps_per_direction": 900.0,
         "exchange_frac_of_nvlink": round(sent / max(t[2].item(), 1e-9) / 1e6 / 900.0, 4),

@@ -36,13 +36,11 @@
 
 namespace tqb_umma {
 
-constexpr uint32_t kHi = 4;                     // raw / hi planes: tiles in flight between TMA load and the end of their MMAs
-constexpr uint32_t kLo = 3;                     // lo planes, reused as the tile's output staging until the TMA store has read it
 constexpr uint32_t kAcc = 3;                    // TMEM accumulators (128 columns each)
-constexpr int kThreads = 384;
 constexpr uint32_t kPlane = 32768;              // bytes of one operand plane (hi or lo) of a tile
-constexpr uint32_t kSmemBytes = (kHi + kLo) * kPlane + 1024 /* alignment slack */ + 512 /* barriers, norms */;
+constexpr uint32_t kSmemBytes = 7 * kPlane + 1024 /* alignment slack */ + 1024 /* barriers, norms */;   // 7 planes in both variants
 constexpr uint32_t kTmemCols = 512;
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A K-major (TMEM), B MN-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -184,33 +182,41 @@ __device__ __forceinline__ uint32_t swz32(uint32_t row, uint32_t c16) {
 
 #define TQB_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 10 + (slot)] = (unsigned long long)clock64(); } while (0)
 
+// (Tried and dropped, profiles/r02_block6_notes.txt: the epilogue storing its registers straight to global memory, which
+// frees the lo plane at the end of the MMAs and allows 5 hi + 2 lo planes, ran at 0.97 ms against 0.84 ms for the TMA
+// write-back: 32-byte store segments; 8 splitter warps instead of 4 changed nothing, the split is not on the critical path.)
+constexpr uint32_t kHi = 4;                     // raw / hi planes: tiles in flight between TMA load and the end of their MMAs
+constexpr uint32_t kLo = 3;                     // lo planes, reused as the tile's output staging until the TMA store has read it
+constexpr int kSplitWarps = 4, kSplitThreads = 32 * kSplitWarps;
+constexpr int kThreads = 256 + kSplitThreads;
+
 __global__ void __launch_bounds__(kThreads, 1)
 tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // buffer rings (32 KiB planes): kHi planes that receive the raw tile and become its TF32 hi part in place, kLo planes
-  // that hold the TF32 lo part and, once the MMAs of the tile are done, the finished tile on its way to the TMA store
+  // that hold the TF32 lo part (and, with the TMA write-back, the finished tile on its way out)
   auto hi_plane = [&](uint32_t k) { return base + k * kPlane; };
   auto lo_plane = [&](uint32_t k) { return base + (kHi + k) * kPlane; };
   const uint32_t bars = base + (kHi + kLo) * kPlane;
   // barrier slots (8 bytes each); then the TMEM base address
   auto full = [&](uint32_t k) { return bars + 8u * k; };                            // [kHi] raw tile landed (TMA tx)
-  auto ready = [&](uint32_t k) { return bars + 8u * (kHi + k); };                   // [kHi] hi / lo parts written (128 splitters)
+  auto ready = [&](uint32_t k) { return bars + 8u * (kHi + k); };                   // [kHi] hi / lo parts written (all splitters)
   auto empty = [&](uint32_t k) { return bars + 8u * (2 * kHi + k); };               // [kHi] MMAs of the tile done: hi plane free
   auto dfull = [&](uint32_t d) { return bars + 8u * (3 * kHi + d); };               // [kAcc] accumulator complete
   auto dempty = [&](uint32_t d) { return bars + 8u * (3 * kHi + kAcc + d); };       // [kAcc] accumulator read out (128 threads)
   auto outready = [&](uint32_t k) { return bars + 8u * (3 * kHi + 2 * kAcc + k); }; // [kLo] finished tile staged in the lo plane
-  auto stored = [&](uint32_t k) { return bars + 8u * (3 * kHi + 2 * kAcc + kLo + k); };  // [kLo] TMA store has read it: lo plane free
+  auto lofree = [&](uint32_t k) { return bars + 8u * (3 * kHi + 2 * kAcc + kLo + k); };  // [kLo] the TMA store has read the lo plane: free
   const uint32_t tmem_slot = bars + 8u * (3 * kHi + 2 * kAcc + 2 * kLo);
   const uint32_t nin_slot = bars + 256u;    // [8 tiles in flight][4 splitter warps] squared norms of the raw tile
-  const uint32_t nout_slot = bars + 384u;   // [2][4 epilogue warps] squared norms of the computed tile
+  const uint32_t nout_slot = bars + 512u;   // [2][4 epilogue warps] squared norms of the computed tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (uint32_t k = 0; k < kHi; ++k) { mbar_init(full(k), 1); mbar_init(ready(k), 128); mbar_init(empty(k), 1); }
+    for (uint32_t k = 0; k < kHi; ++k) { mbar_init(full(k), 1); mbar_init(ready(k), kSplitThreads); mbar_init(empty(k), 1); }
     for (uint32_t d = 0; d < kAcc; ++d) { mbar_init(dfull(d), 1); mbar_init(dempty(d), 128); }
-    for (uint32_t k = 0; k < kLo; ++k) { mbar_init(outready(k), 1); mbar_init(stored(k), 1); }
+    for (uint32_t k = 0; k < kLo; ++k) { mbar_init(outready(k), 1); mbar_init(lofree(k), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_src) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dst) : "memory");
@@ -309,25 +315,26 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         TQB_TRACE(9);
-        mbar_arrive(stored(l));
+        mbar_arrive(lofree(l));
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= 8) {
     // ---------------- splitters: raw fp32 -> TF32 hi (in place) + TF32 lo ----------------
     const int tid = threadIdx.x - 256;
+    constexpr int kVecs = 2048 / kSplitThreads;   // 16-byte vectors per thread and tile
     uint32_t it = 0;
     for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
       const uint32_t k = it % kHi, l = it % kLo;
       mbar_wait(full(k), (it / kHi) & 1u);
       if (tid == 0) TQB_TRACE(1);
-      mbar_wait(stored(l), ((it / kLo) & 1u) ^ 1u);   // the tile that used this lo plane last has left it
+      mbar_wait(lofree(l), ((it / kLo) & 1u) ^ 1u);   // the tile that used this lo plane last has left it
       if (tid == 0) TQB_TRACE(2);
       const uint32_t bh = hi_plane(k) + 16u * tid, bl = lo_plane(l) + 16u * tid;
       float ss = 0.f;
 #pragma unroll 4
-      for (int v = 0; v < ((p.debug & 1) ? 0 : 16); ++v) {
-        const uint32_t a = bh + 2048u * v;
+      for (int v = 0; v < ((p.debug & 1) ? 0 : kVecs); ++v) {
+        const uint32_t a = bh + 16u * kSplitThreads * v;
         float x0, x1, x2, x3;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(a) : "memory");
         ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
@@ -335,7 +342,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         const uint32_t l0 = tf32_rna(x0 - __uint_as_float(h0)), l1 = tf32_rna(x1 - __uint_as_float(h1));
         const uint32_t l2 = tf32_rna(x2 - __uint_as_float(h2)), l3 = tf32_rna(x3 - __uint_as_float(h3));
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bl + 2048u * v), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bl + 16u * kSplitThreads * v), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
       }
       if (p.renorm) {
 #pragma unroll

@@ -588,8 +588,24 @@ template <int VEC>
 __global__ void __launch_bounds__(256) tqb_exchange_kernel(const float* __restrict__ src, const ExchangeArgs a, long long total_vec) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const unsigned long long slab_mask = (1ull << a.nl) - 1ull;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += stride) {
-    const unsigned long long flat = (unsigned long long)v * VEC;   // amplitude index within [bsz][2^nl]
+  // Iteration order: the destination rank must vary FAST (every 1 KiB chunk of a warp goes to the next rank), otherwise the
+  // grid sweeps the slab region by region and first does all local copies, then all remote ones: the NVLink and the local
+  // HBM phases would run one after the other.  When every victim bit is >= 6 the chunk counter's low g bits are therefore
+  // routed to the victim positions and its other bits fill the remaining index bits in order (a bit deposit with <= 4 holes).
+  const bool interleave = VEC == 2 && a.vpos[0] >= 6;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total_vec; it += stride) {
+    unsigned long long flat = (unsigned long long)it * VEC;   // amplitude index within [bsz][2^nl]
+    if (interleave) {
+      const unsigned long long c = (unsigned long long)it >> 5;       // 64-amplitude chunk counter
+      unsigned long long x = c >> a.g;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < a.g) {
+          const int pos = a.vpos[k] - 6;
+          x = ((x >> pos) << (pos + 1)) | (x & ((1ull << pos) - 1ull)) | (((c >> k) & 1ull) << pos);
+        }
+      flat = (x << 6) | (((unsigned long long)it & 31ull) << 1);
+    }
     unsigned long long i = flat & slab_mask;
     int to = 0;
 #pragma unroll
@@ -600,10 +616,10 @@ __global__ void __launch_bounds__(256) tqb_exchange_kernel(const float* __restri
       }
     const unsigned long long out = (flat & ~slab_mask) | i;
     if (VEC == 2) {
-      const float4 val = __ldcs(reinterpret_cast<const float4*>(src) + v);
+      const float4 val = __ldcs(reinterpret_cast<const float4*>(src) + (flat >> 1));
       reinterpret_cast<float4*>(a.dst[to])[out >> 1] = val;
     } else {
-      const float2 val = __ldcs(reinterpret_cast<const float2*>(src) + v);
+      const float2 val = __ldcs(reinterpret_cast<const float2*>(src) + flat);
       reinterpret_cast<float2*>(a.dst[to])[out] = val;
     }
   }
