@@ -124,6 +124,21 @@ int tqb_probs(const float* state, int n_qubits, long long bsz, float* probs, voi
 int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const float* uniforms, int n_shots,
                       float* cdf_scratch, int* counts, void* stream);
 
+/* Batch collapse (engine.py): a run of gates shared by the whole batch is one 2^n x 2^n unitary, applied to all states at
+ * once as a GEMM on the tensor cores; what the reference's static mode does block-wise with torch.bmm
+ * (graph/graphs.py:713-861 block unitaries, :836-861 QuantumGraph.apply_unitary).
+ * tqb_split_tf32: x[n] -> TF32 hi and lo parts (n % 4 == 0).
+ * tqb_gemm_tf32x3: C[M][N] = A[M][K] * Bt[N][K]^T (all row-major fp32, operands given as their hi / lo parts) with fp32
+ *   accuracy: Alo Bhi + Ahi Blo + Ahi Bhi, tcgen05.mma kind::tf32.  M % 128 == N % 256 == K % 32 == 0.  K is cut into chains
+ *   of <= 512 (the tensor core's truncating accumulation is biased in proportion to the chain length); the partial
+ *   products go to `workspace` (tqb_gemm_workspace_floats(M, N, K) floats, 0 = not needed) and are summed in fp32
+ *   round-to-nearest.  A complex product is this GEMM on the interleaved (re, im) views with Bt the real 2x2 embedding of
+ *   the right factor. */
+int tqb_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+long long tqb_gemm_workspace_floats(long long M, long long N, long long K);
+int tqb_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* bt_hi, const float* bt_lo, float* c, float* workspace,
+                    long long M, long long N, long long K, void* stream);
+
 /* Sharded statevector (no counterpart in the reference, which is single-device: device/devices.py:36-136; README.md:52 only
  * claims multi-GPU): swap the g rank-index qubits with the g local index bits victim_bits_host[0..g) (ascending) by
  * writing every amplitude of `src` (this rank's slab [bsz][2^n_local]) straight into its place in the destination slab of

@@ -410,3 +410,46 @@ def check_reference_test_vectors(device, tmp_path=None):
         # two different float32 circuits for the same derivative (the reference's own values differ by 4e-6 here; its
         # test allows 1e-3, test/hadamard_grad/test_hadamard_grad.py:33)
         assert (torch.stack(hg).cpu() - torch.stack(back).cpu()).abs().max().item() < 1e-4, f"hadamard_grad vs adjoint, circuit {k}"
+
+
+def check_batch_collapse(device, n=7, bsz=300):
+    """engine batch collapse: a long run of shared-parameter gates on a batch larger than the Hilbert space goes through
+    ONE unitary (built on the identity batch) and the 3xTF32 tensor-core GEMM; states, expectation values and all gradients
+    (shared parameters through the GEMM's backward + the adjoint sweep over the unitary's columns, per-sample encoder angles
+    through the GEMM's other backward) must equal the gate-by-gate engine and the oracle."""
+    from tests import cases
+    from torchquantum_b200 import engine
+
+    assert engine.COLLAPSE and bsz >= 2 * 2 ** n
+    launches0 = engine.STATS["launches"]
+    cases.check_cfg2_vqe(device, n=n, reps=4, bsz=bsz)          # vs the oracle, through the collapse (bsz not a multiple of 128)
+    torch.manual_seed(3)
+    ops = cases.brickwork_ops(n, 8, seed=2)                      # shared angles only: the whole circuit is one unitary
+    x = torch.randn(bsz, 2 ** n, dtype=torch.complex64)
+    x = (x / x.norm(dim=1, keepdim=True)).to(device)
+
+    def run(collapse):
+        saved = engine.COLLAPSE
+        engine.COLLAPSE = collapse
+        try:
+            st = x.clone().requires_grad_(True)
+            q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+            q.set_states(st)
+            ps = [o["params"].clone().to(device).requires_grad_(True) if o.get("params") is not None else None for o in ops]
+            cases.apply_ops(q, [dict(o, params=p) if p is not None else o for o, p in zip(ops, ps)], device)
+            out = q.get_states_1d()
+            w = torch.linspace(0.5, 1.5, 2 ** n, device=device)
+            loss = (out.abs() ** 2 * w).sum() + tq.expval_joint_analytical(q, "ZX" + "I" * (n - 2)).sum()
+            grads = torch.autograd.grad(loss, [st] + [p for p in ps if p is not None])
+            return out.detach(), grads
+        finally:
+            engine.COLLAPSE = saved
+
+    assert len(ops) >= engine.COLLAPSE_MIN_GATES
+    s1, g1 = run(True)
+    s0, g0 = run(False)
+    assert_close(s1, s0, what="collapsed states vs gate-by-gate")
+    assert_close(g1[0], g0[0], rtol=GRAD_RTOL, what="dL/dpsi_in through the collapsed run")
+    assert_close(torch.cat([g.reshape(-1) for g in g1[1:]]), torch.cat([g.reshape(-1) for g in g0[1:]]), rtol=GRAD_RTOL,
+                 what="shared-parameter gradients through the collapsed run")
+    assert engine.STATS["launches"] > launches0

@@ -8,6 +8,7 @@
 // Build: g++ -std=c++17 -O2 -shared -fPIC -o tests/emu/libtqb200_emu.so tests/emu/tqb_emu.cpp
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cmath>
@@ -304,6 +305,32 @@ int tqb_sample_counts(const float* probs, int n, long long bsz, const float* u, 
       counts[b * N + lo] += 1;
     }
   }
+  return 0;
+}
+static inline float emu_tf32_rna(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+int tqb_split_tf32(const float* x, float* hi, float* lo, long long n, void*) {
+  for (long long i = 0; i < n; ++i) { hi[i] = emu_tf32_rna(x[i]); lo[i] = emu_tf32_rna(x[i] - hi[i]); }
+  return 0;
+}
+long long tqb_gemm_workspace_floats(long long, long long, long long) { return 0; }
+int tqb_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* bt_hi, const float* bt_lo, float* c, float*, long long M,
+                    long long N, long long K, void*) {
+  if (M % 128 || N % 256 || K % 32) return fail_msg("gemm: M % 128, N % 256, K % 32 must be 0");
+  for (long long m = 0; m < M; ++m)
+    for (long long n = 0; n < N; ++n) {
+      float acc = 0.f;   // same order of the three products as the device kernel
+      for (long long k = 0; k < K; ++k) acc += a_lo[m * K + k] * bt_hi[n * K + k];
+      for (long long k = 0; k < K; ++k) acc += a_hi[m * K + k] * bt_lo[n * K + k];
+      for (long long k = 0; k < K; ++k) acc += a_hi[m * K + k] * bt_hi[n * K + k];
+      c[m * N + n] = acc;
+    }
   return 0;
 }
 int tqb_exchange_p2p(const float*, float* const*, int, long long, int, const int*, int, void*) {

@@ -84,7 +84,8 @@ def test_cfg1_model_from_classes_matches_reference_golden():
                                    "check_parameter_values_are_read_at_the_gate_call", "check_checkpoint_round_trip",
                                    "check_from_op_history_and_get_unitary", "check_static_mode_equals_dynamic",
                                    "check_layer_classes", "check_einsum_broadcast",
-                                   "check_dropped_device_is_freed_by_refcount", "check_reference_test_vectors"])
+                                   "check_dropped_device_is_freed_by_refcount", "check_reference_test_vectors",
+                                   "check_batch_collapse"])
 def test_host_mirror_semantics(check):
     from tests import cases_api
 

@@ -187,7 +187,8 @@ def test_full_size_properties_n24():
                                    "check_parameter_values_are_read_at_the_gate_call", "check_checkpoint_round_trip",
                                    "check_from_op_history_and_get_unitary", "check_static_mode_equals_dynamic",
                                    "check_layer_classes", "check_einsum_broadcast",
-                                   "check_dropped_device_is_freed_by_refcount", "check_reference_test_vectors"])
+                                   "check_dropped_device_is_freed_by_refcount", "check_reference_test_vectors",
+                                   "check_batch_collapse"])
 def test_host_mirror_semantics(check):
     """lazy-queue semantics, record caches, checkpoints, static mode, op_history, layer classes, the pure
     apply_unitary_* functions on the real kernels"""

@@ -24,7 +24,7 @@ OP_NAMES = (
     "tqb_build_mats", "tqb_build_mats_bwd", "tqb_pass_forward", "tqb_pass_backward", "tqb_apply_dense",
     "tqb_apply_dense_tc", "tqb_block_build", "tqb_apply_blocks", "tqb_dense_grad", "tqb_expval_pauli",
     "tqb_expval_pauli_bwd", "tqb_expval_z", "tqb_expval_z_bwd", "tqb_probs", "tqb_sample_counts", "tqb_host_uniforms",
-    "tqb_exchange_p2p",
+    "tqb_exchange_p2p", "tqb_split_tf32", "tqb_gemm_tf32x3",
 )
 
 _ops = None          # name -> OpOverload

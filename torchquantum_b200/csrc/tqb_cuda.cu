@@ -8,6 +8,7 @@
 #include "tqb_dense_tc.cuh"
 #include "tqb_block_umma.cuh"
 #include "tqb_block_build.cuh"
+#include "tqb_gemm_umma.cuh"
 #include "tqb_host_rng.h"
 #include "../../include/tqb200.h"
 
@@ -570,6 +571,22 @@ __global__ void tqb_sample_kernel(const float* cdf, const float* u, long long bs
   atomicAdd(counts + b * N + lo, 1);
 }
 
+// x -> TF32 hi / lo parts (round to nearest on the bit pattern, as the block kernel's splitters do): operand planes of the
+// 3xTF32 GEMM
+__global__ void __launch_bounds__(256) tqb_split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
+                                                             long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 h, l;
+    h.x = __uint_as_float(tqb_umma::tf32_rna(v.x)); h.y = __uint_as_float(tqb_umma::tf32_rna(v.y));
+    h.z = __uint_as_float(tqb_umma::tf32_rna(v.z)); h.w = __uint_as_float(tqb_umma::tf32_rna(v.w));
+    l.x = __uint_as_float(tqb_umma::tf32_rna(v.x - h.x)); l.y = __uint_as_float(tqb_umma::tf32_rna(v.y - h.y));
+    l.z = __uint_as_float(tqb_umma::tf32_rna(v.z - h.z)); l.w = __uint_as_float(tqb_umma::tf32_rna(v.w - h.w));
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K10: global <-> local qubit exchange over peer memory (NVLink P2P stores), pack and transfer in ONE kernel.
 // Rank r swaps its g rank-index bits with the g local index bits `vpos` (any positions, ascending): amplitude i of the
@@ -879,6 +896,26 @@ int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const flo
     tqb_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cdf_scratch, uniforms, bsz, N, n_shots, counts);
     TQB_CHECK_LAUNCH("tqb_sample_kernel");
   }
+  return 0;
+}
+
+int tqb_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) {
+  if (n <= 0) return 0;
+  if (n % 4 || (((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15)) return fail_msg("tqb_split_tf32: n % 4 == 0 and 16-byte aligned pointers");
+  const long long n4 = n / 4;
+  const unsigned grid = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  tqb_split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                                              reinterpret_cast<float4*>(lo), n4);
+  TQB_CHECK_LAUNCH("tqb_split_tf32_kernel");
+  return 0;
+}
+
+long long tqb_gemm_workspace_floats(long long M, long long N, long long K) { return tqb_gemm::gemm_workspace_floats(M, N, K); }
+
+int tqb_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* bt_hi, const float* bt_lo, float* c, float* workspace,
+                    long long M, long long N, long long K, void* stream) {
+  const char* err = tqb_gemm::launch_gemm(a_hi, a_lo, bt_hi, bt_lo, c, workspace, M, N, K, (cudaStream_t)stream);
+  if (err) return fail_msg(err);
   return 0;
 }
 

@@ -41,6 +41,9 @@ struct Abi {
   decltype(&tqb_sample_counts) sample_counts = nullptr;
   decltype(&tqb_host_uniforms) host_uniforms = nullptr;
   decltype(&tqb_exchange_p2p) exchange_p2p = nullptr;
+  decltype(&tqb_split_tf32) split_tf32 = nullptr;
+  decltype(&tqb_gemm_tf32x3) gemm_tf32x3 = nullptr;
+  decltype(&tqb_gemm_workspace_floats) gemm_workspace_floats = nullptr;
 };
 
 Abi g_cuda, g_emu;
@@ -80,6 +83,9 @@ int64_t bind(const std::string& path, bool emulated) {
   resolve(h, "tqb_sample_counts", n.sample_counts, true);
   resolve(h, "tqb_host_uniforms", n.host_uniforms, true);
   resolve(h, "tqb_exchange_p2p", n.exchange_p2p, true);
+  resolve(h, "tqb_split_tf32", n.split_tf32, true);
+  resolve(h, "tqb_gemm_tf32x3", n.gemm_tf32x3, true);
+  resolve(h, "tqb_gemm_workspace_floats", n.gemm_workspace_floats, true);
   TORCH_CHECK(n.abi_version() == TQB_ABI_VERSION, "libtqb200: ABI version ", n.abi_version(), " != ", TQB_ABI_VERSION);
   a = n;
   return n.abi_version();
@@ -248,6 +254,25 @@ void exchange_p2p(const at::Tensor& src, at::Tensor& local_dst, at::IntArrayRef 
   check(a, a.exchange_p2p(fp(src), ptrs, (int)n_local, bsz, g, vb, (int)rank, stream_of(src)), "tqb_exchange_p2p");
 }
 
+void split_tf32(const at::Tensor& x, at::Tensor& hi, at::Tensor& lo) {
+  const Abi& a = abi_for(x);
+  TORCH_CHECK(x.scalar_type() == at::kFloat && hi.numel() == x.numel() && lo.numel() == x.numel(), "tqb_split_tf32: float32, equal sizes");
+  check(a, a.split_tf32(fp(x), fpm(hi), fpm(lo), x.numel(), stream_of(x)), "tqb_split_tf32");
+}
+
+void gemm_tf32x3(const at::Tensor& a_hi, const at::Tensor& a_lo, const at::Tensor& bt_hi, const at::Tensor& bt_lo, at::Tensor& c) {
+  const Abi& a = abi_for(a_hi);
+  TORCH_CHECK(a_hi.dim() == 2 && bt_hi.dim() == 2 && c.dim() == 2 && a_hi.size(1) == bt_hi.size(1) && c.size(0) == a_hi.size(0) &&
+                  c.size(1) == bt_hi.size(0) && a_lo.sizes() == a_hi.sizes() && bt_lo.sizes() == bt_hi.sizes(),
+              "tqb_gemm_tf32x3: C[M][N] = A[M][K] * Bt[N][K]^T");
+  const int64_t M = a_hi.size(0), N = bt_hi.size(0), K = a_hi.size(1);
+  const int64_t ws = a.gemm_workspace_floats(M, N, K);
+  at::Tensor workspace;   // torch's caching allocator: device memory is plumbing
+  if (ws > 0) workspace = at::empty({ws}, c.options());
+  check(a, a.gemm_tf32x3(fp(a_hi), fp(a_lo), fp(bt_hi), fp(bt_lo), fpm(c), ws > 0 ? static_cast<float*>(workspace.data_ptr()) : nullptr,
+                         M, N, K, stream_of(a_hi)), "tqb_gemm_tf32x3");
+}
+
 // HOST helper of the ABI (CPython's Mersenne Twister stream, csrc/tqb_host_rng.h): CPU tensors by design; served by
 // whichever build of the ABI is bound (the stream is the host's in both)
 void host_uniforms(at::Tensor& mt_state, int64_t n, at::Tensor& out) {
@@ -264,6 +289,8 @@ void host_uniforms(at::Tensor& mt_state, int64_t n, at::Tensor& out) {
 
 TORCH_LIBRARY(tqb200, m) {
   m.def("tqb_host_uniforms(Tensor(a!) mt_state, int n, Tensor(b!) out) -> ()");
+  m.def("tqb_split_tf32(Tensor x, Tensor(a!) hi, Tensor(b!) lo) -> ()");
+  m.def("tqb_gemm_tf32x3(Tensor a_hi, Tensor a_lo, Tensor bt_hi, Tensor bt_lo, Tensor(a!) c) -> ()");
   m.def("tqb_exchange_p2p(Tensor src, Tensor(a!) local_dst, int[] peer_ptrs, int n_local, int bsz, int[] victim_bits, "
         "int rank) -> ()");
   m.def("_bind(str path, bool emulated) -> int", &bind);
@@ -311,7 +338,9 @@ TORCH_LIBRARY(tqb200, m) {
   m.impl("tqb_expval_z_bwd", &expval_z_bwd);             \
   m.impl("tqb_probs", &probs);                           \
   m.impl("tqb_sample_counts", &sample_counts);    \
-  m.impl("tqb_exchange_p2p", &exchange_p2p);
+  m.impl("tqb_exchange_p2p", &exchange_p2p);      \
+  m.impl("tqb_split_tf32", &split_tf32);          \
+  m.impl("tqb_gemm_tf32x3", &gemm_tf32x3);
 
 TORCH_LIBRARY_IMPL(tqb200, CUDA, m) { TQB_IMPL_ALL(m) }
 // CPU key: reaches only the injected host-emulation build (tests); abi_for() raises otherwise

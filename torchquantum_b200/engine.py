@@ -7,6 +7,8 @@ the backward, which un-applies the gates in reverse (tqb_pass_backward) while ac
 dL/dU, then maps dL/dU to dL/dtheta (tqb_build_mats_bwd): training memory is O(2^n) per sample
 instead of the reference's O(depth * 2^n) autograd tape.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -309,7 +311,102 @@ def _record_key(record, bsz, grad_mode):
     return (name, wires, inverse, pmode, grad, ext_dim)
 
 
-def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False):
+# ---------------------------------------------------------------------------------------
+# Batch collapse: a long run of gates that are the SAME for every sample (constants and shared [1, p] parameters) acting
+# on a batch larger than the Hilbert space is ONE 2^n x 2^n unitary W: it is built once by running the run on the
+# identity batch (2^n "samples" instead of bsz), and applied to the batch as a complex GEMM on the tensor cores.  The
+# reference's static mode does the same thing block-wise on the host (graph/graphs.py:713-861: unitary of the block,
+# then one bmm for the whole batch).  Autograd: dL/dW comes out of the GEMM's backward (psi^H . lambda, a GEMM again) and
+# flows into the adjoint sweep of the run over 2^n columns instead of bsz samples, so the backward shrinks by the same
+# factor bsz / 2^n.  Config 2 (n = 10, bsz = 4096, 600 shared gates): 4x fewer gate-amplitude updates in both directions.
+# ---------------------------------------------------------------------------------------
+COLLAPSE = os.environ.get("TQB200_COLLAPSE", "1") != "0"
+COLLAPSE_MIN_GATES = 64      # shorter runs are cheaper through the register-tile passes than a W build + GEMM
+COLLAPSE_MIN_N = 7           # the GEMM tiles are 128 x 256 x 32 real: 2 * 2^n >= 256
+COLLAPSE_MAX_N = 12          # W is 2^n x 2^n complex64: 128 MiB at n = 12
+COLLAPSE_MIN_BATCH_RATIO = 2  # bsz >= ratio * 2^n
+_EYE_CACHE = {}
+
+
+def _identity_batch(n, device):
+    k = (n, str(device))
+    t = _EYE_CACHE.get(k)
+    if t is None:
+        t = _EYE_CACHE[k] = torch.eye(2 ** n, dtype=torch.complex64, device=device)
+    return t
+
+
+def _collapsible(record):
+    name, wires, params, inverse = record
+    if name in G.UNITARY_LIKE or G.SPECS[name].kind == G.RESET or not G.SPECS[name].unitary:
+        return False
+    return params is None or (params.dim() == 2 and params.shape[0] == 1)
+
+
+class ComplexGemmFn(torch.autograd.Function):
+    """out[b, :] = sum_c a[b, c] w[c, :]   (a: [bsz, K], w: [K, N], complex64) with the conjugate-transposed GEMMs as its
+    backward."""
+
+    @staticmethod
+    def forward(ctx, a, w):
+        ctx.save_for_backward(a, w)
+        return complex_gemm(a, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w = ctx.saved_tensors
+        g = g.contiguous()
+        ga = complex_gemm(g, w.conj().transpose(0, 1).contiguous()) if ctx.needs_input_grad[0] else None
+        gw = complex_gemm(a.conj().transpose(0, 1).contiguous(), g) if ctx.needs_input_grad[1] else None
+        return ga, gw
+
+
+def _tf32_planes(x):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _native.call("tqb_split_tf32", x, hi, lo)
+    return hi, lo
+
+
+def complex_gemm(a, b):
+    """a [M, K] @ b [K, N], complex64, on the tensor cores (tqb_gemm_tf32x3: 3xTF32, fp32 accuracy).  The complex product is a
+    real GEMM on the interleaved (re, im) views: A = a as [M][2K], Bt[2n + w][2k + v] = the real 2x2 embedding of b[k][n]."""
+    _native.check_device(a)
+    M, K = a.shape
+    N = b.shape[1]
+    Kp = -(-K // 16) * 16            # tile sizes of the kernel: 128 rows, 32 real K, 256 real N (zero padding is exact)
+    if Kp != K:
+        a = torch.nn.functional.pad(a, (0, Kp - K))
+        b = torch.nn.functional.pad(b, (0, 0, 0, Kp - K))
+        K = Kp
+    assert (2 * N) % 256 == 0, "complex_gemm: N must be a multiple of 128"
+    ar = torch.view_as_real(a.contiguous()).reshape(M, 2 * K)
+    Mp = -(-M // 128) * 128
+    if Mp != M:
+        ar = torch.nn.functional.pad(ar, (0, 0, 0, Mp - M))
+    bt = b.transpose(0, 1).conj()                                   # [N, K]: rows 2n of Bt are (re, -im) of b[:, n]
+    btr = torch.view_as_real(torch.stack([bt, 1j * bt], dim=1).contiguous()).reshape(2 * N, 2 * K)   # rows 2n + 1: (im, re)
+    a_hi, a_lo = _tf32_planes(ar)
+    b_hi, b_lo = _tf32_planes(btr)
+    c = torch.empty(Mp, 2 * N, dtype=torch.float32, device=a.device)
+    _native.call("tqb_gemm_tf32x3", a_hi, a_lo, b_hi, b_lo, c)
+    STATS["launches"] += 3
+    return torch.view_as_complex(c[:M].view(M, N, 2))
+
+
+def _run_length(records, k):
+    j = k
+    while j < len(records) and _collapsible(records[j]):
+        j += 1
+    return j - k
+
+
+def _run_collapsed(state, n, records):
+    """records: a run of batch-independent gates -> state @ W^T with W^T[c, :] = circuit |c>"""
+    wt = run_circuit(_identity_batch(n, state.device), n, records, _no_collapse=True)
+    return ComplexGemmFn.apply(state.contiguous(), wt)
+
+
+def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collapse=False):
     """state: [bsz, 2^n] complex64; queue: list of records (name, wires, params, inverse) with canonical
     names and normalised params (2-D float tensors, or complex matrices for unitary-like gates), or
     RecordChunks of such records.
@@ -325,6 +422,28 @@ def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False):
                 records.append(item)
     else:
         records = queue
+    if (COLLAPSE and not _no_collapse and n_total is None and COLLAPSE_MIN_N <= n <= COLLAPSE_MAX_N
+            and len(records) >= COLLAPSE_MIN_GATES
+            and bsz >= COLLAPSE_MIN_BATCH_RATIO * 2 ** n):
+        # split into maximal runs of batch-independent gates; long ones go through W, the rest as before
+        out, i = state, 0
+        while i < len(records):
+            j = i
+            flag = _collapsible(records[i])
+            while j < len(records) and _collapsible(records[j]) == flag:
+                j += 1
+            part = records[i:j]
+            if flag and len(part) >= COLLAPSE_MIN_GATES:
+                out = _run_collapsed(out, n, part)
+            else:
+                # a short batch-independent run stays with its per-sample neighbours: merge forward
+                k = j
+                while k < len(records) and not (_collapsible(records[k]) and _run_length(records, k) >= COLLAPSE_MIN_GATES):
+                    k += 1
+                out = run_circuit(out, n, records[i:k], _no_collapse=True)
+                j = k
+            i = j
+        return out
     grad_mode = torch.is_grad_enabled() and (
         state.requires_grad or any(r[2] is not None and r[2].requires_grad for r in records))
     if chunked:

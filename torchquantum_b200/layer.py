@@ -15,38 +15,43 @@ __all__ = ["RandomLayer", "RandomLayerAllTypes", "Op1QAllLayer", "Op2QAllLayer",
            "LayerTemplate0", "NLocal", "TwoLocal", "EfficientSU2", "RealAmplitudes", "QFTLayer"]
 
 
-def _wires_tuple(wires):
-    return (int(wires),) if isinstance(wires, (int, np.integer)) else tuple(int(w) for w in wires)
-
-
 class _RecordCache:
     """Template layers queue the same records (same Parameter objects, wires, inverse flags) every step.
-    `records(q_device)` returns them from a cache that is re-validated by the operators' version
-    counters (any attribute write on an operator bumps its version) and the parameters' device; it
+    `records(q_device)` returns them from a cache that stays valid while (a) the layer's operator list is the same object
+    with the same mutation counter (QuantumModuleList._list_ver), (b) no attribute of the layer itself was assigned
+    (`__setattr__` below drops the cache: a new op list, another jump, ...), (c) the operators' version counters did not
+    move (any attribute write on an operator bumps its version) and (d) the parameters still live on the device; it
     returns None whenever some operator needs its full `forward` (noise model, op recording, ...)."""
+    _CACHE_KEEPS = frozenset(("q_device", "device", "static_mode", "graph", "parent_graph", "is_graph_top", "training"))
 
     def _layer_ops_wires(self):
         raise NotImplementedError
+
+    def _op_container(self):
+        """the QuantumModuleList this layer's operators live in"""
+        raise NotImplementedError
+
+    def __setattr__(self, name, value):
+        if name not in self._CACHE_KEEPS:
+            self.__dict__["_rec_cache"] = None
+        super().__setattr__(name, value)
 
     def records(self, q_device):
         if q_device.record_op or not getattr(q_device, "accepts_record_chunks", False):
             return None
         dev = q_device._flat.device
         c = self.__dict__.get("_rec_cache")
-        live = self._layer_ops_wires()
-        if c is not None and c[0] == dev and len(live) == len(c[2]):
-            # the cache is good only for the SAME operator objects on the same wires (a rebuilt op list, a replaced
-            # entry of ops_all or a changed jump / wire order invalidates it) whose version counters did not move
-            ver, same = 0, True
-            for (o, wires), oc, rc in zip(live, c[2], c[3]):
-                if o is not oc or _wires_tuple(wires) != rc[1]:
-                    same = False
-                    break
-                ver += o.__dict__["_ver"]
-            if same and ver == c[1] and all(p.device == dev for p in c[4]):
-                return c[3]
+        if c is not None and c[0] == dev:
+            cont = self._op_container()
+            if cont is c[5] and cont.__dict__["_list_ver"] == c[6]:
+                ver = 0
+                for o in c[2]:
+                    ver += o.__dict__["_ver"]
+                if ver == c[1] and all(p.device == dev for p in c[4]):
+                    return c[3]
         ops, recs, ver = [], [], 0
-        for o, wires in live:
+        cont = self._op_container()
+        for o, wires in self._layer_ops_wires():
             r = o.fast_record(q_device, wires)
             if r is None:
                 self.__dict__["_rec_cache"] = None
@@ -56,7 +61,8 @@ class _RecordCache:
             ops.append(o)
             recs.append(r)
             ver += o.__dict__["_ver"]
-        self.__dict__["_rec_cache"] = (dev, ver, ops, recs, [r[2] for r in recs if r[2] is not None])
+        self.__dict__["_rec_cache"] = (dev, ver, ops, recs, [r[2] for r in recs if r[2] is not None], cont,
+                                       cont.__dict__["_list_ver"])
         return recs
 
 
@@ -73,6 +79,9 @@ class Op1QAllLayer(QuantumModule, _RecordCache):
 
     def _layer_ops_wires(self):
         return [(op_k, k) for k, op_k in enumerate(self.ops_all)]
+
+    def _op_container(self):
+        return self.ops_all
 
     @static_support
     def forward(self, q_device):
@@ -108,6 +117,9 @@ class Op2QAllLayer(QuantumModule, _RecordCache):
                 wires.reverse()
             out.append((op_k, wires))
         return out
+
+    def _op_container(self):
+        return self.ops_all
 
     @static_support
     def forward(self, q_device):
@@ -212,6 +224,9 @@ class RandomLayer(QuantumModule, _RecordCache):
 
     def _layer_ops_wires(self):
         return [(operation, operation.wires) for operation in self.op_list]
+
+    def _op_container(self):
+        return self.op_list
 
     @static_support
     def forward(self, q_device):

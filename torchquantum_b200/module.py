@@ -153,8 +153,43 @@ class QuantumModule(nn.Module):
 
 
 class QuantumModuleList(nn.ModuleList, QuantumModule, metaclass=ABCMeta):
+    """nn.ModuleList of quantum modules.  Every mutation bumps `_list_ver`, which the layer templates' queue-record
+    caches (layer._RecordCache) compare instead of re-walking the list every step."""
+
     def __init__(self, *args, **kwargs):
+        self.__dict__["_list_ver"] = 0
         super().__init__(*args, **kwargs)
+
+    def _touch(self):
+        self.__dict__["_list_ver"] = self.__dict__.get("_list_ver", 0) + 1
+
+    def __setitem__(self, idx, module):
+        self._touch()
+        return super().__setitem__(idx, module)
+
+    def __delitem__(self, idx):
+        self._touch()
+        return super().__delitem__(idx)
+
+    def __iadd__(self, modules):
+        self._touch()
+        return super().__iadd__(modules)
+
+    def append(self, module):
+        self._touch()
+        return super().append(module)
+
+    def extend(self, modules):
+        self._touch()
+        return super().extend(modules)
+
+    def insert(self, index, module):
+        self._touch()
+        return super().insert(index, module)
+
+    def pop(self, key):
+        self._touch()
+        return super().pop(key)
 
 
 class QuantumModuleDict(nn.ModuleDict, QuantumModule, metaclass=ABCMeta):
