@@ -280,6 +280,13 @@ class RecordChunk(list):
         self.params = [r[2] for r in records if r[2] is not None]
         self._keys = {}
 
+    def collapsible(self):
+        """every record is the same for all samples (constants / shared [1, p] parameters, unitary): see run_circuit"""
+        c = self.__dict__.get("_collapsible")
+        if c is None:
+            c = self.__dict__["_collapsible"] = all(_collapsible(r) for r in self)
+        return c
+
     def key_for(self, bsz, grad_mode):
         flags = [p.requires_grad for p in self.params]
         hit = self._keys.get((bsz, grad_mode))
@@ -393,13 +400,6 @@ def complex_gemm(a, b):
     return torch.view_as_complex(c[:M].view(M, N, 2))
 
 
-def _run_length(records, k):
-    j = k
-    while j < len(records) and _collapsible(records[j]):
-        j += 1
-    return j - k
-
-
 def _run_collapsed(state, n, records):
     """records: a run of batch-independent gates -> state @ W^T with W^T[c, :] = circuit |c>"""
     wt = run_circuit(_identity_batch(n, state.device), n, records, _no_collapse=True)
@@ -425,24 +425,29 @@ def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collap
     if (COLLAPSE and not _no_collapse and n_total is None and COLLAPSE_MIN_N <= n <= COLLAPSE_MAX_N
             and len(records) >= COLLAPSE_MIN_GATES
             and bsz >= COLLAPSE_MIN_BATCH_RATIO * 2 ** n):
-        # split into maximal runs of batch-independent gates; long ones go through W, the rest as before
-        out, i = state, 0
-        while i < len(records):
-            j = i
-            flag = _collapsible(records[i])
-            while j < len(records) and _collapsible(records[j]) == flag:
-                j += 1
-            part = records[i:j]
-            if flag and len(part) >= COLLAPSE_MIN_GATES:
-                out = _run_collapsed(out, n, part)
+        # maximal runs of batch-independent queue items (single records, or whole RecordChunks of a layer template, whose
+        # cached plan keys keep working); long runs go through W, everything else runs as before
+        runs = []    # [flag, n_gates, items]
+        for item in queue:
+            if type(item) is RecordChunk:
+                flag, count = item.collapsible(), len(item)
             else:
-                # a short batch-independent run stays with its per-sample neighbours: merge forward
-                k = j
-                while k < len(records) and not (_collapsible(records[k]) and _run_length(records, k) >= COLLAPSE_MIN_GATES):
-                    k += 1
-                out = run_circuit(out, n, records[i:k], _no_collapse=True)
-                j = k
-            i = j
+                flag, count = _collapsible(item), 1
+            if runs and runs[-1][0] == flag:
+                runs[-1][1] += count
+                runs[-1][2].append(item)
+            else:
+                runs.append([flag, count, [item]])
+        out, pending = state, []
+        for flag, count, items in runs:
+            if flag and count >= COLLAPSE_MIN_GATES:
+                if pending:
+                    out, pending = run_circuit(out, n, pending, _no_collapse=True), []
+                out = _run_collapsed(out, n, items)
+            else:
+                pending += items   # short batch-independent runs stay with their per-sample neighbours
+        if pending:
+            out = run_circuit(out, n, pending, _no_collapse=True)
         return out
     grad_mode = torch.is_grad_enabled() and (
         state.requires_grad or any(r[2] is not None and r[2].requires_grad for r in records))
