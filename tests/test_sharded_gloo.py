@@ -120,3 +120,59 @@ def test_sharded_flush_makes_progress_or_raises():
     if not os.path.exists(emu):
         pytest.skip("host emulation library not built (run __graft_entry__.build())")
     mp.spawn(_worker_unrunnable, args=(2, _free_port(), emu), nprocs=2, join=True)
+
+
+def _worker_autograd(rank, world, port, n, emu_path):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torchquantum_b200 as tq
+        import torchquantum_b200.functional as tqf
+        from tests.helpers import GRAD_RTOL, assert_close
+        from torchquantum_b200 import _native
+        from torchquantum_b200.measurement import expval_joint_analytical_multi
+
+        _native.use_library_for_testing(emu_path)
+        torch.manual_seed(4)
+        thetas = [torch.randn(1, 1).requires_grad_(True) for _ in range(3 * n)]
+        obs = ["Z" * n, "ZZ" + "I" * (n - 2), "X" + "I" * (n - 2) + "Y", "I" * (n - 1) + "Z"]
+        wts = torch.tensor([0.7, -1.3, 0.4, 2.0])
+
+        def circuit(q):
+            k = 0
+            for w in range(n):
+                tqf.hadamard(q, wires=w)
+            for layer in range(3):
+                for w in range(n):                      # rotations on EVERY wire, incl. the rank-index ones
+                    (tqf.rx, tqf.ry, tqf.rz)[(layer + w) % 3](q, wires=w, params=thetas[k])
+                    k += 1
+                for w in range(layer % 2, n - 1, 2):
+                    tqf.cnot(q, wires=[w, w + 1])
+                tqf.crx(q, wires=[n - 1, 0], params=thetas[(5 * layer) % len(thetas)])
+            return (expval_joint_analytical_multi(q, obs) * wts).sum()
+
+        ref = tq.QuantumDevice(n_wires=n, bsz=2, device="cpu")
+        ref_loss = circuit(ref)
+        want = torch.autograd.grad(ref_loss, thetas)
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=2, device="cpu")
+        loss = circuit(q)
+        assert q.stats["exchanges"] >= 1
+        assert_close(loss.detach().reshape(1), ref_loss.detach().reshape(1), what="sharded loss")
+        for t in thetas:
+            t.grad = None
+        loss.backward()
+        q.allreduce_gradients(thetas)
+        assert_close(torch.cat([t.grad.reshape(-1) for t in thetas]), torch.cat([g.reshape(-1) for g in want]),
+                     rtol=GRAD_RTOL, what=f"rank {rank}: gradients through exchanges")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 7), (4, 8)])
+def test_sharded_adjoint_gradients_match_one_device(world, n):
+    """north_star (2) + (4): adjoint differentiation through the sharded device (exchange = involution in the backward,
+    expectation values all-reduced with a pass-through gradient, shared-parameter partials summed over the ranks)."""
+    emu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libtqb200_emu.so")
+    if not os.path.exists(emu):
+        pytest.skip("host emulation library not built (run __graft_entry__.build())")
+    mp.spawn(_worker_autograd, args=(world, _free_port(), n, emu), nprocs=world, join=True)

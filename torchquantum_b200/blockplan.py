@@ -20,7 +20,6 @@ from . import _codes as C
 K_BLOCK = 6
 LOW = (1 << K_BLOCK) - 1   # logical qubits 0..5 (parked in the identity layout)
 MAX_RUNS = 3
-COST_AWARE = True   # rank candidate blocks by gates absorbed per unit of measured pass time (placement_cost)
 _H = (np.array([[1, 1], [1, -1]]) / np.sqrt(2)).astype(np.complex64)
 
 FUSABLE_TYPES = (C.T_GEN, C.T_REAL, C.T_RX, C.T_DIAG, C.T_PERM, C.T_U2Q, C.T_HS)
@@ -82,23 +81,6 @@ def pad_kpos(phys, n_local):
             return None
     bits = sorted(have)
     return bits if _runs(bits) <= MAX_RUNS else None
-
-
-def placement_cost(kpos):
-    """Relative time of one block pass for a placement of the six block bits (1.0 = 0.82 ms at n = 28), from the sweep in
-    profiles/r02_block6_kpos_sweep.txt: tiles whose 64 rows are ALL >= 4 MiB apart (six bits >= 19) are write-bound
-    (1.1-1.37 ms), as are four or more of the top four bits combined with mid bits; one low / mid bit in the block brings the
-    pass back to 0.80-0.93 ms.  Only used to rank candidate blocks: a slower placement has to absorb that many more gates."""
-    if kpos is None:
-        return 1.0
-    lo = min(kpos)
-    if lo >= 19:
-        return 1.6 if lo < 22 else 1.35
-    if lo >= 16:
-        return 1.12 if lo < 18 else 1.25
-    if lo >= 12 and sum(1 for b in kpos if b >= 24) >= 4:
-        return 1.5
-    return 1.0
 
 
 class _Sched:
@@ -178,13 +160,11 @@ class _Sched:
                 blocked |= q
             if blocked == full:
                 break
-        best, best_score = None, -1.0
+        best = None
         for s in seeds:
             ch, tk = self.grow(remaining, forbidden, s)
-            kpos = pad_kpos([self.phys(b) for b in range(self.n) if (ch >> b) & 1], self.n) if COST_AWARE else None
-            score = len(tk) / placement_cost(kpos)
-            if score > best_score:
-                best, best_score = (ch, tk), score
+            if best is None or len(tk) > len(best[1]):
+                best = (ch, tk)
         return best if best is not None else (0, [])
 
     def exact_low(self, remaining):

@@ -20,8 +20,12 @@ that do not fit one GPU.  One process per GPU (`torch.distributed`, NCCL over NV
   as the pass packer in plan.py);
 * SWAP gates are free: they only relabel `pos`.
 
-Forward only (no autograd through the exchange yet): circuits of this size are simulated, not
-trained, in BASELINE configs 4-5.
+Autograd (north_star items 2 + 4 together): a flush issued with gradients enabled runs every local stage through the
+same adjoint-differentiation nodes as on one GPU, and every exchange through `_ExchangeFn`, whose backward is the same
+exchange applied to the incoming gradient (the swap of rank bits and local bits is an involution).  Expectation values
+are summed over the ranks by an autograd-aware all-reduce.  Parameters shared by the ranks receive, on every rank, the
+PARTIAL gradient of that rank's slab: `allreduce_gradients(params)` sums them (as a data-parallel trainer would).  In this
+mode exchanges use the collective back end and each fused stage keeps its output slab for the backward.
 """
 import numpy as np
 import torch
@@ -46,6 +50,31 @@ def _local_bits_needed(name, wires, params):
         return tuple(wires)
     n_ctrl = spec.n_ctrl if spec.n_ctrl >= 0 else len(wires) - 1
     return tuple(wires[n_ctrl:])
+
+
+class _ExchangeFn(torch.autograd.Function):
+    """Swap physical bits [nl-g, nl) <-> [nl, n) with all_to_all_single; the backward is the same swap of the gradient."""
+
+    @staticmethod
+    def forward(ctx, flat, dev):
+        ctx.dev = dev
+        return dev._collective_swap(flat)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.dev._collective_swap(g.contiguous()), None
+
+
+class _AllReduceSumFn(torch.autograd.Function):
+    """sum over the ranks; d(sum)/d(local) = 1, so the gradient passes through unchanged"""
+
+    @staticmethod
+    def forward(ctx, t, dev):
+        return dev._all_reduce(t.clone())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
 
 
 class ShardedQuantumDevice:
@@ -169,8 +198,11 @@ class ShardedQuantumDevice:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 l0 = engine.STATS["launches"]
                 e0.record()
-            out = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank, inplace=True)
-            if self._symm is not None and out.data_ptr() != self._flat.data_ptr():
+            out = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank,
+                                     inplace=not getattr(self, "_grad_flush", False))
+            if getattr(self, "_grad_flush", False):
+                self._flat = out          # autograd: every stage is out of place and keeps its output for the backward
+            elif self._symm is not None and out.data_ptr() != self._flat.data_ptr():
                 self._flat.copy_(out)   # an out-of-place stage (dense block, reset): back into the symmetric slab
             else:
                 self._flat = out
@@ -183,7 +215,10 @@ class ShardedQuantumDevice:
             return
         remaining, self._queue = self._queue, []
         n, nl = self.n_wires, self.nl
-        with torch.no_grad():
+        grad = torch.is_grad_enabled() and (self._flat.requires_grad or any(
+            r[2] is not None and r[2].requires_grad for r in remaining))
+        self._grad_flush = grad
+        with torch.set_grad_enabled(grad):
             while remaining:
                 runnable, rest, blocked = [], [], 0
                 pos = list(self.pos)
@@ -239,7 +274,7 @@ class ShardedQuantumDevice:
                 local_logical = high
         order = sorted(local_logical, key=lambda l: (-nxt.get(l, 1 << 60), -self.pos[l]))
         victims = order[:g]
-        if self._symm is not None:
+        if self._symm is not None and not getattr(self, "_grad_flush", False):
             self._exchange_p2p(sorted(self.pos[v] for v in victims))   # no pack pass: any local positions
         else:
             self._move_to_top(victims)
@@ -301,9 +336,32 @@ class ShardedQuantumDevice:
         """Swap physical bits [nl-g, nl) <-> [nl, n): chunk j of the slab goes to rank j and the chunk
         received from rank i lands at chunk position i (K10)."""
         nl, g, W = self.nl, self.g, self.world
-        if self._symm is not None:
+        grad = getattr(self, "_grad_flush", False) and torch.is_grad_enabled()
+        if self._symm is not None and not grad:
             return self._exchange_p2p(list(range(nl - g, nl)))
         flat = self._flat
+        bsz = flat.shape[0]
+        chunk = 1 << (nl - g)
+        timed = self.time_exchanges and flat.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._flat = _ExchangeFn.apply(flat, self) if grad else self._collective_swap(flat)
+        if timed:
+            e1.record()
+            self.stats["exchange_ms"].append((e0, e1))
+        self.stats["exchanges"] += 1
+        self.stats["exchange_bytes_sent"] += (W - 1) * chunk * bsz * 8
+        for l, p in enumerate(self.pos):
+            if nl - g <= p < nl:
+                self.pos[l] = p + g
+            elif p >= nl:
+                self.pos[l] = p - g
+
+    def _collective_swap(self, flat):
+        """the data movement of _all_to_all on an arbitrary [bsz, 2^nl] tensor (state or gradient)"""
+        nl, g, W = self.nl, self.g, self.world
+        flat = flat.contiguous()
         bsz = flat.shape[0]
         chunk = 1 << (nl - g)
         if bsz == 1:
@@ -311,10 +369,6 @@ class ShardedQuantumDevice:
         else:
             send = flat.view(bsz, W, chunk).transpose(0, 1).contiguous()
         recv = torch.empty_like(send)
-        timed = self.time_exchanges and flat.is_cuda
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         if flat.is_cuda and dist.get_backend(self.group) == "gloo":
             # a process group that cannot move device memory (several ranks sharing one GPU in the test-suite): the
             # chunks go through pinned host buffers; the kernels on either side are the same
@@ -324,20 +378,9 @@ class ShardedQuantumDevice:
             torch.view_as_real(recv).copy_(h_recv)
         else:
             dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
-        if timed:
-            e1.record()
-            self.stats["exchange_ms"].append((e0, e1))
-        self.stats["exchanges"] += 1
-        self.stats["exchange_bytes_sent"] += (W - 1) * chunk * bsz * 8
         if bsz == 1:
-            self._flat = recv.view(1, -1)
-        else:
-            self._flat = recv.view(W, bsz, chunk).transpose(0, 1).contiguous().view(bsz, -1)
-        for l, p in enumerate(self.pos):
-            if nl - g <= p < nl:
-                self.pos[l] = p + g
-            elif p >= nl:
-                self.pos[l] = p - g
+            return recv.view(1, -1)
+        return recv.view(W, bsz, chunk).transpose(0, 1).contiguous().view(bsz, -1)
 
     def local_run_times(self):
         """[(gates, kernel launches, ms)] of every local fused run since the stats were reset (time_exchanges)."""
@@ -352,7 +395,8 @@ class ShardedQuantumDevice:
         """Restore the identity layout (logical bit l at physical bit l)."""
         self.flush()
         n, nl, g = self.n_wires, self.nl, self.g
-        with torch.no_grad():
+        self._grad_flush = torch.is_grad_enabled() and self._flat.requires_grad
+        with torch.set_grad_enabled(self._grad_flush):
             target_global = list(range(nl, n))
             if any(self.pos[l] != l for l in target_global):
                 if any(self.pos[l] >= nl for l in target_global):
@@ -477,7 +521,21 @@ class ShardedQuantumDevice:
             result[:, t] = self._expval_local(["".join(zs)])[:, 0]
             for name, w in reversed(undo):
                 getattr(tqf, name)(self, wires=w)
+        if torch.is_grad_enabled() and result.requires_grad:
+            return _AllReduceSumFn.apply(result, self)
         return self._all_reduce(result)
+
+    def allreduce_gradients(self, params):
+        """Sum the `.grad` of parameters shared by the ranks (each rank's backward yields the partial gradient of its
+        slab), in place: call after `loss.backward()`, as a data-parallel trainer would."""
+        grads = [p.grad for p in params if p.grad is not None]
+        if grads:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            self._all_reduce(flat)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
 
     def _expval_local(self, observables):
         from .measurement import pauli_masks
@@ -509,10 +567,14 @@ class ShardedQuantumDevice:
         ny = torch.tensor(nys, dtype=torch.int32, device=dev)
         state = self._flat
         _native.check_device(state)
-        out = torch.zeros(self.bsz, len(observables), dtype=torch.float32, device=dev)
-        _native.call("tqb_expval_pauli", state, nl, self.bsz, xm, zm, ny, len(observables),
-                     out)
-        STATS["launches"] += 1
+        if torch.is_grad_enabled() and state.requires_grad:
+            from .measurement import _ExpvalPauliFn
+
+            out = _ExpvalPauliFn.apply(state, nl, xm, zm, ny, tuple(observables), None, None)
+        else:
+            out = torch.zeros(self.bsz, len(observables), dtype=torch.float32, device=dev)
+            _native.call("tqb_expval_pauli", state, nl, self.bsz, xm, zm, ny, len(observables), out)
+            STATS["launches"] += 1
         return out * torch.tensor(signs, dtype=torch.float32, device=dev)
 
     def expval_z_all(self):
