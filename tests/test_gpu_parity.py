@@ -271,6 +271,13 @@ def test_sharded_statevector_ranks_sharing_one_gpu(world, n, bsz):
     assert '"ok": true' in out, out[-1500:]
 
 
+def test_sharded_adjoint_gradients_ranks_sharing_one_gpu():
+    """north_star (2) + (4): adjoint gradients through the sharded device (rank-index rotations, controls, exchanges) equal
+    the one-GPU adjoint; 2 processes on cuda:0 over gloo."""
+    out = _torchrun(2, ["--grad", "16", "--backend", "gloo", "--exchange", "collective"], 29551)
+    assert '"ok": true' in out, out[-1500:]
+
+
 def test_sharded_statevector_two_gpus():
     """Amplitude-sharded device over NCCL / NVLink peer stores vs the same circuit on one GPU (needs >= 2 visible GPUs)."""
     if torch.cuda.device_count() < 2:

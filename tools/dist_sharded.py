@@ -54,6 +54,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--check-bsz", type=int, default=1)
+    ap.add_argument("--grad", type=int, default=0, help="n: adjoint gradients through the sharded device vs one GPU")
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="gloo: several ranks may share one GPU")
     ap.add_argument("--bench", type=int, default=0)
     ap.add_argument("--layers", type=int, default=4)
@@ -100,6 +101,38 @@ def main():
                             "state_rel_l2_vs_one_gpu": rel, "max_abs_expval_err": m[0].item(),
                             "exchanges": q.stats["exchanges"], "ok": bool(rel < 1e-5 and m[0].item() < 1e-5)}
         assert results["check"]["ok"], results["check"]
+
+    if a.grad:
+        n = a.grad
+        torch.manual_seed(4)
+        thetas = [torch.randn(1, 1, device=dev).requires_grad_(True) for _ in range(3 * n)]
+        obs = ["Z" * n, "ZZ" + "I" * (n - 2), "X" + "I" * (n - 2) + "Y", "I" * (n - 1) + "Z"]
+        wts = torch.tensor([0.7, -1.3, 0.4, 2.0], device=dev)
+
+        def circuit(q):
+            k = 0
+            for w in range(n):
+                tqf.hadamard(q, wires=w)
+            for layer in range(3):
+                for w in range(n):   # rotations on EVERY wire, incl. the rank-index ones
+                    (tqf.rx, tqf.ry, tqf.rz)[(layer + w) % 3](q, wires=w, params=thetas[k])
+                    k += 1
+                for w in range(layer % 2, n - 1, 2):
+                    tqf.cnot(q, wires=[w, w + 1])
+                tqf.crx(q, wires=[n - 1, 0], params=thetas[(5 * layer) % len(thetas)])
+            return (tq.expval_joint_analytical_multi(q, obs) * wts).sum()
+
+        ref_loss = circuit(tq.QuantumDevice(n_wires=n, bsz=2, device=dev))
+        want = torch.cat([g.reshape(-1) for g in torch.autograd.grad(ref_loss, thetas)])
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=2, device=dev, exchange="auto" if a.exchange == "both" else a.exchange)
+        loss = circuit(q)
+        loss.backward()
+        q.allreduce_gradients(thetas)
+        got = torch.cat([t.grad.reshape(-1) for t in thetas])
+        rel = float((got - want).norm() / want.norm())
+        results["grad"] = {"n": n, "world": world, "exchanges": q.stats["exchanges"], "loss_abs_err": abs(float(loss - ref_loss)),
+                           "grad_rel_l2_vs_one_gpu": rel, "ok": bool(rel < 1e-5 and abs(float(loss - ref_loss)) < 1e-5)}
+        assert results["grad"]["ok"], results["grad"]
 
     if a.bench:
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

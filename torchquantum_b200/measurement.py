@@ -180,21 +180,30 @@ def expval_joint_analytical_multi(qdev, observables: List[str]):
         return qdev.expval_pauli(list(observables))
     states = qdev.get_states_1d()
     obs = tuple(o.upper() for o in observables)
-    pre = _speculative_readout(qdev, states, obs[0]) if len(obs) == 1 else None
-    xm, zm, ny = _mask_tensors(observables, states.device)
+    if len(obs) == 1:
+        hit = _speculative_readout(qdev, states, obs[0])
+        if hit is not None:
+            return hit
+    return _readout(qdev, states, obs)
+
+
+def _readout(qdev, states, obs):
+    xm, zm, ny = _mask_tensors(obs, states.device)
     pending = None
     if torch.is_grad_enabled() and states.requires_grad:
         states, pending = _hub(qdev, states)
-    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny, obs, pending, pre)
+    return _ExpvalPauliFn.apply(states, qdev.n_wires, xm, zm, ny, obs, pending, None)
 
 
 # The reference API evaluates a Hamiltonian with ONE call per Pauli string (algorithm/vqe.py:88-95, examples/vqe), so a
 # training step asks for the same strings on every new state.  The strings read on the previous state of the same width
 # are remembered; the first single-string read-out on a new state evaluates all of them in one multi-term launch (the
-# terms share every load of the state) and the following calls are served from that result.  Values are identical to
-# per-string launches (same accumulation order per term); a string that was not predicted is simply launched on its own.
+# terms share every load of the state) UNDER ONE AUTOGRAD NODE, and the following calls return columns of that result: a
+# step with 19 strings costs one read-out kernel, one node and one backward kernel instead of 19 of each, and the host
+# does a dictionary lookup per call.  Values are identical to per-string launches (same accumulation order per term); a
+# string that was not predicted is simply launched on its own.
 _READOUT_HISTORY = {}   # (n_wires, device) -> tuple of strings read on the previous state of that width
-_READOUT_CURRENT = {}   # (n_wires, device) -> [weakref to the state being read, {string: [bsz, 1] values}, [strings so far], version]
+_READOUT_CURRENT = {}   # (n_wires, device) -> [weakref to the state being read, {string: [bsz, 1] column}, [strings so far], version, grad mode]
 SPECULATIVE_READOUT = True
 
 
@@ -203,15 +212,14 @@ def _speculative_readout(qdev, states, ob):
         return None
     key = (qdev.n_wires, states.device)
     c = _READOUT_CURRENT.get(key)
-    if c is None or c[0]() is not states or c[3] != states._version:   # (a state edited in place is a new state)
+    grad = torch.is_grad_enabled() and states.requires_grad
+    if c is None or c[0]() is not states or c[3] != states._version or c[4] != grad:   # (a state edited in place is a new state)
         if c is not None and len(c[2]) > 1:
             _READOUT_HISTORY[key] = tuple(dict.fromkeys(c[2]))   # what the previous state was asked for, in order
-        c = _READOUT_CURRENT[key] = [weakref.ref(states), {}, [], states._version]
+        c = _READOUT_CURRENT[key] = [weakref.ref(states), {}, [], states._version, grad]
         predicted = _READOUT_HISTORY.get(key, ())
         if len(predicted) > 1 and ob in predicted:
-            xm, zm, ny = _mask_tensors(list(predicted), states.device)
-            with torch.no_grad():
-                vals = _launch_expval(states.detach().contiguous(), qdev.n_wires, xm, zm, ny)
+            vals = _readout(qdev, states, predicted)
             for t, name in enumerate(predicted):
                 c[1][name] = vals[:, t:t + 1]
     c[2].append(ob)
