@@ -130,6 +130,7 @@ def _time_planned_circuit(n, key, thetas, dev, reps=3):
     plan = engine.get_plan(n, tuple(key), False)
     state = torch.zeros(1, 2 ** n, dtype=torch.complex64, device=dev)
     state[0, 0] = 1
+    other = torch.empty_like(state) if any(getattr(s, "n_rotating", 0) for s in plan.stages) else None
     evs = {"block": [], "pass": []}
     per_rep = {"block": 0, "pass": 0}
     pps = torch.zeros(1, 1, dtype=torch.float32, device=dev)
@@ -138,7 +139,9 @@ def _time_planned_circuit(n, key, thetas, dev, reps=3):
             psh = torch.tensor([thetas[r] for r in stage.sh_recs] or [0.0], dtype=torch.float32, device=dev)
             if stage.kind == "blocks":
                 t = []
-                engine.run_blocks(state, stage, n, 0, psh, True, timing=t)
+                out = engine.run_blocks(state, stage, n, 0, psh, True, timing=t, scratch=other)
+                if out is not state:      # rotating blocks move the state between the two buffers
+                    state, other = out, state
                 if rep > 0:
                     evs["block"] += t
                 elif rep == 0:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 4
+#define TQB_ABI_VERSION 5
 
 int tqb_abi_version(void);
 const char* tqb_last_error(void);
@@ -91,12 +91,18 @@ int tqb_apply_dense_tc(const float* in, float* out, int n_qubits, long long bsz,
  * tqb_block_build: blocks_dev [n_blocks][TQB_KB_WORDS], ops_dev [*][TQB_KO_WORDS], constant pool, shared parameters
  *   -> a_planes [n_blocks][2][128][64] float (TF32 hi / lo planes of A[2i+w][j] = (Re, Im)[w] U[i][j]).  `rank` resolves
  *   controls / parity bits that live in the rank index of a sharded state.
- * tqb_apply_blocks: applies the blocks in order; the first reads src, the others work in place on dst (dst may equal
- *   src).  blocks_host: the same block headers on the HOST (bit positions for the tensor maps).  n_qubits >= 12.
+ * tqb_apply_blocks: applies the blocks in order; the first reads src and the result ends up in dst.  A block without
+ *   TQB_KBF_ROTATE writes its tiles back where they came from (in place once the state is in dst / scratch).  A block
+ *   with TQB_KBF_ROTATE reads its tiles from wherever its six bits are and writes each as ONE contiguous 32 KiB piece
+ *   into the other buffer of {dst, scratch}: afterwards the block bits sit in index bits 6-11 (pattern order) and all
+ *   other bits >= 6 follow above them in their previous relative order (gathering reads run at full speed for every
+ *   placement, scattered 512-byte writes at strides >= 4 MiB do not; the caller tracks the qubit layout).  scratch may
+ *   be null when no block rotates; with an odd number of rotating blocks dst must differ from src (src may then serve
+ *   as scratch).  blocks_host: the same block headers on the HOST (bit positions for the tensor maps).  n_qubits >= 12.
  *   renorm != 0: every block is unitary, tiles are rescaled to the norm they came in with. */
 int tqb_block_build(const int32_t* blocks_dev, int n_blocks, const int32_t* ops_dev, const float* consts,
                     const float* params_sh, unsigned rank, float* a_planes, void* stream);
-int tqb_apply_blocks(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
+int tqb_apply_blocks(const float* src, float* dst, float* scratch, int n_qubits, long long bsz, const float* a_planes,
                      const int32_t* blocks_host, int n_blocks, int renorm, void* stream);
 /* G[b][r][c] = sum_rest lam_out[b][r,rest] conj(psi_in[b][c,rest]) (complex64 [bsz][2^k][2^k]) */
 int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long long bsz, int k,

@@ -571,3 +571,35 @@ def check_depth_parity(device, n, depth, mode, blocks=None, expect_blocks=None, 
         assert ("blocks" in kinds) == expect_blocks, kinds
     assert rel <= bar and norm_err <= bar, f"n={n} depth={depth} {mode}: rel_l2={rel:.3e} |norm-1|={norm_err:.3e}"
     return rel, norm_err
+
+
+def check_block_write_back_modes(device, n=18, depth=10):
+    """Block stages (tensor-core 6-qubit blocks) under both write-back disciplines of blockplan.py: in place (layout
+    only changes through transposing blocks) and rotating (every block writes contiguous tiles into the other buffer,
+    the scheduler tracks the qubit layout and sorts it home at the end): both equal the float64 oracle, and the state
+    comes back in the reference's qubit order."""
+    from torchquantum_b200 import blockplan as B, _codes as C, engine
+
+    saved = B.MODE
+    try:
+        for mode, want_rot in (("inplace", False), ("rotate", True), ("auto", None)):
+            B.MODE = mode
+            rel, norm_err, kinds = depth_parity(device, n, depth, "fwd", blocks=True)
+            assert "blocks" in kinds, kinds
+            assert rel <= 1e-5 and norm_err <= 1e-5, (mode, rel, norm_err)
+        # the plan really used what it was asked for
+        for mode, want_rot in (("inplace", False), ("rotate", True)):
+            B.MODE = mode
+            engine._PLAN_CACHE.clear()
+            ops = brickwork_ops(n, depth, seed=5)
+            q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+            with torch.no_grad():
+                apply_ops(q, [dict(o, params=o["params"].to(device)) if o.get("params") is not None else o for o in ops],
+                          device)
+                s = q.get_states_1d()
+            stages = [st for st in next(reversed(engine._PLAN_CACHE.values())).stages if st.kind == "blocks"]
+            assert stages and all((st.n_rotating == st.n_blocks) == want_rot for st in stages), mode
+            assert torch.allclose(s[0], s[1])      # both batch members (outer bits above n) take the same path
+    finally:
+        B.MODE = saved
+        engine._PLAN_CACHE.clear()

@@ -165,12 +165,23 @@ int tqb_block_build(const int32_t* blocks, int n_blocks, const int32_t* ops, con
 }
 
 // host restatement of tqb_block6_kernel's arithmetic contract: out tile = (A_hi + A_lo) * tile, the block's bits and the
-// index bits 0-5 exchanged on the way out when the block is transposing (fp32 data, double accumulation)
-int tqb_apply_blocks(const float* src_, float* dst_, int n, long long bsz, const float* planes_all, const int32_t* blocks_host,
-                     int n_blocks, int, void*) {
+// index bits 0-5 exchanged on the way out when the block is transposing, the tile written contiguously (block bits ->
+// index bits 6-11, outer bits compacted above) when it is rotating (fp32 data, double accumulation).  Same buffer chain
+// as the CUDA library: rotating blocks alternate between dst and scratch, the last block leaves the state in dst.
+int tqb_apply_blocks(const float* src_, float* dst_, float* scratch_, int n, long long bsz, const float* planes_all,
+                     const int32_t* blocks_host, int n_blocks, int, void*) {
   if (n < 12) return fail_msg("block6 needs n_qubits >= 12");
+  if (bsz <= 0 || n_blocks <= 0) return 0;
   const u64 N = 1ull << n;
   std::vector<cf> tmp(N);
+  int flips = 0;
+  for (int b = 1; b < n_blocks; ++b) flips += (blocks_host[(size_t)b * TQB_KB_WORDS + TQB_KB_FLAGS] & TQB_KBF_ROTATE) ? 1 : 0;
+  const int rot0 = (blocks_host[TQB_KB_FLAGS] & TQB_KBF_ROTATE) ? 1 : 0;
+  if ((flips + rot0) > 0 && scratch_ == nullptr && (flips > 0 || src_ == dst_))
+    return fail_msg("tqb_apply_blocks: rotating blocks need a scratch state");
+  float* bufs[2] = {dst_, scratch_};
+  int at = flips & 1;
+  const float* cur = src_;
   for (int blk = 0; blk < n_blocks; ++blk) {
     const int32_t* bh = blocks_host + (size_t)blk * TQB_KB_WORDS;
     const float* pl = planes_all + (size_t)blk * 2 * 128 * 64;
@@ -178,34 +189,49 @@ int tqb_apply_blocks(const float* src_, float* dst_, int n, long long bsz, const
     u64 kmask = 0;
     for (int k = 0; k < 6; ++k) {
       kpos[k] = bh[TQB_KB_KPOS + k];
-      if (kpos[k] < 6 || kpos[k] >= n || (k && kpos[k] <= kpos[k - 1])) return fail_msg("block bit out of range (must be >= 6)");
+      if (kpos[k] < 6 || kpos[k] >= n) return fail_msg("block bit out of range (must be >= 6)");
+      if ((kmask >> kpos[k]) & 1) return fail_msg("block bits must be distinct");
       kmask |= 1ull << kpos[k];
     }
     const bool tr = bh[TQB_KB_FLAGS] & TQB_KBF_TRANSPOSE;
+    const bool rotate = bh[TQB_KB_FLAGS] & TQB_KBF_ROTATE;
+    if (blk > 0 && rotate) at ^= 1;
+    float* outp = bufs[at];
+    if (rotate && outp == cur) return fail_msg("tqb_apply_blocks: with an odd number of rotating blocks dst must differ from src (pass src as scratch)");
     std::vector<cd> U(64 * 64);
     for (int i = 0; i < 64; ++i)
       for (int j = 0; j < 64; ++j)
         U[i * 64 + j] = cd((double)pl[(2 * i) * 64 + j] + (double)pl[(128 + 2 * i) * 64 + j],
                            (double)pl[(2 * i + 1) * 64 + j] + (double)pl[(128 + 2 * i + 1) * 64 + j]);
     auto spread = [&](int pat) { u64 o = 0; for (int k = 0; k < 6; ++k) if ((pat >> k) & 1) o |= 1ull << kpos[k]; return o; };
+    // destination of the tile's outer bits: compacted above bit 11 for a rotating block, unchanged otherwise
+    auto outer_dst = [&](u64 base) {
+      if (!rotate) return base;
+      u64 o = 0; int r = 12;
+      for (int bit = 6; bit < n; ++bit) if (!((kmask >> bit) & 1)) { o |= ((base >> bit) & 1ull) << r; ++r; }
+      return o;
+    };
     for (long long b = 0; b < bsz; ++b) {
-      const cf* in = reinterpret_cast<const cf*>(blk == 0 ? src_ : dst_) + (u64)b * N;
-      cf* out = reinterpret_cast<cf*>(dst_) + (u64)b * N;
+      const cf* in = reinterpret_cast<const cf*>(cur) + (u64)b * N;
+      cf* out = reinterpret_cast<cf*>(outp) + (u64)b * N;
       for (u64 base = 0; base < N; ++base) {
         if (base & (kmask | 63ull)) continue;
+        const u64 ob = outer_dst(base);
         for (int nn = 0; nn < 64; ++nn) {
           cd v[64];
           for (int j = 0; j < 64; ++j) v[j] = cd(in[base | spread(j) | (u64)nn]);
           for (int i = 0; i < 64; ++i) {
             cd acc = 0;
             for (int j = 0; j < 64; ++j) acc += U[i * 64 + j] * v[j];
-            const u64 at = tr ? (base | spread(nn) | (u64)i) : (base | spread(i) | (u64)nn);
-            tmp[at] = cf((float)acc.real(), (float)acc.imag());
+            const u64 blk_bits = rotate ? ((u64)(tr ? nn : i) << 6) : spread(tr ? nn : i);
+            const u64 at_ = ob | blk_bits | (u64)(tr ? i : nn);
+            tmp[at_] = cf((float)acc.real(), (float)acc.imag());
           }
         }
       }
       for (u64 a = 0; a < N; ++a) out[a] = tmp[a];
     }
+    cur = outp;
   }
   return 0;
 }

@@ -140,5 +140,9 @@ def test_dense_blocks():
     cases.check_dense_blocks("cpu", n=8)
 
 
+def test_block_write_back_modes():
+    cases.check_block_write_back_modes("cpu", n=18, depth=8)
+
+
 def test_op_hamil_exp():
     cases.check_op_hamil_exp("cpu")

@@ -60,6 +60,11 @@ def test_mnist_cfg1():
     cases.check_mnist_cfg1(DEV)
 
 
+def test_block_write_back_modes():
+    """tensor-core block stages, in place and rotating (contiguous tile write-back into a second buffer), vs the oracle"""
+    cases.check_block_write_back_modes(DEV, n=20, depth=24)
+
+
 @pytest.mark.parametrize("n,bsz,depth", [(10, 8, 20), (13, 2, 12), (14, 2, 10), (16, 1, 10), (18, 1, 8)])
 def test_brickwork_vs_oracle(n, bsz, depth):
     """config-4 family at sizes the oracle finishes in seconds; n >= 14 streams tiles through HBM."""

@@ -98,3 +98,76 @@ def test_segments_respect_staging_capacity():
         for si in range(w[C.H_NSEG]):
             off = w[C.H_SEGOFF + si]
             assert w[off + C.S_NOPS] <= C.SEG_MAX_OPS and w[off + C.S_G_LEN] <= C.SEG_MAX_G
+
+
+# ---- block scheduler (blockplan.py): in-place and rotating write-back ----
+
+def _brick_masks(n, depth):
+    masks = []
+    for d in range(depth):
+        masks += [1 << q for q in range(n)]
+        masks += [3 << q for q in range(d % 2, n - 1, 2)]
+    return masks
+
+
+def _random_masks(n, count, seed):
+    rng = np.random.default_rng(seed)
+    masks = []
+    for _ in range(count):
+        k = int(rng.integers(1, 4))
+        qs = rng.choice(n, size=k, replace=False)
+        masks.append(int(sum(1 << int(q) for q in qs)))
+    return masks
+
+
+def _check_rotating_schedule(masks, n):
+    from torchquantum_b200 import blockplan as B
+
+    sched = B.schedule_rotating(masks, n)
+    assert sched is not None
+    pos = list(range(n))            # logical -> physical, replayed from the kernel's contract (tqb_apply_blocks)
+    done, seen = set(), []
+    for kpos, gates, tr, where in sched:
+        assert len(set(kpos)) == 6 and all(6 <= p < n for p in kpos)
+        inv = {p: l for l, p in enumerate(pos)}
+        qs = [inv[p] for p in kpos]
+        assert all(where[q] == i for i, q in enumerate(qs))          # block-local bit i <-> physical kpos[i]
+        blockmask = sum(1 << q for q in qs)
+        for g in gates:
+            assert masks[g] & ~blockmask == 0                          # every gate of the block acts inside it
+            assert all(h in done for h in range(g) if masks[h] & masks[g])   # program order per qubit is kept
+            done.add(g)
+        seen += gates
+        # layout after the pass: block bits -> 6..11 (0..5 when transposing, the parked six then at 6..11), rest above
+        new = [None] * n
+        for i, q in enumerate(qs):
+            new[q] = i if tr else 6 + i
+        for b in range(6):
+            new[inv[b]] = 6 + b if tr else b
+        r = 12
+        for p in range(6, n):
+            if inv[p] not in qs:
+                new[inv[p]] = r
+                r += 1
+        pos = new
+    assert sorted(seen) == list(range(len(masks)))                      # every gate exactly once
+    assert pos == list(range(n))                                        # the stage ends in the identity layout
+    return len(sched)
+
+
+def test_rotating_block_schedule_keeps_order_and_comes_home():
+    assert _check_rotating_schedule(_brick_masks(20, 12), 20) <= 24
+    assert _check_rotating_schedule(_brick_masks(28, 100), 28) <= 150     # 4150 gates (in place: 166 blocks)
+    for seed in range(3):
+        _check_rotating_schedule(_random_masks(19, 150, seed), 19)
+        _check_rotating_schedule(_random_masks(26, 300, seed + 10), 26)
+
+
+def test_block_stage_picks_the_cheaper_write_back():
+    from torchquantum_b200 import blockplan as B
+
+    deep, n_deep = B.plan_blocks(_brick_masks(28, 100), 28)
+    assert all(e[2] & C.KBF_ROTATE for e in deep)                        # deep circuits: rotating, fewer + cheaper passes
+    assert B.schedule_rotating(_brick_masks(16, 8), 16) is None          # small states stay with the in-place schedule
+    small, _ = B.plan_blocks(_brick_masks(16, 8), 16)
+    assert not any(e[2] & C.KBF_ROTATE for e in small)

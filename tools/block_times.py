@@ -23,6 +23,7 @@ def main():
     plan = engine.get_plan(a.n, tuple(key), False)
     state = torch.zeros(1, 2 ** a.n, dtype=torch.complex64, device=dev)
     state[0, 0] = 1
+    other = torch.empty_like(state)
     for stage in plan.stages:
         if stage.kind != "blocks":
             print("stage", stage.kind)
@@ -31,7 +32,9 @@ def main():
         acc = np.zeros(stage.n_blocks)
         for rep in range(4):
             t = []
-            engine.run_blocks(state, stage, a.n, 0, psh, True, timing=t)
+            out = engine.run_blocks(state, stage, a.n, 0, psh, True, timing=t, scratch=other)
+            if out is not state:
+                state, other = out, state
             torch.cuda.synchronize()
             if rep:
                 acc += np.array([s.elapsed_time(e) for s, e in t])
@@ -39,8 +42,8 @@ def main():
         for b in range(stage.n_blocks):
             hdr = stage.blocks[b]
             kpos = [int(hdr[C.KB_KPOS + i]) for i in range(6)]
-            print(f"block {b:3d} kpos {kpos} T={int(hdr[C.KB_FLAGS]) & C.KBF_TRANSPOSE} gates={int(hdr[C.KB_NOPS]):3d}  {acc[b]:.3f} ms")
-        print("mean", acc.mean())
+            print(f"block {b:3d} kpos {kpos} T={int(hdr[C.KB_FLAGS]) & C.KBF_TRANSPOSE} R={(int(hdr[C.KB_FLAGS]) & C.KBF_ROTATE) >> 1} gates={int(hdr[C.KB_NOPS]):3d}  {acc[b]:.3f} ms")
+        print("mean", acc.mean(), "blocks", stage.n_blocks, "total ms", acc.sum())
 
 
 if __name__ == "__main__":

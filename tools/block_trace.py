@@ -18,10 +18,10 @@ def main():
     ap.add_argument("--n", type=int, default=28)
     ap.add_argument("--kpos", type=int, nargs=6, default=[6, 7, 8, 9, 10, 11])
     a = ap.parse_args()
-    lib = ctypes.CDLL(os.path.join(ROOT, "torchquantum_b200", "lib", "libtqb200.so"))
+    lib = ctypes.CDLL(os.path.join(ROOT, "tools", "_ab", "libtqb200_debug.so"))   # tools/build_debug_lib.sh
     lib.tqb_last_error.restype = ctypes.c_char_p
     fn = lib.tqb_apply_blocks
-    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
                    ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.tqb_debug_block_trace.argtypes = [ctypes.c_void_p]
     dev = "cuda:0"
@@ -36,7 +36,7 @@ def main():
     hdr = (ctypes.c_int32 * 12)(*([0, 0, 0, 0] + list(a.kpos) + [0, 0]))
 
     def run():
-        rc = fn(st.data_ptr(), st.data_ptr(), a.n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1,
+        rc = fn(st.data_ptr(), st.data_ptr(), None, a.n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1,
                 torch.cuda.current_stream().cuda_stream)
         assert rc == 0, lib.tqb_last_error().decode()
 

@@ -12,7 +12,7 @@ from tools.umma_probe import a_planes  # noqa: E402
 
 lib = ctypes.CDLL(os.path.join(ROOT, "torchquantum_b200", "lib", "libtqb200.so"))
 fn = lib.tqb_apply_blocks
-fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                ctypes.c_int, ctypes.c_void_p]
 n = 28
 dev = "cuda:0"
@@ -29,12 +29,12 @@ for kpos in cases:
     for tr in (0, 1):
         hdr = (ctypes.c_int32 * 12)(*([0, 0, tr, 0] + kpos + [0, 0]))
         for _ in range(3):
-            fn(st.data_ptr(), st.data_ptr(), n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1, torch.cuda.current_stream().cuda_stream)
+            fn(st.data_ptr(), st.data_ptr(), None, n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
         ev[0].record()
         for k in range(8):
-            fn(st.data_ptr(), st.data_ptr(), n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1, torch.cuda.current_stream().cuda_stream)
+            fn(st.data_ptr(), st.data_ptr(), None, n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1, torch.cuda.current_stream().cuda_stream)
             ev[k + 1].record()
         torch.cuda.synchronize()
         ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(8))[4]

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TQB200_LIB") or os.path.join(_HERE, "lib", "libtqb200.so")  # env: kernel A/B experiments
 OPS_LIB_PATH = os.path.join(_HERE, "lib", "libtqb200_torch.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # every ABI entry point registered as torch.ops.tqb200.<name> (mirrors include/tqb200.h)
 OP_NAMES = (

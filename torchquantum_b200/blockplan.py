@@ -12,7 +12,22 @@ of `wires_per_block` qubits, :713-861 block unitaries on the host).  Differences
 * a block's six physical bits must form <= 3 contiguous runs (rank-5 TMA tensor map: 128-byte row, row index, 3 runs).
 
 Block choice is greedy with connected growth: a seed gate on the dependency frontier, then every later gate that touches
-the block and still fits, then a free fill; the candidate absorbing the most gates wins."""
+the block and still fits, then a free fill; the candidate absorbing the most gates wins.
+
+Two write-back disciplines (the same block choice logic serves both):
+
+* in place (`schedule`): every tile goes back where it came from; the qubit layout only ever changes through the
+  transposing blocks described above.  Blocks whose six bits are all high write 512-byte rows at strides >= 4 MiB, which
+  the memory system takes at 0.6x the speed of any other placement (profiles/r02_block6_kpos_sweep.txt: 1.1-1.37 ms
+  against 0.80-0.85 ms per pass at n = 28; the gathering READS of the same tiles run at full speed);
+* rotating (`schedule_rotating`, TQB_KBF_ROTATE): every block reads its tiles from wherever its qubits are and writes
+  each tile as one contiguous 32 KiB piece into a second buffer, so the block's qubits land in index bits 6-11 (or 0-5
+  when it also transposes) and all other bits >= 6 move up in their previous relative order.  Any six un-parked qubits
+  are a block (bits beyond three contiguous runs are enumerated by the kernel); the scheduler tracks the logical ->
+  physical map and ends the stage with <= ceil((n-6)/6) gate-free passes that sort the qubits home.
+`build_block_stage` plans both and keeps the cheaper one by a per-placement cost model taken from the sweep."""
+import os
+
 import numpy as np
 
 from . import _codes as C
@@ -86,11 +101,12 @@ def pad_kpos(phys, n_local):
 class _Sched:
     """masks: logical local-qubit mask of every gate, program order."""
 
-    def __init__(self, masks, n_local):
+    def __init__(self, masks, n_local, rotating=False):
         self.masks, self.n = masks, n_local
         self.full = (1 << n_local) - 1
         self.parked = LOW          # logical qubits in physical bits 0-5
         self.K = None              # K layout: sorted logical qubits parked; logical b < 6 sits at physical K[b]
+        self.rotating = rotating   # rotating blocks: any six un-parked qubits can be one block
         self._feas = {}
 
     def phys(self, l):
@@ -100,6 +116,8 @@ class _Sched:
 
     def feasible(self, mask):
         """the logical set can be one block in the current layout"""
+        if self.rotating:
+            return not (mask & self.parked) and bin(mask).count("1") <= K_BLOCK
         key = (mask, None if self.K is None else tuple(self.K))
         hit = self._feas.get(key)
         if hit is None:
@@ -252,6 +270,143 @@ def _with_layouts(blocks):
     return res
 
 
+def _next_use(masks, remaining, n_local):
+    nxt = {}
+    for at, i in enumerate(remaining):
+        m = masks[i]
+        b = 0
+        while m >> b:
+            if (m >> b) & 1 and b not in nxt:
+                nxt[b] = at
+            b += 1
+        if len(nxt) == n_local:
+            break
+    return nxt
+
+
+def schedule_rotating(masks, n_local):
+    """Rotating write-back: -> list of (kpos in pattern order, [gate indices], transposing, where) with `where` = logical
+    qubit -> block-local bit; the last entries are the gate-free passes that bring every qubit home.  Any block may
+    transpose, which parks ITS six qubits in index bits 0-5 and frees the six parked before; it does when its qubits
+    (after the block) stay idle longer than the parked ones."""
+    if n_local < 3 * K_BLOCK:
+        return None      # the way home needs six un-parked qubits outside 0-5 (smaller states: in-place schedule)
+    s = _Sched(masks, n_local, rotating=True)
+    remaining = list(range(len(masks)))
+    out = []   # (logical qubit mask, gates, transposing, fixed pattern order or None)
+
+    def drop(rem, tk):
+        t = set(tk)
+        return [i for i in rem if i not in t]
+
+    def fill(ch, rem, avoid):
+        """pad the chosen set to six qubits with un-parked qubits, those used furthest in the future first"""
+        nxt = _next_use(masks, rem, n_local)
+        order = sorted((b for b in range(n_local) if not ((ch | avoid) >> b) & 1), key=lambda b: -nxt.get(b, 1 << 60))
+        for b in order:
+            if bin(ch).count("1") >= K_BLOCK:
+                break
+            ch |= 1 << b
+        return ch
+
+    while remaining:
+        ch, tk = s.best_block(remaining, s.parked)
+        if not tk:
+            # every frontier gate touches a parked qubit: a gate-free exchange that parks the idlest six instead
+            ch = fill(0, remaining, s.parked)
+            out.append((ch, [], True, None))
+            s.parked = ch
+            continue
+        rem2 = drop(remaining, tk)
+        chB = fill(ch, rem2, s.parked)
+        nxt = _next_use(masks, rem2, n_local)
+        idle = lambda m: sum(min(nxt.get(b, len(rem2)), len(rem2)) for b in range(n_local) if (m >> b) & 1)
+        stay, swap = idle(s.parked), idle(chB)   # park whichever six qubits stay idle longer (summed distance to next use)
+        if swap > stay:
+            out.append((chB, tk, True, None))
+            s.parked = chB
+        else:
+            out.append((ch, tk, False, None))
+        remaining = rem2
+    # the way home for the parked set: logical 0-5 into index bits 0-5, in order
+    # (a transposing block on exactly the qubits 0-5 always uses the pattern order 0..5: _rotating_layouts)
+    if s.parked & LOW and s.parked != LOW:
+        ch = fill(0, [], s.parked | LOW)
+        out.append((ch, [], True, None))
+        s.parked = ch
+    if s.parked != LOW:
+        out.append((LOW, [], True, None))
+    return _rotating_layouts(out, n_local)
+
+
+def _rotate(pos, qs, transposing, n_local):
+    """logical -> physical map after a rotating block on the logical qubits qs (pattern order)"""
+    inv = {p: l for l, p in enumerate(pos)}
+    new = [None] * n_local
+    for i, q in enumerate(qs):
+        new[q] = i if transposing else K_BLOCK + i
+    for b in range(K_BLOCK):
+        new[inv[b]] = K_BLOCK + b if transposing else b
+    r = 2 * K_BLOCK
+    inblock = set(qs)
+    for p in range(K_BLOCK, n_local):
+        if inv[p] not in inblock:
+            new[inv[p]] = r
+            r += 1
+    return new
+
+
+def _rotating_layouts(blocks, n_local):
+    pos = list(range(n_local))
+    res = []
+
+    def emit(qs, tk, tr):
+        nonlocal pos
+        res.append(([pos[q] for q in qs], tk, tr, {q: i for i, q in enumerate(qs)}))
+        pos = _rotate(pos, qs, tr, n_local)
+
+    for ch, tk, tr, order in blocks:
+        if order is None and tr and ch == LOW:
+            order = list(range(K_BLOCK))     # the parked qubits 0-5 come home in order
+        if order is None:
+            qs = [b for b in range(n_local) if (ch >> b) & 1]
+            # pad with un-parked neighbours (physically adjacent first: fewer TMA pieces), then anything un-parked
+            while len(qs) < K_BLOCK:
+                have = {pos[q] for q in qs}
+                inv = {p: l for l, p in enumerate(pos)}
+                cands = [p for p in range(K_BLOCK, n_local) if p not in have]
+                cands.sort(key=lambda p: (0 if (p - 1 in have or p + 1 in have) else 1, p))
+                qs.append(inv[cands[0]])
+            qs.sort(key=lambda q: pos[q])
+        else:
+            qs = list(order)
+        emit(qs, tk, tr)
+    assert all(pos[b] == b for b in range(K_BLOCK))
+    # sort the qubits >= 6 home: every pass moves six of them to the front, the top chunk first; the qubits T.. that are
+    # already in ascending relative order are never moved (they end up on top, in order)
+    T = n_local
+    while T - 1 > K_BLOCK - 1 and (T == n_local or pos[T - 1] < pos[T]):
+        T -= 1
+    if any(pos[l] != l for l in range(n_local)):
+        todo = list(range(K_BLOCK, T))
+        chunks = []
+        while todo:
+            chunks.append(todo[:K_BLOCK])
+            todo = todo[K_BLOCK:]
+        nxt, low = T, K_BLOCK
+        while len(chunks[-1]) < K_BLOCK:      # pad the top chunk with the lowest qubits of the sorted rest, or (no rest
+            if nxt < n_local:                 # left) with qubits that a later pass moves again anyway
+                chunks[-1].append(nxt)
+                nxt += 1
+            else:
+                chunks[-1].append(low)
+                low += 1
+        for chunk in reversed(chunks):
+            emit(chunk, [], False)
+    assert pos == list(range(n_local)), pos
+    return res
+
+
 class BlockStage:
     """A run of gates executed as dense 6-qubit blocks (no autograd)."""
     kind = "blocks"
@@ -263,6 +418,7 @@ class BlockStage:
         self.sh_recs = []     # queue indices of the shared-parameter records, parameter order
         self.P_sh = 0
         self.n_ops = self.n_blocks = 0
+        self.n_rotating = 0   # blocks with TQB_KBF_ROTATE: each moves the state to the other buffer
 
 
 def _full_const(op):
@@ -274,30 +430,69 @@ def _full_const(op):
     return np.asarray(op.const, dtype=np.float32).reshape(-1)
 
 
+# Relative cost of one in-place block pass by placement (profiles/r02_block6_kpos_sweep.txt, n = 28: 0.80-0.85 ms when
+# a block bit is <= 11 or at most two are >= 19, up to 1.37 ms when all six are high); a rotating pass always writes
+# contiguous tiles (ROTATING_COST, measured: profiles/r02_block6_rotate_sweep.txt).
+ROTATING_COST = 1.0
+MODE = os.environ.get("TQB200_BLOCK_WRITEBACK", "auto")   # auto | inplace | rotate
+
+
+def inplace_cost(kpos):
+    if min(kpos) <= 11:
+        return 1.0
+    high = sum(1 for b in kpos if b >= 19)
+    return 1.04 if high <= 2 else (1.2 if high <= 4 else 1.5)
+
+
+def plan_blocks(masks, n_local):
+    """-> (list of (kpos, gates, flags, where), estimated cost in units of one fast pass) for the cheaper of the two
+    write-back disciplines, or None"""
+    cands = []
+    if MODE != "rotate":
+        sched = schedule(masks, n_local)
+        if sched:
+            ent = []
+            for kpos, gates, tr, K in sched:
+                at = {p: i for i, p in enumerate(kpos)}
+                where = {l: at[p] for l in range(n_local)
+                         for p in [l if K is None else (K[l] if l < K_BLOCK else l)] if p in at}
+                ent.append((kpos, gates, C.KBF_TRANSPOSE if tr else 0, where))
+            cands.append((sum(inplace_cost(e[0]) for e in ent), ent))
+    if MODE != "inplace":
+        sched = schedule_rotating(masks, n_local)
+        if sched:
+            ent = [(kpos, gates, C.KBF_ROTATE | (C.KBF_TRANSPOSE if tr else 0), where) for kpos, gates, tr, where in sched]
+            cands.append((ROTATING_COST * len(ent), ent))
+    if not cands:
+        return None
+    cost, ent = min(cands, key=lambda c: c[0])
+    return ent, cost
+
+
 def build_block_stage(lops, n_local, min_avg=0.0):
     """lops: fusable lowered ops (plan.LOp) in program order -> BlockStage, or None when the schedule averages fewer
     than `min_avg` gates per block (the register-tile pass kernel is the better tool then)."""
     lmask = (1 << n_local) - 1
     masks = [op.qmask & lmask for op in lops]
-    sched = schedule(masks, n_local)
-    if sched is None or not sched or len(lops) / len(sched) < min_avg:
+    planned = plan_blocks(masks, n_local)
+    if planned is None or len(lops) / planned[1] < min_avg:
         return None
+    sched = planned[0]
     st = BlockStage()
+    st.n_rotating = sum(1 for e in sched if e[2] & C.KBF_ROTATE)
     for op in lops:
         if op.pmode == "sh":
             op.poff = st.P_sh
             st.P_sh += op.nparam
             st.sh_recs.append(op.rec)
     blocks, words, consts, coff = [], [], [], 0
-    for kpos, gates, tr, K in sched:
-        where = {p: i for i, p in enumerate(kpos)}
+    for kpos, gates, flags, where in sched:
 
         def bl(l):
-            p = l if K is None else (K[l] if l < K_BLOCK else l)
-            return where[p]
+            return where[l]
 
         hdr = [0] * C.KB_WORDS
-        hdr[C.KB_OPFIRST], hdr[C.KB_NOPS], hdr[C.KB_FLAGS] = len(words), len(gates), (C.KBF_TRANSPOSE if tr else 0)
+        hdr[C.KB_OPFIRST], hdr[C.KB_NOPS], hdr[C.KB_FLAGS] = len(words), len(gates), flags
         for i, p in enumerate(kpos):
             hdr[C.KB_KPOS + i] = p
         blocks.append(hdr)

@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace tqb_umma {
 
@@ -44,17 +45,33 @@ constexpr uint32_t kTmemCols = 512;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A K-major (TMEM), B MN-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// Where the 4096 amplitudes of tile number t live in a state: the outer (non-tile) index bits as <= 7 runs (bits
+// [lo, lo+len) of the tile number go to index bit pos), and how one 8 KiB group (64 rows of 128 bytes, one per 6-bit
+// pattern of the block bits) is cut into TMA boxes: the first 6 - ext block bits are <= 3 runs of contiguous index bits
+// and sit in the tensor map's box, the last `ext` block bits are enumerated: piece e of 2^ext covers the rows
+// [e * 64 >> ext, (e + 1) * 64 >> ext) of the group and starts at the 128-byte row sum_i e_i << (ebit_i - 4) of the tile.
+// Packed into 32 bytes: the whole kernel parameter block must stay within 384 bytes (two tensor maps + <= 128 bytes of
+// Params).  Measured on B200: the SAME kernel binary runs 7 % slower (0.842 -> 0.904 ms per pass at n = 28) as soon as
+// the parameter block is longer than that (profiles/r02_block6_notes.txt).
+struct TileMap {
+  uint32_t seg[7];   // lo | len << 8 | pos << 16
+  uint32_t meta;     // nseg | ext << 4 | ebit_0 << 8 | ebit_1 << 16 | ebit_2 << 24
+};
+
 struct Params {
   const float* a_planes;   // [2][128][64]: TF32-rounded hi plane, lo plane of A
   uint32_t n_tiles;
   uint32_t tile_mult;      // odd: tile index -> (index * tile_mult) mod n_tiles (n_tiles is a power of two) spreads concurrent tiles
-  int transpose;
-  unsigned long long* trace;  // debug: [64 tiles][10] clock64 stamps of CTA 0 (tools/block_trace.py), or null
-  int debug;               // TQB200_BLOCK_DEBUG bit mask (timing experiments only): 1 no split, 2 8 MMAs, 4 no epilogue math, 8 no store
   int renorm;              // block is unitary: rescale every tile to the norm it came in with (see the epilogue)
-  int nseg;                // outer (non-tile) index bits as <= 4 runs: bits [lo, lo+len) of the tile id go to bit pos
-  int seg_lo[4], seg_len[4], seg_pos[4];
+#ifdef TQB_BLOCK_DEBUG
+  int debug;               // TQB200_BLOCK_DEBUG bit mask (timing experiments only): 1 no split, 2 8 MMAs, 4 no epilogue math, 8 no store
+  unsigned long long* trace;  // [64 tiles][10] clock64 stamps of CTA 0 (tools/block_trace.py), or null
+#endif
+  TileMap src, dst;        // where a tile lives in the source / destination state (they differ for rotating blocks)
 };
+#ifndef TQB_BLOCK_DEBUG
+static_assert(sizeof(Params) <= 128, "keep the kernel parameter block within 384 bytes");
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -163,16 +180,26 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 }
 
 // 128-byte row index of the tile's first amplitude
-__device__ __forceinline__ uint32_t tile_row(const Params& p, uint32_t tile) {
+__device__ __forceinline__ uint32_t tile_row(const Params& p, const TileMap& m, uint32_t tile) {
   tile = (tile * p.tile_mult) & (p.n_tiles - 1u);
+  const int nseg = (int)(m.meta & 15u);
   unsigned long long off = 0;
 #pragma unroll
-  for (int s = 0; s < 4; ++s)
-    if (s < p.nseg) {
-      const unsigned long long part = (tile >> p.seg_lo[s]) & ((p.seg_len[s] >= 32 ? 0ull : (1ull << p.seg_len[s])) - 1ull);
-      off |= part << p.seg_pos[s];
+  for (int s = 0; s < 7; ++s)
+    if (s < nseg) {
+      const uint32_t sg = m.seg[s], lo = sg & 255u, len = (sg >> 8) & 255u, pos = sg >> 16;
+      const unsigned long long part = (tile >> lo) & ((len >= 32u ? 0ull : (1ull << len)) - 1ull);
+      off |= part << pos;
     }
   return (uint32_t)(off >> 4);
+}
+// row offset of piece e of a group (enumerated block bits, see TileMap)
+__device__ __forceinline__ uint32_t piece_row(const TileMap& m, int e) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if ((e >> i) & 1) r += 1u << (((m.meta >> (8 + 8 * i)) & 255u) - 4u);
+  return r;
 }
 
 // byte offset of 16-byte chunk c16 of row `row` inside an 8 KiB group: 32-byte units are XOR-ed with row % 4
@@ -180,7 +207,17 @@ __device__ __forceinline__ uint32_t swz32(uint32_t row, uint32_t c16) {
   return row * 128u + ((((c16 >> 1) ^ (row & 3u)) << 5) | ((c16 & 1u) << 4));
 }
 
+// the stage-ablation switches (TQB200_BLOCK_DEBUG, profiles/r02_block6_ablation.txt) and the clock64 trace of CTA 0
+// (tools/block_trace.py) only exist in -DTQB_BLOCK_DEBUG builds (tools/build_debug_lib.sh): as run-time tests they sit
+// in the loop bounds of the hot loops
+#ifdef TQB_BLOCK_DEBUG
+#define TQB_DBG(mask) (p.debug & (mask))
 #define TQB_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 10 + (slot)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TQB_DBG(mask) false
+#define TQB_TRACE(slot) do { } while (0)
+#endif
+
 
 // (Tried and dropped, profiles/r02_block6_notes.txt: the epilogue storing its registers straight to global memory, which
 // frees the lo plane at the end of the MMAs and allows 5 hi + 2 lo planes, ran at 0.97 ms against 0.84 ms for the TMA
@@ -190,6 +227,9 @@ constexpr uint32_t kLo = 3;                     // lo planes, reused as the tile
 constexpr int kSplitWarps = 4, kSplitThreads = 32 * kSplitWarps;
 constexpr int kThreads = 256 + kSplitThreads;
 
+// kTranspose is a compile-time flag: with a run-time select in the epilogue's address arithmetic ptxas' if-conversion of
+// that loop flips between builds (measured: the same source 0.85 or 0.92-1.03 ms per pass depending on unrelated changes)
+template <bool kTranspose>
 __global__ void __launch_bounds__(kThreads, 1)
 tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -267,9 +307,21 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         mbar_wait(empty(k), ph ^ 1u);
         TQB_TRACE(0);
         mbar_expect_tx(full(k), kPlane);
-        const uint32_t row = tile_row(p, t);
+        const uint32_t row = tile_row(p, p.src, t);
+        const int ext = (int)((p.src.meta >> 4) & 15u);
+        if (ext == 0) {
 #pragma unroll
-        for (int ng = 0; ng < 4; ++ng) tma_load_5d(hi_plane(k) + ng * 8192u, &tm_src, full(k), 0, (int)(row + ng), 0, 0, 0);
+          for (int ng = 0; ng < 4; ++ng) tma_load_5d(hi_plane(k) + ng * 8192u, &tm_src, full(k), 0, (int)(row + ng), 0, 0, 0);
+        } else {
+          const uint32_t piece = 8192u >> ext;
+#pragma unroll 1
+          for (int e = 0; e < (1 << ext); ++e) {
+            const uint32_t prow = row + piece_row(p.src, e);
+#pragma unroll 1
+            for (int ng = 0; ng < 4; ++ng)
+              tma_load_5d(hi_plane(k) + ng * 8192u + e * piece, &tm_src, full(k), 0, (int)(prow + ng), 0, 0, 0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -289,7 +341,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         // the tensor core's truncating fp32 accumulation costs 8 full-size roundings per tile instead of 24
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_alo + 8u * ks, b_desc(bh + ks * 1024u), ks > 0);
-        if (!(p.debug & 2)) {
+        if (!TQB_DBG(2)) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(dt, t_ahi + 8u * ks, b_desc(bl + ks * 1024u), 1u);
 #pragma unroll
@@ -307,10 +359,22 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         const uint32_t l = it % kLo;
         mbar_wait(outready(l), (it / kLo) & 1u);
         TQB_TRACE(8);
-        if (!(p.debug & 8)) {
-          const uint32_t row = tile_row(p, t);
+        if (!TQB_DBG(8)) {
+          const uint32_t row = tile_row(p, p.dst, t);
+          const int ext = (int)((p.dst.meta >> 4) & 15u);
+          if (ext == 0) {
 #pragma unroll
-          for (int ng = 0; ng < 4; ++ng) tma_store_5d(&tm_dst, lo_plane(l) + ng * 8192u, 0, (int)(row + ng), 0, 0, 0);
+            for (int ng = 0; ng < 4; ++ng) tma_store_5d(&tm_dst, lo_plane(l) + ng * 8192u, 0, (int)(row + ng), 0, 0, 0);
+          } else {
+            const uint32_t piece = 8192u >> ext;
+#pragma unroll 1
+            for (int e = 0; e < (1 << ext); ++e) {
+              const uint32_t prow = row + piece_row(p.dst, e);
+#pragma unroll 1
+              for (int ng = 0; ng < 4; ++ng)
+                tma_store_5d(&tm_dst, lo_plane(l) + ng * 8192u + e * piece, 0, (int)(prow + ng), 0, 0, 0);
+            }
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
@@ -333,7 +397,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       const uint32_t bh = hi_plane(k) + 16u * tid, bl = lo_plane(l) + 16u * tid;
       float ss = 0.f;
 #pragma unroll 4
-      for (int v = 0; v < ((p.debug & 1) ? 0 : kVecs); ++v) {
+      for (int v = 0; v < (TQB_DBG(1) ? 0 : kVecs); ++v) {
         const uint32_t a = bh + 16u * kSplitThreads * v;
         float x0, x1, x2, x3;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(a) : "memory");
@@ -370,7 +434,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       if (et == 0) TQB_TRACE(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (uint32_t ld = 0; ld < ((p.debug & 4) ? 0u : 4u); ++ld) {
+      for (uint32_t ld = 0; ld < (TQB_DBG(4) ? 0u : 4u); ++ld) {
         // 16 accumulator lanes (8 output patterns, P and Q) x 64 columns (32 amplitudes) per load
         const uint32_t h = ld >> 1, half = ld & 1u;
         const uint32_t i = 16u * q + 8u * h + (lane >> 2);   // output pattern of this thread
@@ -387,7 +451,7 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
           ss_out = fmaf(im, im, ss_out);
           const uint32_t n = 32u * half + 4u * c + (lane & 3u);
           uint32_t a;
-          if (!p.transpose) a = stg + (n >> 4) * 8192u + swz32(i, (n & 15u) >> 1) + (n & 1u) * 8u;
+          if constexpr (!kTranspose) a = stg + (n >> 4) * 8192u + swz32(i, (n & 15u) >> 1) + (n & 1u) * 8u;
           else a = stg + (i >> 4) * 8192u + swz32(n, (i & 15u) >> 1) + (i & 1u) * 8u;
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(re * g), "f"(im * g) : "memory");
         }
@@ -442,37 +506,63 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// tensor map over the whole state for tiles of {index bits 0-5} x {kpos[0..5]}: dims (fastest first)
-//   32 floats | 128-byte rows of the state | up to three runs of contiguous block bits
-// box = 32 x 1 x run sizes = 64 rows of 128 bytes (one n/16 group of a tile)
-inline const char* make_tensor_map(CUtensorMap* tm, const float* state, int n_qubits, long long bsz, const int* kpos) {
+// Tile geometry of a state for the block bits kpos[0..5] (pattern bit b <-> index bit kpos[b]; any order, all distinct,
+// >= 6 and < n_qubits): the leading block bits that form <= 3 ascending runs of contiguous index bits go into the
+// tensor map's box, the remaining <= 3 are enumerated by the kernel (TileMap::ext), and every other index bit >= 6 is an
+// outer bit (ascending; the batch index continues the top run).
+// Tensor map dims (fastest first): 32 floats | 128-byte rows of the whole state | up to three runs of block bits;
+// box = 32 x 1 x run sizes = 64 >> ext rows of 128 bytes.
+inline const char* make_tile_map(CUtensorMap* tm, TileMap* m, const float* state, int n_qubits, long long bsz, const int* kpos) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled not available";
-  int run_start[3], run_len[3], nruns = 0;
-  for (int b = 0; b < 6;) {
+  unsigned long long used = 0;
+  for (int b = 0; b < 6; ++b) {
+    if (kpos[b] < 6 || kpos[b] >= n_qubits) return "block bit out of range (must be >= 6)";
+    if ((used >> kpos[b]) & 1ull) return "block bits must be distinct";
+    used |= 1ull << kpos[b];
+  }
+  int run_start[3], run_len[3], nruns = 0, b = 0;
+  while (b < 6 && nruns < 3) {
     int e = b;
     while (e + 1 < 6 && kpos[e + 1] == kpos[e] + 1) ++e;
-    if (nruns == 3) return "block bits form more than three runs";
     run_start[nruns] = kpos[b];
     run_len[nruns] = e - b + 1;
     ++nruns;
     b = e + 1;
   }
+  const int ext = 6 - b;   // <= 3: the first three runs hold at least three bits
+  m->meta = (uint32_t)ext << 4;
+  for (int i = 0; i < ext; ++i) m->meta |= (uint32_t)kpos[b + i] << (8 + 8 * i);
+  // outer bits as runs
+  int nseg = 0;
+  int consumed = 0, pos = 6;
+  while (pos < 64) {
+    while (pos < 64 && ((used >> pos) & 1ull)) ++pos;
+    if (pos >= 64) break;
+    int e = pos;
+    while (e < 64 && !((used >> e) & 1ull)) ++e;
+    if (nseg == 7) return "too many outer runs";
+    m->seg[nseg] = (uint32_t)consumed | ((uint32_t)(e >= 64 ? 32 : e - pos) << 8) | ((uint32_t)pos << 16);
+    consumed += e - pos;
+    ++nseg;
+    pos = e;
+  }
+  for (int s = nseg; s < 7; ++s) m->seg[s] = 0;
+  m->meta |= (uint32_t)nseg;
+
   cuuint64_t dims[5], strides[4];
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   dims[0] = 32; box[0] = 32;
   dims[1] = ((cuuint64_t)bsz << n_qubits) >> 4; box[1] = 1;
   strides[0] = 128;
-  cuuint64_t prev = 128ull * 4;  // filler stride for absent runs: any multiple of 16
   for (int r = 0; r < 3; ++r) {
     if (r < nruns) {
       dims[2 + r] = 1ull << run_len[r];
       box[2 + r] = 1u << run_len[r];
       strides[1 + r] = 8ull << run_start[r];
-      prev = strides[1 + r] * dims[2 + r];
     } else {
       dims[2 + r] = 1; box[2 + r] = 1;
-      strides[1 + r] = prev;
+      strides[1 + r] = 128ull * 4;   // filler stride for absent runs: any multiple of 16
     }
   }
   CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(state), dims, strides, box, estr,
@@ -484,60 +574,46 @@ inline const char* make_tensor_map(CUtensorMap* tm, const float* state, int n_qu
 
 static unsigned long long* g_block_trace = nullptr;   // set by tqb_debug_block_trace (tools/block_trace.py)
 
-// kpos: 6 ascending physical bit positions, all >= 6 and < n_qubits
+// kpos: the block's 6 physical bit positions in pattern order (all >= 6 and < n_qubits).  rotate: the tile is written to
+// dst as ONE contiguous 32 KiB piece (block bits -> index bits 6-11, outer bits compacted above them in ascending
+// order), which needs dst != src; otherwise it goes back to where it came from (dst may equal src).
 inline const char* launch_block6(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
-                                 const int* kpos, int transpose, int renorm, int num_sms, cudaStream_t st) {
+                                 const int* kpos, int transpose, int rotate, int renorm, int num_sms, cudaStream_t st) {
   if (n_qubits < 12) return "block6 needs n_qubits >= 12";
-  for (int b = 0; b < 6; ++b) {
-    if (kpos[b] < 6 || kpos[b] >= n_qubits) return "block bit out of range (must be >= 6)";
-    if (b && kpos[b] <= kpos[b - 1]) return "block bits must ascend";
-  }
+  if (rotate && src == dst) return "a rotating block cannot work in place";
   static int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev != configured_dev) {
-    if (cudaFuncSetAttribute(tqb_block6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tqb_block6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tqb_block6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
       return "cudaFuncSetAttribute(block6) failed";
     configured_dev = dev;
   }
   CUtensorMap tm_src, tm_dst;
-  const char* err = make_tensor_map(&tm_src, src, n_qubits, bsz, kpos);
-  if (err) return err;
-  err = make_tensor_map(&tm_dst, dst, n_qubits, bsz, kpos);
-  if (err) return err;
   Params p;
+  const char* err = make_tile_map(&tm_src, &p.src, src, n_qubits, bsz, kpos);
+  if (err) return err;
+  const int front[6] = {6, 7, 8, 9, 10, 11};
+  err = make_tile_map(&tm_dst, &p.dst, dst, n_qubits, bsz, rotate ? front : kpos);
+  if (err) return err;
   p.a_planes = a_planes;
-  p.transpose = transpose;
   p.renorm = renorm;
+#ifdef TQB_BLOCK_DEBUG
   static int debug = -1;
   if (debug < 0) { const char* e = getenv("TQB200_BLOCK_DEBUG"); debug = e ? atoi(e) : 0; }
   p.debug = debug;
+  p.trace = g_block_trace;
+#endif
   static long long mult = -1;
   if (mult < 0) { const char* e = getenv("TQB200_TILE_MULT"); mult = e ? atoll(e) : 1; }
   p.tile_mult = (uint32_t)mult | 1u;
-  p.trace = g_block_trace;
   const unsigned long long tiles = ((unsigned long long)bsz << n_qubits) >> 12;
   if (tiles > 0xffffffffull) return "too many tiles";
   p.n_tiles = (uint32_t)tiles;
-  // outer bits = everything except bits 0-5 and kpos, as runs (the batch index continues the top run)
-  p.nseg = 0;
-  int consumed = 0;
-  int pos = 6;
-  for (int b = 0; b <= 6; ++b) {
-    const int upto = b < 6 ? kpos[b] : 64;
-    if (upto > pos) {
-      if (p.nseg == 4) return "too many outer runs";
-      p.seg_lo[p.nseg] = consumed;
-      p.seg_len[p.nseg] = b < 6 ? upto - pos : 32;
-      p.seg_pos[p.nseg] = pos;
-      consumed += upto - pos;
-      ++p.nseg;
-    }
-    pos = upto + 1;
-  }
-  for (int s = p.nseg; s < 4; ++s) { p.seg_lo[s] = 0; p.seg_len[s] = 0; p.seg_pos[s] = 0; }
   const unsigned grid = (unsigned)(tiles < (unsigned long long)num_sms ? tiles : num_sms);
-  tqb_block6_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_src, tm_dst, p);
+  if (transpose) tqb_block6_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tm_src, tm_dst, p);
+  else tqb_block6_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tm_src, tm_dst, p);
   if (cudaGetLastError() != cudaSuccess) return "block6 launch failed";
   return nullptr;
 }

@@ -754,24 +754,40 @@ int tqb_block_build(const int32_t* blocks_dev, int n_blocks, const int32_t* ops_
   return 0;
 }
 
-int tqb_apply_blocks(const float* src, float* dst, int n_qubits, long long bsz, const float* a_planes,
+int tqb_apply_blocks(const float* src, float* dst, float* scratch, int n_qubits, long long bsz, const float* a_planes,
                      const int32_t* blocks_host, int n_blocks, int renorm, void* stream) {
   if (bsz <= 0 || n_blocks <= 0) return 0;
-  if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)a_planes) & 15) != 0) return fail_msg("tqb_apply_blocks: pointers must be 16-byte aligned");
+  if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)scratch | (uintptr_t)a_planes) & 15) != 0)
+    return fail_msg("tqb_apply_blocks: pointers must be 16-byte aligned");
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
+  // A rotating block moves the state to the other one of {dst, scratch}, the rest work where the state is; the chain is
+  // laid out backwards from "the last block leaves it in dst".  The first block reads the caller's src.
+  int flips = 0;
+  for (int b = 1; b < n_blocks; ++b) flips += (blocks_host[(size_t)b * TQB_KB_WORDS + TQB_KB_FLAGS] & TQB_KBF_ROTATE) ? 1 : 0;
+  const int rot0 = (blocks_host[TQB_KB_FLAGS] & TQB_KBF_ROTATE) ? 1 : 0;
+  if ((flips + rot0) > 0 && scratch == nullptr && (flips > 0 || src == dst))
+    return fail_msg("tqb_apply_blocks: rotating blocks need a scratch state");
+  float* bufs[2] = {dst, scratch};
+  int at = flips & 1;   // where the state is after block 0
+  const float* cur = src;
   for (int b = 0; b < n_blocks; ++b) {
     const int32_t* bh = blocks_host + (size_t)b * TQB_KB_WORDS;
     int kpos[6];
     for (int k = 0; k < 6; ++k) kpos[k] = bh[TQB_KB_KPOS + k];
-    // the first block reads the caller's state, every later one works in place on dst
-    const char* err = tqb_umma::launch_block6(b == 0 ? src : dst, dst, n_qubits, bsz, a_planes + (size_t)b * 2 * 128 * 64, kpos,
-                                              bh[TQB_KB_FLAGS] & TQB_KBF_TRANSPOSE, renorm, g_num_sms, (cudaStream_t)stream);
+    const int rotate = (bh[TQB_KB_FLAGS] & TQB_KBF_ROTATE) ? 1 : 0;
+    if (b > 0 && rotate) at ^= 1;
+    float* out = bufs[at];
+    if (rotate && out == cur)
+      return fail_msg("tqb_apply_blocks: with an odd number of rotating blocks dst must differ from src (pass src as scratch)");
+    const char* err = tqb_umma::launch_block6(cur, out, n_qubits, bsz, a_planes + (size_t)b * 2 * 128 * 64, kpos,
+                                              bh[TQB_KB_FLAGS] & TQB_KBF_TRANSPOSE, rotate, renorm, g_num_sms, (cudaStream_t)stream);
     if (err) return fail_msg(err);
+    cur = out;
   }
   return 0;
 }

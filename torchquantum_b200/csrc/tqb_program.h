@@ -155,9 +155,11 @@ enum {
 #define TQB_KB_WORDS 12
 #define TQB_KB_OPFIRST 0   // first op record of the block
 #define TQB_KB_NOPS 1
-#define TQB_KB_FLAGS 2     // bit 0: transposed write-back (block bits <-> index bits 0-5 exchanged afterwards)
-#define TQB_KB_KPOS 4      // 6 words: ascending physical bit positions (all >= 6) of block-local bits 0..5
-#define TQB_KBF_TRANSPOSE 1
+#define TQB_KB_FLAGS 2     // TQB_KBF_*
+#define TQB_KB_KPOS 4      // 6 words: physical bit positions (distinct, all >= 6, any order) of block-local bits 0..5
+#define TQB_KBF_TRANSPOSE 1  // transposed write-back: block-local bits and index bits 0-5 exchange their roles on the way out
+#define TQB_KBF_ROTATE 2     // out of place: the tile is written contiguously (block bits -> index bits 6-11, the other
+                             // bits >= 6 compacted above them in ascending order); see tqb_apply_blocks
 // Block op record: 8 words.  Bits are block-local (0..5) unless stated.
 #define TQB_KO_WORDS 8
 #define TQB_KO_W0 0        // bits 0-3 form, 4-7 number of parameters, bit 8 inverse

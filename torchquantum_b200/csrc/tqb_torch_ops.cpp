@@ -187,11 +187,17 @@ void block_build(const at::Tensor& blocks, int64_t n_blocks, const at::Tensor& o
                          stream_of(a_planes)), "tqb_block_build");
 }
 
-void apply_blocks(const at::Tensor& src, at::Tensor& dst, int64_t n, int64_t bsz, const at::Tensor& a_planes,
-                  const at::Tensor& blocks_host, int64_t n_blocks, int64_t renorm) {
+void apply_blocks(const at::Tensor& src, at::Tensor& dst, const c10::optional<at::Tensor>& scratch, int64_t n, int64_t bsz,
+                  const at::Tensor& a_planes, const at::Tensor& blocks_host, int64_t n_blocks, int64_t renorm) {
   const Abi& a = abi_for(src);
   TORCH_CHECK(!blocks_host.is_cuda(), "tqb_apply_blocks: the block headers are read on the host");
-  check(a, a.apply_blocks(fp(src), fpm(dst), (int)n, bsz, fp(a_planes), ip(blocks_host), (int)n_blocks, (int)renorm,
+  float* sc = nullptr;
+  if (scratch.has_value() && scratch->defined()) {
+    TORCH_CHECK(scratch->is_contiguous() && scratch->device() == src.device() && scratch->nbytes() >= dst.nbytes(),
+                "tqb_apply_blocks: scratch must be a contiguous state of the same size on the same device");
+    sc = reinterpret_cast<float*>(scratch->data_ptr());
+  }
+  check(a, a.apply_blocks(fp(src), fpm(dst), sc, (int)n, bsz, fp(a_planes), ip(blocks_host), (int)n_blocks, (int)renorm,
                           stream_of(src)), "tqb_apply_blocks");
 }
 
@@ -308,7 +314,7 @@ TORCH_LIBRARY(tqb200, m) {
         "int conj_transpose) -> ()");
   m.def("tqb_block_build(Tensor blocks, int n_blocks, Tensor ops, Tensor consts, Tensor params_sh, int rank, "
         "Tensor(a!) a_planes) -> ()");
-  m.def("tqb_apply_blocks(Tensor src, Tensor(a!) dst, int n_qubits, int bsz, Tensor a_planes, Tensor blocks_host, "
+  m.def("tqb_apply_blocks(Tensor src, Tensor(a!) dst, Tensor(b!)? scratch, int n_qubits, int bsz, Tensor a_planes, Tensor blocks_host, "
         "int n_blocks, int renorm) -> ()");
   m.def("tqb_dense_grad(Tensor psi_in, Tensor lam_out, int n_qubits, int bsz, int k, Tensor bitpos, Tensor(a!) G) -> ()");
   m.def("tqb_expval_pauli(Tensor state, int n_qubits, int bsz, Tensor xmask, Tensor zmask, Tensor ny, int n_terms, "

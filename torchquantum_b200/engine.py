@@ -96,9 +96,11 @@ def run_fused_inplace(state, stage, n, rank, psh, pps, externs):
     return state
 
 
-def run_blocks(state, stage, n, rank, psh, inplace, timing=None):
+def run_blocks(state, stage, n, rank, psh, inplace, timing=None, scratch=None):
     """Forward-only block stage (plan.BlockStage): the block unitaries are built on the device from the live parameters,
-    then every block is one tensor-core pass; the first reads `state`, the rest work in place on the result.
+    then every block is one tensor-core pass.  Blocks that rotate the layout (TQB_KBF_ROTATE) are out of place: the state
+    alternates between two buffers (`state` itself when `inplace`, and `scratch` or a fresh one), so the result may come
+    back in either; the others work where the state is.
     timing: a list -> the blocks are launched one ABI call each and (start, end) CUDA events of every launch are
     appended (bench.py's per-launch roofline)."""
     _native.check_device(state)
@@ -110,17 +112,36 @@ def run_blocks(state, stage, n, rank, psh, inplace, timing=None):
     planes = torch.empty(stage.n_blocks, 2, 128, 64, dtype=torch.float32, device=dev)
     _native.call("tqb_block_build", blocks_dev, stage.n_blocks, ops_dev, consts, psh, rank,
                  planes)
-    out = state if inplace else torch.empty_like(state)
+    rot = [bool(int(f) & C.KBF_ROTATE) for f in stage.blocks[:, C.KB_FLAGS]]
+    n_rot = sum(rot)
+    # two buffers a / b; the first block reads `state`; the result is in `out`
+    a = state if inplace else torch.empty_like(state)
+    need_b = n_rot > 0 and (inplace or n_rot - rot[0] > 0)
+    if scratch is not None and (scratch.data_ptr() == state.data_ptr() or scratch.shape != state.shape
+                                or not scratch.is_contiguous()):
+        scratch = None
+    b = (scratch if scratch is not None else torch.empty_like(state)) if need_b else None
     if timing is not None:
-        for b in range(stage.n_blocks):
+        cur = state
+        for k in range(stage.n_blocks):
+            if rot[k]:
+                dst = b if cur is a else a
+            else:
+                dst = cur if (cur is not state or inplace) else a
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _native.call("tqb_apply_blocks", state if b == 0 else out, out, n, bsz, planes[b],
-                         torch.from_numpy(stage.blocks[b:b + 1]), 1, 1)
+            _native.call("tqb_apply_blocks", cur, dst, None, n, bsz, planes[k],
+                         torch.from_numpy(stage.blocks[k:k + 1]), 1, 1)
             e1.record()
             timing.append((e0, e1))
+            cur = dst
+        out = cur
     else:
-        _native.call("tqb_apply_blocks", state, out, n, bsz, planes, torch.from_numpy(stage.blocks),
+        if inplace and n_rot % 2:
+            out, other = b, a        # an odd number of moves ends in the other buffer; `state` serves as the scratch
+        else:
+            out, other = a, b
+        _native.call("tqb_apply_blocks", state, out, other, n, bsz, planes, torch.from_numpy(stage.blocks),
                      stage.n_blocks, 1)
     STATS["launches"] += 1 + stage.n_blocks
     return out
@@ -406,11 +427,13 @@ def _run_collapsed(state, n, records):
     return ComplexGemmFn.apply(state.contiguous(), wt)
 
 
-def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collapse=False):
+def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collapse=False, scratch=None):
     """state: [bsz, 2^n] complex64; queue: list of records (name, wires, params, inverse) with canonical
     names and normalised params (2-D float tensors, or complex matrices for unitary-like gates), or
     RecordChunks of such records.
-    n_total / rank: sharded statevector (plan.build_plan); inplace: overwrite `state` (no-grad only)."""
+    n_total / rank: sharded statevector (plan.build_plan); inplace: overwrite `state` (no-grad only).
+    scratch: a second state-sized buffer the caller owns (with inplace): block stages that rotate the qubit layout
+    alternate between the two, so the result may come back in either."""
     bsz = state.shape[0]
     chunked = any(type(item) is RecordChunk for item in queue)
     if chunked:
@@ -486,7 +509,10 @@ def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collap
                 psh = psh.detach().to(device=dev, dtype=torch.float32)
             else:
                 psh = torch.zeros(1, dtype=torch.float32, device=dev)
-            state = run_blocks(state, stage, n, rank, psh, inplace)
+            prev = state
+            state = run_blocks(state, stage, n, rank, psh, inplace, scratch=scratch)
+            if inplace and state.data_ptr() != prev.data_ptr():
+                scratch = prev     # the state moved to the other buffer: the one it left is the spare now
         elif stage.kind == "dense":
             name, wires, params, inverse = records[stage.rec]
             if stage.const is not None:

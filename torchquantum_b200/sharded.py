@@ -198,10 +198,15 @@ class ShardedQuantumDevice:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 l0 = engine.STATS["launches"]
                 e0.record()
+            grad = getattr(self, "_grad_flush", False)
+            spare = self._symm_view(1 - self._symm[2], self.bsz) if (self._symm is not None and not grad) else None
             out = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank,
-                                     inplace=not getattr(self, "_grad_flush", False))
-            if getattr(self, "_grad_flush", False):
+                                     inplace=not grad, scratch=spare)
+            if grad:
                 self._flat = out          # autograd: every stage is out of place and keeps its output for the backward
+            elif spare is not None and out.data_ptr() == spare.data_ptr():
+                self._symm[2] = 1 - self._symm[2]   # rotating block passes left the state in the other symmetric slab
+                self._flat = spare
             elif self._symm is not None and out.data_ptr() != self._flat.data_ptr():
                 self._flat.copy_(out)   # an out-of-place stage (dense block, reset): back into the symmetric slab
             else:
