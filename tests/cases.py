@@ -226,6 +226,13 @@ def check_cfg2_vqe(device, n=5, reps=3, bsz=6, graphed=False):
         return e, g
 
     step = None
+    if graphed:
+        # the order of bench.py: eager steps first (their read-out cache keeps the last autograd graph alive, with the
+        # parameters' AccumulateGrad nodes on the default stream), then the capture on its own stream
+        for _ in range(2):
+            for p in params:
+                p.grad = None
+            ours((torch.rand(bsz, n) * np.pi).to(device)).backward()
     for it in range(3):
         if it == 2:
             ops_mods[1].inverse = True

@@ -23,18 +23,30 @@ class GraphedStep:
         assert dev.type == "cuda", "GraphedStep needs CUDA tensors"
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        self._drop_stale_graphs()
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
                 self._zero()
                 loss_fn(*self.static_inputs).backward()
         torch.cuda.current_stream(dev).wait_stream(side)
         self._zero()
+        self._drop_stale_graphs()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = loss_fn(*self.static_inputs)
             self.loss.backward()
         self._leaves = self.params + [x for x in self.static_inputs if x.requires_grad]
         self._grads = [p.grad for p in self._leaves]   # the captured gradient buffers
+
+    @staticmethod
+    def _drop_stale_graphs():
+        """The read-out cache (measurement._READOUT_CURRENT) holds the columns of the last state that was read, and through
+        their grad_fn the autograd graph of that step with the parameters' AccumulateGrad nodes.  A node that survives
+        is reused by the next step on the stream it was created on, which breaks the capture (the warm-up and the
+        capture run on their own streams): drop it so that every phase builds fresh nodes."""
+        from . import measurement
+
+        measurement._READOUT_CURRENT.clear()
 
     def _zero(self):
         for p in self.params + self.static_inputs:
