@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 5
+#define TQB_ABI_VERSION 6
 
 int tqb_abi_version(void);
 const char* tqb_last_error(void);
@@ -104,6 +104,13 @@ int tqb_block_build(const int32_t* blocks_dev, int n_blocks, const int32_t* ops_
                     const float* params_sh, unsigned rank, float* a_planes, void* stream);
 int tqb_apply_blocks(const float* src, float* dst, float* scratch, int n_qubits, long long bsz, const float* a_planes,
                      const int32_t* blocks_host, int n_blocks, int renorm, void* stream);
+/* Fused quadratic-phase diagonal pass: state[b][x] *= exp(2 pi i (c0 + sum_k alpha_k x_k + sum_{j<k} beta_jk x_j x_k)) with
+ * x_k = bit k of the amplitude index (bits >= n_local: the bits of `rank`, sharded states), in place.  coef_dev:
+ * TQB_QP_WORDS uint32 fractions of a turn (csrc/tqb_program.h).  Any number of commuting 1- / 2-qubit diagonal gates
+ * (rz, phaseshift, cz, cu1, crz, rzz, folded cnot-rz-cnot sandwiches; constants or shared parameters) in ONE trip
+ * through HBM; replaces one apply_unitary_bmm per gate (functional/gate_wrapper.py:96-140 via functional/rz.py,
+ * functional/phase_shift.py, functional/u1.py ...).  n_local >= 12, n_local <= n_bits <= TQB_QP_BITS. */
+int tqb_quadphase(float* state, int n_local, long long bsz, const uint32_t* coef_dev, int n_bits, unsigned rank, void* stream);
 /* G[b][r][c] = sum_rest lam_out[b][r,rest] conj(psi_in[b][c,rest]) (complex64 [bsz][2^k][2^k]) */
 int tqb_dense_grad(const float* psi_in, const float* lam_out, int n_qubits, long long bsz, int k,
                    const int* bitpos_dev, float* G, void* stream);

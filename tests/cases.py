@@ -610,3 +610,73 @@ def check_block_write_back_modes(device, n=18, depth=10):
     finally:
         B.MODE = saved
         engine._PLAN_CACHE.clear()
+
+
+def check_quadphase_kernel(device, nl=13, g=2, rank=2, bsz=2):
+    """tqb_quadphase (fused quadratic-phase diagonal pass) against the formula it implements, evaluated in float64:
+    psi[x] *= exp(2 pi i (c0 + sum alpha_b x_b + sum_{a<b} beta_ab x_a x_b)), bits >= nl taken from `rank`."""
+    from torchquantum_b200 import _native, _codes as C
+
+    rng = np.random.default_rng(0)
+    nb = nl + g
+    coef = np.zeros(C.QP_WORDS, dtype=np.float64)
+    coef[0] = rng.random()
+    coef[1:1 + nb] = rng.random(nb)
+    for a in range(nb):
+        for b in range(a + 1, nb):
+            if rng.random() < 0.5:
+                coef[1 + C.QP_BITS + a * C.QP_BITS + b] = rng.random()
+    words = ((coef % 1.0) * 2 ** 32).astype(np.uint64) & 0xFFFFFFFF
+    cw = torch.from_numpy(words.astype(np.uint32).view(np.int32).copy()).to(device)
+    st = torch.randn(bsz, 2 ** nl, dtype=torch.complex64, generator=torch.Generator().manual_seed(1))
+    out = st.clone().to(device)
+    _native.call("tqb_quadphase", out, nl, bsz, cw, nb, rank)
+    x = np.arange(2 ** nl, dtype=np.int64) | (rank << nl)
+    bits = np.stack([(x >> b) & 1 for b in range(nb)], 1).astype(np.float64)
+    B = coef[1 + C.QP_BITS:].reshape(C.QP_BITS, C.QP_BITS)[:nb, :nb]
+    ph = coef[0] + bits @ coef[1:1 + nb] + np.einsum("xa,ab,xb->x", bits, np.triu(B, 1), bits)
+    ref = torch.from_numpy(st.numpy().astype(np.complex128) * np.exp(2j * np.pi * ph)[None, :])
+    assert_close(out.cpu(), ref.to(torch.complex64), what="tqb_quadphase")
+
+
+def check_qft_blocks_and_quadphase(device, n=18, bsz=1):
+    """QFT-like circuits on a streamed state of >= 18 qubits: dense 6-qubit QFT blocks on the tensor cores, the controlled
+    phases between the windows as quadratic-phase passes, the SWAPs as relabelling (blockplan.schedule_rotating);
+    vs the oracle on a random state (QFT, inverse QFT, QFT + extra diagonals: rz / crz / rzz / cz with shared and
+    constant angles), and vs the analytic QFT amplitudes of a basis state."""
+    from torchquantum_b200 import engine
+
+    g = torch.Generator().manual_seed(7)
+    init = torch.randn(bsz, 2 ** n, 2, generator=g)
+    init = torch.view_as_complex(init / init.flatten(1).norm(dim=1).reshape(bsz, 1, 1)).contiguous()
+    t = lambda v: torch.tensor([[v]], dtype=torch.float32)
+    extra = []
+    for w in range(n - 1):
+        extra += [{"name": "rz", "wires": [w], "params": t(0.1 + 0.05 * w)},
+                  {"name": "crz", "wires": [w, (w + 7) % n], "params": t(-0.3 + 0.02 * w), "inverse": bool(w % 2)},
+                  {"name": "rzz", "wires": [w, (w + 3) % n], "params": t(0.4 - 0.01 * w)},
+                  {"name": "cz", "wires": [w, (w + 9) % n]}]
+    engine._PLAN_CACHE.clear()
+    for ops in (qft_ops(n), [dict(o, inverse=True) for o in reversed(qft_ops(n))], qft_ops(n, do_swaps=False) + extra):
+        q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+        q.set_states(init.clone().to(device))
+        with torch.no_grad():
+            apply_ops(q, [dict(o, params=o["params"].to(device)) if "params" in o else o for o in ops], device)
+            got = q.get_states_1d()
+        stages = next(reversed(engine._PLAN_CACHE.values())).stages
+        assert any(s.kind == "blocks" and s.quads for s in stages), [s.kind for s in stages]
+        want = O.run_ops(n, bsz, ops, init_states=init.clone())
+        assert_close(got, want, what=f"qft-like circuit through blocks + quadratic-phase passes, n={n}")
+    x = 0b1011001110001101011 & ((1 << n) - 1)
+    basis = torch.zeros(1, 2 ** n, dtype=torch.complex64)
+    basis[0, x] = 1
+    q = tq.QuantumDevice(n_wires=n, bsz=1, device=device)
+    q.set_states(basis.to(device))
+    with torch.no_grad():
+        apply_ops(q, [dict(o, params=o["params"].to(device)) if "params" in o else o for o in qft_ops(n)], device)
+        got = q.get_states_1d().cpu().to(torch.complex128)
+    # wire 0 is the most significant bit of both the input and the output register (the circuit ends with the SWAPs)
+    k = torch.arange(2 ** n, dtype=torch.float64)
+    ref = torch.exp(2j * np.pi * ((x * k) % 2 ** n) / 2 ** n) / np.sqrt(2 ** n)
+    rel = ((got[0] - ref).norm() / ref.norm()).item()
+    assert rel <= 1e-5, rel

@@ -236,6 +236,33 @@ int tqb_apply_blocks(const float* src_, float* dst_, float* scratch_, int n, lon
   return 0;
 }
 
+// host restatement of tqb_quadphase_kernel: the same wrapping uint32 turn arithmetic, sin / cos in double
+int tqb_quadphase(float* state_, int n_local, long long bsz, const uint32_t* coef, int n_bits, unsigned rank, void*) {
+  if (n_local < 12) return fail_msg("quadphase needs n_local >= 12");
+  if (n_bits < n_local || n_bits > TQB_QP_BITS) return fail_msg("quadphase: n_bits must be in [n_local, TQB_QP_BITS]");
+  cf* st = reinterpret_cast<cf*>(state_);
+  const u64 N = 1ull << n_local;
+  const uint32_t* alpha = coef + 1;
+  const uint32_t* beta = coef + 1 + TQB_QP_BITS;
+  for (u64 k = 0; k < N; ++k) {
+    const u64 x = k | ((u64)rank << n_local);
+    uint32_t t = coef[0];
+    for (int b = 0; b < n_bits; ++b)
+      if ((x >> b) & 1ull) {
+        t += alpha[b];
+        for (int a = 0; a < b; ++a)
+          if ((x >> a) & 1ull) t += beta[a * TQB_QP_BITS + b];
+      }
+    const double ang = (double)(int32_t)t * (3.14159265358979323846 / 2147483648.0);
+    const cd ph(std::cos(ang), std::sin(ang));
+    for (long long b = 0; b < bsz; ++b) {
+      const cd v = cd(st[(u64)b * N + k]) * ph;
+      st[(u64)b * N + k] = cf((float)v.real(), (float)v.imag());
+    }
+  }
+  return 0;
+}
+
 int tqb_dense_grad(const float* psi_, const float* lam_, int n, long long bsz, int k, const int* bitpos, float* G_, void*) {
   const cf* psi = reinterpret_cast<const cf*>(psi_);
   const cf* lam = reinterpret_cast<const cf*>(lam_);

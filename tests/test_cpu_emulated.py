@@ -144,5 +144,13 @@ def test_block_write_back_modes():
     cases.check_block_write_back_modes("cpu", n=18, depth=8)
 
 
+def test_quadphase_kernel():
+    cases.check_quadphase_kernel("cpu")
+
+
+def test_qft_blocks_and_quadphase():
+    cases.check_qft_blocks_and_quadphase("cpu", n=18)
+
+
 def test_op_hamil_exp():
     cases.check_op_hamil_exp("cpu")

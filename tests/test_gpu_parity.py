@@ -60,6 +60,18 @@ def test_mnist_cfg1():
     cases.check_mnist_cfg1(DEV)
 
 
+def test_quadphase_kernel():
+    """K12: fused quadratic-phase diagonal pass vs its formula in float64 (local bits, rank bits, batch)"""
+    cases.check_quadphase_kernel(DEV)
+    cases.check_quadphase_kernel(DEV, nl=16, g=3, rank=5, bsz=1)
+
+
+def test_qft_blocks_and_quadphase():
+    """QFT-like circuits on streamed states: 6-qubit QFT blocks + quadratic-phase twiddle passes + relabelled SWAPs"""
+    cases.check_qft_blocks_and_quadphase(DEV, n=18)
+    cases.check_qft_blocks_and_quadphase(DEV, n=21, bsz=2)
+
+
 def test_block_write_back_modes():
     """tensor-core block stages, in place and rotating (contiguous tile write-back into a second buffer), vs the oracle"""
     cases.check_block_write_back_modes(DEV, n=20, depth=24)

@@ -120,54 +120,135 @@ def _random_masks(n, count, seed):
     return masks
 
 
-def _check_rotating_schedule(masks, n):
+def _check_rotating_schedule(masks, n, diag=None, swaps=None):
+    """Replays a rotating schedule against the kernel's contract (tqb_apply_blocks): every gate exactly once, inside its
+    block, after everything it depends on (diagonal gates may pass each other, a relabelled SWAP exchanges the two
+    wires of all later gates); the layout the scheduler tracks matches the replay and ends as the identity."""
     from torchquantum_b200 import blockplan as B
 
-    sched = B.schedule_rotating(masks, n)
+    sched = B.schedule_rotating(masks, n, diag, swaps)
     assert sched is not None
-    pos = list(range(n))            # logical -> physical, replayed from the kernel's contract (tqb_apply_blocks)
-    done, seen = set(), []
-    for kpos, gates, tr, where in sched:
+    pos = list(range(n))            # DATA item (initial wire) d -> physical bit
+    wire = list(range(n))           # data item currently on logical wire w (SWAPs exchange them)
+    done = set()
+    is_diag = lambda g: diag is not None and diag[g]
+    is_swap = lambda g: swaps is not None and swaps[g] is not None
+
+    def retire_swaps():
+        # a SWAP whose predecessors are all done has been turned into a relabelling by the scheduler
+        progress = True
+        while progress:
+            progress = False
+            for g in range(len(masks)):
+                if g not in done and is_swap(g) and all(h in done for h in range(g) if masks[h] & masks[g]):
+                    a, b = swaps[g]
+                    wire[a], wire[b] = wire[b], wire[a]
+                    done.add(g)
+                    progress = True
+
+    def check_deps(g):
+        for h in range(g):
+            if masks[h] & masks[g] and h not in done:
+                assert is_diag(h) and is_diag(g), (h, g)     # only diagonal gates may overtake each other
+
+    n_quads = 0
+    for ent in sched:
+        retire_swaps()
+        if ent[0] == "quad":
+            _, gates, qpos = ent
+            assert qpos == [pos[wire[w]] for w in range(n)]
+            for g in gates:
+                assert is_diag(g)
+                check_deps(g)
+            done.update(gates)
+            n_quads += 1
+            continue
+        _, kpos, gates, tr, where, perm = ent
         assert len(set(kpos)) == 6 and all(6 <= p < n for p in kpos)
-        inv = {p: l for l, p in enumerate(pos)}
+        assert kpos == sorted(kpos)                                   # tiles are gathered in ascending physical order
+        inv = {pos[wire[w]]: w for w in range(n)}          # physical bit -> logical wire
         qs = [inv[p] for p in kpos]
         assert all(where[q] == i for i, q in enumerate(qs))          # block-local bit i <-> physical kpos[i]
         blockmask = sum(1 << q for q in qs)
         for g in gates:
+            assert not is_swap(g) or True
             assert masks[g] & ~blockmask == 0                          # every gate of the block acts inside it
-            assert all(h in done for h in range(g) if masks[h] & masks[g])   # program order per qubit is kept
+            check_deps(g)
             done.add(g)
-        seen += gates
         # layout after the pass: block bits -> 6..11 (0..5 when transposing, the parked six then at 6..11), rest above
-        new = [None] * n
-        for i, q in enumerate(qs):
-            new[q] = i if tr else 6 + i
+        new = {}
+        pinv = {p: d for d, p in enumerate(pos)}
+        arrive = list(kpos)                                           # block-local bit i holds the data of physical arrive[i]
+        for i, j in perm:
+            arrive[i], arrive[j] = arrive[j], arrive[i]
+        for i, p in enumerate(arrive):
+            new[pinv[p]] = i if tr else 6 + i
         for b in range(6):
-            new[inv[b]] = 6 + b if tr else b
+            new[pinv[b]] = 6 + b if tr else b
         r = 12
         for p in range(6, n):
-            if inv[p] not in qs:
-                new[inv[p]] = r
+            if p not in kpos:
+                new[pinv[p]] = r
                 r += 1
-        pos = new
-    assert sorted(seen) == list(range(len(masks)))                      # every gate exactly once
-    assert pos == list(range(n))                                        # the stage ends in the identity layout
-    return len(sched)
+        pos = [new[d] for d in range(n)]
+    retire_swaps()
+    assert done == set(range(len(masks)))                               # every gate exactly once
+    assert [pos[wire[w]] for w in range(n)] == list(range(n))           # every wire's data is home
+    return sum(1 for e in sched if e[0] == "block"), n_quads
 
 
 def test_rotating_block_schedule_keeps_order_and_comes_home():
-    assert _check_rotating_schedule(_brick_masks(20, 12), 20) <= 24
-    assert _check_rotating_schedule(_brick_masks(28, 100), 28) <= 150     # 4150 gates (in place: 166 blocks)
+    assert _check_rotating_schedule(_brick_masks(20, 12), 20)[0] <= 24
+    assert _check_rotating_schedule(_brick_masks(28, 100), 28)[0] <= 150     # 4150 gates (in place: 166 blocks)
     for seed in range(3):
         _check_rotating_schedule(_random_masks(19, 150, seed), 19)
         _check_rotating_schedule(_random_masks(26, 300, seed + 10), 26)
+
+
+def _qft_program(n):
+    masks, diag, swaps = [], [], []
+    for top in range(n):
+        masks.append(1 << top); diag.append(False); swaps.append(None)
+        for w in range(top + 1, n):
+            masks.append((1 << top) | (1 << w)); diag.append(True); swaps.append(None)
+    for w in range(n // 2):
+        masks.append((1 << w) | (1 << (n - 1 - w))); diag.append(False); swaps.append((w, n - 1 - w))
+    return masks, diag, swaps
+
+
+def test_qft_becomes_dense_blocks_and_quadratic_phase_passes():
+    """Cooley-Tukey shape: a 6-qubit QFT block per window, the controlled phases between the windows as ONE
+    quadratic-phase pass each, the final SWAPs as relabelling; the sort passes bring the wires home."""
+    for n in (20, 31):
+        masks, diag, swaps = _qft_program(n)
+        blocks, quads = _check_rotating_schedule(masks, n, diag, swaps)
+        # one block per 6-qubit window, one quadratic-phase pass per window boundary that carries >= QUAD_MIN phases;
+        # the rest is layout: one parking pass at the start, <= 2 + ceil((n - 6) / 6) passes to bring the wires home
+        assert quads >= (n - 8) // 6 and blocks + quads <= 2 * -(-n // 6) + 9, (n, blocks, quads)
+    # random mixes of diagonal / non-diagonal gates and SWAPs keep their dependencies
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        n = 20
+        masks, diag, swaps = [], [], []
+        for _ in range(400):
+            kind = rng.integers(4)
+            qs = [int(q) for q in rng.choice(n, size=2, replace=False)]
+            if kind == 0:
+                masks.append(1 << qs[0]); diag.append(False); swaps.append(None)
+            elif kind == 3 and rng.random() < 0.3:
+                masks.append((1 << qs[0]) | (1 << qs[1])); diag.append(False); swaps.append((qs[0], qs[1]))
+            elif kind >= 2:
+                masks.append((1 << qs[0]) | (1 << qs[1])); diag.append(True); swaps.append(None)
+            else:
+                masks.append((1 << qs[0]) | (1 << qs[1])); diag.append(False); swaps.append(None)
+        _check_rotating_schedule(masks, n, diag, swaps)
 
 
 def test_block_stage_picks_the_cheaper_write_back():
     from torchquantum_b200 import blockplan as B
 
     deep, n_deep = B.plan_blocks(_brick_masks(28, 100), 28)
-    assert all(e[2] & C.KBF_ROTATE for e in deep)                        # deep circuits: rotating, fewer + cheaper passes
+    assert all(e[3] & C.KBF_ROTATE for e in deep)                        # deep circuits: rotating, fewer + cheaper passes
     assert B.schedule_rotating(_brick_masks(16, 8), 16) is None          # small states stay with the in-place schedule
     small, _ = B.plan_blocks(_brick_masks(16, 8), 16)
-    assert not any(e[2] & C.KBF_ROTATE for e in small)
+    assert not any(e[3] & C.KBF_ROTATE for e in small)

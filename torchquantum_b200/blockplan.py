@@ -284,16 +284,29 @@ def _next_use(masks, remaining, n_local):
     return nxt
 
 
-def schedule_rotating(masks, n_local):
-    """Rotating write-back: -> list of (kpos in pattern order, [gate indices], transposing, where) with `where` = logical
-    qubit -> block-local bit; the last entries are the gate-free passes that bring every qubit home.  Any block may
-    transpose, which parks ITS six qubits in index bits 0-5 and frees the six parked before; it does when its qubits
-    (after the block) stay idle longer than the parked ones."""
+QUAD_MIN = 8       # fewest commuting diagonal gates worth a quadratic-phase pass of their own
+QUAD_RATIO = 1.5   # ... and they must outnumber what the best block would absorb by this factor
+
+
+def schedule_rotating(masks, n_local, diag=None, swaps=None):
+    """Rotating write-back: -> list of entries in execution order,
+         ("block", kpos in pattern order, [gate indices], transposing, where, perm)   where = logical qubit -> block-local
+                                            bit while the gates act, perm = swaps of block-local bits applied after them
+         ("quad", [gate indices], pos)      commuting 1- / 2-qubit diagonal gates as ONE quadratic-phase pass; pos = logical
+                                            -> physical bit while it runs
+       the last blocks are the gate-free passes that bring every qubit home.  Any block may transpose, which parks ITS
+       six qubits in index bits 0-5 and frees the six parked before; it does when its qubits (after the block) stay
+       idle longer than the parked ones.
+       diag[i]: gate i is a diagonal of degree <= 2 (quad_terms); such gates commute with each other, and when the
+       dependency frontier holds many more of them than the best block would absorb they run as a quadratic-phase pass
+       (the twiddle stages of a QFT).  swaps[i] = (a, b): gate i is a plain SWAP; at the frontier it only relabels the two
+       logical qubits (the layout is sorted at the end anyway)."""
     if n_local < 3 * K_BLOCK:
         return None      # the way home needs six un-parked qubits outside 0-5 (smaller states: in-place schedule)
     s = _Sched(masks, n_local, rotating=True)
     remaining = list(range(len(masks)))
-    out = []   # (logical qubit mask, gates, transposing, fixed pattern order or None)
+    out = []   # ("block", logical qubit mask, gates, transposing) | ("quad", gates) | ("relabel", a, b)
+    full = (1 << n_local) - 1
 
     def drop(rem, tk):
         t = set(tk)
@@ -309,12 +322,49 @@ def schedule_rotating(masks, n_local):
             ch |= 1 << b
         return ch
 
+    def frontier(rem, want):
+        """gates of `rem` flagged by want(i) that no earlier un-flagged gate blocks (flagged gates commute with each other)"""
+        blocked, got = 0, []
+        for i in rem:
+            if want(i) and not (masks[i] & blocked):
+                got.append(i)
+            elif not want(i):
+                blocked |= masks[i]
+                if blocked == full:
+                    break
+        return got
+
     while remaining:
+        if swaps is not None:
+            # a SWAP at the frontier of everything (diagonals included) is a relabelling
+            blocked, done = 0, []
+            for i in remaining:
+                if swaps[i] is not None and not (masks[i] & blocked):
+                    a, b = swaps[i]
+                    out.append(("relabel", a, b))
+                    pa, pb = (s.parked >> a) & 1, (s.parked >> b) & 1
+                    if pa != pb:
+                        s.parked ^= (1 << a) | (1 << b)
+                    done.append(i)
+                else:
+                    blocked |= masks[i]
+                    if blocked == full:
+                        break
+            if done:
+                remaining = drop(remaining, done)
+                if not remaining:
+                    break
         ch, tk = s.best_block(remaining, s.parked)
+        if diag is not None:
+            D = frontier(remaining, lambda i: diag[i])
+            if len(D) >= QUAD_MIN and len(D) > QUAD_RATIO * len(tk):
+                out.append(("quad", D))
+                remaining = drop(remaining, D)
+                continue
         if not tk:
             # every frontier gate touches a parked qubit: a gate-free exchange that parks the idlest six instead
             ch = fill(0, remaining, s.parked)
-            out.append((ch, [], True, None))
+            out.append(("block", ch, [], True))
             s.parked = ch
             continue
         rem2 = drop(remaining, tk)
@@ -323,19 +373,11 @@ def schedule_rotating(masks, n_local):
         idle = lambda m: sum(min(nxt.get(b, len(rem2)), len(rem2)) for b in range(n_local) if (m >> b) & 1)
         stay, swap = idle(s.parked), idle(chB)   # park whichever six qubits stay idle longer (summed distance to next use)
         if swap > stay:
-            out.append((chB, tk, True, None))
+            out.append(("block", chB, tk, True))
             s.parked = chB
         else:
-            out.append((ch, tk, False, None))
+            out.append(("block", ch, tk, False))
         remaining = rem2
-    # the way home for the parked set: logical 0-5 into index bits 0-5, in order
-    # (a transposing block on exactly the qubits 0-5 always uses the pattern order 0..5: _rotating_layouts)
-    if s.parked & LOW and s.parked != LOW:
-        ch = fill(0, [], s.parked | LOW)
-        out.append((ch, [], True, None))
-        s.parked = ch
-    if s.parked != LOW:
-        out.append((LOW, [], True, None))
     return _rotating_layouts(out, n_local)
 
 
@@ -356,31 +398,51 @@ def _rotate(pos, qs, transposing, n_local):
     return new
 
 
-def _rotating_layouts(blocks, n_local):
+def _rotating_layouts(entries, n_local):
     pos = list(range(n_local))
     res = []
 
     def emit(qs, tk, tr):
+        """qs: the block's qubits in the order they are to ARRIVE (pattern bit i of the written tile = qs[i]).  The tile is
+        always gathered in ascending physical order (longest TMA runs); a different arrival order is a permutation of the
+        block-local bits multiplied into the block unitary (0 / 1 entries: exact), given as swaps after the gates."""
         nonlocal pos
-        res.append(([pos[q] for q in qs], tk, tr, {q: i for i, q in enumerate(qs)}))
+        load = sorted(qs, key=lambda q: pos[q])
+        at = {q: i for i, q in enumerate(load)}       # where each qubit sits while the gates act
+        cur, perm = list(load), []
+        for i, q in enumerate(qs):                     # selection sort of the block-local bits into arrival order
+            j = cur.index(q)
+            if j != i:
+                perm.append((i, j))
+                cur[i], cur[j] = cur[j], cur[i]
+        res.append(("block", [pos[q] for q in load], tk, tr, at, perm))
         pos = _rotate(pos, qs, tr, n_local)
 
-    for ch, tk, tr, order in blocks:
-        if order is None and tr and ch == LOW:
-            order = list(range(K_BLOCK))     # the parked qubits 0-5 come home in order
-        if order is None:
-            qs = [b for b in range(n_local) if (ch >> b) & 1]
-            # pad with un-parked neighbours (physically adjacent first: fewer TMA pieces), then anything un-parked
-            while len(qs) < K_BLOCK:
-                have = {pos[q] for q in qs}
-                inv = {p: l for l, p in enumerate(pos)}
-                cands = [p for p in range(K_BLOCK, n_local) if p not in have]
-                cands.sort(key=lambda p: (0 if (p - 1 in have or p + 1 in have) else 1, p))
-                qs.append(inv[cands[0]])
-            qs.sort(key=lambda q: pos[q])
-        else:
-            qs = list(order)
+    for ent in entries:
+        if ent[0] == "relabel":
+            _, a, b = ent
+            pos[a], pos[b] = pos[b], pos[a]
+            continue
+        if ent[0] == "quad":
+            res.append(("quad", ent[1], list(pos)))
+            continue
+        _, ch, tk, tr = ent
+        qs = [b for b in range(n_local) if (ch >> b) & 1]
+        # pad with un-parked neighbours (physically adjacent first: fewer TMA pieces), then anything un-parked
+        while len(qs) < K_BLOCK:
+            have = {pos[q] for q in qs}
+            inv = {p: l for l, p in enumerate(pos)}
+            cands = [p for p in range(K_BLOCK, n_local) if p not in have]
+            cands.sort(key=lambda p: (0 if (p - 1 in have or p + 1 in have) else 1, p))
+            qs.append(inv[cands[0]])
+        qs.sort(key=lambda q: pos[q])
         emit(qs, tk, tr)
+    # the way home for the parked set: logical 0-5 into index bits 0-5, in order
+    if pos[:K_BLOCK] != list(range(K_BLOCK)):
+        if any(pos[l] < K_BLOCK for l in range(K_BLOCK)):
+            # some of the qubits 0-5 are parked (but not all of them in place): park six others first (the highest ones)
+            emit(sorted((l for l in range(K_BLOCK, n_local) if pos[l] >= K_BLOCK), key=lambda l: pos[l])[-K_BLOCK:], [], True)
+        emit(list(range(K_BLOCK)), [], True)
     assert all(pos[b] == b for b in range(K_BLOCK))
     # sort the qubits >= 6 home: every pass moves six of them to the front, the top chunk first; the qubits T.. that are
     # already in ascending relative order are never moved (they end up on top, in order)
@@ -419,6 +481,8 @@ class BlockStage:
         self.P_sh = 0
         self.n_ops = self.n_blocks = 0
         self.n_rotating = 0   # blocks with TQB_KBF_ROTATE: each moves the state to the other buffer
+        self.items = []       # execution order: ("blocks", first block, count) | ("quad", index into quads)
+        self.quads = []       # QuadRecipe of every quadratic-phase pass
 
 
 def _full_const(op):
@@ -444,9 +508,85 @@ def inplace_cost(kpos):
     return 1.04 if high <= 2 else (1.2 if high <= 4 else 1.5)
 
 
-def plan_blocks(masks, n_local):
-    """-> (list of (kpos, gates, flags, where), estimated cost in units of one fast pass) for the cheaper of the two
-    write-back disciplines, or None"""
+QUAD_COST = 0.95     # a quadratic-phase pass streams the state once (no tensor-core work)
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex64).view(np.float32).reshape(-1)
+
+
+def quad_terms(op, n_local):
+    """A lowered diagonal op as terms of a quadratic form over index bits, or None when it is not one of degree <= 2.
+    The op multiplies by d[parity(x & pmask)] where (x & cmask) == cval, with d_k = exp(i theta_k).  -> list of
+    (bits, w0, w1): the coefficient of prod_{b in bits} x_b grows by w0 * theta_0 + w1 * theta_1.  Bits are the op's own
+    (logical local bits, rank bits at >= n_local)."""
+    if op.type != C.T_DIAG or op.pmode not in (None, "sh") or op.kind == C.K_EXTERN or not op.unitary:
+        return None
+    if op.postx is not None or op.nounapply or op.cval != op.cmask:
+        return None
+    if op.kind == C.K_CONST:
+        d = np.asarray(op.const, dtype=np.float64)
+        if abs(d[0] ** 2 + d[1] ** 2 - 1) > 1e-5 or abs(d[2] ** 2 + d[3] ** 2 - 1) > 1e-5:
+            return None
+    elif op.kind not in (C.K_RZ, C.K_PHASE, C.K_GPHASE):
+        return None
+    bits = lambda m: tuple(b for b in range(m.bit_length()) if (m >> b) & 1)
+    ctrl, free = bits(op.cmask), bits(op.pmask & ~op.cmask)
+    if len(ctrl) + len(free) > 2:
+        return None
+    flip = bin(op.pmask & op.cmask).count("1") & 1        # parity bits that are also controls are set on the support
+    a0 = (0.0, 1.0) if flip else (1.0, 0.0)              # factor on the support where the free parity is even ...
+    dl = (1.0, -1.0) if flip else (-1.0, 1.0)            # ... and the step to where it is odd, as weights of (theta_0, theta_1)
+    terms = [(ctrl, a0[0], a0[1])]
+    if len(free) == 1:
+        terms.append((tuple(sorted(ctrl + free)), dl[0], dl[1]))
+    elif len(free) == 2:      # x_a xor x_b = x_a + x_b - 2 x_a x_b
+        terms += [((free[0],), dl[0], dl[1]), ((free[1],), dl[0], dl[1]), (free, -2 * dl[0], -2 * dl[1])]
+    return terms
+
+
+def _thetas(op):
+    """(theta_0, theta_1) of a diagonal op: constants (radians), or the weights of its one parameter"""
+    sgn = -1.0 if op.inverse else 1.0
+    if op.kind == C.K_CONST:    # (inverse already folded into the constant)
+        d = np.asarray(op.const, dtype=np.float64)
+        return ("const", float(np.arctan2(d[1], d[0])), float(np.arctan2(d[3], d[2])))
+    if op.kind == C.K_RZ:
+        return ("param", -0.5 * sgn, 0.5 * sgn)
+    if op.kind == C.K_PHASE:
+        return ("param", 0.0, sgn)
+    return ("param", sgn, sgn)      # K_GPHASE
+
+
+class QuadRecipe:
+    """coefficients (in turns) of one quadratic-phase pass: base + sum_k weight_k * params_sh[pidx_k] at slot idx_k"""
+
+    def __init__(self, lops, gates, pos, n_local):
+        base = np.zeros(C.QP_WORDS, dtype=np.float64)
+        idx, w, pidx = [], [], []
+        top = n_local
+        for gi in gates:
+            op = lops[gi]
+            kind, t0, t1 = _thetas(op)
+            for bits, w0, w1 in quad_terms(op, n_local):
+                phys = sorted(pos[b] if b < n_local else b for b in bits)
+                top = max([top] + [b + 1 for b in phys])
+                slot = 0 if not phys else (1 + phys[0] if len(phys) == 1 else 1 + C.QP_BITS + phys[0] * C.QP_BITS + phys[1])
+                if kind == "const":
+                    base[slot] += (w0 * t0 + w1 * t1) / (2 * np.pi)
+                else:
+                    idx.append(slot)
+                    w.append((w0 * t0 + w1 * t1) / (2 * np.pi))
+                    pidx.append(op.poff)
+        assert top <= C.QP_BITS
+        self.n_bits, self.n_gates = top, len(gates)
+        self.base = base
+        self.idx = np.array(idx, dtype=np.int64)
+        self.w = np.array(w, dtype=np.float64)
+        self.pidx = np.array(pidx, dtype=np.int64)
+
+
+def plan_blocks(masks, n_local, diag=None, swaps=None):
+    """-> (entries, estimated cost in units of one fast pass) for the cheaper of the two write-back disciplines, or None.
+    entries: ("block", kpos, gates, flags, where, perm) | ("quad", gates, pos), see schedule_rotating; perm: swaps of
+    block-local bits multiplied into the block unitary after the gates"""
     cands = []
     if MODE != "rotate":
         sched = schedule(masks, n_local)
@@ -456,13 +596,14 @@ def plan_blocks(masks, n_local):
                 at = {p: i for i, p in enumerate(kpos)}
                 where = {l: at[p] for l in range(n_local)
                          for p in [l if K is None else (K[l] if l < K_BLOCK else l)] if p in at}
-                ent.append((kpos, gates, C.KBF_TRANSPOSE if tr else 0, where))
-            cands.append((sum(inplace_cost(e[0]) for e in ent), ent))
+                ent.append(("block", kpos, gates, C.KBF_TRANSPOSE if tr else 0, where, []))
+            cands.append((sum(inplace_cost(e[1]) for e in ent), ent))
     if MODE != "inplace":
-        sched = schedule_rotating(masks, n_local)
+        sched = schedule_rotating(masks, n_local, diag, swaps)
         if sched:
-            ent = [(kpos, gates, C.KBF_ROTATE | (C.KBF_TRANSPOSE if tr else 0), where) for kpos, gates, tr, where in sched]
-            cands.append((ROTATING_COST * len(ent), ent))
+            ent = [("block", e[1], e[2], C.KBF_ROTATE | (C.KBF_TRANSPOSE if e[3] else 0), e[4], e[5]) if e[0] == "block" else e
+                   for e in sched]
+            cands.append((sum(ROTATING_COST if e[0] == "block" else QUAD_COST for e in ent), ent))
     if not cands:
         return None
     cost, ent = min(cands, key=lambda c: c[0])
@@ -471,28 +612,40 @@ def plan_blocks(masks, n_local):
 
 def build_block_stage(lops, n_local, min_avg=0.0):
     """lops: fusable lowered ops (plan.LOp) in program order -> BlockStage, or None when the schedule averages fewer
-    than `min_avg` gates per block (the register-tile pass kernel is the better tool then)."""
+    than `min_avg` gates per pass (the register-tile pass kernel is the better tool then)."""
     lmask = (1 << n_local) - 1
     masks = [op.qmask & lmask for op in lops]
-    planned = plan_blocks(masks, n_local)
+    diag = [quad_terms(op, n_local) is not None for op in lops]
+    swaps = [(op.targets[0], op.targets[1]) if (op.type == C.T_U2Q and op.kind == C.K_CONST and not op.cmask
+                                                 and np.array_equal(np.asarray(op.const, dtype=np.float32).reshape(-1), _SWAP))
+             else None for op in lops]
+    planned = plan_blocks(masks, n_local, diag if any(diag) else None, swaps if any(sw is not None for sw in swaps) else None)
     if planned is None or len(lops) / planned[1] < min_avg:
         return None
     sched = planned[0]
     st = BlockStage()
-    st.n_rotating = sum(1 for e in sched if e[2] & C.KBF_ROTATE)
     for op in lops:
         if op.pmode == "sh":
             op.poff = st.P_sh
             st.P_sh += op.nparam
             st.sh_recs.append(op.rec)
-    blocks, words, consts, coff = [], [], [], 0
-    for kpos, gates, flags, where in sched:
+    blocks, words, consts, coff, swap_off = [], [], [], 0, None
+    for ent in sched:
+        if ent[0] == "quad":
+            st.items.append(("quad", len(st.quads)))
+            st.quads.append(QuadRecipe(lops, ent[1], ent[2], n_local))
+            continue
+        _, kpos, gates, flags, where, perm = ent
+        if st.items and st.items[-1][0] == "blocks":
+            st.items[-1] = ("blocks", st.items[-1][1], st.items[-1][2] + 1)
+        else:
+            st.items.append(("blocks", len(blocks), 1))
 
         def bl(l):
             return where[l]
 
         hdr = [0] * C.KB_WORDS
-        hdr[C.KB_OPFIRST], hdr[C.KB_NOPS], hdr[C.KB_FLAGS] = len(words), len(gates), flags
+        hdr[C.KB_OPFIRST], hdr[C.KB_NOPS], hdr[C.KB_FLAGS] = len(words), len(gates) + len(perm), flags
         for i, p in enumerate(kpos):
             hdr[C.KB_KPOS + i] = p
         blocks.append(hdr)
@@ -538,8 +691,18 @@ def build_block_stage(lops, n_local, min_avg=0.0):
                 w[C.KO_W0] = form | (op.nparam << 4) | ((1 << 8) if op.inverse else 0)
                 w[C.KO_KIND], w[C.KO_OFF] = op.kind, op.poff
             words.append(w)
+        for i, j in perm:      # arrival order of the block's qubits: constant SWAPs of block-local bits
+            if swap_off is None:
+                swap_off = coff
+                consts.append(_SWAP)
+                coff += len(_SWAP)
+            w = [0] * C.KO_WORDS
+            w[C.KO_BITS] = i | (j << 8)
+            w[C.KO_W0], w[C.KO_KIND], w[C.KO_OFF] = C.KF_U2, C.K_CONST, swap_off
+            words.append(w)
     st.blocks = np.array(blocks, dtype=np.int32).reshape(-1, C.KB_WORDS)
     st.ops = np.array(words if words else [[0] * C.KO_WORDS], dtype=np.int32).reshape(-1, C.KO_WORDS)
     st.consts = np.concatenate(consts + [np.zeros(4, np.float32)]).astype(np.float32)
     st.n_ops, st.n_blocks = len(lops), len(blocks)
+    st.n_rotating = int(sum(1 for h in blocks if h[C.KB_FLAGS] & C.KBF_ROTATE))
     return st

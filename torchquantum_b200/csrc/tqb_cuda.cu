@@ -9,6 +9,7 @@
 #include "tqb_block_umma.cuh"
 #include "tqb_block_build.cuh"
 #include "tqb_gemm_umma.cuh"
+#include "tqb_quadphase.cuh"
 #include "tqb_host_rng.h"
 #include "../../include/tqb200.h"
 
@@ -789,6 +790,19 @@ int tqb_apply_blocks(const float* src, float* dst, float* scratch, int n_qubits,
     if (err) return fail_msg(err);
     cur = out;
   }
+  return 0;
+}
+
+int tqb_quadphase(float* state, int n_local, long long bsz, const uint32_t* coef_dev, int n_bits, unsigned rank, void* stream) {
+  if (((uintptr_t)state & 15) != 0) return fail_msg("tqb_quadphase: state must be 16-byte aligned");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const char* err = tqb_qp::launch_quadphase(state, n_local, bsz, coef_dev, n_bits, rank, g_num_sms, (cudaStream_t)stream);
+  if (err) return fail_msg(err);
   return 0;
 }
 

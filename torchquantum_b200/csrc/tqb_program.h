@@ -171,6 +171,10 @@ enum {
 #define TQB_KO_KIND 6      // TQB_K_CONST or a parametric builder kind (TQB_K_RX ...)
 #define TQB_KO_OFF 7       // K_CONST: float offset in the constant pool (full complex form, inverse folded in);
                            // parametric: first parameter (float offset in params_sh)
+// Quadratic-phase diagonal passes (tqb_quadphase): coefficient words, uint32 fractions of a turn:
+// [0] c0, [1 + b] alpha_b, [1 + TQB_QP_BITS + a * TQB_QP_BITS + b] beta_ab (a < b) over physical index bits b (rank bits above the local ones)
+#define TQB_QP_BITS 40
+#define TQB_QP_WORDS 1641
 #define TQB_KF_U1 0        // 2x2 complex on t0 where the controls hold            (consts: 8 floats)
 #define TQB_KF_DIAG 1      // amp *= d[parity] where the controls hold               (consts: 4 floats)
 #define TQB_KF_U2 2        // 4x4 complex on (t1, t0) where the controls hold      (consts: 32 floats)

@@ -17,6 +17,7 @@
 #include <string>
 
 #include "../../include/tqb200.h"
+#include "tqb_program.h"
 
 namespace {
 
@@ -33,6 +34,7 @@ struct Abi {
   decltype(&tqb_block_build) block_build = nullptr;
   decltype(&tqb_apply_blocks) apply_blocks = nullptr;
   decltype(&tqb_dense_grad) dense_grad = nullptr;
+  decltype(&tqb_quadphase) quadphase = nullptr;
   decltype(&tqb_expval_pauli) expval_pauli = nullptr;
   decltype(&tqb_expval_pauli_bwd) expval_pauli_bwd = nullptr;
   decltype(&tqb_expval_z) expval_z = nullptr;
@@ -75,6 +77,7 @@ int64_t bind(const std::string& path, bool emulated) {
   resolve(h, "tqb_block_build", n.block_build, true);
   resolve(h, "tqb_apply_blocks", n.apply_blocks, true);
   resolve(h, "tqb_dense_grad", n.dense_grad, true);
+  resolve(h, "tqb_quadphase", n.quadphase, true);
   resolve(h, "tqb_expval_pauli", n.expval_pauli, true);
   resolve(h, "tqb_expval_pauli_bwd", n.expval_pauli_bwd, true);
   resolve(h, "tqb_expval_z", n.expval_z, true);
@@ -201,6 +204,14 @@ void apply_blocks(const at::Tensor& src, at::Tensor& dst, const c10::optional<at
                           stream_of(src)), "tqb_apply_blocks");
 }
 
+void quadphase(at::Tensor& state, int64_t n_local, int64_t bsz, const at::Tensor& coef, int64_t n_bits, int64_t rank) {
+  const Abi& a = abi_for(state);
+  TORCH_CHECK(coef.is_contiguous() && coef.scalar_type() == at::kInt && coef.numel() >= TQB_QP_WORDS && coef.device() == state.device(),
+              "tqb_quadphase: coef must be TQB_QP_WORDS int32 words on the state's device");
+  check(a, a.quadphase(fpm(state), (int)n_local, bsz, reinterpret_cast<const uint32_t*>(coef.data_ptr()), (int)n_bits,
+                       (unsigned)rank, stream_of(state)), "tqb_quadphase");
+}
+
 void dense_grad(const at::Tensor& psi_in, const at::Tensor& lam_out, int64_t n, int64_t bsz, int64_t k, const at::Tensor& bitpos,
                 at::Tensor& G) {
   const Abi& a = abi_for(psi_in);
@@ -316,6 +327,7 @@ TORCH_LIBRARY(tqb200, m) {
         "Tensor(a!) a_planes) -> ()");
   m.def("tqb_apply_blocks(Tensor src, Tensor(a!) dst, Tensor(b!)? scratch, int n_qubits, int bsz, Tensor a_planes, Tensor blocks_host, "
         "int n_blocks, int renorm) -> ()");
+  m.def("tqb_quadphase(Tensor(a!) state, int n_local, int bsz, Tensor coef, int n_bits, int rank) -> ()");
   m.def("tqb_dense_grad(Tensor psi_in, Tensor lam_out, int n_qubits, int bsz, int k, Tensor bitpos, Tensor(a!) G) -> ()");
   m.def("tqb_expval_pauli(Tensor state, int n_qubits, int bsz, Tensor xmask, Tensor zmask, Tensor ny, int n_terms, "
         "Tensor(a!) out) -> ()");
@@ -337,6 +349,7 @@ TORCH_LIBRARY(tqb200, m) {
   m.impl("tqb_apply_dense_tc", &apply_dense_tc);         \
   m.impl("tqb_block_build", &block_build);               \
   m.impl("tqb_apply_blocks", &apply_blocks);             \
+  m.impl("tqb_quadphase", &quadphase);                   \
   m.impl("tqb_dense_grad", &dense_grad);                 \
   m.impl("tqb_expval_pauli", &expval_pauli);             \
   m.impl("tqb_expval_pauli_bwd", &expval_pauli_bwd);     \

@@ -116,35 +116,58 @@ def run_blocks(state, stage, n, rank, psh, inplace, timing=None, scratch=None):
     n_rot = sum(rot)
     # two buffers a / b; the first block reads `state`; the result is in `out`
     a = state if inplace else torch.empty_like(state)
-    need_b = n_rot > 0 and (inplace or n_rot - rot[0] > 0)
+    need_b = n_rot > 0 and (inplace or n_rot - rot[0] > 0 or len(stage.items) > 1)
     if scratch is not None and (scratch.data_ptr() == state.data_ptr() or scratch.shape != state.shape
                                 or not scratch.is_contiguous()):
         scratch = None
     b = (scratch if scratch is not None else torch.empty_like(state)) if need_b else None
-    if timing is not None:
-        cur = state
-        for k in range(stage.n_blocks):
-            if rot[k]:
-                dst = b if cur is a else a
-            else:
-                dst = cur if (cur is not state or inplace) else a
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _native.call("tqb_apply_blocks", cur, dst, None, n, bsz, planes[k],
-                         torch.from_numpy(stage.blocks[k:k + 1]), 1, 1)
-            e1.record()
-            timing.append((e0, e1))
-            cur = dst
-        out = cur
-    else:
-        if inplace and n_rot % 2:
-            out, other = b, a        # an odd number of moves ends in the other buffer; `state` serves as the scratch
+    cur = state
+    psh64 = None
+    for item in stage.items:
+        if item[0] == "quad":
+            # quadratic-phase pass: coefficients (turns) = base + W . params, assembled on the device in float64
+            q = stage.quads[item[1]]
+            coef = _dev(q, "base", dev)
+            if len(q.idx):
+                if psh64 is None:
+                    psh64 = psh.to(torch.float64)
+                coef = coef.index_add(0, _dev(q, "idx", dev), _dev(q, "w", dev) * psh64[_dev(q, "pidx", dev)])
+            words = ((coef - torch.floor(coef)) * 4294967296.0).to(torch.int64).bitwise_and_(0xFFFFFFFF).to(torch.int32)
+            if cur is state and not inplace:     # the caller's state must survive: the pass works on a copy
+                a.copy_(state)
+                cur = a
+            _native.call("tqb_quadphase", cur, n, bsz, words, q.n_bits, rank)
+            STATS["launches"] += 1
+            continue
+        _, first, count = item
+        if timing is not None:
+            for k in range(first, first + count):
+                if rot[k]:
+                    dst = b if cur is a else a
+                else:
+                    dst = cur if (cur is not state or inplace) else a
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _native.call("tqb_apply_blocks", cur, dst, None, n, bsz, planes[k],
+                             torch.from_numpy(stage.blocks[k:k + 1]), 1, 1)
+                e1.record()
+                timing.append((e0, e1))
+                cur = dst
+            continue
+        # one ABI call for the run of blocks: rotating blocks alternate between the two buffers, the rest work where the
+        # state is; the call leaves the result in `dst` (an odd number of moves ends in the other buffer)
+        r = sum(rot[first:first + count])
+        if cur is state and not inplace:
+            dst, other = (a, b)                          # first write goes to a fresh buffer, `state` is only read
+        elif r % 2:
+            dst, other = (b if cur is a else a), cur     # the buffer the state leaves serves as the scratch
         else:
-            out, other = a, b
-        _native.call("tqb_apply_blocks", state, out, other, n, bsz, planes, torch.from_numpy(stage.blocks),
-                     stage.n_blocks, 1)
+            dst, other = cur, (b if cur is a else a)
+        _native.call("tqb_apply_blocks", cur, dst, other, n, bsz, planes[first:first + count],
+                     torch.from_numpy(stage.blocks[first:first + count]), count, 1)
+        cur = dst
     STATS["launches"] += 1 + stage.n_blocks
-    return out
+    return cur
 
 
 class FusedFn(torch.autograd.Function):

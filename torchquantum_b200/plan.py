@@ -821,7 +821,7 @@ class CircuitPlan:
 
     @property
     def n_passes(self):
-        return sum(len(s.passes) if s.kind == "fused" else s.n_blocks for s in self.stages if s.kind in ("fused", "blocks"))
+        return sum(len(s.passes) if s.kind == "fused" else s.n_blocks + len(s.quads) for s in self.stages if s.kind in ("fused", "blocks"))
 
 
 def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
@@ -843,12 +843,14 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
     def close():
         if cur:
             ops = fold_cnot_sandwiches(cur)
-            if fast:
-                ops = fold_h_into_ladders(fold_phase_ladders(ops))
+            # block stages are cut out of the UNFOLDED program (controlled phases stay 2-qubit diagonals there: inside a
+            # block, or many at once in a quadratic-phase pass); what is left gets the ladder folds of the register-tile kernel
             for kind, part in _split_block_runs(ops, n) if (fast and BLOCKS and n >= BLOCK_MIN_N) else [("fused", ops)]:
                 if kind == "blocks":
                     plan.stages.append(part)
                 else:
+                    if fast:
+                        part = fold_h_into_ladders(fold_phase_ladders(part))
                     plan.stages.append(build_fused_stage(part, n, n_total, **tile_kw))
             cur.clear()
 
