@@ -247,8 +247,8 @@ def test_qft_becomes_dense_blocks_and_quadratic_phase_passes():
 def test_block_stage_picks_the_cheaper_write_back():
     from torchquantum_b200 import blockplan as B
 
-    deep, n_deep = B.plan_blocks(_brick_masks(28, 100), 28)
+    deep, n_deep, _ = B.plan_blocks(_brick_masks(28, 100), 28)
     assert all(e[3] & C.KBF_ROTATE for e in deep)                        # deep circuits: rotating, fewer + cheaper passes
     assert B.schedule_rotating(_brick_masks(16, 8), 16) is None          # small states stay with the in-place schedule
-    small, _ = B.plan_blocks(_brick_masks(16, 8), 16)
+    small, _, _ = B.plan_blocks(_brick_masks(16, 8), 16)
     assert not any(e[3] & C.KBF_ROTATE for e in small)

@@ -58,6 +58,8 @@ def _worker(rank, world, port, n, seed, emu_path, tiles):
         assert_close(ev, ev_want, rtol=GRAD_RTOL, what=f"rank {rank} expvals")
         nl = q.nl
         assert q.stats["exchanges"] >= 1
+        if nl >= 18:   # rotating block stages left their layouts to the device instead of sorting the qubits home
+            assert q.stats.get("layouts_kept", 0) >= 1, q.stats
         slab = q.get_states_1d()
         assert_close(slab, want[:, rank << nl:(rank + 1) << nl], rtol=RTOL, what=f"rank {rank} slab")
         full = q.gather_states_1d()
@@ -69,12 +71,14 @@ def _worker(rank, world, port, n, seed, emu_path, tiles):
         want2 = O.run_ops(n, 1, [{"name": "rx", "wires": [0], "params": torch.tensor([[0.3]])},
                                  {"name": "cnot", "wires": [n - 1, 0]}], want.reshape([1] + [2] * n))
         zw, _ = O.expval(want2.reshape([1] + [2] * n), list(range(n)), ["Z"] * n)
-        assert_close(z, zw, rtol=GRAD_RTOL, what="per-wire Z")
+        # (n = 19: the complex64 oracle's own float32 marginals over 2^19 probabilities are only good to a few 1e-6)
+        assert_close(z, zw, rtol=GRAD_RTOL if n < 16 else 5e-5, what="per-wire Z")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,tiles", [(2, 8, None), (4, 9, None), (2, 9, (4, 5, 2)), (4, 10, (5, 6, 3))])
+@pytest.mark.parametrize("world,n,tiles", [(2, 8, None), (4, 9, None), (2, 9, (4, 5, 2)), (4, 10, (5, 6, 3)),
+                                           (2, 19, None)])   # 18 local qubits: rotating tensor-core blocks, quadratic-phase passes, layouts kept across exchanges
 def test_sharded_qft_brickwork_matches_oracle(world, n, tiles):
     emu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libtqb200_emu.so")
     if not os.path.exists(emu):

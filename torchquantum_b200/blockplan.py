@@ -288,7 +288,7 @@ QUAD_MIN = 8       # fewest commuting diagonal gates worth a quadratic-phase pas
 QUAD_RATIO = 1.5   # ... and they must outnumber what the best block would absorb by this factor
 
 
-def schedule_rotating(masks, n_local, diag=None, swaps=None):
+def schedule_rotating(masks, n_local, diag=None, swaps=None, final=None):
     """Rotating write-back: -> list of entries in execution order,
          ("block", kpos in pattern order, [gate indices], transposing, where, perm)   where = logical qubit -> block-local
                                             bit while the gates act, perm = swaps of block-local bits applied after them
@@ -300,7 +300,9 @@ def schedule_rotating(masks, n_local, diag=None, swaps=None):
        diag[i]: gate i is a diagonal of degree <= 2 (quad_terms); such gates commute with each other, and when the
        dependency frontier holds many more of them than the best block would absorb they run as a quadratic-phase pass
        (the twiddle stages of a QFT).  swaps[i] = (a, b): gate i is a plain SWAP; at the frontier it only relabels the two
-       logical qubits (the layout is sorted at the end anyway)."""
+       logical qubits (the layout is sorted at the end anyway).
+       final: a list -> the stage does NOT bring the qubits home; the logical -> physical map it ends with is appended
+       (callers that track the layout themselves: the sharded device)."""
     if n_local < 3 * K_BLOCK:
         return None      # the way home needs six un-parked qubits outside 0-5 (smaller states: in-place schedule)
     s = _Sched(masks, n_local, rotating=True)
@@ -378,7 +380,7 @@ def schedule_rotating(masks, n_local, diag=None, swaps=None):
         else:
             out.append(("block", ch, tk, False))
         remaining = rem2
-    return _rotating_layouts(out, n_local)
+    return _rotating_layouts(out, n_local, final)
 
 
 def _rotate(pos, qs, transposing, n_local):
@@ -398,7 +400,7 @@ def _rotate(pos, qs, transposing, n_local):
     return new
 
 
-def _rotating_layouts(entries, n_local):
+def _rotating_layouts(entries, n_local, final=None):
     pos = list(range(n_local))
     res = []
 
@@ -437,6 +439,9 @@ def _rotating_layouts(entries, n_local):
             qs.append(inv[cands[0]])
         qs.sort(key=lambda q: pos[q])
         emit(qs, tk, tr)
+    if final is not None:
+        final.append(list(pos))
+        return res
     # the way home for the parked set: logical 0-5 into index bits 0-5, in order
     if pos[:K_BLOCK] != list(range(K_BLOCK)):
         if any(pos[l] < K_BLOCK for l in range(K_BLOCK)):
@@ -483,6 +488,7 @@ class BlockStage:
         self.n_rotating = 0   # blocks with TQB_KBF_ROTATE: each moves the state to the other buffer
         self.items = []       # execution order: ("blocks", first block, count) | ("quad", index into quads)
         self.quads = []       # QuadRecipe of every quadratic-phase pass
+        self.final_pos = None # logical -> physical bit after the stage when it does not bring the qubits home
 
 
 def _full_const(op):
@@ -583,8 +589,9 @@ class QuadRecipe:
         self.pidx = np.array(pidx, dtype=np.int64)
 
 
-def plan_blocks(masks, n_local, diag=None, swaps=None):
-    """-> (entries, estimated cost in units of one fast pass) for the cheaper of the two write-back disciplines, or None.
+def plan_blocks(masks, n_local, diag=None, swaps=None, come_home=True):
+    """-> (entries, estimated cost in units of one fast pass, final layout or None = identity) for the cheaper of the two
+    write-back disciplines, or None.  come_home=False: a rotating schedule may leave the qubits where they are.
     entries: ("block", kpos, gates, flags, where, perm) | ("quad", gates, pos), see schedule_rotating; perm: swaps of
     block-local bits multiplied into the block unitary after the gates"""
     cands = []
@@ -597,33 +604,39 @@ def plan_blocks(masks, n_local, diag=None, swaps=None):
                 where = {l: at[p] for l in range(n_local)
                          for p in [l if K is None else (K[l] if l < K_BLOCK else l)] if p in at}
                 ent.append(("block", kpos, gates, C.KBF_TRANSPOSE if tr else 0, where, []))
-            cands.append((sum(inplace_cost(e[1]) for e in ent), ent))
+            cands.append((sum(inplace_cost(e[1]) for e in ent), ent, None))
     if MODE != "inplace":
-        sched = schedule_rotating(masks, n_local, diag, swaps)
+        final = None if come_home else []
+        sched = schedule_rotating(masks, n_local, diag, swaps, final)
         if sched:
             ent = [("block", e[1], e[2], C.KBF_ROTATE | (C.KBF_TRANSPOSE if e[3] else 0), e[4], e[5]) if e[0] == "block" else e
                    for e in sched]
-            cands.append((sum(ROTATING_COST if e[0] == "block" else QUAD_COST for e in ent), ent))
+            cands.append((sum(ROTATING_COST if e[0] == "block" else QUAD_COST for e in ent), ent, final[0] if final else None))
     if not cands:
         return None
-    cost, ent = min(cands, key=lambda c: c[0])
-    return ent, cost
+    cost, ent, fin = min(cands, key=lambda c: c[0])
+    if fin is not None and fin == list(range(n_local)):
+        fin = None
+    return ent, cost, fin
 
 
-def build_block_stage(lops, n_local, min_avg=0.0):
+def build_block_stage(lops, n_local, min_avg=0.0, come_home=True):
     """lops: fusable lowered ops (plan.LOp) in program order -> BlockStage, or None when the schedule averages fewer
-    than `min_avg` gates per pass (the register-tile pass kernel is the better tool then)."""
+    than `min_avg` gates per pass (the register-tile pass kernel is the better tool then).  come_home=False: the stage
+    may end in another qubit layout (BlockStage.final_pos: logical -> physical bit)."""
     lmask = (1 << n_local) - 1
     masks = [op.qmask & lmask for op in lops]
     diag = [quad_terms(op, n_local) is not None for op in lops]
     swaps = [(op.targets[0], op.targets[1]) if (op.type == C.T_U2Q and op.kind == C.K_CONST and not op.cmask
                                                  and np.array_equal(np.asarray(op.const, dtype=np.float32).reshape(-1), _SWAP))
              else None for op in lops]
-    planned = plan_blocks(masks, n_local, diag if any(diag) else None, swaps if any(sw is not None for sw in swaps) else None)
+    planned = plan_blocks(masks, n_local, diag if any(diag) else None, swaps if any(sw is not None for sw in swaps) else None,
+                          come_home)
     if planned is None or len(lops) / planned[1] < min_avg:
         return None
     sched = planned[0]
     st = BlockStage()
+    st.final_pos = planned[2]
     for op in lops:
         if op.pmode == "sh":
             op.poff = st.P_sh

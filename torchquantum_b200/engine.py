@@ -22,11 +22,11 @@ _DEV_CACHE = {}
 STATS = {"launches": 0, "plans_built": 0}
 
 
-def get_plan(n, key, grad_mode, n_total=None):
-    k = (n, n_total, grad_mode, key)
+def get_plan(n, key, grad_mode, n_total=None, leave_layout=False):
+    k = (n, n_total, grad_mode, key) if not leave_layout else (n, n_total, grad_mode, key, "leave")
     plan = _PLAN_CACHE.get(k)
     if plan is None:
-        plan = P.build_plan(n, key, grad_mode, n_total)
+        plan = P.build_plan(n, key, grad_mode, n_total, leave_layout=leave_layout)
         _PLAN_CACHE[k] = plan
         STATS["plans_built"] += 1
         if len(_PLAN_CACHE) > 512:
@@ -450,13 +450,15 @@ def _run_collapsed(state, n, records):
     return ComplexGemmFn.apply(state.contiguous(), wt)
 
 
-def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collapse=False, scratch=None):
+def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collapse=False, scratch=None, leave_layout=False):
     """state: [bsz, 2^n] complex64; queue: list of records (name, wires, params, inverse) with canonical
     names and normalised params (2-D float tensors, or complex matrices for unitary-like gates), or
     RecordChunks of such records.
     n_total / rank: sharded statevector (plan.build_plan); inplace: overwrite `state` (no-grad only).
     scratch: a second state-sized buffer the caller owns (with inplace): block stages that rotate the qubit layout
-    alternate between the two, so the result may come back in either."""
+    alternate between the two, so the result may come back in either.
+    leave_layout: the caller tracks the qubit layout itself (sharded device): -> (state, final_pos) where final_pos is
+    None or the logical -> physical bit map the last (rotating block) stage left behind instead of sorting the qubits home."""
     bsz = state.shape[0]
     chunked = any(type(item) is RecordChunk for item in queue)
     if chunked:
@@ -503,7 +505,7 @@ def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collap
             key += item.key_for(bsz, grad_mode) if type(item) is RecordChunk else (_record_key(item, bsz, grad_mode),)
     else:
         key = [_record_key(r, bsz, grad_mode) for r in records]
-    plan = get_plan(n, tuple(key), grad_mode, n_total)
+    plan = get_plan(n, tuple(key), grad_mode, n_total, leave_layout and not grad_mode)
     for stage in plan.stages:
         if stage.kind == "fused":
             dev = state.device
@@ -545,4 +547,4 @@ def run_circuit(state, n, queue, n_total=None, rank=0, inplace=False, _no_collap
             state = DenseFn.apply(state, mat, tuple(stage.bitpos), n, inverse)
         else:
             state = _reset(state, n, stage.wires)
-    return state
+    return (state, plan.final_pos) if leave_layout else state

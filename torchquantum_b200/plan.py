@@ -782,7 +782,7 @@ def build_fused_stage(lops, n_local, n_total=None, t_single=None, t_multi=None, 
     return st
 
 
-def _split_block_runs(ops, n_local):
+def _split_block_runs(ops, n_local, leave_last=False):
     """Forward-only program -> [("blocks", BlockStage) | ("fused", [LOp])]: maximal runs of block-fusable ops that the
     block scheduler packs densely enough go to the tensor-core block kernel, everything else (ladders, per-sample
     parameters, explicit matrices, sparse runs) stays with the register-tile pass kernel."""
@@ -800,7 +800,8 @@ def _split_block_runs(ops, n_local):
             while k < len(ops) and B.fusable(ops[k], n_local):
                 k += 1
             run = ops[i:k]
-            stage = B.build_block_stage(run, n_local, BLOCK_MIN_AVG) if len(run) >= BLOCK_MIN_RUN else None
+            stage = (B.build_block_stage(run, n_local, BLOCK_MIN_AVG, come_home=not (leave_last and k == len(ops)))
+                     if len(run) >= BLOCK_MIN_RUN else None)
             if stage is not None:
                 out.append(("blocks", stage))
             else:
@@ -818,13 +819,14 @@ class CircuitPlan:
         self.n = n
         self.stages = []
         self.n_gates = 0
+        self.final_pos = None   # leave_layout plans: logical -> physical bit of the local qubits after the last stage
 
     @property
     def n_passes(self):
         return sum(len(s.passes) if s.kind == "fused" else s.n_blocks + len(s.quads) for s in self.stages if s.kind in ("fused", "blocks"))
 
 
-def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
+def build_plan(n, key, grad_mode, n_total=None, leave_layout=False, **tile_kw):
     """key: tuple of (name, wires, inverse, pmode, grad, ext_dim) in queue order.
 
     Sharded statevector (n_total > n): this rank holds the n low index bits, `wires` count from the
@@ -840,12 +842,13 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
     if fast:
         tile_kw = dict(tile_kw, fast=True)
 
-    def close():
+    def close(last=False):
         if cur:
             ops = fold_cnot_sandwiches(cur)
             # block stages are cut out of the UNFOLDED program (controlled phases stay 2-qubit diagonals there: inside a
             # block, or many at once in a quadratic-phase pass); what is left gets the ladder folds of the register-tile kernel
-            for kind, part in _split_block_runs(ops, n) if (fast and BLOCKS and n >= BLOCK_MIN_N) else [("fused", ops)]:
+            for kind, part in (_split_block_runs(ops, n, leave_last=last and leave_layout)
+                               if (fast and BLOCKS and n >= BLOCK_MIN_N) else [("fused", ops)]):
                 if kind == "blocks":
                     plan.stages.append(part)
                 else:
@@ -880,5 +883,7 @@ def build_plan(n, key, grad_mode, n_total=None, **tile_kw):
             plan.stages.append(stg)
             continue
         cur.append(op)
-    close()
+    close(last=True)
+    if plan.stages and plan.stages[-1].kind == "blocks":
+        plan.final_pos = plan.stages[-1].final_pos     # (only set when leave_layout asked for it)
     return plan

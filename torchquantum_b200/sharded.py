@@ -191,7 +191,9 @@ class ShardedQuantumDevice:
     def _pwire(self, logical_bit, pos=None):
         return self.n_wires - 1 - (self.pos if pos is None else pos)[logical_bit]
 
-    def _run_local(self, records):
+    def _run_local(self, records, leave=False):
+        """leave: the gates of the user's circuit (flush): rotating block stages may leave the local qubits in another
+        layout, which goes into `pos`; the device's own permutation passes need the layout they ask for."""
         if records:
             timed = self.time_exchanges and self._flat.is_cuda
             if timed:
@@ -201,7 +203,13 @@ class ShardedQuantumDevice:
             grad = getattr(self, "_grad_flush", False)
             spare = self._symm_view(1 - self._symm[2], self.bsz) if (self._symm is not None and not grad) else None
             out = engine.run_circuit(self._flat, self.nl, records, n_total=self.n_wires, rank=self.rank,
-                                     inplace=not grad, scratch=spare)
+                                     inplace=not grad, scratch=spare, leave_layout=leave and not grad)
+            if leave and not grad:
+                # rotating block stages do not sort the local qubits home: their final layout goes into `pos`
+                out, moved = out
+                if moved is not None:
+                    self.pos = [moved[p] if p < self.nl else p for p in self.pos]
+                    self.stats["layouts_kept"] = self.stats.get("layouts_kept", 0) + 1
             if grad:
                 self._flat = out          # autograd: every stage is out of place and keeps its output for the backward
             elif spare is not None and out.data_ptr() == spare.data_ptr():
@@ -243,7 +251,7 @@ class ShardedQuantumDevice:
                         continue
                     runnable.append((name, tuple(n - 1 - pos[b] for b in lbits), params, inverse))
                 self.pos = pos
-                self._run_local(runnable)
+                self._run_local(runnable, leave=True)
                 if rest:
                     self._exchange(rest)
                 remaining = rest
