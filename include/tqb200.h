@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 6
+#define TQB_ABI_VERSION 7
 
 int tqb_abi_version(void);
 const char* tqb_last_error(void);
@@ -148,6 +148,12 @@ int tqb_sample_counts(const float* probs, int n_qubits, long long bsz, const flo
  *   round-to-nearest.  A complex product is this GEMM on the interleaved (re, im) views with Bt the real 2x2 embedding of
  *   the right factor. */
 int tqb_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+/* Operands of the complex GEMM from a complex64 matrix x [rows][cols] (row-major, interleaved re / im) in one pass,
+ * already cut into TF32 hi / lo planes (rows, cols multiples of 32):
+ *   mode 1: A of x^H:  out [cols][2 rows],   out[c][2r + v]      = (re, -im)[v] x[r][c]
+ *   mode 2: Bt of x:   out [2 cols][2 rows], out[2c][2r + v]     = (re, -im)[v] x[r][c],  out[2c + 1][2r + v] = (im, re)[v] x[r][c]
+ * so that x^H . g = tqb_gemm_tf32x3(A(mode 1 of x), Bt(mode 2 of g)) and a . b = tqb_gemm_tf32x3(split(a), Bt(mode 2 of b)). */
+int tqb_gemm_prep(const float* x, long long rows, long long cols, int mode, float* hi, float* lo, void* stream);
 long long tqb_gemm_workspace_floats(long long M, long long N, long long K);
 int tqb_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* bt_hi, const float* bt_lo, float* c, float* workspace,
                     long long M, long long N, long long K, void* stream);

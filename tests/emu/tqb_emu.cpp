@@ -368,6 +368,28 @@ static inline float emu_tf32_rna(float x) {
   memcpy(&r, &u, 4);
   return r;
 }
+int tqb_gemm_prep(const float* x_, long long rows, long long cols, int mode, float* hi, float* lo, void*) {
+  if (rows <= 0 || cols <= 0 || rows % 32 || cols % 32) return fail_msg("tqb_gemm_prep: rows and cols must be positive multiples of 32");
+  if (mode != 1 && mode != 2) return fail_msg("tqb_gemm_prep: mode must be 1 (A of x^H) or 2 (Bt of x)");
+  auto rna = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); u = (u + 0x1000u) & 0xffffe000u; float r; std::memcpy(&r, &u, 4); return r; };
+  auto put = [&](long long row, long long col, float v) {   // planes are [.][2 rows] floats
+    const float h = rna(v);
+    hi[row * 2 * rows + col] = h;
+    lo[row * 2 * rows + col] = rna(v - h);
+  };
+  for (long long r = 0; r < rows; ++r)
+    for (long long c = 0; c < cols; ++c) {
+      const float re = x_[2 * (r * cols + c)], im = x_[2 * (r * cols + c) + 1];
+      if (mode == 1) {
+        put(c, 2 * r, re); put(c, 2 * r + 1, -im);
+      } else {
+        put(2 * c, 2 * r, re); put(2 * c, 2 * r + 1, -im);
+        put(2 * c + 1, 2 * r, im); put(2 * c + 1, 2 * r + 1, re);
+      }
+    }
+  return 0;
+}
+
 int tqb_split_tf32(const float* x, float* hi, float* lo, long long n, void*) {
   for (long long i = 0; i < n; ++i) { hi[i] = emu_tf32_rna(x[i]); lo[i] = emu_tf32_rna(x[i] - hi[i]); }
   return 0;

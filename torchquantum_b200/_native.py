@@ -17,14 +17,14 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TQB200_LIB") or os.path.join(_HERE, "lib", "libtqb200.so")  # env: kernel A/B experiments
 OPS_LIB_PATH = os.path.join(_HERE, "lib", "libtqb200_torch.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # every ABI entry point registered as torch.ops.tqb200.<name> (mirrors include/tqb200.h)
 OP_NAMES = (
     "tqb_build_mats", "tqb_build_mats_bwd", "tqb_pass_forward", "tqb_pass_backward", "tqb_apply_dense",
     "tqb_apply_dense_tc", "tqb_block_build", "tqb_apply_blocks", "tqb_quadphase", "tqb_dense_grad", "tqb_expval_pauli",
     "tqb_expval_pauli_bwd", "tqb_expval_z", "tqb_expval_z_bwd", "tqb_probs", "tqb_sample_counts", "tqb_host_uniforms",
-    "tqb_exchange_p2p", "tqb_split_tf32", "tqb_gemm_tf32x3",
+    "tqb_exchange_p2p", "tqb_split_tf32", "tqb_gemm_prep", "tqb_gemm_tf32x3",
 )
 
 _ops = None          # name -> OpOverload

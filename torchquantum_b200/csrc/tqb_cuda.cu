@@ -588,6 +588,44 @@ __global__ void __launch_bounds__(256) tqb_split_tf32_kernel(const float4* __res
   }
 }
 
+// Operand preparation of the complex GEMM in ONE pass over the complex matrix x [rows][cols] (replaces conj / transpose /
+// stack / split chains of 5-7 elementwise kernels): the real operand the tensor-core GEMM wants, already cut into its TF32
+// hi / lo planes.  32 x 32 tiles go through shared memory (reads contiguous along cols, writes contiguous along rows).
+//   MODE 1  A  of x^H:  out[c][2r + v]      = (re, -im)[v] of x[r][c]                      out: [cols][2 rows]
+//   MODE 2  Bt of x:    out[2c][2r + v]     = (re, -im)[v] of x[r][c],
+//                       out[2c + 1][2r + v] = (im,  re)[v] of x[r][c]                      out: [2 cols][2 rows]
+template <int MODE>
+__global__ void __launch_bounds__(256) tqb_gemm_prep_kernel(const float2* __restrict__ x, long long rows, long long cols,
+                                                            float2* __restrict__ hi, float2* __restrict__ lo) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = x[(r0 + ty + 8 * i) * cols + c0 + tx];
+  __syncthreads();
+  auto split = [](float v, float& h, float& l) {
+    h = __uint_as_float(tqb_umma::tf32_rna(v));
+    l = __uint_as_float(tqb_umma::tf32_rna(v - h));
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = tile[tx][ty + 8 * i];        // x[r0 + tx][c0 + ty + 8 i]
+    const long long c = c0 + ty + 8 * i, r = r0 + tx;
+    float2 h, l;
+    split(v.x, h.x, l.x);
+    split(-v.y, h.y, l.y);
+    if (MODE == 1) {
+      hi[c * rows + r] = h;
+      lo[c * rows + r] = l;
+    } else {
+      hi[(2 * c) * rows + r] = h;
+      lo[(2 * c) * rows + r] = l;
+      hi[(2 * c + 1) * rows + r] = make_float2(-h.y, h.x);     // (im, re): the split of -(-im) and of re
+      lo[(2 * c + 1) * rows + r] = make_float2(-l.y, l.x);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K10: global <-> local qubit exchange over peer memory (NVLink P2P stores), pack and transfer in ONE kernel.
 // Rank r swaps its g rank-index bits with the g local index bits `vpos` (any positions, ascending): amplitude i of the
@@ -946,6 +984,23 @@ int tqb_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* bt_hi, co
                     long long M, long long N, long long K, void* stream) {
   const char* err = tqb_gemm::launch_gemm(a_hi, a_lo, bt_hi, bt_lo, c, workspace, M, N, K, (cudaStream_t)stream);
   if (err) return fail_msg(err);
+  return 0;
+}
+
+int tqb_gemm_prep(const float* x, long long rows, long long cols, int mode, float* hi, float* lo, void* stream) {
+  if (rows <= 0 || cols <= 0 || rows % 32 || cols % 32) return fail_msg("tqb_gemm_prep: rows and cols must be positive multiples of 32");
+  if ((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 7) != 0) return fail_msg("tqb_gemm_prep: pointers must be 8-byte aligned");
+  if (cols / 32 > 0x7fffffffll || rows / 32 > 65535) return fail_msg("tqb_gemm_prep: matrix too large");
+  dim3 grid((unsigned)(cols / 32), (unsigned)(rows / 32));
+  if (mode == 1)
+    tqb_gemm_prep_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(x), rows, cols,
+                                                                   reinterpret_cast<float2*>(hi), reinterpret_cast<float2*>(lo));
+  else if (mode == 2)
+    tqb_gemm_prep_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(x), rows, cols,
+                                                                   reinterpret_cast<float2*>(hi), reinterpret_cast<float2*>(lo));
+  else
+    return fail_msg("tqb_gemm_prep: mode must be 1 (A of x^H) or 2 (Bt of x)");
+  TQB_CHECK_LAUNCH("tqb_gemm_prep_kernel");
   return 0;
 }
 

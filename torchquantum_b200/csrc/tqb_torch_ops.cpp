@@ -44,6 +44,7 @@ struct Abi {
   decltype(&tqb_host_uniforms) host_uniforms = nullptr;
   decltype(&tqb_exchange_p2p) exchange_p2p = nullptr;
   decltype(&tqb_split_tf32) split_tf32 = nullptr;
+  decltype(&tqb_gemm_prep) gemm_prep = nullptr;
   decltype(&tqb_gemm_tf32x3) gemm_tf32x3 = nullptr;
   decltype(&tqb_gemm_workspace_floats) gemm_workspace_floats = nullptr;
 };
@@ -87,6 +88,7 @@ int64_t bind(const std::string& path, bool emulated) {
   resolve(h, "tqb_host_uniforms", n.host_uniforms, true);
   resolve(h, "tqb_exchange_p2p", n.exchange_p2p, true);
   resolve(h, "tqb_split_tf32", n.split_tf32, true);
+  resolve(h, "tqb_gemm_prep", n.gemm_prep, true);
   resolve(h, "tqb_gemm_tf32x3", n.gemm_tf32x3, true);
   resolve(h, "tqb_gemm_workspace_floats", n.gemm_workspace_floats, true);
   TORCH_CHECK(n.abi_version() == TQB_ABI_VERSION, "libtqb200: ABI version ", n.abi_version(), " != ", TQB_ABI_VERSION);
@@ -277,6 +279,16 @@ void split_tf32(const at::Tensor& x, at::Tensor& hi, at::Tensor& lo) {
   check(a, a.split_tf32(fp(x), fpm(hi), fpm(lo), x.numel(), stream_of(x)), "tqb_split_tf32");
 }
 
+void gemm_prep(const at::Tensor& x, int64_t mode, at::Tensor& hi, at::Tensor& lo) {
+  const Abi& a = abi_for(x);
+  TORCH_CHECK(x.dim() == 2 && x.scalar_type() == at::kComplexFloat && hi.scalar_type() == at::kFloat && lo.scalar_type() == at::kFloat,
+              "tqb_gemm_prep: x complex64 [rows][cols], planes float32");
+  const int64_t want = (mode == 1 ? 2 : 4) * x.numel();
+  TORCH_CHECK(hi.numel() == want && lo.numel() == want, "tqb_gemm_prep: plane size");
+  check(a, a.gemm_prep(reinterpret_cast<const float*>(x.data_ptr()), x.size(0), x.size(1), (int)mode, fpm(hi), fpm(lo), stream_of(x)),
+        "tqb_gemm_prep");
+}
+
 void gemm_tf32x3(const at::Tensor& a_hi, const at::Tensor& a_lo, const at::Tensor& bt_hi, const at::Tensor& bt_lo, at::Tensor& c) {
   const Abi& a = abi_for(a_hi);
   TORCH_CHECK(a_hi.dim() == 2 && bt_hi.dim() == 2 && c.dim() == 2 && a_hi.size(1) == bt_hi.size(1) && c.size(0) == a_hi.size(0) &&
@@ -307,6 +319,7 @@ void host_uniforms(at::Tensor& mt_state, int64_t n, at::Tensor& out) {
 TORCH_LIBRARY(tqb200, m) {
   m.def("tqb_host_uniforms(Tensor(a!) mt_state, int n, Tensor(b!) out) -> ()");
   m.def("tqb_split_tf32(Tensor x, Tensor(a!) hi, Tensor(b!) lo) -> ()");
+  m.def("tqb_gemm_prep(Tensor x, int mode, Tensor(a!) hi, Tensor(b!) lo) -> ()");
   m.def("tqb_gemm_tf32x3(Tensor a_hi, Tensor a_lo, Tensor bt_hi, Tensor bt_lo, Tensor(a!) c) -> ()");
   m.def("tqb_exchange_p2p(Tensor src, Tensor(a!) local_dst, int[] peer_ptrs, int n_local, int bsz, int[] victim_bits, "
         "int rank) -> ()");
@@ -359,6 +372,7 @@ TORCH_LIBRARY(tqb200, m) {
   m.impl("tqb_sample_counts", &sample_counts);    \
   m.impl("tqb_exchange_p2p", &exchange_p2p);      \
   m.impl("tqb_split_tf32", &split_tf32);          \
+  m.impl("tqb_gemm_prep", &gemm_prep);            \
   m.impl("tqb_gemm_tf32x3", &gemm_tf32x3);
 
 TORCH_LIBRARY_IMPL(tqb200, CUDA, m) { TQB_IMPL_ALL(m) }

@@ -408,7 +408,7 @@ class ComplexGemmFn(torch.autograd.Function):
         a, w = ctx.saved_tensors
         g = g.contiguous()
         ga = complex_gemm(g, w.conj().transpose(0, 1).contiguous()) if ctx.needs_input_grad[0] else None
-        gw = complex_gemm(a.conj().transpose(0, 1).contiguous(), g) if ctx.needs_input_grad[1] else None
+        gw = complex_gemm(a, g, a_h=True) if ctx.needs_input_grad[1] else None
         return ga, gw
 
 
@@ -418,12 +418,40 @@ def _tf32_planes(x):
     return hi, lo
 
 
-def complex_gemm(a, b):
-    """a [M, K] @ b [K, N], complex64, on the tensor cores (tqb_gemm_tf32x3: 3xTF32, fp32 accuracy).  The complex product is a
-    real GEMM on the interleaved (re, im) views: A = a as [M][2K], Bt[2n + w][2k + v] = the real 2x2 embedding of b[k][n]."""
+def _prep_planes(x, mode):
+    """tqb_gemm_prep: the GEMM operand of x^H (mode 1: A) or of x (mode 2: Bt) as TF32 hi / lo planes, one kernel"""
+    rows, cols = x.shape
+    shape = (cols, 2 * rows) if mode == 1 else (2 * cols, 2 * rows)
+    hi = torch.empty(shape, dtype=torch.float32, device=x.device)
+    lo = torch.empty(shape, dtype=torch.float32, device=x.device)
+    _native.call("tqb_gemm_prep", x, mode, hi, lo)
+    return hi, lo
+
+
+def complex_gemm(a, b, a_h=False):
+    """a [M, K] @ b [K, N] (a_h: a^H @ b with a [K, M]), complex64, on the tensor cores (tqb_gemm_tf32x3: 3xTF32, fp32
+    accuracy).  The complex product is a real GEMM on the interleaved (re, im) views: A = a as [M][2K], Bt[2n + w][2k + v]
+    = the real 2x2 embedding of b[k][n].  Tile-aligned shapes take their operands from ONE fused preparation kernel each
+    (tqb_gemm_prep: conjugate / transpose / embed / TF32 split in a single pass)."""
     _native.check_device(a)
-    M, K = a.shape
+    if a_h:
+        K, M = a.shape
+    else:
+        M, K = a.shape
     N = b.shape[1]
+    if K % 32 == 0 and M % 128 == 0 and N % 128 == 0:
+        a, b = a.contiguous(), b.contiguous()
+        if a_h:
+            a_hi, a_lo = _prep_planes(a, 1)
+        else:
+            a_hi, a_lo = _tf32_planes(torch.view_as_real(a).reshape(M, 2 * K))
+        b_hi, b_lo = _prep_planes(b, 2)
+        c = torch.empty(M, 2 * N, dtype=torch.float32, device=a.device)
+        _native.call("tqb_gemm_tf32x3", a_hi, a_lo, b_hi, b_lo, c)
+        STATS["launches"] += 3
+        return torch.view_as_complex(c.view(M, N, 2))
+    if a_h:
+        a = a.conj().transpose(0, 1).contiguous()
     Kp = -(-K // 16) * 16            # tile sizes of the kernel: 128 rows, 32 real K, 256 real N (zero padding is exact)
     if Kp != K:
         a = torch.nn.functional.pad(a, (0, Kp - K))
