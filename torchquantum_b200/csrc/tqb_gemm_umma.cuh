@@ -34,9 +34,9 @@ constexpr int kThreads = 256;
 // instruction descriptor: D fp32, A / B tf32, both K-major, N = 256, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 
@@ -61,11 +61,13 @@ struct GemmParams {
   long long split_stride;  // M * N
   int ldc;               // = N
   int k_slices;          // K slices of BK floats handled by one CTA (one split)
+  int a_hi_plane, b_hi_plane;   // which plane (0 / 1) of the operand's tensor map is its TF32 hi part
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
-                       const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
+tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
+  // ONE 3-D tensor map per operand (K, rows, {hi, lo} plane): four maps made the parameter block 536 bytes, and kernels
+  // whose parameter block is longer than 384 bytes run slower on B200 (measured on tqb_block6_kernel)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + kStages * kStage;
@@ -80,10 +82,8 @@ tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
     for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ahi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_alo) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
@@ -107,8 +107,8 @@ tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
         mbar_wait(empty(s), ph ^ 1u);
         mbar_expect_tx(full(s), kStage);
         const uint32_t sa = base + s * kStage, sb = sa + kABytes;
-        tma_load_2d(sa, pass == 0 ? &tm_alo : &tm_ahi, full(s), (ks0 + ks) * BK, m0);
-        tma_load_2d(sb, pass == 1 ? &tm_blo : &tm_bhi, full(s), (ks0 + ks) * BK, n0);
+        tma_load_3d(sa, &tm_a, full(s), (ks0 + ks) * BK, m0, pass == 0 ? 1 - p.a_hi_plane : p.a_hi_plane);
+        tma_load_3d(sb, &tm_b, full(s), (ks0 + ks) * BK, n0, pass == 1 ? 1 - p.b_hi_plane : p.b_hi_plane);
       }
     }
   } else if (warp == 1) {
@@ -151,15 +151,21 @@ tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
   }
 }
 
-// 2-D tensor map over a row-major [rows][K] fp32 matrix, box = BK floats x box_rows, SWIZZLE_128B
-inline const char* make_map_2d(CUtensorMap* tm, const float* ptr, long long rows, long long K, int box_rows) {
+// 3-D tensor map over the two planes (TF32 hi / lo parts, anywhere in memory) of a row-major [rows][K] fp32 matrix:
+// dims (K, rows, 2), box = BK floats x box_rows x 1, SWIZZLE_128B.  *hi_plane: the plane index of `hi`.
+inline const char* make_map_planes(CUtensorMap* tm, const float* hi, const float* lo, long long rows, long long K, int box_rows,
+                                   int* hi_plane) {
   tqb_umma::EncodeTiledFn enc = tqb_umma::encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled not available";
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  const float* ptr = hi < lo ? hi : lo;
+  *hi_plane = hi < lo ? 0 : 1;
+  const unsigned long long gap = (unsigned long long)((hi < lo ? lo : hi) - ptr) * 4ull;
+  if (gap == 0 || (gap & 15ull) || gap >= (1ull << 40)) return "gemm: the hi / lo planes of an operand must be distinct and within 2^40 bytes";
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)gap};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed (gemm)";
@@ -210,19 +216,17 @@ inline const char* launch_gemm(const float* a_hi, const float* a_lo, const float
   }
   const long long splits = gemm_splits(K);
   if (splits > 1 && !workspace) return "gemm: workspace of splits * M * N floats needed";
-  CUtensorMap ta, tal, tb, tbl;
+  CUtensorMap ta, tb;
   const char* err;
-  if ((err = make_map_2d(&ta, a_hi, M, K, BM))) return err;
-  if ((err = make_map_2d(&tal, a_lo, M, K, BM))) return err;
-  if ((err = make_map_2d(&tb, bt_hi, N, K, BN))) return err;
-  if ((err = make_map_2d(&tbl, bt_lo, N, K, BN))) return err;
   GemmParams p;
+  if ((err = make_map_planes(&ta, a_hi, a_lo, M, K, BM, &p.a_hi_plane))) return err;
+  if ((err = make_map_planes(&tb, bt_hi, bt_lo, N, K, BN, &p.b_hi_plane))) return err;
   p.c = splits > 1 ? workspace : c;
   p.split_stride = M * N;
   p.ldc = (int)N;
   p.k_slices = (int)(K / BK / splits);
   dim3 grid((unsigned)(N / BN), (unsigned)(M / BM), (unsigned)splits);
-  tqb_gemm_tf32x3_kernel<<<grid, kThreads, kSmem, st>>>(ta, tal, tb, tbl, p);
+  tqb_gemm_tf32x3_kernel<<<grid, kThreads, kSmem, st>>>(ta, tb, p);
   if (cudaGetLastError() != cudaSuccess) return "gemm launch failed";
   if (splits > 1) {
     const long long n4 = M * N / 4;
