@@ -17,6 +17,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=28)
     ap.add_argument("--kpos", type=int, nargs=6, default=[6, 7, 8, 9, 10, 11])
+    ap.add_argument("--rotate", type=int, default=0, help="1: rotating write-back into a second buffer")
+    ap.add_argument("--warm", type=int, default=3, help="untraced passes first (1500: the board reaches its power cap)")
     a = ap.parse_args()
     lib = ctypes.CDLL(os.path.join(ROOT, "tools", "_ab", "libtqb200_debug.so"))   # tools/build_debug_lib.sh
     lib.tqb_last_error.restype = ctypes.c_char_p
@@ -33,14 +35,16 @@ def main():
     st = torch.randn(1, 2 ** a.n, 2, device=dev, dtype=torch.float32)
     st /= st.norm()
     trace = torch.zeros(64 * 10, dtype=torch.int64, device=dev)
-    hdr = (ctypes.c_int32 * 12)(*([0, 0, 0, 0] + list(a.kpos) + [0, 0]))
+    hdr = (ctypes.c_int32 * 12)(*([0, 0, 2 * a.rotate, 0] + list(a.kpos) + [0, 0]))
+    bufs = [st, torch.empty_like(st) if a.rotate else st]
 
     def run():
-        rc = fn(st.data_ptr(), st.data_ptr(), None, a.n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1,
+        rc = fn(bufs[0].data_ptr(), bufs[1].data_ptr(), None, a.n, 1, planes.data_ptr(), ctypes.addressof(hdr), 1, 1,
                 torch.cuda.current_stream().cuda_stream)
         assert rc == 0, lib.tqb_last_error().decode()
+        bufs.reverse()
 
-    for _ in range(3):
+    for _ in range(a.warm):
         run()
     torch.cuda.synchronize()
     lib.tqb_debug_block_trace(trace.data_ptr())

@@ -384,9 +384,22 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_warp_kernel(const float2
 #pragma unroll 4
     for (u32 p = lane; p < npairs; p += 32u) {
       const float4 a = psi4[p];
+      const float m0 = fmaf(a.y, a.y, a.x * a.x), m1 = fmaf(a.w, a.w, a.z * a.z);
 #pragma unroll
       for (int t = 0; t < TB; ++t) {
-        float4 c = x[t] ? psi4[p ^ (x[t] >> 1)] : a;
+        // (the branches are uniform over the warp: every lane works on the same term)
+        if (x[t] == 0u) {            // Z / I string: +- |psi_k|^2, no partner amplitude, no complex product
+          const u32 par = (u32)__popc((2u * p) & z[t]);
+          acc[t] += ((par & 1u) ? -m0 : m0) + (((par + (z[t] & 1u)) & 1u) ? -m1 : m1);
+          continue;
+        }
+        if (z[t] == 0u && ph[t] == 0) {   // X / I string: Re(conj(psi[k^x]) psi[k]), no sign
+          float4 c = psi4[p ^ (x[t] >> 1)];
+          if (x[t] & 1u) c = make_float4(c.z, c.w, c.x, c.y);
+          acc[t] += fmaf(c.y, a.y, c.x * a.x) + fmaf(c.w, a.w, c.z * a.z);
+          continue;
+        }
+        float4 c = psi4[p ^ (x[t] >> 1)];
         if (x[t] & 1u) c = make_float4(c.z, c.w, c.x, c.y);
         // w = conj(psi[k^x]) psi[k] for k = 2p, 2p+1
         const float w0x = fmaf(c.y, a.y, c.x * a.x), w0y = fmaf(-c.y, a.x, c.x * a.y);
@@ -456,9 +469,16 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_bwd_warp_kernel(const fl
     if (!live) continue;
     for (u32 p = lane; p < npairs; p += 32u) {
       float4 acc = t0 == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : out4[p];
+      float d0 = 0.f, d1 = 0.f;                        // Z / I strings: real factors on psi[2p], psi[2p + 1]
       for (int t = 0; t < nt; ++t) {
         const u32 x = s_x[wib][t], z = s_z[wib][t], ph = s_ph[wib][t];
         const float g = s_g[wib][t];
+        if (x == 0u) {               // (uniform over the warp) diagonal string: no partner amplitude
+          const u32 par = (u32)__popc((2u * p) & z);
+          d0 += (par & 1u) ? -g : g;
+          d1 += ((par + (z & 1u)) & 1u) ? -g : g;
+          continue;
+        }
         float4 v = psi4[p ^ (x >> 1)];                 // psi[j], j = k ^ x for k = 2p, 2p + 1
         if (x & 1u) v = make_float4(v.z, v.w, v.x, v.y);
         // i^ny psi[j]
@@ -472,6 +492,9 @@ __global__ void __launch_bounds__(256) tqb_expval_pauli_bwd_warp_kernel(const fl
         acc.x = fmaf(g0, v.x, acc.x); acc.y = fmaf(g0, v.y, acc.y);
         acc.z = fmaf(g1, v.z, acc.z); acc.w = fmaf(g1, v.w, acc.w);
       }
+      const float4 a = psi4[p];
+      acc.x = fmaf(d0, a.x, acc.x); acc.y = fmaf(d0, a.y, acc.y);
+      acc.z = fmaf(d1, a.z, acc.z); acc.w = fmaf(d1, a.w, acc.w);
       out4[p] = acc;
     }
   }

@@ -219,11 +219,29 @@ def _speculative_readout(qdev, states, ob):
         c = _READOUT_CURRENT[key] = [weakref.ref(states), {}, [], states._version, grad]
         predicted = _READOUT_HISTORY.get(key, ())
         if len(predicted) > 1 and ob in predicted:
-            vals = _readout(qdev, states, predicted)
-            for t, name in enumerate(predicted):
-                c[1][name] = vals[:, t:t + 1]
+            if grad and states.is_cuda and torch.cuda.is_current_stream_capturing():
+                # Inside a CUDA-graph capture (tq.GraphedStep) the host is free and kernels are what counts: one
+                # multi-term launch for the values, then every call gets its own node on the state's hub with its column
+                # precomputed.  The backward of those nodes launches nothing (they file dL/d<P_t> with the hub, which
+                # runs ONE kernel for all terms); slicing columns out of one node's output instead costs a zero-fill and
+                # a copy per column in its backward (~80 tiny kernels per step in config 2).
+                xm, zm, ny = _mask_tensors(predicted, states.device)
+                with torch.no_grad():
+                    vals = _launch_expval(states.contiguous(), qdev.n_wires, xm, zm, ny)
+                hub, pending = _hub(qdev, states)
+                for t, name in enumerate(predicted):
+                    c[1][name] = (hub, pending, vals[:, t:t + 1])
+            else:
+                vals = _readout(qdev, states, predicted)
+                for t, name in enumerate(predicted):
+                    c[1][name] = vals[:, t:t + 1]
     c[2].append(ob)
-    return c[1].get(ob)
+    hit = c[1].get(ob)
+    if type(hit) is tuple:
+        hub, pending, col = hit
+        xm, zm, ny = _mask_tensors((ob,), states.device)
+        return _ExpvalPauliFn.apply(hub, qdev.n_wires, xm, zm, ny, (ob,), pending, col)
+    return hit
 
 
 def expval_joint_analytical(qdev, observable: str):

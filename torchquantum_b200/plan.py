@@ -41,6 +41,8 @@ BLOCKS = os.environ.get("TQB200_BLOCKS", "1") != "0"
 BLOCK_MIN_N = 16
 BLOCK_MIN_RUN = 24
 BLOCK_MIN_AVG = 8.0
+BLOCK_MIN_RUN_KEPT = 6     # ... when the stage may leave its qubit layout behind (no sort passes to pay)
+BLOCK_MIN_AVG_KEPT = 3.0
 SCALED_ROT = False
 SCALED_MAX = 24   # most scaled ops (H with its 1/sqrt(2) deferred) in one pass: intermediates grow by <= 2^12
 
@@ -800,8 +802,12 @@ def _split_block_runs(ops, n_local, leave_last=False):
             while k < len(ops) and B.fusable(ops[k], n_local):
                 k += 1
             run = ops[i:k]
-            stage = (B.build_block_stage(run, n_local, BLOCK_MIN_AVG, come_home=not (leave_last and k == len(ops)))
-                     if len(run) >= BLOCK_MIN_RUN else None)
+            # the last run of a plan whose caller keeps the layout (sharded device) pays no way home: blocks win against
+            # register-tile passes much earlier there (a register-tile pass over high free bits writes 256-byte rows at
+            # large strides, the slow pattern; 16 X gates of a state preparation at 31 local qubits: 3 passes, 39 ms)
+            free = leave_last and k == len(ops)
+            stage = (B.build_block_stage(run, n_local, BLOCK_MIN_AVG_KEPT if free else BLOCK_MIN_AVG, come_home=not free)
+                     if len(run) >= (BLOCK_MIN_RUN_KEPT if free else BLOCK_MIN_RUN) else None)
             if stage is not None:
                 out.append(("blocks", stage))
             else:
