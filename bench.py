@@ -174,7 +174,7 @@ def _sustained(ms_sus, dom, per_rep, alg_bytes, peak):
     return {"avg_launch_ms": round(avg, 4), "GBps": round(alg_bytes / avg / 1e6, 1), "frac": round(alg_bytes / avg / 1e6 / peak, 4),
             "launches_timed": len(tail), "run_ms": round(float(sum(np.sum(x) for x in ms_sus.values())), 1),
             "note": "same launches back to back until the board is power capped (~1000 W, SM clock ~1.3 GHz): the block "
-                    "kernel's per-tile pipeline (TF32 split, 24 tcgen05.mma, epilogue: ~2 750 cycles per tile) then "
+                    "kernel's per-tile pipeline (TF32 split, 24 tcgen05.mma, epilogue: ~2 500 cycles per tile) then "
                     "takes longer than the tile's HBM traffic; `frac` above is the un-capped figure"}
 
 
