@@ -7,9 +7,10 @@
 // same kernel serves the two GEMMs of the backward.  It replaces what the reference's static mode does with one torch.bmm
 // per fused block (torchquantum/graph/graphs.py:836-861, QuantumGraph.apply_unitary).
 //
-// One CTA computes a 128 x 256 tile of C: warp 0 streams 128-byte K slices of the operand planes with TMA (2-D tensor maps,
+// Persistent CTAs (one per SM) walk the 128 x 256 tiles of C: warp 0 streams 128-byte K slices of the operand planes with TMA (2-D tensor maps,
 // SWIZZLE_128B, 4 stages of 16 + 32 KiB), warp 1 issues 4 MMAs (M = 128, N = 256, K = 8) per slice into a 128 x 256 fp32
-// accumulator in TMEM, warps 4-7 read it back (tcgen05.ld 32x32b) and store 128 contiguous bytes per thread and load.
+// accumulator in TMEM (two of them: the epilogue of a tile overlaps the MMAs of the next), warps 4-7 read it back
+// (tcgen05.ld 32x32b) and store 128 contiguous bytes per thread and load.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -60,10 +61,14 @@ struct GemmParams {
   float* c;              // [splits][M][N] partial products (splits == 1: the result itself)
   long long split_stride;  // M * N
   int ldc;               // = N
-  int k_slices;          // K slices of BK floats handled by one CTA (one split)
+  int k_slices;          // K slices of BK floats handled by one tile (one split)
   int a_hi_plane, b_hi_plane;   // which plane (0 / 1) of the operand's tensor map is its TF32 hi part
+  int tiles_n, tiles_m, n_tiles;   // tile grid: tile = (split * tiles_m + m) * tiles_n + n
 };
 
+constexpr uint32_t kAccs = 2;   // TMEM accumulators (BN columns each): the epilogue of a tile overlaps the next tile's MMAs
+
+// Persistent: one CTA per SM walks the tiles (stride gridDim.x); the TMA / MMA pipelines run on across tile boundaries.
 __global__ void __launch_bounds__(kThreads, 1)
 tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   // ONE 3-D tensor map per operand (K, rows, {hi, lo} plane): four maps made the parameter block 536 bytes, and kernels
@@ -73,20 +78,20 @@ tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   const uint32_t bars = base + kStages * kStage;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (kStages + s); };
-  const uint32_t accfull = bars + 8u * (2 * kStages);
-  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 1);
+  auto accfull = [&](uint32_t a) { return bars + 8u * (2 * kStages + a); };
+  auto accempty = [&](uint32_t a) { return bars + 8u * (2 * kStages + kAccs + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 2 * kAccs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(accfull, 1);
+    for (uint32_t a = 0; a < kAccs; ++a) { mbar_init(accfull(a), 1); mbar_init(accempty(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(kAccs * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -95,59 +100,78 @@ tqb_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
-  const int ks0 = blockIdx.z * p.k_slices;   // split-K: this CTA's share of the K slices
   const int total = 3 * p.k_slices;   // pass 0: Alo Bhi, pass 1: Ahi Blo, pass 2: Ahi Bhi (the small products first: the
                                       // accumulator is still tiny while the truncating fp32 adds of the tensor core hit them)
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
-        const int pass = it / p.k_slices, ks = it - pass * p.k_slices;
-        mbar_wait(empty(s), ph ^ 1u);
-        mbar_expect_tx(full(s), kStage);
-        const uint32_t sa = base + s * kStage, sb = sa + kABytes;
-        tma_load_3d(sa, &tm_a, full(s), (ks0 + ks) * BK, m0, pass == 0 ? 1 - p.a_hi_plane : p.a_hi_plane);
-        tma_load_3d(sb, &tm_b, full(s), (ks0 + ks) * BK, n0, pass == 1 ? 1 - p.b_hi_plane : p.b_hi_plane);
+      uint32_t it = 0;       // slices issued by this CTA so far (the stage ring runs across tiles)
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.tiles_n) * BN, m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+        const int ks0 = (tile / (p.tiles_n * p.tiles_m)) * p.k_slices;   // split-K: this tile's share of the K slices
+        for (int i = 0; i < total; ++i, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          const int pass = i / p.k_slices, ks = i - pass * p.k_slices;
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_expect_tx(full(s), kStage);
+          const uint32_t sa = base + s * kStage, sb = sa + kABytes;
+          tma_load_3d(sa, &tm_a, full(s), (ks0 + ks) * BK, m0, pass == 0 ? 1 - p.a_hi_plane : p.a_hi_plane);
+          tma_load_3d(sb, &tm_b, full(s), (ks0 + ks) * BK, n0, pass == 1 ? 1 - p.b_hi_plane : p.b_hi_plane);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
-        mbar_wait(full(s), ph);
+      uint32_t it = 0, lt = 0;   // slices / tiles done by this CTA
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt % kAccs;
+        mbar_wait(accempty(acc), ((lt / kAccs) & 1u) ^ 1u);    // the epilogue has read this accumulator's previous tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * kStage, sb = sa + kABytes;
+        const uint32_t d = tmem + acc * (uint32_t)BN;
+        for (int i = 0; i < total; ++i, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(full(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * kStage, sb = sa + kABytes;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k)   // K = 8 per MMA: 32 bytes further along the swizzled 128-byte row
-          umma_tf32_ss(tmem, k_desc(sa + 32u * k), k_desc(sb + 32u * k), (it | k) != 0);
-        umma_commit(empty(s));
+          for (int k = 0; k < BK / 8; ++k)   // K = 8 per MMA: 32 bytes further along the swizzled 128-byte row
+            umma_tf32_ss(d, k_desc(sa + 32u * k), k_desc(sb + 32u * k), (i | k) != 0);
+          umma_commit(empty(s));
+        }
+        umma_commit(accfull(acc));
       }
-      umma_commit(accfull);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    mbar_wait(accfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* crow = p.c + (size_t)blockIdx.z * p.split_stride + (size_t)(m0 + 32 * q + lane) * p.ldc + n0;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt % kAccs;
+      const int n0 = (tile % p.tiles_n) * BN, m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+      const int split = tile / (p.tiles_n * p.tiles_m);
+      mbar_wait(accfull(acc), (lt / kAccs) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* crow = p.c + (size_t)split * p.split_stride + (size_t)(m0 + 32 * q + lane) * p.ldc + n0;
 #pragma unroll 1
-    for (int g = 0; g < BN / 32; ++g) {
-      uint32_t v[32];
-      tqb_umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32u * g, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float4* dst = reinterpret_cast<float4*>(crow + 32 * g);
+      for (int g = 0; g < BN / 32; ++g) {
+        uint32_t v[32];
+        tqb_umma::tmem_ld32(tmem + acc * (uint32_t)BN + ((uint32_t)(32 * q) << 16) + 32u * g, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float4* dst = reinterpret_cast<float4*>(crow + 32 * g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                             __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(accempty(acc));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(kAccs * BN)) : "memory");
   }
 }
 
@@ -225,7 +249,15 @@ inline const char* launch_gemm(const float* a_hi, const float* a_lo, const float
   p.split_stride = M * N;
   p.ldc = (int)N;
   p.k_slices = (int)(K / BK / splits);
-  dim3 grid((unsigned)(N / BN), (unsigned)(M / BM), (unsigned)splits);
+  p.tiles_n = (int)(N / BN);
+  p.tiles_m = (int)(M / BM);
+  const long long n_tiles = (N / BN) * (M / BM) * splits;
+  if (n_tiles > 0x7fffffffll) return "gemm: too many tiles";
+  p.n_tiles = (int)n_tiles;
+  int dev_id = 0, sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
   tqb_gemm_tf32x3_kernel<<<grid, kThreads, kSmem, st>>>(ta, tb, p);
   if (cudaGetLastError() != cudaSuccess) return "gemm launch failed";
   if (splits > 1) {
