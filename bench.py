@@ -420,9 +420,11 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def reduce_grads():
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
+        if world > 1:   # eager data parallelism: one all-reduce of the flattened gradients, written back into .grad
+            grads = [p.grad for p in params]
+            flat = torch.cat([g.reshape(-1) for g in grads])
             dist.all_reduce(flat)
+            torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
 
     def eager_step(x, read_loss):
         for p in params:
@@ -436,7 +438,8 @@ def run_ours(args):
 
     def graphed_step(x, read_loss):
         loss = graphed(x)  # copies x into the captured input buffer, replays fwd + bwd
-        reduce_grads()
+        if world > 1:
+            graphed.allreduce_gradients()   # one all-reduce of the replay's flat gradient + a captured scatter into .grad
         return loss.item() if read_loss else loss
 
     def barrier():

@@ -244,6 +244,8 @@ def check_cfg2_vqe(device, n=5, reps=3, bsz=6, graphed=False):
                 step = tq.GraphedStep(ours, [x.detach().requires_grad_(True)], params)
             loss = step(x.detach())
             gx = step.static_inputs[0].grad
+            # the replay also produces all parameter gradients as one flat tensor (what data-parallel training all-reduces)
+            assert torch.equal(step.flat_grad, torch.cat([p.grad.reshape(-1) for p in params]))
         else:
             loss = ours(x)
             loss.backward()

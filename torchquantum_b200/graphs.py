@@ -35,8 +35,17 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.loss = loss_fn(*self.static_inputs)
             self.loss.backward()
+            # all parameter gradients as ONE tensor, produced by the replay itself: data-parallel training all-reduces
+            # this (one collective, no per-parameter Python) and `allreduce_gradients` writes the sums back
+            pg = [p.grad for p in self.params if p.grad is not None]
+            self.flat_grad = torch.cat([g.reshape(-1) for g in pg]) if pg else None
         self._leaves = self.params + [x for x in self.static_inputs if x.requires_grad]
         self._grads = [p.grad for p in self._leaves]   # the captured gradient buffers
+        self._scatter = None
+        if self.flat_grad is not None:
+            self._scatter = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._scatter):
+                torch._foreach_copy_([g.view(-1) for g in pg], list(self.flat_grad.split([g.numel() for g in pg])))
 
     @staticmethod
     def _drop_stale_graphs():
@@ -51,6 +60,18 @@ class GraphedStep:
     def _zero(self):
         for p in self.params + self.static_inputs:
             p.grad = None
+
+    def allreduce_gradients(self, group=None, average=False):
+        """Sum (or average) the parameter gradients of the last replay over the ranks of `group`: ONE all-reduce of the
+        flat gradient the replay produced, then a captured scatter back into every parameter's `.grad`."""
+        import torch.distributed as dist
+
+        if self.flat_grad is None:
+            return
+        dist.all_reduce(self.flat_grad, group=group)
+        if average:
+            self.flat_grad /= dist.get_world_size(group)
+        self._scatter.replay()
 
     def __call__(self, *inputs):
         """Copy `inputs` (device or pinned host tensors) into the captured buffers, replay the step and
