@@ -1048,6 +1048,50 @@ int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local,
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const long long total = bsz << n_local;
+  // Large contiguous runs (lowest victim bit high): the copy engines move them at 0.87 of the NVLink rate (777-781 GB/s
+  // per direction measured with peer copies on this pool, tools/p2p_probe.py) against 0.70-0.77 for the store kernel,
+  // and leave the SMs alone: one cudaMemcpyAsync per run of 2^vpos[0] amplitudes, peers first.
+  static int use_ce = -1;
+  if (use_ce < 0) { const char* e = getenv("TQB200_EXCHANGE_CE"); use_ce = e ? atoi(e) : 1; }
+  const long long run_amps = 1ll << a.vpos[0];
+  const long long n_runs = total >> a.vpos[0];
+  if (use_ce && run_amps * 8 >= (8ll << 20) && n_runs <= 1024) {
+    unsigned long long vmask = 0;
+    for (int k = 0; k < g; ++k) vmask |= 1ull << a.vpos[k];
+    const unsigned long long slab_mask = (1ull << n_local) - 1ull;
+    // the local part runs on a side stream next to the peer copies (forked from / joined to the caller's stream)
+    static cudaStream_t side[16] = {};
+    static cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return fail_msg("tqb_exchange_p2p: device index");
+    if (!side[dev]) {
+      if (cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming) != cudaSuccess)
+        return fail_msg("tqb_exchange_p2p: side stream");
+    }
+    cudaEventRecord(ev_fork[dev], (cudaStream_t)stream);
+    cudaStreamWaitEvent(side[dev], ev_fork[dev], 0);
+    for (int pass = 0; pass < 2; ++pass)          // peer destinations on the caller's stream, the local one on the side stream
+      for (long long r = 0; r < n_runs; ++r) {
+        const unsigned long long src_idx = (unsigned long long)r << a.vpos[0];   // first amplitude of the run (flat, incl. batch)
+        unsigned long long i = src_idx & slab_mask;
+        int to = 0;
+        for (int k = 0; k < g; ++k) {
+          to |= (int)((i >> a.vpos[k]) & 1ull) << k;
+          i = (i & ~(1ull << a.vpos[k])) | ((unsigned long long)((rank >> k) & 1) << a.vpos[k]);
+        }
+        if ((to == rank) != (pass == 1)) continue;
+        const unsigned long long dst_idx = (src_idx & ~slab_mask) | i;
+        if (cudaMemcpyAsync(a.dst[to] + 2 * dst_idx, src + 2 * src_idx, (size_t)run_amps * 8, cudaMemcpyDeviceToDevice,
+                            pass == 1 ? side[dev] : (cudaStream_t)stream) != cudaSuccess)
+          return fail_msg("tqb_exchange_p2p: peer copy failed");
+      }
+    cudaEventRecord(ev_join[dev], side[dev]);
+    cudaStreamWaitEvent((cudaStream_t)stream, ev_join[dev], 0);
+    return 0;
+  }
   const unsigned grid = (unsigned)g_num_sms * 8u;
   if (a.vpos[0] >= 1) {
     tqb_exchange_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(src, a, total / 2);

@@ -323,12 +323,12 @@ class ShardedQuantumDevice:
         bufs, handles, cur = self._symm
         dst = 1 - cur
         timed = self.time_exchanges
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         # the destination slab is every rank's spare one, which rotating block passes use as their second buffer: nobody
         # may store into a peer's spare slab before that peer's local passes are done
         handles[dst].barrier(channel=1)
+        if timed:   # from "every rank is ready" to "every rank's data has landed"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _native.call("tqb_exchange_p2p", self._flat, bufs[dst], [int(p) for p in handles[dst].buffer_ptrs], nl, self.bsz,
                      [int(p) for p in vpos], self.rank)
         STATS["launches"] += 1
