@@ -1055,7 +1055,8 @@ int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local,
   if (use_ce < 0) { const char* e = getenv("TQB200_EXCHANGE_CE"); use_ce = e ? atoi(e) : 1; }
   const long long run_amps = 1ll << a.vpos[0];
   const long long n_runs = total >> a.vpos[0];
-  if (use_ce && run_amps * 8 >= (8ll << 20) && n_runs <= 1024) {
+  // (use_ce: 0 never, 1 between two ranks only, 2 for any number of ranks)
+  if ((use_ce >= 2 || (use_ce == 1 && g == 1)) && run_amps * 8 >= (8ll << 20) && n_runs <= 1024) {
     unsigned long long vmask = 0;
     for (int k = 0; k < g; ++k) vmask |= 1ull << a.vpos[k];
     const unsigned long long slab_mask = (1ull << n_local) - 1ull;
@@ -1073,8 +1074,14 @@ int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local,
     }
     cudaEventRecord(ev_fork[dev], (cudaStream_t)stream);
     cudaStreamWaitEvent(side[dev], ev_fork[dev], 0);
-    for (int pass = 0; pass < 2; ++pass)          // peer destinations on the caller's stream, the local one on the side stream
+    // destinations in the order rank + 1, rank + 2, ... (mod 2^g): at any time every rank receives from ONE sender (with
+    // the same order on all ranks they would all store into rank 0 first: 7-to-1 incast, 200 GB/s per sender on 8 GPUs);
+    // peer destinations on the caller's stream, the local one (step 0, last) on the side stream
+    const int W = 1 << g;
+    for (int step = 1; step <= W; ++step)
       for (long long r = 0; r < n_runs; ++r) {
+        const int want = (rank + step) % W;
+        const int pass = want == rank ? 1 : 0;
         const unsigned long long src_idx = (unsigned long long)r << a.vpos[0];   // first amplitude of the run (flat, incl. batch)
         unsigned long long i = src_idx & slab_mask;
         int to = 0;
@@ -1082,7 +1089,7 @@ int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local,
           to |= (int)((i >> a.vpos[k]) & 1ull) << k;
           i = (i & ~(1ull << a.vpos[k])) | ((unsigned long long)((rank >> k) & 1) << a.vpos[k]);
         }
-        if ((to == rank) != (pass == 1)) continue;
+        if (to != want) continue;
         const unsigned long long dst_idx = (src_idx & ~slab_mask) | i;
         if (cudaMemcpyAsync(a.dst[to] + 2 * dst_idx, src + 2 * src_idx, (size_t)run_amps * 8, cudaMemcpyDeviceToDevice,
                             pass == 1 ? side[dev] : (cudaStream_t)stream) != cudaSuccess)
