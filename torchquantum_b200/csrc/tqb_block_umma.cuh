@@ -466,7 +466,8 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) mbar_arrive(outready(l));
+      const bool first = p.renorm && it == 0;     // (the first tile is handed to the store warp after its own rescale)
+      if (!first && et == 0) mbar_arrive(outready(l));
       if (p.renorm) {
         float4 a, b;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(nin_slot + 16u * (it & 7u)) : "memory");
@@ -474,8 +475,24 @@ tqb_block6_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_const
         const float sin2 = (a.x + a.y) + (a.z + a.w), sout2 = (b.x + b.y) + (b.z + b.w);
         float gn = 1.f;
         if (sout2 > 0.f && sin2 > 0.f) gn = sqrtf(sin2 / sout2);
-        g = fabsf(gn - 1.f) < 1e-4f ? gn : 1.f;
+        gn = fabsf(gn - 1.f) < 1e-4f ? gn : 1.f;
+        if (it == 0 && gn != 1.f) {
+          // the CTA's FIRST tile has no predecessor to take the factor from: it is rescaled in the staging buffer by its own
+          // measured ratio (one extra pass over 32 KiB of shared memory per CTA and launch).  Without it a state of 2^20
+          // amplitudes (256 tiles on 148 CTAs) got no correction on most of its tiles and drifted by ~1e-7 per pass.
+          const uint32_t a0 = stg + 256u * (uint32_t)et;
+#pragma unroll 4
+          for (uint32_t v = 0; v < 16u; ++v) {
+            float x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(a0 + 16u * v) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + 16u * v), "f"(x0 * gn), "f"(x1 * gn), "f"(x2 * gn), "f"(x3 * gn) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        g = gn;
       }
+      if (first && et == 0) mbar_arrive(outready(l));
     }
   }
 
