@@ -163,7 +163,10 @@ int tqb_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* bt_hi, co
  * writing every amplitude of `src` (this rank's slab [bsz][2^n_local]) straight into its place in the destination slab of
  * the rank that owns it afterwards.  peer_dst_host: 2^g device pointers (HOST array), entry r = destination slab of rank r
  * mapped into this process (CUDA IPC / symmetric memory), entry `rank` = the local destination (must differ from src).
- * The caller synchronises the ranks after the launch (all slabs complete) before anybody reads a destination. */
+ * The caller synchronises the ranks before the call (nobody is still using a destination slab) and after it (all slabs
+ * complete) before anybody reads a destination.  Between two ranks, exchanges whose lowest victim bit leaves contiguous
+ * runs of >= 8 MiB are issued as peer copies on the copy engines instead of the store kernel (TQB200_EXCHANGE_CE = 0 / 1 /
+ * 2: never / two ranks only / any number of ranks). */
 int tqb_exchange_p2p(const float* src, float* const* peer_dst_host, int n_local, long long bsz, int g,
                      const int* victim_bits_host, int rank, void* stream);
 
