@@ -453,3 +453,16 @@ def check_batch_collapse(device, n=7, bsz=300):
     assert_close(torch.cat([g.reshape(-1) for g in g1[1:]]), torch.cat([g.reshape(-1) for g in g0[1:]]), rtol=GRAD_RTOL,
                  what="shared-parameter gradients through the collapsed run")
     assert engine.STATS["launches"] > launches0
+    if bsz == 300:
+        # tile-aligned shapes take their GEMM operands from the fused preparation kernel (tqb_gemm_prep: conjugate /
+        # transpose / real embedding / TF32 split in one pass), forward and backward
+        check_batch_collapse(device, n=n, bsz=256)
+        g = torch.Generator().manual_seed(9)
+        a = torch.randn(256, 64, dtype=torch.complex64, generator=g).to(device)
+        b = torch.randn(64, 128, dtype=torch.complex64, generator=g).to(device)
+        assert_close(engine.complex_gemm(a, b), (a.cpu().to(torch.complex128) @ b.cpu().to(torch.complex128)).to(torch.complex64),
+                     what="complex_gemm, fused operand preparation")
+        x = torch.randn(64, 128, dtype=torch.complex64, generator=g).to(device)
+        y = torch.randn(64, 256, dtype=torch.complex64, generator=g).to(device)
+        want = (x.cpu().to(torch.complex128).conj().T @ y.cpu().to(torch.complex128)).to(torch.complex64)
+        assert_close(engine.complex_gemm(x, y, a_h=True), want, what="complex_gemm(a^H b), fused operand preparation")
