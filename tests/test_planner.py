@@ -252,3 +252,35 @@ def test_block_stage_picks_the_cheaper_write_back():
     assert B.schedule_rotating(_brick_masks(16, 8), 16) is None          # small states stay with the in-place schedule
     small, _, _ = B.plan_blocks(_brick_masks(16, 8), 16)
     assert not any(e[3] & C.KBF_ROTATE for e in small)
+
+
+def test_rotating_schedule_can_leave_its_layout_to_the_caller():
+    """final=[]: no passes that bring the qubits home; the logical -> physical map the stage ends with is reported (the
+    sharded device composes it into its own layout) and equals the replay of the kernel's contract"""
+    from torchquantum_b200 import blockplan as B
+
+    n = 22
+    masks = _brick_masks(n, 10)
+    home = B.schedule_rotating(masks, n)
+    final = []
+    kept = B.schedule_rotating(masks, n, final=final)
+    assert len(final) == 1 and sorted(final[0]) == list(range(n))
+    assert len(kept) < len(home) and all(e[2] for e in kept)          # only blocks that carry gates
+    pos = list(range(n))
+    for _, kpos, gates, tr, where, perm in kept:
+        pinv = {p: d for d, p in enumerate(pos)}
+        arrive = list(kpos)
+        for i, j in perm:
+            arrive[i], arrive[j] = arrive[j], arrive[i]
+        new = {}
+        for i, p in enumerate(arrive):
+            new[pinv[p]] = i if tr else 6 + i
+        for b in range(6):
+            new[pinv[b]] = 6 + b if tr else b
+        r = 12
+        for p in range(6, n):
+            if p not in kpos:
+                new[pinv[p]] = r
+                r += 1
+        pos = [new[d] for d in range(n)]
+    assert pos == final[0]
