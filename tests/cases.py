@@ -682,3 +682,16 @@ def check_qft_blocks_and_quadphase(device, n=18, bsz=1):
     ref = torch.exp(2j * np.pi * ((x * k) % 2 ** n) / 2 ** n) / np.sqrt(2 ** n)
     rel = ((got[0] - ref).norm() / ref.norm()).item()
     assert rel <= 1e-5, rel
+
+
+def check_large_batch_readout(device, bsz=70000):
+    """batches beyond the 65 535 limit of a grid's y dimension: per-wire <Z> (tqb_expval_z, sliced) and a
+    Pauli string (warp-per-sample kernel) on 2 qubits after a per-sample ry: <Z_0> = cos(theta), <Z_1> = 1"""
+    theta = torch.linspace(-3.0, 3.0, bsz, dtype=torch.float32).reshape(bsz, 1).to(device)
+    q = tq.QuantumDevice(n_wires=2, bsz=bsz, device=device)
+    tqf.ry(q, wires=0, params=theta)
+    z = expval(q, [0, 1], [_Obs("Z")] * 2)
+    want = torch.stack([torch.cos(theta[:, 0]), torch.ones(bsz, device=device)], dim=1)
+    assert_close(z.cpu(), want.cpu(), what="per-wire Z, bsz > 65535")
+    zi = expval_joint_analytical(q, "ZI")
+    assert_close(zi.cpu(), want[:, 0].cpu(), what="ZI, bsz > 65535")

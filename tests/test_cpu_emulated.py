@@ -144,6 +144,10 @@ def test_block_write_back_modes():
     cases.check_block_write_back_modes("cpu", n=18, depth=8)
 
 
+def test_large_batch_readout():
+    cases.check_large_batch_readout("cpu", bsz=66000)
+
+
 def test_quadphase_kernel():
     cases.check_quadphase_kernel("cpu")
 

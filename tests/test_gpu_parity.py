@@ -60,6 +60,10 @@ def test_mnist_cfg1():
     cases.check_mnist_cfg1(DEV)
 
 
+def test_large_batch_readout():
+    cases.check_large_batch_readout(DEV)
+
+
 def test_quadphase_kernel():
     """K12: fused quadratic-phase diagonal pass vs its formula in float64 (local bits, rank bits, batch)"""
     cases.check_quadphase_kernel(DEV)

@@ -947,12 +947,15 @@ int tqb_expval_pauli_bwd(const float* state, int n_qubits, long long bsz, const 
 
 int tqb_expval_z(const float* state, int n_qubits, long long bsz, float* out, void* stream) {
   if (bsz <= 0) return 0;
-  if (bsz > 65535) return fail_msg("tqb_expval_z: bsz > 65535");
   const int cl = expval_chunk_log2(n_qubits);
-  dim3 grid(1u << (n_qubits - cl), (unsigned)bsz);
-  tqb_expval_z_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(state), n_qubits, out,
-                                                             cl, grid.x > 1);
-  TQB_CHECK_LAUNCH("tqb_expval_z_kernel");
+  // the sample index is gridDim.y (<= 65535): larger batches go in slices
+  for (long long b0 = 0; b0 < bsz; b0 += 65535) {
+    const long long nb = bsz - b0 < 65535 ? bsz - b0 : 65535;
+    dim3 grid(1u << (n_qubits - cl), (unsigned)nb);
+    tqb_expval_z_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(state) + (b0 << n_qubits), n_qubits,
+                                                               out + b0 * (n_qubits + 1), cl, grid.x > 1);
+    TQB_CHECK_LAUNCH("tqb_expval_z_kernel");
+  }
   return 0;
 }
 
