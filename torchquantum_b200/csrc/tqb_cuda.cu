@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(256) tqb_exchange_kernel(const float* __restri
   // HBM phases would run one after the other.  When every victim bit is >= 6 the chunk counter's low g bits are therefore
   // routed to the victim positions and its other bits fill the remaining index bits in order (a bit deposit with <= 4 holes).
   const bool interleave = VEC == 2 && a.vpos[0] >= 6;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total_vec; it += stride) {
+  // source vector index and destination (rank, vector index) of iteration `it`
+  auto route = [&](long long it, unsigned long long& from, int& to, unsigned long long& out) {
     unsigned long long flat = (unsigned long long)it * VEC;   // amplitude index within [bsz][2^nl]
     if (interleave) {
       const unsigned long long c = (unsigned long long)it >> 5;       // 64-amplitude chunk counter
@@ -686,20 +687,46 @@ __global__ void __launch_bounds__(256) tqb_exchange_kernel(const float* __restri
       flat = (x << 6) | (((unsigned long long)it & 31ull) << 1);
     }
     unsigned long long i = flat & slab_mask;
-    int to = 0;
+    to = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (k < a.g) {
         to |= (int)((i >> a.vpos[k]) & 1ull) << k;
         i = (i & ~(1ull << a.vpos[k])) | ((unsigned long long)((a.rank >> k) & 1) << a.vpos[k]);
       }
-    const unsigned long long out = (flat & ~slab_mask) | i;
+    from = flat;
+    out = (flat & ~slab_mask) | i;
+  };
+  // four vectors per thread and trip: all loads first, then the (peer) stores
+  constexpr int U = 4;
+  long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; it + (U - 1) * stride < total_vec; it += U * stride) {
+    unsigned long long from[U], out[U];
+    int to[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) route(it + u * stride, from[u], to[u], out[u]);
     if (VEC == 2) {
-      const float4 val = __ldcs(reinterpret_cast<const float4*>(src) + (flat >> 1));
-      reinterpret_cast<float4*>(a.dst[to])[out >> 1] = val;
+      float4 val[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) val[u] = __ldcs(reinterpret_cast<const float4*>(src) + (from[u] >> 1));
+#pragma unroll
+      for (int u = 0; u < U; ++u) reinterpret_cast<float4*>(a.dst[to[u]])[out[u] >> 1] = val[u];
     } else {
-      const float2 val = __ldcs(reinterpret_cast<const float2*>(src) + flat);
-      reinterpret_cast<float2*>(a.dst[to])[out] = val;
+      float2 val[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) val[u] = __ldcs(reinterpret_cast<const float2*>(src) + from[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) reinterpret_cast<float2*>(a.dst[to[u]])[out[u]] = val[u];
+    }
+  }
+  for (; it < total_vec; it += stride) {
+    unsigned long long from, out;
+    int to;
+    route(it, from, to, out);
+    if (VEC == 2) {
+      reinterpret_cast<float4*>(a.dst[to])[out >> 1] = __ldcs(reinterpret_cast<const float4*>(src) + (from >> 1));
+    } else {
+      reinterpret_cast<float2*>(a.dst[to])[out] = __ldcs(reinterpret_cast<const float2*>(src) + from);
     }
   }
 }
