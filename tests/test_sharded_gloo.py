@@ -180,3 +180,89 @@ def test_sharded_adjoint_gradients_match_one_device(world, n):
     if not os.path.exists(emu):
         pytest.skip("host emulation library not built (run __graft_entry__.build())")
     mp.spawn(_worker_autograd, args=(world, _free_port(), n, emu), nprocs=world, join=True)
+
+
+def _worker_semantics(rank, world, port, emu_path):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torchquantum_b200 as tq
+        import torchquantum_b200.functional as tqf
+        from tests.helpers import GRAD_RTOL, assert_close
+        from torchquantum_b200 import _native
+        from torchquantum_b200.measurement import expval, expval_joint_analytical_multi
+
+        _native.use_library_for_testing(emu_path)
+        n = 5
+
+        def circuit(q, p, peek):
+            tqf.hadamard(q, wires=1)
+            tqf.rx(q, wires=0, params=p)              # wire 0 lives in the rank index: exchange
+            tqf.cnot(q, wires=[0, 3])
+            if peek:
+                with torch.no_grad():                 # logging / debugging read in the middle of the circuit
+                    q.get_states_1d()
+            tqf.ry(q, wires=1, params=p)
+            tqf.crx(q, wires=[4, 0], params=p)
+            return (expval_joint_analytical_multi(q, ["ZZIII", "XIIZY"]) * torch.tensor([0.6, -1.1])).sum()
+
+        p0 = torch.tensor([[0.45]], requires_grad=True)
+        want_loss = circuit(tq.QuantumDevice(n_wires=n, bsz=2, device="cpu"), p0, False)
+        want, = torch.autograd.grad(want_loss, p0)
+        for peek in (False, True):
+            p = torch.tensor([[0.45]], requires_grad=True)
+            q = tq.ShardedQuantumDevice(n_wires=n, bsz=2, device="cpu")
+            loss = circuit(q, p, peek)
+            assert_close(loss.detach().reshape(1), want_loss.detach().reshape(1), what=f"loss (peek={peek})")
+            loss.backward()
+            q.allreduce_gradients([p])
+            assert_close(p.grad, want, rtol=GRAD_RTOL, what=f"rank {rank}: gradient with a no_grad peek={peek}")
+
+        # gates issued under no_grad are not tracked even when the flush happens outside it, and they do not overwrite the
+        # slab a pending backward still needs
+        p = torch.tensor([[0.45]], requires_grad=True)
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=2, device="cpu")
+        tqf.rx(q, wires=2, params=p)
+        first = expval_joint_analytical_multi(q, ["IIZII"]).sum()
+        with torch.no_grad():
+            tqf.rx(q, wires=2, params=p)
+            tqf.rx(q, wires=0, params=p)
+        second = expval_joint_analytical_multi(q, ["IIZII"])
+        assert not second.requires_grad
+        first.backward()
+        q.allreduce_gradients([p])
+        assert_close(p.grad.reshape(1), -2 * torch.sin(torch.tensor([0.45])), rtol=GRAD_RTOL, what="first read-out's gradient")
+        assert_close(second, torch.cos(torch.tensor([0.9])).expand(2, 1), what="second read-out")
+
+        # parameter values are those at the gate call: plain tensors are snapshotted, an in-place edit of a tensor that
+        # takes part in autograd raises at the flush
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device="cpu")
+        v = torch.tensor([[0.3]])
+        tqf.rx(q, wires=2, params=v)
+        v.fill_(1.1)
+        assert_close(expval_joint_analytical_multi(q, ["IIZII"]), torch.cos(torch.tensor([[0.3]])), what="snapshot")
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device="cpu")
+        w = torch.tensor([[0.3]], requires_grad=True)
+        tqf.rx(q, wires=2, params=w)
+        with torch.no_grad():
+            w.fill_(1.1)
+        with pytest.raises(RuntimeError, match="modified in place"):
+            q.flush()
+
+        # per-wire read-out has no backward on the sharded device: loud, not silently detached
+        q = tq.ShardedQuantumDevice(n_wires=n, bsz=1, device="cpu")
+        tqf.rx(q, wires=2, params=torch.tensor([[0.3]], requires_grad=True))
+        from tests import cases
+        with pytest.raises(NotImplementedError, match="not differentiable"):
+            expval(q, [2], [cases._Obs("Z")])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_device_call_time_semantics():
+    """ADVICE r1 for the sharded device too: the autograd mode is the one the gates were issued under (a no_grad peek in
+    the middle of a circuit neither drops the graph nor corrupts it), parameter values are those at the call."""
+    emu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libtqb200_emu.so")
+    if not os.path.exists(emu):
+        pytest.skip("host emulation library not built (run __graft_entry__.build())")
+    mp.spawn(_worker_semantics, args=(2, _free_port(), emu), nprocs=2, join=True)

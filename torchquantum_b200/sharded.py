@@ -12,9 +12,12 @@ that do not fit one GPU.  One process per GPU (`torch.distributed`, NCCL over NV
   controls and parity bits of diagonal gates may sit in the rank index at no cost (the rank
   supplies the missing index bits to the kernel: K11, no traffic);
 * a gate with a non-diagonal target on a global qubit triggers ONE exchange of all g global
-  qubits with g local qubits that are not needed for the longest time: victims are moved to
-  the top local bits by a fused local pass, then a zero-copy `all_to_all_single` of 2^g equal
-  chunks swaps physical bits [nl-g, nl) <-> [nl, n).  Every rank sends (1 - 2^-g) of its shard;
+  qubits with g local qubits that are not needed for the longest time.  Default back end ("p2p"): the
+  slabs live in symmetric memory and ONE kernel per rank (`tqb_exchange_p2p`) stores every amplitude
+  straight into the slab of the rank that owns it afterwards (NVLink peer stores; victims at any local
+  positions, no pack pass).  Fallback ("collective", also what the gloo tests run): victims are moved to
+  the top local bits by a fused local pass, then `all_to_all_single` of 2^g equal chunks swaps physical
+  bits [nl-g, nl) <-> [nl, n).  Either way every rank sends (1 - 2^-g) of its shard;
 * gates commute when they share no qubit, so before paying for an exchange the queue is scanned
   for everything that can still run in the current layout (same dependency-respecting greedy
   as the pass packer in plan.py);
@@ -33,6 +36,7 @@ import torch.distributed as dist
 
 from . import _native, engine
 from . import gates as G
+from .device import GateQueue
 from .engine import STATS
 from .macro import C_DTYPE
 
@@ -104,7 +108,7 @@ class ShardedQuantumDevice:
         self.device = torch.device(device)
         self.record_op = record_op
         self._op_history, self._history_pending = [], []
-        self._queue = []
+        self._queue = GateQueue(self)
         self.stats = {"exchanges": 0, "exchange_bytes_sent": 0, "exchange_ms": [], "local_permute_passes": 0}
         self.time_exchanges = False
         if exchange not in ("auto", "p2p", "collective"):
@@ -151,7 +155,7 @@ class ShardedQuantumDevice:
         if self.rank == 0:
             flat[:, 0] = 1
         self._flat = flat
-        self._queue = []
+        self._queue = GateQueue(self)
         self.pos = list(range(self.n_wires))  # logical bit -> physical bit
 
     def set_local_states(self, flat):
@@ -161,7 +165,7 @@ class ShardedQuantumDevice:
         slab = self._new_slab(self.bsz)
         slab.copy_(flat)
         self._flat = slab
-        self._queue = []
+        self._queue = GateQueue(self)
         self.pos = list(range(self.n_wires))
 
     @property
@@ -226,11 +230,18 @@ class ShardedQuantumDevice:
     def flush(self):
         if not self._queue:
             return
-        remaining, self._queue = self._queue, []
+        remaining, self._queue = self._queue, GateQueue(self)
+        # same call-time semantics as QuantumDevice (device.GateQueue): parameters must not have been edited in place
+        # since the gate call, and the gates run under the autograd mode they were ISSUED under
+        remaining.check()
         n, nl = self.n_wires, self.nl
-        grad = torch.is_grad_enabled() and (self._flat.requires_grad or any(
+        grad = remaining.grad and (self._flat.requires_grad or any(
             r[2] is not None and r[2].requires_grad for r in remaining))
         self._grad_flush = grad
+        if not grad and self._flat.requires_grad:
+            # gates issued under no_grad on a state that carries a graph: the reference replaces the state tensor and
+            # leaves the old one to its graph; the in-place passes here must not write into a slab a backward still needs
+            self._flat = self._own_copy(self._flat)
         with torch.set_grad_enabled(grad):
             while remaining:
                 runnable, rest, blocked = [], [], 0
@@ -255,6 +266,15 @@ class ShardedQuantumDevice:
                 if rest:
                     self._exchange(rest)
                 remaining = rest
+
+    def _own_copy(self, flat):
+        """a graph-free copy of the slab that in-place passes may overwrite (in the symmetric slab when there is one)"""
+        if self._symm is None:
+            return flat.detach().clone()
+        slab = self._symm_view(self._symm[2], self.bsz)
+        if slab.data_ptr() != flat.data_ptr():
+            slab.copy_(flat.detach())
+        return slab
 
     def _next_need(self, rest):
         """logical bit -> index of the first record of `rest` that needs it local (inf if none)."""
@@ -411,7 +431,9 @@ class ShardedQuantumDevice:
         """Restore the identity layout (logical bit l at physical bit l)."""
         self.flush()
         n, nl, g = self.n_wires, self.nl, self.g
-        self._grad_flush = torch.is_grad_enabled() and self._flat.requires_grad
+        # a state that carries a graph keeps it through the layout change, whatever mode the READ happens under (a
+        # `no_grad` peek must neither cut the graph nor permute a slab the backward still needs in place)
+        self._grad_flush = self._flat.requires_grad
         with torch.set_grad_enabled(self._grad_flush):
             target_global = list(range(nl, n))
             if any(self.pos[l] != l for l in target_global):
@@ -598,6 +620,9 @@ class ShardedQuantumDevice:
         n, nl = self.n_wires, self.nl
         self.flush()
         state = self._flat
+        if torch.is_grad_enabled() and state.requires_grad:
+            raise NotImplementedError("per-wire expval / MeasureAll on a sharded device is not differentiable: "
+                                      "use expval_joint_analytical (e.g. 'IIZI') for a loss, or read under torch.no_grad()")
         dev = state.device
         loc = torch.zeros(self.bsz, nl + 1, dtype=torch.float32, device=dev)
         _native.call("tqb_expval_z", state, nl, self.bsz, loc)
