@@ -10,6 +10,7 @@
 // Dispatch keys: CUDA -> the sm_100a library.  CPU -> ONLY the host emulation build that the test-suite injects with
 // tqb200::_bind(path, emulated=True); without it a CPU tensor raises (there is no CPU fallback).
 #include <ATen/ATen.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <dlfcn.h>
 #include <torch/library.h>
@@ -107,6 +108,13 @@ const Abi& abi_for(const at::Tensor& t) {
   return g_emu;
 }
 
+// The kernels launch on the CURRENT device: make it the tensor's device for the duration of the op (a state on cuda:1
+// while cuda:0 is current would otherwise launch on the wrong device with a foreign stream).
+#define TQB_ABI(a, t)                            \
+  c10::cuda::OptionalCUDAGuard tqb_device_guard; \
+  if ((t).is_cuda()) tqb_device_guard.set_device((t).device()); \
+  const Abi& a = abi_for(t)
+
 void* stream_of(const at::Tensor& t) {
   return t.is_cuda() ? static_cast<void*>(c10::cuda::getCurrentCUDAStream(t.device().index()).stream()) : nullptr;
 }
@@ -134,7 +142,7 @@ const unsigned long long* up(const at::Tensor& t) {
 void build_mats(const at::Tensor& table, int64_t n_records, int64_t n_shared, int64_t bsz,
                 const c10::optional<at::Tensor>& params_sh, const c10::optional<at::Tensor>& params_ps, int64_t ps_stride,
                 const c10::optional<at::Tensor>& consts, at::Tensor& msh, at::Tensor& mps, int64_t mps_stride) {
-  const Abi& a = abi_for(msh);
+  TQB_ABI(a, msh);
   check(a, a.build_mats(ip(table), (int)n_records, (int)n_shared, bsz, fp(params_sh), fp(params_ps), (int)ps_stride, fp(consts),
                         fpm(msh), fpm(mps), mps_stride, stream_of(msh)), "tqb_build_mats");
 }
@@ -142,14 +150,14 @@ void build_mats(const at::Tensor& table, int64_t n_records, int64_t n_shared, in
 void build_mats_bwd(const at::Tensor& table, int64_t n_records, int64_t bsz, const c10::optional<at::Tensor>& params_sh,
                     const c10::optional<at::Tensor>& params_ps, int64_t ps_stride, const at::Tensor& gr, int64_t gr_stride,
                     at::Tensor& gsh_partial, int64_t sh_stride, at::Tensor& gps) {
-  const Abi& a = abi_for(gr);
+  TQB_ABI(a, gr);
   check(a, a.build_mats_bwd(ip(table), (int)n_records, bsz, fp(params_sh), fp(params_ps), (int)ps_stride, fp(gr), gr_stride,
                             fpm(gsh_partial), (int)sh_stride, fpm(gps), stream_of(gr)), "tqb_build_mats_bwd");
 }
 
 void pass_forward(const at::Tensor& src, at::Tensor& dst, int64_t n, int64_t bsz, const at::Tensor& prog, at::IntArrayRef desc,
                   const at::Tensor& msh, const at::Tensor& mps, int64_t mps_stride, int64_t ext_hi) {
-  const Abi& a = abi_for(src);
+  TQB_ABI(a, src);
   TORCH_CHECK(desc.size() == 8, "tqb_pass_forward: desc holds 8 ints");
   int d[8];
   for (int i = 0; i < 8; ++i) d[i] = (int)desc[i];
@@ -160,7 +168,7 @@ void pass_forward(const at::Tensor& src, at::Tensor& dst, int64_t n, int64_t bsz
 void pass_backward(const at::Tensor& psi_src, const at::Tensor& lam_src, at::Tensor& psi_dst, at::Tensor& lam_dst, int64_t n,
                    int64_t bsz, const at::Tensor& prog, at::IntArrayRef desc, const at::Tensor& msh, const at::Tensor& mps,
                    int64_t mps_stride, at::Tensor& gr, int64_t gr_stride, int64_t ext_hi) {
-  const Abi& a = abi_for(psi_src);
+  TQB_ABI(a, psi_src);
   TORCH_CHECK(desc.size() == 8, "tqb_pass_backward: desc holds 8 ints");
   int d[8];
   for (int i = 0; i < 8; ++i) d[i] = (int)desc[i];
@@ -170,14 +178,14 @@ void pass_backward(const at::Tensor& psi_src, const at::Tensor& lam_src, at::Ten
 
 void apply_dense(const at::Tensor& in, at::Tensor& out, int64_t n, int64_t bsz, const at::Tensor& mats, int64_t mat_stride,
                  int64_t k, const at::Tensor& bitpos, int64_t conj_t) {
-  const Abi& a = abi_for(in);
+  TQB_ABI(a, in);
   check(a, a.apply_dense(fp(in), fpm(out), (int)n, bsz, fp(mats), mat_stride, (int)k, ip(bitpos), (int)conj_t, stream_of(in)),
         "tqb_apply_dense");
 }
 
 void apply_dense_tc(const at::Tensor& in, at::Tensor& out, int64_t n, int64_t bsz, const at::Tensor& mat, int64_t k,
                     at::IntArrayRef bitpos_host, int64_t conj_t) {
-  const Abi& a = abi_for(in);
+  TQB_ABI(a, in);
   TORCH_CHECK(a.apply_dense_tc != nullptr, "tqb_apply_dense_tc: not available in this build");
   TORCH_CHECK((int64_t)bitpos_host.size() == k && k <= 16, "tqb_apply_dense_tc: bitpos holds k ints");
   int b[16];
@@ -187,14 +195,14 @@ void apply_dense_tc(const at::Tensor& in, at::Tensor& out, int64_t n, int64_t bs
 
 void block_build(const at::Tensor& blocks, int64_t n_blocks, const at::Tensor& ops, const at::Tensor& consts,
                  const at::Tensor& params_sh, int64_t rank, at::Tensor& a_planes) {
-  const Abi& a = abi_for(a_planes);
+  TQB_ABI(a, a_planes);
   check(a, a.block_build(ip(blocks), (int)n_blocks, ip(ops), fp(consts), fp(params_sh), (unsigned)rank, fpm(a_planes),
                          stream_of(a_planes)), "tqb_block_build");
 }
 
 void apply_blocks(const at::Tensor& src, at::Tensor& dst, const c10::optional<at::Tensor>& scratch, int64_t n, int64_t bsz,
                   const at::Tensor& a_planes, const at::Tensor& blocks_host, int64_t n_blocks, int64_t renorm) {
-  const Abi& a = abi_for(src);
+  TQB_ABI(a, src);
   TORCH_CHECK(!blocks_host.is_cuda(), "tqb_apply_blocks: the block headers are read on the host");
   float* sc = nullptr;
   if (scratch.has_value() && scratch->defined()) {
@@ -207,7 +215,7 @@ void apply_blocks(const at::Tensor& src, at::Tensor& dst, const c10::optional<at
 }
 
 void quadphase(at::Tensor& state, int64_t n_local, int64_t bsz, const at::Tensor& coef, int64_t n_bits, int64_t rank) {
-  const Abi& a = abi_for(state);
+  TQB_ABI(a, state);
   TORCH_CHECK(coef.is_contiguous() && coef.scalar_type() == at::kInt && coef.numel() >= TQB_QP_WORDS && coef.device() == state.device(),
               "tqb_quadphase: coef must be TQB_QP_WORDS int32 words on the state's device");
   check(a, a.quadphase(fpm(state), (int)n_local, bsz, reinterpret_cast<const uint32_t*>(coef.data_ptr()), (int)n_bits,
@@ -216,42 +224,42 @@ void quadphase(at::Tensor& state, int64_t n_local, int64_t bsz, const at::Tensor
 
 void dense_grad(const at::Tensor& psi_in, const at::Tensor& lam_out, int64_t n, int64_t bsz, int64_t k, const at::Tensor& bitpos,
                 at::Tensor& G) {
-  const Abi& a = abi_for(psi_in);
+  TQB_ABI(a, psi_in);
   check(a, a.dense_grad(fp(psi_in), fp(lam_out), (int)n, bsz, (int)k, ip(bitpos), fpm(G), stream_of(psi_in)), "tqb_dense_grad");
 }
 
 void expval_pauli(const at::Tensor& state, int64_t n, int64_t bsz, const at::Tensor& xm, const at::Tensor& zm, const at::Tensor& ny,
                   int64_t n_terms, at::Tensor& out) {
-  const Abi& a = abi_for(state);
+  TQB_ABI(a, state);
   check(a, a.expval_pauli(fp(state), (int)n, bsz, up(xm), up(zm), ip(ny), (int)n_terms, fpm(out), stream_of(state)),
         "tqb_expval_pauli");
 }
 
 void expval_pauli_bwd(const at::Tensor& state, int64_t n, int64_t bsz, const at::Tensor& xm, const at::Tensor& zm,
                       const at::Tensor& ny, int64_t n_terms, const at::Tensor& grad_out, at::Tensor& grad_state) {
-  const Abi& a = abi_for(state);
+  TQB_ABI(a, state);
   check(a, a.expval_pauli_bwd(fp(state), (int)n, bsz, up(xm), up(zm), ip(ny), (int)n_terms, fp(grad_out), fpm(grad_state),
                               stream_of(state)), "tqb_expval_pauli_bwd");
 }
 
 void expval_z(const at::Tensor& state, int64_t n, int64_t bsz, at::Tensor& out) {
-  const Abi& a = abi_for(state);
+  TQB_ABI(a, state);
   check(a, a.expval_z(fp(state), (int)n, bsz, fpm(out), stream_of(state)), "tqb_expval_z");
 }
 
 void expval_z_bwd(const at::Tensor& state, int64_t n, int64_t bsz, const at::Tensor& grad_out, at::Tensor& grad_state) {
-  const Abi& a = abi_for(state);
+  TQB_ABI(a, state);
   check(a, a.expval_z_bwd(fp(state), (int)n, bsz, fp(grad_out), fpm(grad_state), stream_of(state)), "tqb_expval_z_bwd");
 }
 
 void probs(const at::Tensor& state, int64_t n, int64_t bsz, at::Tensor& out) {
-  const Abi& a = abi_for(state);
+  TQB_ABI(a, state);
   check(a, a.probs(fp(state), (int)n, bsz, fpm(out), stream_of(state)), "tqb_probs");
 }
 
 void sample_counts(const at::Tensor& probs_t, int64_t n, int64_t bsz, const at::Tensor& uniforms, int64_t n_shots,
                    at::Tensor& cdf_scratch, at::Tensor& counts) {
-  const Abi& a = abi_for(probs_t);
+  TQB_ABI(a, probs_t);
   TORCH_CHECK(counts.is_contiguous() && counts.scalar_type() == at::kInt, "tqb_sample_counts: counts is int32");
   check(a, a.sample_counts(fp(probs_t), (int)n, bsz, fp(uniforms), (int)n_shots, fpm(cdf_scratch),
                            static_cast<int*>(counts.data_ptr()), stream_of(probs_t)), "tqb_sample_counts");
@@ -260,7 +268,7 @@ void sample_counts(const at::Tensor& probs_t, int64_t n, int64_t bsz, const at::
 // peer_ptrs: the destination slab of every rank as raw device addresses (symmetric memory: _SymmetricMemory.buffer_ptrs)
 void exchange_p2p(const at::Tensor& src, at::Tensor& local_dst, at::IntArrayRef peer_ptrs, int64_t n_local, int64_t bsz,
                   at::IntArrayRef victim_bits, int64_t rank) {
-  const Abi& a = abi_for(src);
+  TQB_ABI(a, src);
   const int g = (int)victim_bits.size();
   TORCH_CHECK(g >= 1 && g <= 4 && (int64_t)peer_ptrs.size() == (1ll << g), "tqb_exchange_p2p: 2^g peer pointers for g victim bits");
   TORCH_CHECK(rank >= 0 && rank < (int64_t)peer_ptrs.size() &&
@@ -274,13 +282,13 @@ void exchange_p2p(const at::Tensor& src, at::Tensor& local_dst, at::IntArrayRef 
 }
 
 void split_tf32(const at::Tensor& x, at::Tensor& hi, at::Tensor& lo) {
-  const Abi& a = abi_for(x);
+  TQB_ABI(a, x);
   TORCH_CHECK(x.scalar_type() == at::kFloat && hi.numel() == x.numel() && lo.numel() == x.numel(), "tqb_split_tf32: float32, equal sizes");
   check(a, a.split_tf32(fp(x), fpm(hi), fpm(lo), x.numel(), stream_of(x)), "tqb_split_tf32");
 }
 
 void gemm_prep(const at::Tensor& x, int64_t mode, at::Tensor& hi, at::Tensor& lo) {
-  const Abi& a = abi_for(x);
+  TQB_ABI(a, x);
   TORCH_CHECK(x.dim() == 2 && x.scalar_type() == at::kComplexFloat && hi.scalar_type() == at::kFloat && lo.scalar_type() == at::kFloat,
               "tqb_gemm_prep: x complex64 [rows][cols], planes float32");
   const int64_t want = (mode == 1 ? 2 : 4) * x.numel();
@@ -290,7 +298,7 @@ void gemm_prep(const at::Tensor& x, int64_t mode, at::Tensor& hi, at::Tensor& lo
 }
 
 void gemm_tf32x3(const at::Tensor& a_hi, const at::Tensor& a_lo, const at::Tensor& bt_hi, const at::Tensor& bt_lo, at::Tensor& c) {
-  const Abi& a = abi_for(a_hi);
+  TQB_ABI(a, a_hi);
   TORCH_CHECK(a_hi.dim() == 2 && bt_hi.dim() == 2 && c.dim() == 2 && a_hi.size(1) == bt_hi.size(1) && c.size(0) == a_hi.size(0) &&
                   c.size(1) == bt_hi.size(0) && a_lo.sizes() == a_hi.sizes() && bt_lo.sizes() == bt_hi.sizes(),
               "tqb_gemm_tf32x3: C[M][N] = A[M][K] * Bt[N][K]^T");

@@ -76,8 +76,13 @@ class GraphedStep:
     def __call__(self, *inputs):
         """Copy `inputs` (device or pinned host tensors) into the captured buffers, replay the step and
         return the captured loss tensor; gradients are in the parameters' `.grad`."""
+        if len(inputs) != len(self.static_inputs):
+            raise ValueError(f"GraphedStep was captured with {len(self.static_inputs)} inputs, got {len(inputs)}")
         with torch.no_grad():
             for s, x in zip(self.static_inputs, inputs):
+                if x.shape != s.shape:   # (copy_ would broadcast a smaller batch silently)
+                    raise ValueError(f"GraphedStep was captured for an input of shape {tuple(s.shape)}, got "
+                                     f"{tuple(x.shape)}: the batch size and circuit structure are fixed at capture")
                 if x is not s:
                     s.copy_(x, non_blocking=True)
         self.graph.replay()
