@@ -695,3 +695,66 @@ def check_large_batch_readout(device, bsz=70000):
     assert_close(z.cpu(), want.cpu(), what="per-wire Z, bsz > 65535")
     zi = expval_joint_analytical(q, "ZI")
     assert_close(zi.cpu(), want[:, 0].cpu(), what="ZI, bsz > 65535")
+
+
+def random_catalogue_ops(n, count, seed, bsz=1, p_per_sample=0.0, p_inverse=0.3, p_near=0.6, max_wires=None):
+    """Random gates drawn from the WHOLE in-tile catalogue (every U1Q / DIAG / U2Q name of gates.SPECS: multi-controlled,
+    negative controls, parity diagonals, 2-qubit dense ...) on random wires, some inverted; `p_near` of them on wires
+    inside one 6-wire window (the shape block fusion likes), the rest anywhere."""
+    from torchquantum_b200 import gates as G
+
+    names = [k for k, s in G.SPECS.items() if s.kind in (G.U1Q, G.DIAG, G.U2Q) and k != "globalphase"]
+    rng = np.random.default_rng(seed)
+    ops = []
+    while len(ops) < count:
+        name = names[rng.integers(len(names))]
+        spec = G.SPECS[name]
+        k = spec.n_wires if spec.n_wires is not None else int(rng.integers(2, 5))
+        if max_wires is not None and k > max_wires:
+            continue
+        if n > 6 and rng.random() < p_near:
+            base = int(rng.integers(0, n - 5))
+            wires = [int(w) for w in rng.choice(np.arange(base, base + 6), k, replace=False)]
+        else:
+            wires = [int(w) for w in rng.choice(n, k, replace=False)]
+        op = {"name": name, "wires": wires, "inverse": bool(rng.random() < p_inverse)}
+        if spec.n_params:
+            rows = bsz if rng.random() < p_per_sample else 1
+            op["params"] = torch.tensor(rng.uniform(-np.pi, np.pi, (rows, spec.n_params)), dtype=torch.float32)
+        ops.append(op)
+    return ops
+
+
+def check_random_gates_through_blocks(device, seeds=(1, 2)):
+    """Forward-only programs of random catalogue gates on a streamed state, with the block thresholds lowered so that
+    fusable runs become tensor-core blocks (mixed with register-tile stages for what is not fusable), under each
+    write-back discipline, against the oracle.  Two families: the whole catalogue (short fusable runs: in-place
+    blocks between register-tile stages) and gates on <= 2 wires (long fusable runs: rotating stages that track the
+    qubit layout and sort it home)."""
+    from torchquantum_b200 import blockplan as B, engine, plan as P
+
+    saved = (P.BLOCK_MIN_RUN, P.BLOCK_MIN_AVG, B.MODE)
+    P.BLOCK_MIN_RUN, P.BLOCK_MIN_AVG = 4, 1.0
+    try:
+        for seed in seeds:
+            # (the rotating discipline needs >= 18 local qubits: three groups of six)
+            for n, max_wires, count, modes in ((16, None, 150, ("auto", "inplace")), (18, 2, 300, ("rotate", "auto"))):
+                ops = random_catalogue_ops(n, count, seed, max_wires=max_wires)
+                want = O.run_ops(n, 1, ops)
+                for mode in modes:
+                    B.MODE = mode
+                    engine._PLAN_CACHE.clear()
+                    with torch.no_grad():
+                        q = tq.QuantumDevice(n_wires=n, bsz=1, device=device)
+                        apply_ops(q, [dict(o, params=o["params"].to(device)) if o.get("params") is not None else o
+                                      for o in ops], device)
+                        got = q.get_states_1d()
+                    stages = next(reversed(engine._PLAN_CACHE.values())).stages
+                    blocks = [st for st in stages if st.kind == "blocks"]
+                    assert blocks, (seed, max_wires, mode, [st.kind for st in stages])
+                    if mode == "rotate":
+                        assert any(st.n_rotating for st in blocks), (seed, mode)
+                    assert_close(got, want, what=f"random catalogue gates (<= {max_wires} wires), seed {seed}, write-back {mode}")
+    finally:
+        P.BLOCK_MIN_RUN, P.BLOCK_MIN_AVG, B.MODE = saved
+        engine._PLAN_CACHE.clear()

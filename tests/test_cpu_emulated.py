@@ -144,6 +144,10 @@ def test_block_write_back_modes():
     cases.check_block_write_back_modes("cpu", n=18, depth=8)
 
 
+def test_random_gates_through_blocks():
+    cases.check_random_gates_through_blocks("cpu", seeds=(1,))
+
+
 def test_large_batch_readout():
     cases.check_large_batch_readout("cpu", bsz=66000)
 

@@ -76,6 +76,12 @@ def test_qft_blocks_and_quadphase():
     cases.check_qft_blocks_and_quadphase(DEV, n=21, bsz=2)
 
 
+def test_random_gates_through_blocks():
+    """random gates from the whole in-tile catalogue (multi-controlled, parity diagonals, 2-qubit dense, inverses) fused into
+    tensor-core blocks between register-tile stages, in place and rotating, vs the oracle"""
+    cases.check_random_gates_through_blocks(DEV, seeds=(1, 2, 4, 5))
+
+
 def test_block_write_back_modes():
     """tensor-core block stages, in place and rotating (contiguous tile write-back into a second buffer), vs the oracle"""
     cases.check_block_write_back_modes(DEV, n=20, depth=24)
