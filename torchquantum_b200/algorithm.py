@@ -96,9 +96,11 @@ class Hamiltonian(object):
                 "hamil_list": [{"coeff": c, "pauli_string": p} for c, p in zip(self.coeffs, self.paulis)]}
 
     def coeff_tensor(self, device) -> torch.Tensor:
-        t = self._coeff_cache.get(device)
+        key = (device, tuple(self.coeffs))   # `coeffs` is a public, mutable attribute in the reference: follow edits
+        t = self._coeff_cache.get(key)
         if t is None:
-            t = self._coeff_cache[device] = torch.tensor(self.coeffs, dtype=torch.float32, device=device)
+            self._coeff_cache.clear()
+            t = self._coeff_cache[key] = torch.tensor(self.coeffs, dtype=torch.float32, device=device)
         return t
 
     def expval(self, qdev) -> torch.Tensor:
