@@ -62,6 +62,44 @@ def check_record_cache_follows_the_op_list(device):
             o(q, wires=w)
     assert_close(run(es), q.get_states_1d(), what="EfficientSU2 after replacing an operator")
 
+    # ... and its epoch fast path (no walk over the layers while nothing was mutated) notices every kind of change
+    def direct(model):
+        q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+        q.h(wires=0)
+        for layer_k in model.layers_all:
+            for o, w in layer_k._layer_ops_wires():
+                o(q, wires=w)
+        return q.get_states_1d().clone()
+
+    es = tq.EfficientSU2(n_wires=n, reps=2, entanglement_layer="linear").to(device)
+    s0 = run(es)
+    assert_close(run(es), s0, what="cached chunk, unchanged model")
+    assert es.__dict__["_chunk_cache"][2] == tq.module.MUTATION_EPOCH[0]          # the fast path is what served it
+    es.layers_all[0].ops_all[2].inverse = True                                     # attribute write on an operator
+    s1 = run(es)
+    assert_close(s1, direct(es), what="epoch: operator attribute")
+    assert (s1 - s0).abs().max().item() > 1e-3
+    es.layers_all[1].ops_all[0].params = torch.nn.Parameter(torch.tensor([[0.77]], device=device))   # new Parameter object
+    s2 = run(es)
+    assert_close(s2, direct(es), what="epoch: replaced Parameter")
+    assert (s2 - s1).abs().max().item() > 1e-3
+    es.layers_all[2].jump = 2                                                      # attribute write on a template layer
+    assert_close(run(es), direct(es), what="epoch: layer attribute")
+    es.layers_all[3] = tq.Op1QAllLayer(op=tq.RX, n_wires=n, has_params=True, trainable=True).to(device)   # list mutation
+    s3 = run(es)
+    assert_close(s3, direct(es), what="epoch: replaced layer")
+    with torch.no_grad():                                                          # in-place edits need no invalidation
+        es.layers_all[0].ops_all[0].params.add_(0.3)
+    assert_close(run(es), direct(es), what="in-place parameter edit is read live")
+    calls = []
+    handle = es.layers_all[0].register_forward_hook(lambda *a: calls.append(1))   # a hook forces the per-layer path
+    run(es)
+    assert calls, "forward hook of a layer inside a template must run"
+    handle.remove()
+    qrec = tq.QuantumDevice(n_wires=n, bsz=2, device=device, record_op=True)       # op recording: no cached records
+    es(qrec)
+    assert len(qrec.op_history) == sum(len(layer_k._layer_ops_wires()) for layer_k in es.layers_all)
+
 
 def check_grad_mode_is_sampled_when_gates_are_issued(device):
     """reading the state under no_grad mid-circuit must not drop the graph of the gates before it, and

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import operator as op
-from .module import QuantumModule, QuantumModuleList, static_support
+from .module import MUTATION_EPOCH, QuantumModule, QuantumModuleList, static_support
 from .operator import op_name_dict
 
 __all__ = ["RandomLayer", "RandomLayerAllTypes", "Op1QAllLayer", "Op2QAllLayer", "Op2QDenseLayer",
@@ -34,6 +34,7 @@ class _RecordCache:
     def __setattr__(self, name, value):
         if name not in self._CACHE_KEEPS:
             self.__dict__["_rec_cache"] = None
+            MUTATION_EPOCH[0] += 1
         super().__setattr__(name, value)
 
     def records(self, q_device):
@@ -265,8 +266,23 @@ class LayerTemplate0(QuantumModule):
     def build_layers(self):
         raise NotImplementedError
 
+    def __setattr__(self, name, value):
+        if name not in _RecordCache._CACHE_KEEPS:    # (forward() assigns `q_device` every step)
+            MUTATION_EPOCH[0] += 1
+        super().__setattr__(name, value)
+
     def _chunk(self, q_device):
         """All layers' records as one engine.RecordChunk when every layer is a cacheable template."""
+        c = self.__dict__.get("_chunk_cache")
+        if c is not None and c[2] == MUTATION_EPOCH[0]:
+            # nothing any of the caches below validates against has changed since this chunk was last validated (no
+            # attribute write on an operator or layer, no list mutation, no `.to()`): skip the walk over the layers.
+            # What has no epoch is checked here: hooks registered on a layer, the device the parameters live on
+            if (not q_device.record_op and getattr(q_device, "accepts_record_chunks", False) and not any(c[3])):
+                dev = q_device._flat.device
+                if all(p.device == dev for p in c[1].params):
+                    return c[1]
+        epoch = MUTATION_EPOCH[0]
         parts = []
         for layer in self.layers_all:
             if not isinstance(layer, _RecordCache) or layer._forward_hooks or layer._forward_pre_hooks:
@@ -275,13 +291,14 @@ class LayerTemplate0(QuantumModule):
             if recs is None:
                 return None
             parts.append(recs)
-        c = self.__dict__.get("_chunk_cache")
+        hooks = [h for layer in self.layers_all for h in (layer._forward_hooks, layer._forward_pre_hooks)]
         if c is not None and len(c[0]) == len(parts) and all(a is b for a, b in zip(c[0], parts)):
+            self.__dict__["_chunk_cache"] = (c[0], c[1], epoch, hooks)
             return c[1]
         from .engine import RecordChunk
 
         chunk = RecordChunk([r for recs in parts for r in recs])
-        self.__dict__["_chunk_cache"] = (parts, chunk)
+        self.__dict__["_chunk_cache"] = (parts, chunk, epoch, hooks)
         return chunk
 
     @static_support

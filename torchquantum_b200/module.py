@@ -152,6 +152,12 @@ class QuantumModule(nn.Module):
         return qdev.get_states_1d().T
 
 
+# Global mutation epoch: bumped by every structural change the layer templates' record caches validate against (an
+# attribute write on an operator or a template layer, a mutation of a QuantumModuleList, `.to()` on an operator).  While
+# it stands still, a whole template (LayerTemplate0._chunk) can reuse its cached records without re-walking its layers.
+MUTATION_EPOCH = [0]
+
+
 class QuantumModuleList(nn.ModuleList, QuantumModule, metaclass=ABCMeta):
     """nn.ModuleList of quantum modules.  Every mutation bumps `_list_ver`, which the layer templates' queue-record
     caches (layer._RecordCache) compare instead of re-walking the list every step."""
@@ -162,6 +168,7 @@ class QuantumModuleList(nn.ModuleList, QuantumModule, metaclass=ABCMeta):
 
     def _touch(self):
         self.__dict__["_list_ver"] = self.__dict__.get("_list_ver", 0) + 1
+        MUTATION_EPOCH[0] += 1
 
     def __setitem__(self, idx, module):
         self._touch()

@@ -18,7 +18,7 @@ from . import gates as G
 from .functional import mat_dict
 from .functional import matrices as M
 from .macro import C_DTYPE, F_DTYPE
-from .module import QuantumModule
+from .module import MUTATION_EPOCH, QuantumModule
 
 __all__ = ["op_name_dict", "Operator", "Operation", "DiagonalOperation", "Observable", "WiresEnum", "NParamsEnum",
            "AnyNParams", "AllWires", "AnyWires", "fixed_ops", "parameterized_ops"]
@@ -166,6 +166,7 @@ class Operator(QuantumModule):
     def _apply(self, fn, *args, **kwargs):
         # .to() / .cuda() / .float() may swap Parameter objects without going through __setattr__
         self.__dict__["_ver"] = self.__dict__.get("_ver", 0) + 1
+        MUTATION_EPOCH[0] += 1
         return super()._apply(fn, *args, **kwargs)
 
     _PLAIN_ATTRS = frozenset(("wires", "inverse", "n_wires", "static_matrix", "clifford_quantization"))
@@ -175,6 +176,7 @@ class Operator(QuantumModule):
         # and re-validate them by version (layer._RecordCache)
         d = self.__dict__
         d["_ver"] = d.get("_ver", 0) + 1
+        MUTATION_EPOCH[0] += 1
         if name in Operator._PLAIN_ATTRS:  # plain python state: skip nn.Module's type dispatch
             d[name] = value
             return
