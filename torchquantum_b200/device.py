@@ -70,26 +70,23 @@ class QuantumDevice(nn.Module):
     def __init__(self, n_wires: int, device_name: str = "default", bsz: int = 1,
                  device: Union[torch.device, str] = "cpu", record_op: bool = False):
         super().__init__()
-        self.n_wires = n_wires
-        self.device_name = device_name
-        self.bsz = bsz
-        self.device = device
+        # plain python state goes straight into __dict__ (what nn.Module.__setattr__ does after its type dispatch): user code
+        # builds a device per forward pass, as the reference's examples do
+        self.__dict__.update(n_wires=n_wires, device_name=device_name, bsz=bsz, device=device, record_op=record_op,
+                             _op_history=[], _history_pending=[], _flat=None)
         _state = torch.zeros(2 ** n_wires, dtype=C_DTYPE, device=device)  # built on the device: no H2D copy
         _state[:1].fill_(1)
         _state = torch.reshape(_state, [2] * n_wires)
         self.register_buffer("state", _state)
-        self._queue = GateQueue(self)
-        self._flat = None
+        self.__dict__["_queue"] = GateQueue(self)
         self._buffers["states"] = None
         self.reset_states(bsz)
-        self.record_op = record_op
-        self._op_history = []
-        self._history_pending = []
 
     # --- state container --------------------------------------------------------------
     def _set_flat(self, flat):
-        self._queue = GateQueue(self)
-        self._flat = flat
+        d = self.__dict__
+        d["_queue"] = GateQueue(self)
+        d["_flat"] = flat
         self._buffers["states"] = None  # materialised lazily as a view
 
     @property

@@ -26,7 +26,16 @@ class MeasureAll(QuantumModule):
         self.v_c_reg_mapping = v_c_reg_mapping
 
     def forward(self, qdev):
-        x = expval(qdev, list(range(qdev.n_wires)), [self.obs()] * qdev.n_wires)
+        # the reference builds `self.obs()` per call (measurements.py:331-336); a parameter-free observable is only asked for
+        # its diagonalizing gates and eigenvalues, so one instance per module serves every step
+        cached = self.__dict__.get("_obs_instance")
+        if cached is not None and cached[0] is self.obs:
+            observable = cached[1]
+        else:
+            observable = self.obs()
+            if getattr(observable, "params", None) is None:
+                self.__dict__["_obs_instance"] = (self.obs, observable)
+        x = expval(qdev, list(range(qdev.n_wires)), [observable] * qdev.n_wires)
         x = _permute(x, self.v_c_reg_mapping)
         if self.noise_model_tq is not None and self.noise_model_tq.is_add_noise:
             return self.noise_model_tq.apply_readout_error(x)

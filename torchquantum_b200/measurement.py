@@ -50,6 +50,7 @@ def pauli_masks(observable: str):
 
 _MASK_CACHE = {}
 _EXPVAL_COEF = {}
+_EV_FLOATS = {}    # id(eigvals tensor) -> (tensor, version, (ev0, ev1) as python floats)
 
 
 def _mask_tensors(observables, device):
@@ -267,11 +268,19 @@ def expval(qdev, wires: Union[int, List[int]], observables):
     evs = []
     for observable in observables:
         ev = observable.eigvals
+        hit = _EV_FLOATS.get(id(ev))     # (fixed observables hand out one class-level tensor: no .item() per wire and step)
+        if hit is not None and hit[0] is ev and hit[1] == ev._version:
+            evs.append(hit[2])
+            continue
         if ev.is_cuda or ev.requires_grad:
             evs = None
             break
-        ev = ev.real if ev.is_complex() else ev
-        evs.append((float(ev[0]), float(ev[1])))
+        evr = ev.real if ev.is_complex() else ev
+        pair = (float(evr[0]), float(evr[1]))
+        if len(_EV_FLOATS) > 64:
+            _EV_FLOATS.clear()
+        _EV_FLOATS[id(ev)] = (ev, ev._version, pair)   # keeps `ev` alive, so the id stays unique
+        evs.append(pair)
     if evs is not None:
         key = (tuple(int(w) for w in wires), tuple(evs), n, z.device)
         c = _EXPVAL_COEF.get(key)
