@@ -99,6 +99,20 @@ def test_errors_match_reference_behaviour():
     tqf.rx(q, wires=0, params=torch.rand(5))  # batch mismatch: bmm raises RuntimeError in the reference
     with pytest.raises(RuntimeError):
         q.get_states_1d()
+    # wire indices fail at the gate call, as the reference's permute does (gate_wrapper.py:96-140), not at the lazy flush
+    q = tq.QuantumDevice(n_wires=3, bsz=2)
+    with pytest.raises(IndexError, match="out of range"):
+        tqf.rx(q, wires=3, params=torch.tensor([[0.1]]))
+    with pytest.raises(IndexError, match="out of range"):
+        q.cnot(wires=[0, -1])
+    with pytest.raises(RuntimeError, match="repeated wire"):
+        q.cnot(wires=[1, 1])
+    with pytest.raises(IndexError, match="out of range"):
+        tq.RX(has_params=True)(q, wires=7)
+    with pytest.raises(IndexError, match="out of range"):
+        tq.Op1QAllLayer(op=tq.RX, n_wires=4, has_params=True)(q)      # a 4-wire template on a 3-wire device
+    q.h(wires=2)
+    assert q.get_states_1d().shape == (2, 8)                         # nothing half-queued by the failed calls
 
 
 def test_cfg2_vqe_class_api_record_cache():

@@ -60,6 +60,16 @@ def _normalize_params(name, params):
     return params
 
 
+def check_wires(name, wires_t, n_wires):
+    """Wire indices are validated at the gate call (the reference fails there too: `permute` raises on an index out of
+    range or a repeated dim, gate_wrapper.py:96-140), not when the lazy queue runs."""
+    for w in wires_t:
+        if not 0 <= w < n_wires:
+            raise IndexError(f"{name}: wire {w} is out of range for a device with {n_wires} wires")
+    if len(wires_t) > 1 and len(set(wires_t)) != len(wires_t):
+        raise RuntimeError(f"{name}: repeated wire in {list(wires_t)}")
+
+
 def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, static=False, parent_graph=None,
                  inverse=False):
     """Queue one gate on `q_device` (reference: functional/gate_wrapper.py:324-446).
@@ -71,6 +81,7 @@ def gate_wrapper(name, mat, method, q_device, wires, params=None, n_wires=None, 
     params = _normalize_params(cname, params)
     wires = [wires] if isinstance(wires, (int, np.integer)) else list(wires)
     wires_t = tuple(int(w) for w in wires)
+    check_wires(name, wires_t, q_device.n_wires)
 
     if q_device.record_op:
         q_device._record({
@@ -128,6 +139,7 @@ def _make(name):
                 wires_t = tuple([int(w) for w in wires])
             if n_wires_fixed is not None and n_wires_fixed != len(wires_t):
                 raise AssertionError(f"{name}: expected {n_wires_fixed} wires, got {len(wires_t)}")
+            check_wires(name, wires_t, q_device.n_wires)
             if n_params == 0:
                 params = None
             else:
@@ -168,6 +180,7 @@ for _n in _NAMES:
 def reset(q_device, wires, inverse=False):
     """functional/reset.py:19-42: project the wires on |0> and renormalise (non-unitary)."""
     wires = [wires] if isinstance(wires, (int, np.integer)) else list(wires)
+    check_wires("reset", tuple(int(w) for w in wires), q_device.n_wires)
     q_device.enqueue("reset", tuple(int(w) for w in wires), None, False)
 
 

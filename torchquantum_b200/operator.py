@@ -132,6 +132,7 @@ class Operator(QuantumModule):
                 or (p is not None and (p.dim() != 2 or p.device != q_device._flat.device))):
             return None
         wires_t = (int(wires),) if isinstance(wires, (int, np.integer)) else tuple([int(w) for w in wires])
+        tqf.check_wires(cname, wires_t, q_device.n_wires)
         return (cname, wires_t, p, bool(self.inverse))
 
     def queue_on(self, q_device, wires):
