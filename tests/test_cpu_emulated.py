@@ -113,6 +113,10 @@ def test_errors_match_reference_behaviour():
         tq.Op1QAllLayer(op=tq.RX, n_wires=4, has_params=True)(q)      # a 4-wire template on a 3-wire device
     q.h(wires=2)
     assert q.get_states_1d().shape == (2, 8)                         # nothing half-queued by the failed calls
+    for template in (tq.Op1QAllLayer(op=tq.RX, n_wires=4, has_params=True), tq.EfficientSU2(n_wires=4, reps=1)):
+        template(tq.QuantumDevice(n_wires=4, bsz=2))                 # records cached for a 4-wire device ...
+        with pytest.raises(IndexError, match="out of range"):
+            template(tq.QuantumDevice(n_wires=3, bsz=2))             # ... are not replayed on a narrower one
 
 
 def test_cfg2_vqe_class_api_record_cache():

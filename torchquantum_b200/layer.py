@@ -42,7 +42,7 @@ class _RecordCache:
             return None
         dev = q_device._flat.device
         c = self.__dict__.get("_rec_cache")
-        if c is not None and c[0] == dev:
+        if c is not None and c[0] == dev and c[7] == q_device.n_wires:   # (wire indices were validated for that width)
             cont = self._op_container()
             if cont is c[5] and cont.__dict__["_list_ver"] == c[6]:
                 ver = 0
@@ -63,7 +63,7 @@ class _RecordCache:
             recs.append(r)
             ver += o.__dict__["_ver"]
         self.__dict__["_rec_cache"] = (dev, ver, ops, recs, [r[2] for r in recs if r[2] is not None], cont,
-                                       cont.__dict__["_list_ver"])
+                                       cont.__dict__["_list_ver"], q_device.n_wires)
         return recs
 
 
@@ -278,7 +278,8 @@ class LayerTemplate0(QuantumModule):
             # nothing any of the caches below validates against has changed since this chunk was last validated (no
             # attribute write on an operator or layer, no list mutation, no `.to()`): skip the walk over the layers.
             # What has no epoch is checked here: hooks registered on a layer, the device the parameters live on
-            if (not q_device.record_op and getattr(q_device, "accepts_record_chunks", False) and not any(c[3])):
+            if (not q_device.record_op and getattr(q_device, "accepts_record_chunks", False) and not any(c[3])
+                    and c[4] == q_device.n_wires):
                 dev = q_device._flat.device
                 if all(p.device == dev for p in c[1].params):
                     return c[1]
@@ -293,12 +294,12 @@ class LayerTemplate0(QuantumModule):
             parts.append(recs)
         hooks = [h for layer in self.layers_all for h in (layer._forward_hooks, layer._forward_pre_hooks)]
         if c is not None and len(c[0]) == len(parts) and all(a is b for a, b in zip(c[0], parts)):
-            self.__dict__["_chunk_cache"] = (c[0], c[1], epoch, hooks)
+            self.__dict__["_chunk_cache"] = (c[0], c[1], epoch, hooks, q_device.n_wires)
             return c[1]
         from .engine import RecordChunk
 
         chunk = RecordChunk([r for recs in parts for r in recs])
-        self.__dict__["_chunk_cache"] = (parts, chunk, epoch, hooks)
+        self.__dict__["_chunk_cache"] = (parts, chunk, epoch, hooks, q_device.n_wires)
         return chunk
 
     @static_support
