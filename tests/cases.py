@@ -758,3 +758,33 @@ def check_random_gates_through_blocks(device, seeds=(1, 2)):
     finally:
         P.BLOCK_MIN_RUN, P.BLOCK_MIN_AVG, B.MODE = saved
         engine._PLAN_CACHE.clear()
+
+
+def check_unitary_gates(device):
+    """`qubitunitary` / `qubitunitarystrict` (functional/qubit_unitary.py:19-86) against the reference's own outputs
+    (tests/golden/unitary_gates.npz, oracle/gen_unitary_golden.py): explicit matrices on 1-4 wires in any order, plain and
+    inverse, shared and per-sample; the strict variant is fed non-unitary matrices (its SVD projection is part of the gate);
+    plus the reference's refusal of a non-unitary `qubitunitary`."""
+    import pytest
+
+    z, man = load("unitary_gates.npz")
+    n = man["n"]
+    for k, case in enumerate(man["cases"]):
+        bsz = case["bsz"]
+        q = tq.QuantumDevice(n_wires=n, bsz=bsz, device=device)
+        q.set_states(torch.tensor(z["init"][:bsz]).to(device))
+        getattr(tqf, case["name"])(q, wires=case["wires"], params=torch.tensor(z[f"mat{k}"]).to(device),
+                                    inverse=case["inverse"])
+        assert_close(q.get_states_1d(), z[f"out{k}"],
+                     what=f"{case['name']} wires {case['wires']} inverse={case['inverse']} batched={case['batched']}")
+    q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+    with pytest.raises(AssertionError):
+        tqf.qubitunitary(q, wires=[1, 2], params=torch.tensor(z["mat0"][:1, :1]).repeat(4, 4).to(device))   # not unitary
+    # the operator classes reach the same path
+    k = next(i for i, c in enumerate(man["cases"]) if c["name"] == "qubitunitary" and len(c["wires"]) == 2
+             and not c["inverse"] and not c["batched"])
+    case = man["cases"][k]
+    q = tq.QuantumDevice(n_wires=n, bsz=2, device=device)
+    q.set_states(torch.tensor(z["init"]).to(device))
+    tq.QubitUnitary(has_params=True, init_params=torch.tensor(z[f"mat{k}"]), n_wires=2).to(device)(q, wires=case["wires"])
+    assert_close(q.get_states_1d(), z[f"out{k}"], what="tq.QubitUnitary")

@@ -41,6 +41,10 @@ def test_every_gate():
     cases.check_all_gates("cpu")
 
 
+def test_unitary_gates():
+    cases.check_unitary_gates("cpu")
+
+
 def test_random_circuits_fwd_bwd():
     cases.check_random_circuits("cpu")
 

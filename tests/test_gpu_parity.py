@@ -60,6 +60,11 @@ def test_mnist_cfg1():
     cases.check_mnist_cfg1(DEV)
 
 
+def test_unitary_gates():
+    """qubitunitary / qubitunitarystrict vs the reference's outputs (56 cases: wire orders, inverse, per-sample, SVD projection)"""
+    cases.check_unitary_gates(DEV)
+
+
 def test_large_batch_readout():
     cases.check_large_batch_readout(DEV)
 

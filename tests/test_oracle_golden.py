@@ -23,6 +23,17 @@ def test_every_gate_matches_reference():
         assert_close(out.reshape(init.shape[0], -1), z[case["out"]], what=str(case["name"]))
 
 
+def test_explicit_unitaries_match_reference():
+    """qubitunitary / qubitunitarystrict (functional/qubit_unitary.py:19-86): the oracle against the reference's outputs"""
+    z, man = load("unitary_gates.npz")
+    n = man["n"]
+    for k, case in enumerate(man["cases"]):
+        bsz = case["bsz"]
+        s = torch.tensor(z["init"][:bsz]).reshape([bsz] + [2] * n)
+        out = O.apply_op(s, case["name"], case["wires"], torch.tensor(z[f"mat{k}"]), None, case["inverse"])
+        assert_close(out.reshape(bsz, -1), z[f"out{k}"], what=f"{case['name']} {case['wires']}")
+
+
 def _run_circuit(z, c, requires_grad):
     pre = c["prefix"]
     init = torch.tensor(z[pre + "init"]).requires_grad_(requires_grad)
