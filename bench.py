@@ -11,10 +11,13 @@ parameters) behind a per-sample `10_ry` encoder, bsz=4096 per GPU, 19-term energ
   roofline : every gate-pass launch of a config-4 style circuit as the planner schedules it (tensor-core block
              passes + register-tile passes), timed live on an n=28 state (2 GiB, larger than L2) against the
              measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference : the CPU oracle port of the reference path (torch on the
-             host cores) on a bounded sample of the same workload.
+  cpu_baseline / --impl reference : the reference's OWN code (the unmodified package in baseline/_ref: gate_wrapper +
+             bmm + torch autograd on the host cores, all threads) running the same model class on the same workload in
+             bsz-1024 chunks; the oracle port (oracle/tq_oracle.py) only if that package cannot be imported (`kind` says which).
+  eager    : the same step through the plain eager API (no tq.GraphedStep), device-timed and end to end.
 N > 1 (torchrun): the batch is sharded, 4096 circuits per rank (weak scaling); the only exchange is
-the all-reduce of the 420 shared-parameter gradients.
+the all-reduce of the 420 shared-parameter gradients; the line also carries `sharded_configs`: config 3 strong-scaled
+over the ranks and the config-5 family (QFT + brickwork on a statevector sharded over the ranks, n = 30 + log2 N).
 """
 import argparse
 import json
