@@ -266,3 +266,49 @@ def test_sharded_device_call_time_semantics():
     if not os.path.exists(emu):
         pytest.skip("host emulation library not built (run __graft_entry__.build())")
     mp.spawn(_worker_semantics, args=(2, _free_port(), emu), nprocs=2, join=True)
+
+
+def _worker_batch_axis(rank, world, port, emu_path):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        import torchquantum_b200 as tq
+        from tests.helpers import GRAD_RTOL, assert_close
+        from torchquantum_b200 import _native
+
+        _native.use_library_for_testing(emu_path)
+        n, reps, total = 5, 3, 12
+        torch.manual_seed(0)
+        np.random.seed(0)
+        model = bench.VQEModel(tq, n=n, reps=reps)          # the bench's model class, same seed on every rank
+        model.encoder = tq.GeneralEncoder([{"input_idx": [k], "func": "ry", "wires": [k]} for k in range(n)])
+        params = [p for p in model.parameters() if p.requires_grad]
+        x_all = torch.rand(total, n, generator=torch.Generator().manual_seed(7)) * np.pi
+        per = total // world
+        x = x_all[rank * per:(rank + 1) * per]               # contiguous batch shard
+        loss = model(x)
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in params])   # what bench.py's reduce_grads() does
+        dist.all_reduce(flat)
+        flat /= world                                            # mean over equal shards = mean over the whole batch
+        losses = torch.tensor([loss.item()])
+        dist.all_reduce(losses)
+        for p in params:
+            p.grad = None
+        whole = model(x_all)
+        whole.backward()
+        want = torch.cat([p.grad.reshape(-1) for p in params])
+        assert_close(losses / world, whole.detach().reshape(1), what="mean energy over the shards")
+        assert_close(flat, want, rtol=GRAD_RTOL, what=f"rank {rank}: all-reduced shared-parameter gradients")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batch_sharded_step_matches_one_process():
+    """SURVEY §8e, batch axis (configs 1-3): every rank runs its contiguous shard of the batch, no data-path collective;
+    the one exchange is the all-reduce of the shared-parameter gradients, which must equal the whole-batch gradient."""
+    emu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libtqb200_emu.so")
+    if not os.path.exists(emu):
+        pytest.skip("host emulation library not built (run __graft_entry__.build())")
+    mp.spawn(_worker_batch_axis, args=(2, _free_port(), emu), nprocs=2, join=True)
