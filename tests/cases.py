@@ -794,3 +794,18 @@ def check_unitary_gates(device):
     q.set_states(torch.tensor(z["init"]).to(device))
     tq.QubitUnitary(has_params=True, init_params=torch.tensor(z[f"mat{k}"]), n_wires=2).to(device)(q, wires=case["wires"])
     assert_close(q.get_states_1d(), z[f"out{k}"], what="tq.QubitUnitary")
+
+
+def check_random_catalogue_gradients(device, seeds=range(8)):
+    """Grad-mode programs of random catalogue gates (shared and per-sample parameters, inverses, the non-unitary cu2 with its
+    own checkpointed stage) against the oracle's autograd: states, one expectation value, every parameter gradient."""
+    from torchquantum_b200 import engine
+
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        n, bsz = int(rng.integers(2, 9)), int(rng.integers(1, 4))
+        ops = random_catalogue_ops(n, int(rng.integers(8, 40)), seed, bsz=bsz, p_per_sample=0.4, max_wires=n)
+        if not any(o.get("params") is not None for o in ops):
+            continue
+        engine._PLAN_CACHE.clear()
+        check_against_oracle(device, n, bsz, ops, grad=True)

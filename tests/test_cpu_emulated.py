@@ -170,6 +170,16 @@ def test_random_gates_through_blocks():
     cases.check_random_gates_through_blocks("cpu", seeds=(1,))
 
 
+def test_random_catalogue_gradients():
+    cases.check_random_catalogue_gradients("cpu")
+
+
+@pytest.mark.parametrize("tiles", [(4, 5, 2)])
+def test_random_catalogue_gradients_multi_tile(tiles):
+    P.T_SINGLE, P.T_MULTI, P.L_MIN = tiles      # (restored by the autouse fixture)
+    cases.check_random_catalogue_gradients("cpu", seeds=range(20, 26))
+
+
 def test_large_batch_readout():
     cases.check_large_batch_readout("cpu", bsz=66000)
 
