@@ -312,3 +312,16 @@ def test_batch_sharded_step_matches_one_process():
     if not os.path.exists(emu):
         pytest.skip("host emulation library not built (run __graft_entry__.build())")
     mp.spawn(_worker_batch_axis, args=(2, _free_port(), emu), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize("grad", [False, True])
+def test_sharded_random_catalogue_gates(grad):
+    """Random gates from the whole in-tile catalogue (controls / parity bits in the rank index, 2-qubit dense gates across it,
+    per-sample parameters, inverses) on a sharded device vs the oracle (states, expectation values) and, with `grad`, the
+    sharded adjoint vs one device: a few seeds of tools/fuzz_sharded.py."""
+    emu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "libtqb200_emu.so")
+    if not os.path.exists(emu):
+        pytest.skip("host emulation library not built (run __graft_entry__.build())")
+    from tools.fuzz_sharded import worker
+
+    mp.spawn(worker, args=(2, _free_port(), 7, [0, 1, 2], 40, emu, 2, grad), nprocs=2, join=True)

@@ -84,6 +84,7 @@ def worker(rank, world, port, n, seeds, count, emu, bsz, grad):
             print(f"rank {rank} seed {seed}: EXCEPTION {type(e).__name__}: {e}", flush=True)
             break
     dist.destroy_process_group()
+    assert bad == 0, f"rank {rank}: {bad} mismatching circuit(s)"
 
 if __name__ == "__main__":
     world, n, s0, s1, count = [int(a) for a in sys.argv[1:6]]
