@@ -166,6 +166,20 @@ def check_parameter_values_are_read_at_the_gate_call(device):
         v.add_(1.0)
     with pytest.raises(RuntimeError, match="modified in place"):
         q.get_states_1d()
+    # layer templates queue their Parameters by reference (cached records): an optimizer step or any other in-place edit
+    # between the layer call and the state read is an error too, for single layers and whole templates
+    for layer in (tq.Op1QAllLayer(op=tq.RX, n_wires=3, has_params=True, trainable=True).to(device),
+                  tq.EfficientSU2(n_wires=3, reps=1).to(device)):
+        for _ in range(2):                       # second round: the records come from the layer's cache
+            q = tq.QuantumDevice(n_wires=3, bsz=2, device=device)
+            layer(q)
+            q.get_states_1d()                    # untouched parameters: fine
+            q = tq.QuantumDevice(n_wires=3, bsz=2, device=device)
+            layer(q)
+            with torch.no_grad():
+                next(layer.parameters()).add_(0.25)
+            with pytest.raises(RuntimeError, match="modified in place"):
+                q.get_states_1d()
 
 
 def check_checkpoint_round_trip(device):

@@ -50,15 +50,22 @@ class GateQueue(list):
     def append(self, rec):
         q = self._mode()
         list.append(q, rec)
-        if type(rec) is tuple and rec[2] is not None:
-            q.guard.append((rec[2], rec[2]._version))
+        if type(rec) is tuple:
+            if rec[2] is not None:
+                q.guard.append((rec[2], rec[2]._version))
+        else:   # engine.RecordChunk of a layer template: its Parameters are queued by reference
+            q.guard.append((rec.params, [p._version for p in rec.params]))
 
     def extend(self, recs):
-        list.extend(self._mode(), recs)
+        q = self._mode()
+        list.extend(q, recs)
+        ps = [r[2] for r in recs if r[2] is not None]
+        if ps:
+            q.guard.append((ps, [p._version for p in ps]))
 
     def check(self):
         for t, v in self.guard:
-            if t._version != v:
+            if (t._version != v) if type(v) is int else ([p._version for p in t] != v):
                 raise RuntimeError(
                     "a gate parameter tensor was modified in place after the gate was queued and before the state "
                     "was read (gates run lazily): read the state (`qdev.states`) before modifying it, or pass a clone")
